@@ -1,0 +1,84 @@
+// bhrt_render -- headless C++ host program: the replacement for the reference's main()
+// (reference Main.cpp:418-431: LoadScene(literal path) -> ShowViewport() -> BeginRender()).
+// It stays C++ and reaches the GPU only through the C ABI of include/bhrt.h.
+//
+// usage: bhrt_render <scene.xml> <out_prefix> [--det] [--spp N] [--gi N] [--seed S] [--size W H]
+//                    [--device D] [--aov] [--photons N]
+// writes <out_prefix>.png (RenderImage::SaveImage equivalent) and, with --aov, <out_prefix>.aov in
+// the layout of oracle/ref_build/driver.cpp; prints one JSON line.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../../include/bhrt.h"
+#include "../../../include/bhrt_host.h"
+
+int main(int argc, char **argv)
+{
+    if (argc < 3) { fprintf(stderr, "usage: %s scene.xml out_prefix [--det] [--spp N] [--gi N] [--seed S] [--size W H] [--device D] [--aov] [--photons N]\n", argv[0]); return 2; }
+    bhrt_params p;
+    memset(&p, 0, sizeof(p));
+    p.mode = BHRT_MODE_PATH; p.spp = 32; p.gi_depth = 3; p.tir_budget = 16; p.seed = 1;
+    int W = 0, H = 0, device = 0, aov = 0, photons = 0;
+    for (int a = 3; a < argc; a++) {
+        if (!strcmp(argv[a], "--det")) p.mode = BHRT_MODE_DET;
+        else if (!strcmp(argv[a], "--spp") && a + 1 < argc) p.spp = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--gi") && a + 1 < argc) p.gi_depth = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--seed") && a + 1 < argc) p.seed = strtoull(argv[++a], nullptr, 0);
+        else if (!strcmp(argv[a], "--size") && a + 2 < argc) { W = atoi(argv[++a]); H = atoi(argv[++a]); }
+        else if (!strcmp(argv[a], "--device") && a + 1 < argc) device = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--photons") && a + 1 < argc) photons = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--aov")) aov = 1;
+        else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
+    }
+    if (p.mode == BHRT_MODE_DET) p.spp = 1;
+    bhrt_host_scene *scene = bhrt_host_load_scene(argv[1]);
+    if (!scene) { fprintf(stderr, "LoadScene failed: %s\n", bhrt_host_last_error()); return 3; }
+    if (*bhrt_host_warnings(scene)) fprintf(stderr, "%s", bhrt_host_warnings(scene));
+    if (W > 0 && bhrt_host_set_resolution(scene, W, H)) { fprintf(stderr, "bad --size\n"); return 2; }
+    const bhrt_scene_desc *d = bhrt_host_scene_desc(scene);
+    W = d->camera.width; H = d->camera.height;
+
+    bhrt_ctx *ctx = nullptr;
+    if (bhrt_create(device, &ctx)) { fprintf(stderr, "bhrt_create: %s\n", bhrt_last_error()); return 4; }
+    if (bhrt_upload_scene(ctx, d)) { fprintf(stderr, "bhrt_upload_scene: %s\n", bhrt_last_error()); return 4; }
+    int stored = 0;
+    uint64_t photon_rays = 0;
+    if (photons > 0) {
+        if (bhrt_photons_emit(ctx, photons, p.seed, &stored, &photon_rays) || bhrt_photons_build(ctx, stored)) {
+            fprintf(stderr, "photon map: %s\n", bhrt_last_error()); return 4;
+        }
+        p.use_photon_map = 1; p.photon_k = 1000; p.photon_radius = 0.5f;
+    }
+    size_t n = (size_t)W * H;
+    std::vector<uint8_t> rgb8(n * 3);
+    std::vector<float> linear(n * 3), z(n);
+    std::vector<int32_t> hit(n);
+    bhrt_outputs o;
+    memset(&o, 0, sizeof(o));
+    o.rgb8 = rgb8.data(); o.linear = linear.data(); o.hit_id = hit.data(); o.z = z.data();
+    if (bhrt_render(ctx, &p, &o)) { fprintf(stderr, "bhrt_render: %s\n", bhrt_last_error()); return 5; }
+    std::string prefix = argv[2];
+    if (bhrt_host_save_png((prefix + ".png").c_str(), rgb8.data(), W, H, 3)) fprintf(stderr, "cannot write %s.png\n", prefix.c_str());
+    if (aov) {
+        FILE *fp = fopen((prefix + ".aov").c_str(), "wb");
+        if (fp) {
+            int32_t hdr[4] = { 0x54524842, W, H, p.spp };
+            fwrite(hdr, sizeof(hdr), 1, fp);
+            fwrite(linear.data(), 4, linear.size(), fp);
+            fwrite(rgb8.data(), 1, rgb8.size(), fp);
+            fwrite(hit.data(), 4, hit.size(), fp);
+            fwrite(z.data(), 4, z.size(), fp);
+            fclose(fp);
+        }
+    }
+    double rays = (double)o.rays_closest + (double)o.rays_shadow;
+    printf("{\"scene\": \"%s\", \"width\": %d, \"height\": %d, \"spp\": %d, \"mode\": \"%s\", \"kernel_ms\": %.4f, "
+           "\"rays_closest\": %llu, \"rays_shadow\": %llu, \"mrays_per_s\": %.2f, \"photons_stored\": %d}\n",
+           argv[1], W, H, p.spp, p.mode == BHRT_MODE_DET ? "det" : "path", o.kernel_ms,
+           (unsigned long long)o.rays_closest, (unsigned long long)o.rays_shadow, rays / (o.kernel_ms * 1e3), stored);
+    bhrt_destroy(ctx);
+    bhrt_host_free_scene(scene);
+    return 0;
+}

@@ -1,0 +1,107 @@
+// TEST-ONLY harness: compiles the device code of the renderer (csrc/device/core.cuh, the very
+// source nvcc builds into the sm_100a kernels) with g++ and runs it per pixel on the CPU, so
+// that the CPU-only CI (`pytest -m "not gpu"`) can compare the kernel LOGIC with the oracle.
+// It is never linked into libbhrt.so / libbhrt_host.so and nothing in the product loads it.
+//
+// usage: emu_render <scene.xml> <out_prefix> [--det] [--spp N] [--gi N] [--seed S] [--size W H]
+// writes <out_prefix>.aov in the layout of oracle/ref_build/driver.cpp.
+#include <omp.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../bhraytracer_b200/csrc/device/core.cuh"
+#include "../../bhraytracer_b200/csrc/device/setup.hpp"
+#include "../../bhraytracer_b200/csrc/host/scene.hpp"
+
+using namespace bhrt;
+
+int main(int argc, char **argv)
+{
+    if (argc < 3) { fprintf(stderr, "usage: %s scene.xml out_prefix [--det] [--spp N] [--gi N] [--seed S] [--size W H]\n", argv[0]); return 2; }
+    int det = 0, spp = 32, gi = 3, W = 0, H = 0;
+    unsigned long long seed = 1;
+    for (int a = 3; a < argc; a++) {
+        if (!strcmp(argv[a], "--det")) det = 1;
+        else if (!strcmp(argv[a], "--spp") && a + 1 < argc) spp = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--gi") && a + 1 < argc) gi = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--seed") && a + 1 < argc) seed = strtoull(argv[++a], nullptr, 0);
+        else if (!strcmp(argv[a], "--size") && a + 2 < argc) { W = atoi(argv[++a]); H = atoi(argv[++a]); }
+        else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
+    }
+    if (det) spp = 1;
+    host::Scene sc;
+    host::FlatScene flat;
+    std::string err;
+    if (!host::LoadScene(argv[1], sc, &err)) { fprintf(stderr, "LoadScene: %s\n", err.c_str()); return 3; }
+    if (!host::Flatten(sc, flat, &err)) { fprintf(stderr, "Flatten: %s\n", err.c_str()); return 3; }
+    for (auto &w : sc.warnings) fprintf(stderr, "warning: %s\n", w.c_str());
+    bhrt_scene_desc &D = flat.desc;
+    if (W > 0) { D.camera.width = W; D.camera.height = H; }
+    W = D.camera.width; H = D.camera.height;
+
+    std::vector<bhrt_light> lights(D.lights, D.lights + D.n_lights);
+    float allI = 0;
+    sort_lights(lights, allI);
+    std::vector<float> offs = texture_filter_offsets();
+    FrameConstants fc = camera_setup(D.camera);
+
+    SceneView s;
+    memset(&s, 0, sizeof(s));
+    s.n_nodes = D.n_nodes; s.n_lights = D.n_lights;
+    s.max_depth = 1;
+    for (int i = 0; i < D.n_nodes; i++) if (D.nodes[i].depth > s.max_depth) s.max_depth = D.nodes[i].depth;
+    s.nodes = D.nodes; s.materials = D.materials; s.lights = lights.data();
+    s.texmaps = D.texmaps; s.textures = D.textures; s.texels = D.texels;
+    s.meshes = D.meshes; s.mesh_data = D.mesh_data; s.tex_offsets = offs.data();
+    s.background = D.background; s.environment = D.environment;
+    s.all_light_intensity = allI;
+    s.cam_pos = fc.cam_pos; s.top_left = fc.top_left; s.dd_x = fc.dd_x; s.dd_y = fc.dd_y;
+    s.width = W; s.height = H;
+
+    PhotonGather pg; memset(&pg, 0, sizeof(pg));
+    ShadeCfg cfg; cfg.mode = det ? BHRT_MODE_DET : BHRT_MODE_PATH; cfg.gi_depth = gi; cfg.tir_budget = 16;
+    std::vector<float> linear((size_t)W * H * 3), z((size_t)W * H);
+    std::vector<uint8_t> rgb8((size_t)W * H * 3);
+    std::vector<int32_t> hitid((size_t)W * H);
+    unsigned long long closest = 0, shadow = 0;
+    double t0 = omp_get_wtime();
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : closest, shadow)
+    for (int j = 0; j < H; j++) {
+        for (int i = 0; i < W; i++) {
+            RayCounters rc; rc.closest = 0; rc.shadow = 0;
+            V3 sum(0, 0, 0);
+            int id0 = -1; float z0 = BHRT_BIGFLOAT;
+            for (int sidx = 0; sidx < spp; sidx++) {
+                Rng rng; rng.seed(seed, (uint64_t)j * W + i, sidx);
+                Ray pr = primary_ray(s, i, j, !det, rng);
+                int id; float zz;
+                V3 c = trace_sample(s, cfg, pg, pr, (float)i / W, (float)j / H, rng, rc, id, zz);
+                if (sidx == 0) { id0 = id; z0 = zz; }
+                sum = sum + c;
+            }
+            V3 out = sum / (float)spp;
+            size_t p = (size_t)j * W + i;
+            linear[3 * p] = out.x; linear[3 * p + 1] = out.y; linear[3 * p + 2] = out.z;
+            V3 g = gamma_correct(out);
+            rgb8[3 * p] = float_to_byte(g.x); rgb8[3 * p + 1] = float_to_byte(g.y); rgb8[3 * p + 2] = float_to_byte(g.z);
+            hitid[p] = id0; z[p] = z0;
+            closest += rc.closest; shadow += rc.shadow;
+        }
+    }
+    double ms = (omp_get_wtime() - t0) * 1e3;
+    std::string path = std::string(argv[2]) + ".aov";
+    FILE *fp = fopen(path.c_str(), "wb");
+    if (!fp) return 4;
+    int32_t hdr[4] = { 0x54524842, W, H, spp };
+    fwrite(hdr, sizeof(hdr), 1, fp);
+    fwrite(linear.data(), 4, linear.size(), fp);
+    fwrite(rgb8.data(), 1, rgb8.size(), fp);
+    fwrite(hitid.data(), 4, hitid.size(), fp);
+    fwrite(z.data(), 4, z.size(), fp);
+    fclose(fp);
+    printf("{\"emu\": true, \"width\": %d, \"height\": %d, \"spp\": %d, \"ms\": %.3f, \"rays_closest\": %llu, \"rays_shadow\": %llu, \"nodes\": %d}\n",
+           W, H, spp, ms, closest, shadow, D.n_nodes);
+    return 0;
+}
