@@ -79,7 +79,8 @@ class Outputs(C.Structure):
 
 # every symbol include/bhrt.h and include/bhrt_host.h declare
 DEVICE_SYMBOLS = ["bhrt_abi_version", "bhrt_last_error", "bhrt_create", "bhrt_destroy", "bhrt_upload_scene",
-                  "bhrt_render", "bhrt_render_device", "bhrt_accum_buffer", "bhrt_resolve",
+                  "bhrt_render", "bhrt_render_device", "bhrt_accum_buffer", "bhrt_aov_buffers", "bhrt_resolve",
+                  "bhrt_set_stream", "bhrt_launch_count",
                   "bhrt_photons_emit", "bhrt_photons_buffer", "bhrt_photons_set", "bhrt_photons_get",
                   "bhrt_photons_build"]
 HOST_SYMBOLS = ["bhrt_host_load_scene", "bhrt_host_free_scene", "bhrt_host_last_error", "bhrt_host_scene_desc",
@@ -128,6 +129,9 @@ def device_lib():
         L.bhrt_render_device.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Outputs)]
         L.bhrt_accum_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.bhrt_resolve.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Outputs)]
+        L.bhrt_aov_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.bhrt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.bhrt_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.bhrt_photons_emit.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
         L.bhrt_photons_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
         L.bhrt_photons_set.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int]
@@ -257,6 +261,13 @@ class Renderer:
         bufs.update(rays_closest=int(o.rays_closest), rays_shadow=int(o.rays_shadow), kernel_ms=float(o.kernel_ms))
         return bufs
 
+    def render_into(self, params, rgb8=None, linear=None, hit_id=None, z=None):
+        """bhrt_render with caller-owned HOST buffers given as raw addresses (e.g. pinned memory)."""
+        o = Outputs()
+        o.rgb8, o.linear, o.hit_id, o.z = rgb8, linear, hit_id, z
+        self._check(self._L.bhrt_render(self._ctx, C.byref(params), C.byref(o)))
+        return dict(rays_closest=int(o.rays_closest), rays_shadow=int(o.rays_shadow), kernel_ms=float(o.kernel_ms))
+
     def render_device(self, params=None, stats=True, **kw):
         """Render into the device accumulation buffer only (nothing crosses PCIe except counters)."""
         p = params or self.params(**kw)
@@ -270,10 +281,28 @@ class Renderer:
         self._check(self._L.bhrt_accum_buffer(self._ctx, C.byref(ptr), C.byref(n)))
         return ptr.value, n.value
 
+    def aov_buffers(self):
+        """Device pointers of the int32 hit-id and float z buffers (W*H each)."""
+        a, z = C.c_void_p(), C.c_void_p()
+        self._check(self._L.bhrt_aov_buffers(self._ctx, C.byref(a), C.byref(z)))
+        return a.value, z.value
+
     def resolve(self, total_spp, want=("rgb8", "linear", "hit_id", "z")):
+        if not want:
+            self._check(self._L.bhrt_resolve(self._ctx, int(total_spp), None))
+            return {}
         o, bufs = self._alloc_outputs(want)
         self._check(self._L.bhrt_resolve(self._ctx, int(total_spp), C.byref(o)))
         return bufs
+
+    def set_stream(self, cuda_stream):
+        """Run this ctx's work on the given cudaStream_t (int handle; 0/None = its own stream)."""
+        self._check(self._L.bhrt_set_stream(self._ctx, C.c_void_p(int(cuda_stream) if cuda_stream else None)))
+
+    def launch_count(self):
+        n = C.c_uint64()
+        self._check(self._L.bhrt_launch_count(self._ctx, C.byref(n)))
+        return n.value
 
     # ---- caustic photon map -------------------------------------------------------------------
     def photons_emit(self, target_stored, seed=1):

@@ -40,7 +40,8 @@ struct DevBuf {
 struct bhrt_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    unsigned long long launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool have_scene = false;
     SceneView view;
@@ -136,7 +137,8 @@ int bhrt_create(int device, bhrt_ctx **out)
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     if (c->counters.ensure(8 * sizeof(unsigned long long))) { delete c; return set_err(BHRT_ERR_CUDA, "cudaMalloc(counters)"); }
@@ -156,7 +158,7 @@ int bhrt_destroy(bhrt_ctx *c)
     for (auto b : bufs) b->release();
     c->photons.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->own_stream);
     delete c;
     return BHRT_OK;
 }
@@ -276,7 +278,7 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     CU(cudaEventRecord(c->ev0, c->stream));
     if (a.n_rows > 0 && a.sample_end > a.sample_begin)
         render_kernel<<<grid, block, 0, c->stream>>>(c->view, a, (float4 *)c->accum.p, (int *)c->hit_id.p, (float *)c->z.p,
-                                                     (unsigned long long *)c->counters.p);
+                                                     (unsigned long long *)c->counters.p), c->launches++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev1, c->stream));
     c->rendered_spp = a.sample_end - a.sample_begin;
@@ -301,6 +303,30 @@ int bhrt_accum_buffer(bhrt_ctx *c, void **ptr, size_t *bytes)
     return BHRT_OK;
 }
 
+int bhrt_aov_buffers(bhrt_ctx *c, void **hit_id, void **z)
+{
+    if (!c || !c->have_scene) return set_err(BHRT_ERR_STATE, "bhrt_aov_buffers: no scene uploaded");
+    if (hit_id) *hit_id = c->hit_id.p;
+    if (z) *z = c->z.p;
+    return BHRT_OK;
+}
+
+int bhrt_set_stream(bhrt_ctx *c, void *stream)
+{
+    if (!c) return set_err(BHRT_ERR_ARG, "bhrt_set_stream: null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return BHRT_OK;
+}
+
+int bhrt_launch_count(bhrt_ctx *c, uint64_t *launches)
+{
+    if (!c || !launches) return set_err(BHRT_ERR_ARG, "bhrt_launch_count: null argument");
+    *launches = c->launches;
+    return BHRT_OK;
+}
+
 int bhrt_resolve(bhrt_ctx *c, int32_t total_spp, bhrt_outputs *out)
 {
     if (!c || !c->have_scene) return set_err(BHRT_ERR_STATE, "bhrt_resolve: no scene uploaded");
@@ -308,6 +334,7 @@ int bhrt_resolve(bhrt_ctx *c, int32_t total_spp, bhrt_outputs *out)
     CU(cudaSetDevice(c->device));
     int n = c->width * c->height;
     resolve_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>((const float4 *)c->accum.p, n, (float)total_spp, (float *)c->linear.p, (uint8_t *)c->rgb8.p);
+    c->launches++;
     CU(cudaGetLastError());
     if (out) {
         if (out->rgb8) CU(cudaMemcpyAsync(out->rgb8, c->rgb8.p, (size_t)n * 3, cudaMemcpyDeviceToHost, c->stream));

@@ -217,8 +217,22 @@ int bhrt_render_device(bhrt_ctx *ctx, const bhrt_params *params, bhrt_outputs *o
  * multi-GPU host can all-reduce it (NCCL) between bhrt_render_device and bhrt_resolve. */
 int bhrt_accum_buffer(bhrt_ctx *ctx, void **device_ptr, size_t *bytes);
 
-/* Divide by total_spp, gamma, 8-bit; copy requested outputs to HOST buffers. */
+/* Device pointers of the sample-0 AOV buffers (int32 hit_id[H*W], float z[H*W]); rows a
+ * launch did not cover hold zeros, so a multi-GPU host can sum-reduce them like the
+ * accumulation buffer (tile sharding). */
+int bhrt_aov_buffers(bhrt_ctx *ctx, void **hit_id_device_ptr, void **z_device_ptr);
+
+/* Divide by total_spp, gamma, 8-bit; copy requested outputs to HOST buffers (out may be NULL:
+ * the resolved image then stays in device memory). */
 int bhrt_resolve(bhrt_ctx *ctx, int32_t total_spp, bhrt_outputs *out);
+
+/* Run all further work of this ctx on the caller's CUDA stream (a cudaStream_t; NULL = the
+ * ctx's own stream), so a host that interleaves collectives can order and time everything on
+ * one stream. */
+int bhrt_set_stream(bhrt_ctx *ctx, void *cuda_stream);
+
+/* Number of kernels this ctx has launched since bhrt_create (bench.py's gpu_launches). */
+int bhrt_launch_count(bhrt_ctx *ctx, uint64_t *launches);
 
 /* Caustic photon map (reference Main.cpp:342-386, cyPhotonMap.h).
  * emit: traces photons until `target_stored` are stored on this GPU; records are the

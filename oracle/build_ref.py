@@ -20,6 +20,9 @@ Patch list (numbers = SURVEY.md section 8(c)):
   D-4  det mode: refraction gloss = 0   (MtlBlinn.cpp:116)
 All D-* patches are runtime-switched by g_bhrt_det, so one binary serves both modes.
 `bhrt_ref_pm` is the same build with -DUSE_PhotonMap (reference Main.cpp:51, MtlBlinn.cpp:25).
+`bhrt_ref_cnt` is bhrt_ref with -DBHRT_COUNT_ALL: five more per-thread counters (instances
+tested, BVH boxes tested, triangles tested, triangles accepted, file-texture taps) that define
+the ALGORITHMIC bytes per ray of SURVEY.md 8(d); it is never used for timing.
 """
 import os
 import shutil
@@ -37,6 +40,8 @@ HOOKS = (
     "class Node; void bhrt_record_primary(int,int,const Node*,float); void bhrt_record_linear(int,int,float,float,float);\n"
     "void bhrt_count_closest(); void bhrt_count_shadow(); void bhrt_photon_begin(); void bhrt_photon_end();\n"
 )
+# work counters of the -DBHRT_COUNT_ALL build (0 inst, 1 box, 2 tri, 3 tri accepted, 4 texture tap)
+CNT = "#ifdef BHRT_COUNT_ALL\nvoid bhrt_count(int);\n#define BHRT_CNT(k) bhrt_count(k)\n#else\n#define BHRT_CNT(k)\n#endif\n"
 
 DET_DIRECT = (
     "if (g_bhrt_det) { for (int li = 0; li < (int)lights.size(); ++li) { Light* light = lights[li];"
@@ -49,7 +54,8 @@ DET_DIRECT = (
 # (line number, substring that must be on that line, replacement function)
 PATCHES = {
     "Main.cpp": [
-        (1, "", lambda s: HOOKS + s),
+        (1, "", lambda s: HOOKS + CNT + s),
+        (393, "Ray transformedRay = root->GetChild(i)->ToNodeCoords(ray);", lambda s: s + "\t\tBHRT_CNT(0);\n"),
         (52, "#define MAX_PhotonCount 1000000", lambda s: "#define MAX_PhotonCount g_bhrt_photons\n"),
         (53, "#define MAX_CausticPhotonCount 1000000", lambda s: "#define MAX_CausticPhotonCount g_bhrt_photons\n"),
         (130, "#define GIBounceCount 3", lambda s: "#define GIBounceCount g_bhrt_gi\n"),
@@ -78,14 +84,27 @@ PATCHES = {
         (308, "{", lambda s: DET_DIRECT + s),
     ],
     "Lights/GenLight.cpp": [
-        (1, "", lambda s: "void bhrt_count_shadow();\n" + s),
+        (1, "", lambda s: "void bhrt_count_shadow();\n" + CNT + s),
+        (17, "Ray transformedRay = root->ToNodeCoords(ray);", lambda s: s + "\tif (root != &rootNode) BHRT_CNT(0);\n"),
         (12, "return ShadowRayRecursive(&rootNode, ray, t_max) ? 0.f : 1.f;", lambda s: "\tbhrt_count_shadow();\n" + s),
+    ],
+    "Objects/Box/Box.cpp": [
+        (1, "", lambda s: CNT + s),
+        (4, "{", lambda s: "{ BHRT_CNT(1);\n"),
+    ],
+    "Objects/TriObj/TriObj.cpp": [
+        (1, "", lambda s: CNT + s),
+        (69, "{", lambda s: "{ BHRT_CNT(2);\n"),
+        (169, "Vec3f hitPointNormal = GetNormal(faceID, bc);", lambda s: "\tBHRT_CNT(3);\n" + s),
+    ],
+    "Textures/Texture.cpp": [
+        (1, "", lambda s: CNT + s),
+        (99, "if (width + height == 0) return Color(0, 0, 0);", lambda s: "\tBHRT_CNT(4);\n" + s),
     ],
 }
 
 UNPATCHED = [
-    "xmlload.cpp", "Lights/PointLight.cpp", "Objects/Box/Box.cpp", "Objects/Plane/Plane.cpp",
-    "Objects/Sphere/Sphere.cpp", "Objects/TriObj/TriObj.cpp", "Textures/Texture.cpp",
+    "xmlload.cpp", "Lights/PointLight.cpp", "Objects/Plane/Plane.cpp", "Objects/Sphere/Sphere.cpp",
     "Tinyxml2/tinyxml2.cpp", "LoadPNG/lodepng.cpp",
 ]
 
@@ -118,13 +137,21 @@ def main():
         for rel in UNPATCHED:
             jobs.append((os.path.join(REF, rel), os.path.join(tmp, rel.replace("/", "_") + ".o"), []))
         jobs.append((os.path.join(HERE, "ref_build/gl_stubs.cpp"), os.path.join(tmp, "gl_stubs.o"), []))
-        jobs.append((os.path.join(HERE, "ref_build/driver.cpp"), os.path.join(tmp, "driver.o"), []))
-        jobs.append((patched_copy("Lights/GenLight.cpp", tmp), os.path.join(tmp, "GenLight.o"), ["-I" + REF + "/Lights"]))
         main_src = patched_copy("Main.cpp", tmp)
         mtl_src = patched_copy("Materials/Blinn/MtlBlinn.cpp", tmp)
+        # sources whose object differs between the plain and the -DBHRT_COUNT_ALL build
+        counted = [(patched_copy("Lights/GenLight.cpp", tmp), "GenLight", ["-I" + REF + "/Lights"]),
+                   (patched_copy("Objects/Box/Box.cpp", tmp), "Box", ["-I" + REF + "/Objects/Box"]),
+                   (patched_copy("Objects/TriObj/TriObj.cpp", tmp), "TriObj", ["-I" + REF + "/Objects/TriObj"]),
+                   (patched_copy("Textures/Texture.cpp", tmp), "Texture", ["-I" + REF + "/Textures"]),
+                   (main_src, "Main", ["-Dmain=ref_main_unused"]),
+                   (os.path.join(HERE, "ref_build/driver.cpp"), "driver", [])]
+        for src, stem, extra in counted:
+            jobs.append((src, os.path.join(tmp, "V_%s.o" % stem), extra))
+            jobs.append((src, os.path.join(tmp, "V_%s_cnt.o" % stem), extra + ["-DBHRT_COUNT_ALL"]))
+        jobs.append((main_src, os.path.join(tmp, "V_Main_pm.o"), ["-Dmain=ref_main_unused", "-DUSE_PhotonMap"]))
         for tag, extra in (("", []), ("_pm", ["-DUSE_PhotonMap"])):
-            jobs.append((main_src, os.path.join(tmp, "Main%s.o" % tag), ["-Dmain=ref_main_unused"] + extra))
-            jobs.append((mtl_src, os.path.join(tmp, "MtlBlinn%s.o" % tag), ["-I" + REF + "/Materials/Blinn"] + extra))
+            jobs.append((mtl_src, os.path.join(tmp, "V_MtlBlinn%s.o" % tag), ["-I" + REF + "/Materials/Blinn"] + extra))
 
         def cc(job):
             src, obj, extra = job
@@ -133,11 +160,17 @@ def main():
 
         with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
             objs = list(ex.map(cc, jobs))
-        common = [o for o in objs if "/Main" not in o and "/MtlBlinn" not in o]
-        for tag in ("", "_pm"):
-            exe = os.path.join(OUT, "bhrt_ref" + tag)
-            subprocess.check_call(["g++", "-fopenmp", "-o", exe] + common +
-                                  [os.path.join(tmp, "Main%s.o" % tag), os.path.join(tmp, "MtlBlinn%s.o" % tag)])
+        common = [o for o in objs if "/V_" not in o]
+        V = lambda stem: os.path.join(tmp, "V_%s.o" % stem)
+        plain = [V("GenLight"), V("Box"), V("TriObj"), V("Texture"), V("driver")]
+        variants = {
+            "bhrt_ref": plain + [V("Main"), V("MtlBlinn")],
+            "bhrt_ref_pm": plain + [V("Main_pm"), V("MtlBlinn_pm")],
+            "bhrt_ref_cnt": [V(st + "_cnt") for st in ("GenLight", "Box", "TriObj", "Texture", "driver", "Main")] + [V("MtlBlinn")],
+        }
+        for name, extra_objs in variants.items():
+            exe = os.path.join(OUT, name)
+            subprocess.check_call(["g++", "-fopenmp", "-o", exe] + common + extra_objs)
             print("built", exe)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

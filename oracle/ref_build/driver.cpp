@@ -64,6 +64,13 @@ void bhrt_record_linear(int i, int j, float r, float g, float b)
 	int idx = (j * s_W + i) * 3;
 	s_linear[idx] = r; s_linear[idx + 1] = g; s_linear[idx + 2] = b;
 }
+#ifdef BHRT_COUNT_ALL
+// work counters of the instrumented build (see build_ref.py): 0 instances tested, 1 BVH boxes
+// tested, 2 triangles tested, 3 triangles accepted (vn+vt fetched), 4 file-texture taps
+struct alignas(64) Work { long long c[8]; };
+static Work s_work[512];
+void bhrt_count(int k) { s_work[omp_get_thread_num() & 511].c[k]++; }
+#endif
 void bhrt_count_closest() { s_cnt[omp_get_thread_num() & 511].closest++; }
 void bhrt_count_shadow() { s_cnt[omp_get_thread_num() & 511].shadow++; }
 void bhrt_photon_begin() { s_photon_t0 = omp_get_wtime(); }
@@ -160,9 +167,16 @@ int main(int argc, char **argv)
 	if (writePng) renderImage.SaveImage((prefix + ".png").c_str());
 
 	fprintf(realOut, "{\"scene\": \"%s\", \"width\": %d, \"height\": %d, \"spp\": %d, \"gi\": %d, \"det\": %d, "
-		"\"threads\": %d, \"rand\": \"%s\", \"ms\": %.3f, \"photon_build_ms\": %.3f, \"rays_closest\": %lld, \"rays_shadow\": %lld, \"nodes\": %d}\n",
+		"\"threads\": %d, \"rand\": \"%s\", \"ms\": %.3f, \"photon_build_ms\": %.3f, \"rays_closest\": %lld, \"rays_shadow\": %lld, \"nodes\": %d",
 		scene, s_W, s_H, g_bhrt_spp, g_bhrt_gi, g_bhrt_det, threads, s_use_libc_rand ? "libc" : "per-thread",
 		ms - s_photon_ms, s_photon_ms, closest, shadow, next);
+#ifdef BHRT_COUNT_ALL
+	long long w[5] = { 0, 0, 0, 0, 0 };
+	for (int i = 0; i < 512; i++) for (int k = 0; k < 5; k++) w[k] += s_work[i].c[k];
+	fprintf(realOut, ", \"inst_tested\": %lld, \"boxes_tested\": %lld, \"tris_tested\": %lld, \"tris_accepted\": %lld, \"texture_taps\": %lld",
+		w[0], w[1], w[2], w[3], w[4]);
+#endif
+	fprintf(realOut, "}\n");
 	fclose(realOut);
 	return 0;
 }

@@ -4,7 +4,10 @@
 // It is never linked into libbhrt.so / libbhrt_host.so and nothing in the product loads it.
 //
 // usage: emu_render <scene.xml> <out_prefix> [--det] [--spp N] [--gi N] [--seed S] [--size W H]
-// writes <out_prefix>.aov in the layout of oracle/ref_build/driver.cpp.
+//                   [--rows B E STRIDE] [--samples B E]
+// writes <out_prefix>.aov in the layout of oracle/ref_build/driver.cpp and <out_prefix>.acc, the
+// float4 accumulation buffer (r,g,b sums + sample count; zeros outside the rendered share) a
+// GPU rank would hold after bhrt_render_device with the same row / sample share.
 #include <omp.h>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +24,7 @@ int main(int argc, char **argv)
 {
     if (argc < 3) { fprintf(stderr, "usage: %s scene.xml out_prefix [--det] [--spp N] [--gi N] [--seed S] [--size W H]\n", argv[0]); return 2; }
     int det = 0, spp = 32, gi = 3, W = 0, H = 0;
+    int row_b = 0, row_e = 0, row_s = 1, smp_b = 0, smp_e = 0;
     unsigned long long seed = 1;
     for (int a = 3; a < argc; a++) {
         if (!strcmp(argv[a], "--det")) det = 1;
@@ -28,6 +32,8 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[a], "--gi") && a + 1 < argc) gi = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--seed") && a + 1 < argc) seed = strtoull(argv[++a], nullptr, 0);
         else if (!strcmp(argv[a], "--size") && a + 2 < argc) { W = atoi(argv[++a]); H = atoi(argv[++a]); }
+        else if (!strcmp(argv[a], "--rows") && a + 3 < argc) { row_b = atoi(argv[++a]); row_e = atoi(argv[++a]); row_s = atoi(argv[++a]); }
+        else if (!strcmp(argv[a], "--samples") && a + 2 < argc) { smp_b = atoi(argv[++a]); smp_e = atoi(argv[++a]); }
         else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
     }
     if (det) spp = 1;
@@ -62,18 +68,21 @@ int main(int argc, char **argv)
 
     PhotonGather pg; memset(&pg, 0, sizeof(pg));
     ShadeCfg cfg; cfg.mode = det ? BHRT_MODE_DET : BHRT_MODE_PATH; cfg.gi_depth = gi; cfg.tir_budget = 16;
-    std::vector<float> linear((size_t)W * H * 3), z((size_t)W * H);
-    std::vector<uint8_t> rgb8((size_t)W * H * 3);
-    std::vector<int32_t> hitid((size_t)W * H);
+    if (row_e == 0) row_e = H;
+    if (row_s < 1) row_s = 1;
+    if (smp_e == 0) smp_e = spp;
+    std::vector<float> linear((size_t)W * H * 3, 0.f), z((size_t)W * H, 0.f), acc((size_t)W * H * 4, 0.f);
+    std::vector<uint8_t> rgb8((size_t)W * H * 3, 0);
+    std::vector<int32_t> hitid((size_t)W * H, 0);
     unsigned long long closest = 0, shadow = 0;
     double t0 = omp_get_wtime();
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : closest, shadow)
-    for (int j = 0; j < H; j++) {
+    for (int j = row_b; j < row_e; j += row_s) {
         for (int i = 0; i < W; i++) {
             RayCounters rc; rc.closest = 0; rc.shadow = 0;
             V3 sum(0, 0, 0);
             int id0 = -1; float z0 = BHRT_BIGFLOAT;
-            for (int sidx = 0; sidx < spp; sidx++) {
+            for (int sidx = smp_b; sidx < smp_e; sidx++) {
                 Rng rng; rng.seed(seed, (uint64_t)j * W + i, sidx);
                 Ray pr = primary_ray(s, i, j, !det, rng);
                 int id; float zz;
@@ -83,6 +92,7 @@ int main(int argc, char **argv)
             }
             V3 out = sum / (float)spp;
             size_t p = (size_t)j * W + i;
+            acc[4 * p] = sum.x; acc[4 * p + 1] = sum.y; acc[4 * p + 2] = sum.z; acc[4 * p + 3] = (float)(smp_e - smp_b);
             linear[3 * p] = out.x; linear[3 * p + 1] = out.y; linear[3 * p + 2] = out.z;
             V3 g = gamma_correct(out);
             rgb8[3 * p] = float_to_byte(g.x); rgb8[3 * p + 1] = float_to_byte(g.y); rgb8[3 * p + 2] = float_to_byte(g.z);
@@ -100,6 +110,10 @@ int main(int argc, char **argv)
     fwrite(rgb8.data(), 1, rgb8.size(), fp);
     fwrite(hitid.data(), 4, hitid.size(), fp);
     fwrite(z.data(), 4, z.size(), fp);
+    fclose(fp);
+    fp = fopen((std::string(argv[2]) + ".acc").c_str(), "wb");
+    if (!fp) return 4;
+    fwrite(acc.data(), 4, acc.size(), fp);
     fclose(fp);
     printf("{\"emu\": true, \"width\": %d, \"height\": %d, \"spp\": %d, \"ms\": %.3f, \"rays_closest\": %llu, \"rays_shadow\": %llu, \"nodes\": %d}\n",
            W, H, spp, ms, closest, shadow, D.n_nodes);
