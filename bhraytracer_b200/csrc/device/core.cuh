@@ -13,6 +13,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 #include "../../../include/bhrt.h"
 
 #ifdef __CUDACC__
@@ -105,11 +106,43 @@ BHRT_HD Ray to_node(const bhrt_xform &t, const Ray &r)
     return o;
 }
 
+// ---- device traversal tables (built at upload by accel.hpp from the bhrt_mesh tables) --------
+struct alignas(16) F4 { float x, y, z, w; };
+BHRT_HD F4 ld4(const F4 *p)
+{
+#ifdef __CUDA_ARCH__
+    float4 v = __ldg(reinterpret_cast<const float4 *>(p));      // one 128-bit read-only load
+    F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+#else
+    return *p;
+#endif
+}
+BHRT_HD uint32_t f2u(float f)
+{
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+// a = (vN.xyz, |vN|)   b = (vN.v0, p0.x, p0.y, p1.x)   c = (p1.y, p2.x, p2.y, bits: face | axis << 30)
+struct alignas(16) TriRec { F4 a, b, c; };
+// both child boxes of one internal cyBVH node + the two child words (leaf: bit31 | (count-1) << 28 |
+// first TriRec; internal: PairNode index)
+struct alignas(64) PairNode { float box1[6], box2[6]; uint32_t word1, word2, pad0, pad1; };
+struct MeshAccel {
+    float root_box[6];
+    uint32_t root_word, pad;
+    int64_t pairs_off, tris_off;            // byte offsets into SceneView::accel_data
+    int64_t vn_off, vt_off, fn_off, ft_off; // byte offsets into SceneView::mesh_data (attributes of the final hit)
+};
+
 // ------------------------------------------------------------------------------------------
 // Device-side view of an uploaded scene.  Pointers are device pointers in render.cu and
 // host pointers in tests/emu.
 struct SceneView {
-    int n_nodes, n_lights, max_depth, pad0;
+    int n_nodes, n_lights, max_depth, n_materials;
     const bhrt_node *nodes;
     const bhrt_material *materials;
     const bhrt_light *lights;           // sorted ascending by grey intensity (Main.cpp:116-118)
@@ -118,6 +151,8 @@ struct SceneView {
     const uint8_t *texels;
     const bhrt_mesh *meshes;
     const uint8_t *mesh_data;
+    const MeshAccel *accels;            // one per mesh
+    const uint8_t *accel_data;
     const float *tex_offsets;           // 31 (x,y) pairs of the elliptical Halton filter (scene.h:322-329)
     bhrt_texcolor background, environment;
     float all_light_intensity;          // Main.cpp:119-122
@@ -152,79 +187,6 @@ struct PhotonGather {
 };
 
 // ------------------------------------------------------------------------------------------
-// Sphere::IntersectRay (reference Objects/Sphere/Sphere.cpp:8-75)
-BHRT_HD bool intersect_sphere(const Ray &ray, Hit &h, int hitSide)
-{
-    V3 dir = ray.dir, oc = ray.p;
-    float A = dot(dir, dir);
-    float B = 2 * dot(dir, oc);
-    float C = dot(oc, oc) - 1;
-    float DD = B * B - 4 * A * C;
-    if (!(DD > 0)) return false;
-    float sq = sqrtf(DD);
-    float t1 = (-B + sq) / (2 * A);
-    float t2 = (-B - sq) / (2 * A);
-    float t = BHRT_BIGFLOAT;
-    bool front = true;
-    if (t1 < 0 && t2 < 0) return false;
-    else if (t1 * t2 <= 0) {
-        if (hitSide == HIT_FRONT) return false;
-        t = t1; front = false;
-    } else if (t1 > 0 && t2 > 0) {
-        if (hitSide == HIT_FRONT || hitSide == HIT_FRONT_AND_BACK) { t = t2; front = true; }
-        else if (hitSide == HIT_BACK) { t = t1; front = false; }
-    }
-    if (h.z < t || t <= 0) return false;
-    h.z = t;
-    h.p = oc + h.z * dir;
-    h.N = h.p;
-    h.front = front;
-    V3 d = normalized(h.N);
-    // 0.5f + atan2(d.y,d.x)/(2*PI): float atan2f promoted to double, PI is a double literal
-    h.uvw.x = (float)(0.5f + atan2f(d.y, d.x) / (2 * BHRT_PI_D));
-    h.uvw.y = (float)(0.5f - asinf(d.z) / (BHRT_PI_D));
-    // uvw.z keeps whatever the default-constructed Vec3f held in the reference (uninitialised
-    // there; never read by 2-D textures).  We define it as 0.
-    h.uvw.z = 0.f;
-    h.duvw0 = V3(0, 0, 0); h.duvw1 = V3(0, 0, 0);
-    return true;
-}
-
-// Plane::IntersectRay (reference Objects/Plane/Plane.cpp:8-77) incl. its ray differentials,
-// which use the PRIMARY-ray pixel steps dd_x, dd_y for every ray (Plane.cpp:3-4,51-70).
-BHRT_HD bool intersect_plane(const Ray &ray, Hit &h, int hitSide, V3 dd_x, V3 dd_y)
-{
-    float rayPz = ray.p.z, rayDz = ray.dir.z;
-    if (rayDz == 0.0f) return false;
-    float t = -rayPz / rayDz;
-    if (t <= 0 || t > h.z) return false;
-    V3 x = ray.p + t * ray.dir;
-    if (x.x < -1 || x.x > 1 || x.y < -1 || x.y > 1) return false;
-    V3 faceNormal(0, 0, 1);
-    bool front = (dot(-ray.dir, faceNormal) > 0);
-    if (!front && hitSide == HIT_FRONT) return false;
-    else if (front && hitSide == HIT_BACK) return false;
-    h.p = x; h.N = faceNormal; h.z = t; h.front = front;
-    h.uvw = V3((1 + h.p.x) / 2.f, (1 + h.p.y) / 2.f, 0.f);
-    {
-        V3 nd = normalized(ray.dir);
-        float scaled_t = length(t * ray.dir);
-        float ndnd = dot(nd, nd);
-        float den = powf(ndnd, 1.5f);
-        V3 dDX = (ndnd * dd_x - dot(nd, dd_x) * nd) / den;
-        V3 dDY = (ndnd * dd_y - dot(nd, dd_y) * nd) / den;
-        float ndN = dot(nd, h.N);
-        float d_t_x = -(0 + scaled_t * dot(dDX, h.N) / ndN);
-        float d_t_y = -(0 + scaled_t * dot(dDY, h.N) / ndN);
-        // "0 + scaled_t * d + d_t * nd": (0 + Vec) is Vec + 0.0f component-wise
-        V3 hx = (scaled_t * dDX + V3(0.f, 0.f, 0.f)) + d_t_x * nd;
-        V3 hy = (scaled_t * dDY + V3(0.f, 0.f, 0.f)) + d_t_y * nd;
-        h.duvw0 = hx / 2.f;
-        h.duvw1 = hy / 2.f;
-    }
-    return true;
-}
-
 // Box::IntersectRay (reference Objects/Box/Box.cpp:3-46)
 BHRT_HD bool intersect_box(const float *b, const Ray &r, float t_max, float &t_min)
 {
@@ -241,63 +203,69 @@ BHRT_HD bool intersect_box(const float *b, const Ray &r, float t_max, float &t_m
 }
 
 // ------------------------------------------------------------------------------------------
-struct MeshView {
-    const float *v, *vn, *vt;
-    const uint32_t *f, *fn, *ft;
-    const bhrt_bvh_node *bvh;
-    const uint32_t *elems;
-};
-BHRT_HD MeshView mesh_view(const SceneView &s, int mesh)
+// Mesh attribute fetch (only for the FINAL closest hit of a ray: the reference interpolates vn/vt
+// for every accepted candidate, TriObj.cpp:169-177, and the last accepted one wins -- the same
+// value as interpolating once for the winner).
+BHRT_HD void mesh_attributes(const SceneView &s, const MeshAccel &A, uint32_t face, float a0, float a1, float a2, V3 &N, V3 &tc)
 {
-    const bhrt_mesh &m = s.meshes[mesh];
-    MeshView mv;
-    mv.v = (const float *)(s.mesh_data + m.v_off);
-    mv.vn = (const float *)(s.mesh_data + m.vn_off);
-    mv.vt = (const float *)(s.mesh_data + m.vt_off);
-    mv.f = (const uint32_t *)(s.mesh_data + m.f_off);
-    mv.fn = (const uint32_t *)(s.mesh_data + m.fn_off);
-    mv.ft = (const uint32_t *)(s.mesh_data + m.ft_off);
-    mv.bvh = (const bhrt_bvh_node *)(s.mesh_data + m.bvh_off);
-    mv.elems = (const uint32_t *)(s.mesh_data + m.elems_off);
-    return mv;
+    const float *vn = (const float *)(s.mesh_data + A.vn_off);
+    const float *vt = (const float *)(s.mesh_data + A.vt_off);
+    const uint32_t *fn = (const uint32_t *)(s.mesh_data + A.fn_off);
+    const uint32_t *ft = (const uint32_t *)(s.mesh_data + A.ft_off);
+    float a = a0 + a1 + a2;
+    V3 bc(a0 / a, a1 / a, a2 / a);
+    // TriMesh::Interpolate (cyTriMesh.h:191): v[f.v[0]]*bc.x + v[f.v[1]]*bc.y + v[f.v[2]]*bc.z
+    uint32_t n0 = fn[3 * face], n1 = fn[3 * face + 1], n2 = fn[3 * face + 2];
+    N = ld3(vn + 3 * n0) * bc.x + ld3(vn + 3 * n1) * bc.y + ld3(vn + 3 * n2) * bc.z;
+    uint32_t t0 = ft[3 * face], t1 = ft[3 * face + 1], t2 = ft[3 * face + 2];
+    tc = ld3(vt + 3 * t0) * bc.x + ld3(vt + 3 * t1) * bc.y + ld3(vt + 3 * t2) * bc.z;
 }
 
-// TriObj::IntersectTriangle (reference Objects/TriObj/TriObj.cpp:68-189)
-BHRT_HD bool intersect_triangle(const MeshView &m, const Ray &ray, Hit &h, int hitSide, uint32_t face)
+// Candidate hit inside a mesh: enough to rebuild the HitInfo of TriObj::IntersectTriangle
+struct MeshHit { uint32_t face; float a0, a1, a2; };
+
+// TriObj::IntersectTriangle (reference Objects/TriObj/TriObj.cpp:68-160) on a precomputed
+// TriRec.  `z` is hInfo.z (in/out); `len_dir` = |ray.dir| (hoisted; same value every call).
+BHRT_HD bool intersect_trirec(const TriRec *rec, const Ray &ray, float len_dir, float &z, bool &front_out, int hitSide, MeshHit &mh)
 {
-    uint32_t i0 = m.f[3 * face], i1 = m.f[3 * face + 1], i2 = m.f[3 * face + 2];
-    V3 v0 = ld3(m.v + 3 * i0), v1 = ld3(m.v + 3 * i1), v2 = ld3(m.v + 3 * i2);
-    V3 vN = cross(v1 - v0, v2 - v0);
+    F4 A = ld4(&rec->a), B = ld4(&rec->b), C = ld4(&rec->c);
+    V3 vN(A.x, A.y, A.z);
     float t_div = dot(vN, ray.dir);
     if (t_div == 0) return false;
-    float perp = t_div / (length(vN) * length(ray.dir));
+    float perp = t_div / (A.w * len_dir);
     if (perp > -BHRT_PERP_DET && perp < BHRT_PERP_DET) return false;
-    float t = (dot(vN, v0) - dot(vN, ray.p)) / t_div;
-    if (t <= 0 || t > h.z) return false;
+    float t = (B.x - dot(vN, ray.p)) / t_div;
+    if (t <= 0 || t > z) return false;
     bool front = t_div < 0;
     if (!front && hitSide == HIT_FRONT) return false;
     else if (front && hitSide == HIT_BACK) return false;
     V3 vX = ray.p + t * ray.dir;
-    float ax = fabsf(vN.x), ay = fabsf(vN.y), az = fabsf(vN.z);
-    float p0x, p0y, p1x, p1y, p2x, p2y, pxx, pxy;
-    if (ax >= ay && ax >= az) { p0x = v0.y; p0y = v0.z; p1x = v1.y; p1y = v1.z; p2x = v2.y; p2y = v2.z; pxx = vX.y; pxy = vX.z; }
-    else if (ay >= ax && ay >= az) { p0x = v0.x; p0y = v0.z; p1x = v1.x; p1y = v1.z; p2x = v2.x; p2y = v2.z; pxx = vX.x; pxy = vX.z; }
-    else { p0x = v0.x; p0y = v0.y; p1x = v1.x; p1y = v1.y; p2x = v2.x; p2y = v2.y; pxx = vX.x; pxy = vX.y; }
+    uint32_t tag = f2u(C.w);
+    uint32_t axis = tag >> 30;
+    float pxx = axis == 0 ? vX.y : vX.x;
+    float pxy = axis == 2 ? vX.y : vX.z;
+    float p0x = B.y, p0y = B.z, p1x = B.w, p1y = C.x, p2x = C.y, p2y = C.z;
     // Vec2::Cross(a,b) = a.x*b.y - a.y*b.x (cyVector.h)
     float a0 = ((p1x - pxx) * (p2y - pxy) - (p1y - pxy) * (p2x - pxx)) / 2.f;
     float a1 = ((p2x - pxx) * (p0y - pxy) - (p2y - pxy) * (p0x - pxx)) / 2.f;
     float a2 = ((p0x - pxx) * (p1y - pxy) - (p0y - pxy) * (p1x - pxx)) / 2.f;
     if ((a2 < 0 || a1 < 0 || a0 < 0) && !(a0 < 0 && a1 < 0 && a2 < 0)) return false;
-    float a = a0 + a1 + a2;
-    V3 bc(a0 / a, a1 / a, a2 / a);
-    // TriMesh::Interpolate (cyTriMesh.h:191): v[f.v[0]]*bc.x + v[f.v[1]]*bc.y + v[f.v[2]]*bc.z
-    uint32_t n0 = m.fn[3 * face], n1 = m.fn[3 * face + 1], n2 = m.fn[3 * face + 2];
-    V3 N = ld3(m.vn + 3 * n0) * bc.x + ld3(m.vn + 3 * n1) * bc.y + ld3(m.vn + 3 * n2) * bc.z;
-    uint32_t t0 = m.ft[3 * face], t1 = m.ft[3 * face + 1], t2 = m.ft[3 * face + 2];
-    V3 tc = ld3(m.vt + 3 * t0) * bc.x + ld3(m.vt + 3 * t1) * bc.y + ld3(m.vt + 3 * t2) * bc.z;
-    h.z = t; h.N = N; h.p = vX; h.front = front; h.uvw = tc;
-    h.duvw0 = V3(0, 0, 0); h.duvw1 = V3(0, 0, 0);
+    z = t; front_out = front;
+    mh.face = tag & 0x3fffffffu; mh.a0 = a0; mh.a1 = a1; mh.a2 = a2;
     return true;
+}
+
+// Both child boxes of one internal node (Box::IntersectRay x2, reference Box.cpp:3-46)
+BHRT_HD void intersect_pair(const PairNode *pn, const Ray &r, float t_max, bool &h1, float &t1, bool &h2, float &t2, uint32_t &w1, uint32_t &w2)
+{
+    const F4 *q = reinterpret_cast<const F4 *>(pn);
+    F4 q0 = ld4(q), q1 = ld4(q + 1), q2 = ld4(q + 2), q3 = ld4(q + 3);
+    float b1[6] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y };
+    float b2[6] = { q1.z, q1.w, q2.x, q2.y, q2.z, q2.w };
+    t1 = BHRT_BIGFLOAT; t2 = BHRT_BIGFLOAT;
+    h1 = intersect_box(b1, r, t_max, t1);
+    h2 = intersect_box(b2, r, t_max, t2);
+    w1 = f2u(q3.x); w2 = f2u(q3.y);
 }
 
 #define BHRT_BVH_LEAF(d) (((d) & 0x80000000u) != 0)
@@ -306,48 +274,67 @@ BHRT_HD bool intersect_triangle(const MeshView &m, const Ray &ray, Hit &h, int h
 #define BHRT_BVH_CHILD(d) ((d) & 0x7fffffffu)
 #define BHRT_BVH_STACK 64
 
-// TriObj::IntersectRay + TraceBVHNode (reference TriObj.cpp:17-39,192-270), made iterative.
-// The visiting order, the near/far rule, the "far child is skipped only when the near child
-// produced a hit and z <= tmin_far" rule and the traversal of box-missed far children are
-// all kept, so ties and rounding cases resolve as in the reference.
-BHRT_HD bool mesh_closest(const MeshView &m, const Ray &ray, Hit &h, int hitSide)
+// One traversal loop for both query kinds (the two heavy parts -- pair slab tests and triangle
+// tests -- are shared, so a warp whose lanes mix closest-hit and shadow queries stays converged):
+//
+//  closest (any_hit == false): TriObj::IntersectRay + TraceBVHNode (reference TriObj.cpp:17-39,
+//    192-270) made iterative.  The visiting order, the near/far rule, "the far child is skipped
+//    only when the near child produced a hit and z <= tmin_far" and the traversal of box-missed
+//    far children are all kept, so ties and rounding cases resolve as in the reference.
+//  shadow (any_hit == true): TriObj::ShadowRecursive + TraceBVHShadow (TriObj.cpp:41-66,272-307):
+//    child 1 before child 2, both visited when EITHER box is hit (boxes tested against BIGFLOAT),
+//    stop at the FIRST leaf containing any front-face hit and range-check only that leaf's t.
+//
+// Returns: closest -> number of accepted triangles > 0 (z, front, mh updated);
+//          shadow  -> the reference's bool.
+BHRT_HD bool mesh_trace(const SceneView &s, const MeshAccel &A, const Ray &ray, bool any_hit, float t_max_shadow,
+                        float &z, bool &front, int hitSide, MeshHit &mh)
 {
     float tmin = -1;
-    if (!intersect_box(m.bvh[1].box, ray, h.z, tmin)) return false;
-    uint32_t st_node[BHRT_BVH_STACK];
+    if (!intersect_box(A.root_box, ray, any_hit ? BHRT_BIGFLOAT : z, tmin)) return false;
+    const PairNode *pairs = (const PairNode *)(s.accel_data + A.pairs_off);
+    const TriRec *tris = (const TriRec *)(s.accel_data + A.tris_off);
+    const float len_dir = length(ray.dir);
+    uint32_t st_word[BHRT_BVH_STACK];
     float st_tmin[BHRT_BVH_STACK];
     int st_hits[BHRT_BVH_STACK];
     int sp = 0, hits = 0;
-    uint32_t cur = 1;
+    uint32_t cur = A.root_word;
     for (;;) {
-        uint32_t d = m.bvh[cur].data;
         bool descend = false;
-        if (BHRT_BVH_LEAF(d)) {
-            uint32_t cnt = BHRT_BVH_COUNT(d), off = BHRT_BVH_OFFSET(d);
-            for (uint32_t i = 0; i < cnt; i++)
-                if (intersect_triangle(m, ray, h, hitSide, m.elems[off + i])) hits++;
+        if (BHRT_BVH_LEAF(cur)) {
+            uint32_t cnt = BHRT_BVH_COUNT(cur), off = BHRT_BVH_OFFSET(cur);
+            if (any_hit) {
+                float lz = BHRT_BIGFLOAT; bool lf; MeshHit lm;
+                bool any = false;
+                for (uint32_t i = 0; i < cnt; i++)
+                    if (intersect_trirec(tris + off + i, ray, len_dir, lz, lf, HIT_FRONT, lm)) any = true;
+                if (any) return lz > BHRT_BIAS && lz < t_max_shadow;
+            } else {
+                for (uint32_t i = 0; i < cnt; i++)
+                    if (intersect_trirec(tris + off + i, ray, len_dir, z, front, hitSide, mh)) hits++;
+            }
         } else {
-            uint32_t c1 = BHRT_BVH_CHILD(d), c2 = c1 + 1;
-            float tmin1 = BHRT_BIGFLOAT, tmin2 = BHRT_BIGFLOAT;
-            bool h1 = intersect_box(m.bvh[c1].box, ray, h.z, tmin1);
-            bool h2 = intersect_box(m.bvh[c2].box, ray, h.z, tmin2);
+            bool h1, h2; float t1, t2; uint32_t w1, w2;
+            intersect_pair(pairs + cur, ray, any_hit ? BHRT_BIGFLOAT : z, h1, t1, h2, t2, w1, w2);
             if (h1 || h2) {
                 uint32_t first, second; float tsecond;
-                if (tmin1 < tmin2) { first = c1; second = c2; tsecond = tmin2; }
-                else { first = c2; second = c1; tsecond = tmin1; }
-                if (sp < BHRT_BVH_STACK) { st_node[sp] = second; st_tmin[sp] = tsecond; st_hits[sp] = hits; sp++; }
+                if (any_hit || t1 < t2) { first = w1; second = w2; tsecond = t2; }
+                else { first = w2; second = w1; tsecond = t1; }
+                if (sp < BHRT_BVH_STACK) { st_word[sp] = second; st_tmin[sp] = tsecond; st_hits[sp] = hits; sp++; }
                 cur = first;
                 descend = true;
             }
         }
         if (descend) continue;
-        // pop
         bool found = false;
         while (sp > 0) {
             sp--;
-            bool nearHit = (hits != st_hits[sp]);
-            if (nearHit && !(h.z > st_tmin[sp])) continue;
-            cur = st_node[sp];
+            if (!any_hit) {
+                bool nearHit = (hits != st_hits[sp]);
+                if (nearHit && !(z > st_tmin[sp])) continue;
+            }
+            cur = st_word[sp];
             found = true;
             break;
         }
@@ -356,65 +343,136 @@ BHRT_HD bool mesh_closest(const MeshView &m, const Ray &ray, Hit &h, int hitSide
     return hits > 0;
 }
 
-// TriObj::ShadowRecursive + TraceBVHShadow (reference TriObj.cpp:41-66,272-307), iterative.
-// Reproduces the reference's behaviour of stopping at the FIRST leaf (depth-first, child1
-// before child2) that contains any front-face hit and range-checking only that leaf's t.
-BHRT_HD bool mesh_shadow(const MeshView &m, const Ray &ray, float t_max)
-{
-    float tmin = -1;
-    if (!intersect_box(m.bvh[1].box, ray, BHRT_BIGFLOAT, tmin)) return false;
-    uint32_t st[BHRT_BVH_STACK];
-    int sp = 0;
-    uint32_t cur = 1;
-    for (;;) {
-        uint32_t d = m.bvh[cur].data;
-        if (BHRT_BVH_LEAF(d)) {
-            uint32_t cnt = BHRT_BVH_COUNT(d), off = BHRT_BVH_OFFSET(d);
-            Hit h; h.init();
-            bool any = false;
-            for (uint32_t i = 0; i < cnt; i++)
-                if (intersect_triangle(m, ray, h, HIT_FRONT, m.elems[off + i])) any = true;
-            if (any) return h.z > BHRT_BIAS && h.z < t_max;
-        } else {
-            uint32_t c1 = BHRT_BVH_CHILD(d), c2 = c1 + 1;
-            float t1 = BHRT_BIGFLOAT, t2 = BHRT_BIGFLOAT;
-            bool h1 = intersect_box(m.bvh[c1].box, ray, BHRT_BIGFLOAT, t1);
-            bool h2 = intersect_box(m.bvh[c2].box, ray, BHRT_BIGFLOAT, t2);
-            if (h1 || h2) {
-                if (sp < BHRT_BVH_STACK) st[sp++] = c2;
-                cur = c1;
-                continue;
-            }
-        }
-        if (sp == 0) return false;
-        cur = st[--sp];
-    }
-}
-
 // ------------------------------------------------------------------------------------------
-// recursive() (reference Main.cpp:389-413): linear DFS over the scene graph, closest hit.
+// A ray query: the ONE place the estimator meets the geometry.  kind CLOSEST = recursive()
+// (reference Main.cpp:389-413, linear DFS over the scene graph); kind SHADOW = GenLight::Shadow /
+// ShadowRayRecursive (reference Lights/GenLight.cpp:10-69, any-hit; the result is the OR over
+// all nodes of the node's own test, so DFS pre-order is as good as the reference's post-order).
+enum { Q_NONE = 0, Q_CLOSEST = 1, Q_SHADOW = 2 };
+struct Query {
+    Ray ray;
+    int kind;
+    int hitSide;        // CLOSEST
+    float t_max;        // SHADOW
+};
+
 // nodes[] is in DFS pre-order; rs[d] is the ray in the space of the current node at depth d.
-BHRT_HD bool scene_closest(const SceneView &s, const Ray &ray, Hit &h, int hitSide)
+// Shadow quirks kept: sphere ignored when the origin is inside (GenLight.cpp:36-37), plane
+// bounds tested with the PARENT-space ray (:54), no rayDz == 0 test (:50).
+// Closest: per-candidate HitInfo fields that only the winner needs (sphere uv with atan2/asin,
+// plane ray differentials with pow, mesh normals/uv) are derived once after the loop from the
+// winner's local ray -- the same expressions on the same inputs as the reference evaluates at
+// accept time.
+BHRT_HD bool scene_trace(const SceneView &s, const Query &q, Hit &h)
 {
+    const bool shadow = (q.kind == Q_SHADOW);
     Ray rs[BHRT_MAX_DEPTH + 1];
-    rs[0] = ray;
-    V3 lp(0, 0, 0), lN(0, 0, 0);
+    rs[0] = q.ray;
+    h.init();
+    Ray wr; wr.p = V3(0, 0, 0); wr.dir = V3(0, 0, 0);   // winner's local ray
+    MeshHit mh; mh.face = 0; mh.a0 = mh.a1 = mh.a2 = 0;
     for (int k = 0; k < s.n_nodes; k++) {
         const bhrt_node &nd = s.nodes[k];
-        int d = nd.depth;
-        Ray r = to_node(nd.xf, rs[d - 1]);
+        const int d = nd.depth;
+        const Ray &pr = rs[d - 1];
+        Ray r = to_node(nd.xf, pr);
         if (d < s.max_depth) rs[d] = r;
         bool hit = false;
-        if (nd.kind == BHRT_OBJ_SPHERE) hit = intersect_sphere(r, h, hitSide);
-        else if (nd.kind == BHRT_OBJ_PLANE) hit = intersect_plane(r, h, hitSide, s.dd_x, s.dd_y);
-        else if (nd.kind == BHRT_OBJ_MESH) hit = mesh_closest(mesh_view(s, nd.mesh), r, h, hitSide);
-        if (hit) { h.node = k; lp = h.p; lN = h.N; }
+        if (nd.kind == BHRT_OBJ_SPHERE) {
+            // Sphere::IntersectRay (Sphere.cpp:8-49) / the inline quadratic of GenLight.cpp:24-43
+            float A = dot(r.dir, r.dir);
+            float B = 2 * dot(r.dir, r.p);
+            float C = dot(r.p, r.p) - 1;
+            float DD = B * B - 4 * A * C;
+            if (DD > 0) {
+                float sq = sqrtf(DD);
+                float t1 = (-B + sq) / (2 * A);
+                float t2 = (-B - sq) / (2 * A);
+                if (shadow) {
+                    float t = fminr(t1, t2);
+                    if (!(t < 0) && t < q.t_max && t > BHRT_SHADOW_BIAS) return true;
+                } else {
+                    float t = BHRT_BIGFLOAT;
+                    bool front = true, cand = true;
+                    if (t1 < 0 && t2 < 0) cand = false;
+                    else if (t1 * t2 <= 0) {
+                        if (q.hitSide == HIT_FRONT) cand = false;
+                        t = t1; front = false;
+                    } else if (t1 > 0 && t2 > 0) {
+                        if (q.hitSide == HIT_FRONT || q.hitSide == HIT_FRONT_AND_BACK) { t = t2; front = true; }
+                        else if (q.hitSide == HIT_BACK) { t = t1; front = false; }
+                    }
+                    if (cand && !(h.z < t || t <= 0)) { h.z = t; h.front = front; hit = true; }
+                }
+            }
+        } else if (nd.kind == BHRT_OBJ_PLANE) {
+            if (shadow) {
+                float t = -r.p.z / r.dir.z;
+                if (!(t < 0)) {
+                    V3 x = pr.p + t * pr.dir;
+                    if (!(x.x < -1 || x.x > 1 || x.y < -1 || x.y > 1) && t < q.t_max && t > BHRT_SHADOW_BIAS) return true;
+                }
+            } else if (r.dir.z != 0.0f) {
+                // Plane::IntersectRay (Plane.cpp:8-49)
+                float t = -r.p.z / r.dir.z;
+                if (!(t <= 0 || t > h.z)) {
+                    V3 x = r.p + t * r.dir;
+                    if (!(x.x < -1 || x.x > 1 || x.y < -1 || x.y > 1)) {
+                        bool front = (dot(-r.dir, V3(0, 0, 1)) > 0);
+                        if (!((!front && q.hitSide == HIT_FRONT) || (front && q.hitSide == HIT_BACK))) { h.z = t; h.front = front; hit = true; }
+                    }
+                }
+            }
+        } else if (nd.kind == BHRT_OBJ_MESH) {
+            bool r_ = mesh_trace(s, s.accels[nd.mesh], r, shadow, q.t_max, h.z, h.front, q.hitSide, mh);
+            if (shadow) { if (r_) return true; }
+            else hit = r_;
+        }
+        if (hit) { h.node = k; wr = r; }
     }
-    if (h.node < 0) return false;
+    if (shadow || h.node < 0) return false;
+
+    // ---- finish the winner's HitInfo in its local space
+    const bhrt_node &nd = s.nodes[h.node];
+    V3 lp, lN;
+    h.duvw0 = V3(0, 0, 0); h.duvw1 = V3(0, 0, 0);
+    if (nd.kind == BHRT_OBJ_SPHERE) {
+        lp = wr.p + h.z * wr.dir;                           // Sphere.cpp:52-54
+        lN = lp;
+        V3 d = normalized(lN);
+        // 0.5f + atan2(d.y,d.x)/(2*PI): float atan2f promoted to double, PI is a double literal
+        h.uvw.x = (float)(0.5f + atan2f(d.y, d.x) / (2 * BHRT_PI_D));
+        h.uvw.y = (float)(0.5f - asinf(d.z) / (BHRT_PI_D));
+        // uvw.z keeps whatever the default-constructed Vec3f held in the reference (uninitialised
+        // there; never read by 2-D textures).  We define it as 0.
+        h.uvw.z = 0.f;
+    } else if (nd.kind == BHRT_OBJ_PLANE) {
+        const float t = h.z;
+        lp = wr.p + t * wr.dir;
+        lN = V3(0, 0, 1);
+        h.uvw = V3((1 + lp.x) / 2.f, (1 + lp.y) / 2.f, 0.f);
+        // ray differentials from the PRIMARY-ray pixel steps dd_x, dd_y, for every ray (Plane.cpp:3-4,51-70)
+        V3 nd_ = normalized(wr.dir);
+        float scaled_t = length(t * wr.dir);
+        float ndnd = dot(nd_, nd_);
+        float den = powf(ndnd, 1.5f);
+        V3 dDX = (ndnd * s.dd_x - dot(nd_, s.dd_x) * nd_) / den;
+        V3 dDY = (ndnd * s.dd_y - dot(nd_, s.dd_y) * nd_) / den;
+        float ndN = dot(nd_, lN);
+        float d_t_x = -(0 + scaled_t * dot(dDX, lN) / ndN);
+        float d_t_y = -(0 + scaled_t * dot(dDY, lN) / ndN);
+        // "0 + scaled_t * d + d_t * nd": (0 + Vec) is Vec + 0.0f component-wise
+        V3 hx = (scaled_t * dDX + V3(0.f, 0.f, 0.f)) + d_t_x * nd_;
+        V3 hy = (scaled_t * dDY + V3(0.f, 0.f, 0.f)) + d_t_y * nd_;
+        h.duvw0 = hx / 2.f;
+        h.duvw1 = hy / 2.f;
+    } else {
+        lp = wr.p + h.z * wr.dir;                           // TriObj.cpp:107
+        mesh_attributes(s, s.accels[nd.mesh], mh.face, mh.a0, mh.a1, mh.a2, lN, h.uvw);
+    }
     // Node::FromNodeCoords of the hit node (Main.cpp:401) and then of its parent
     // (Main.cpp:407-412; the rootNode's identity transform for depth-1 nodes).  Deeper
     // ancestors are NOT applied by the reference; neither are they here.
-    const bhrt_node &nd = s.nodes[h.node];
     h.p = xf_from(nd.xf, lp);
     h.N = normalized(xf_vec_from(nd.xf, lN));
     if (nd.parent >= 0) {
@@ -427,45 +485,6 @@ BHRT_HD bool scene_closest(const SceneView &s, const Ray &ray, Hit &h, int hitSi
         h.N = normalized(V3(1.f * h.N.x + 0.f * h.N.y + 0.f * h.N.z, 0.f * h.N.x + 1.f * h.N.y + 0.f * h.N.z, 0.f * h.N.x + 0.f * h.N.y + 1.f * h.N.z));
     }
     return true;
-}
-
-// GenLight::Shadow / ShadowRayRecursive (reference Lights/GenLight.cpp:10-69): any-hit.
-// The result is the OR over all nodes of the node's own test, so DFS pre-order is as good as
-// the reference's post-order.  Quirks kept: sphere ignored when the origin is inside
-// (:36-37), plane bounds tested with the PARENT-space ray (:54), no rayDz==0 test (:50).
-BHRT_HD bool scene_shadow(const SceneView &s, const Ray &ray, float t_max)
-{
-    Ray rs[BHRT_MAX_DEPTH + 1];
-    rs[0] = ray;     // rootNode.ToNodeCoords is the identity and exact
-    for (int k = 0; k < s.n_nodes; k++) {
-        const bhrt_node &nd = s.nodes[k];
-        int d = nd.depth;
-        const Ray &pr = rs[d - 1];
-        Ray r = to_node(nd.xf, pr);
-        if (d < s.max_depth) rs[d] = r;
-        if (nd.kind == BHRT_OBJ_SPHERE) {
-            float A = dot(r.dir, r.dir);
-            float B = 2 * dot(r.dir, r.p);
-            float C = dot(r.p, r.p) - 1;
-            float DD = B * B - 4 * A * C;
-            if (DD > 0) {
-                float sq = sqrtf(DD);
-                float t1 = (-B + sq) / (2 * A);
-                float t2 = (-B - sq) / (2 * A);
-                float t = fminr(t1, t2);
-                if (!(t < 0) && t < t_max && t > BHRT_SHADOW_BIAS) return true;
-            }
-        } else if (nd.kind == BHRT_OBJ_PLANE) {
-            float t = -r.p.z / r.dir.z;
-            if (!(t < 0)) {
-                V3 x = pr.p + t * pr.dir;
-                if (!(x.x < -1 || x.x > 1 || x.y < -1 || x.y > 1) && t < t_max && t > BHRT_SHADOW_BIAS) return true;
-            }
-        } else if (nd.kind == BHRT_OBJ_MESH) {
-            if (mesh_shadow(mesh_view(s, nd.mesh), r, t_max)) return true;
-        }
-    }
-    return false;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -629,26 +648,32 @@ BHRT_HD V3 sample_semisphere(V3 N, float &theta_out, Rng &rng)
 }
 
 // ------------------------------------------------------------------------------------------
-// Light::Illuminate (PointLight.cpp:7-18, lights.h:33,50).  One shadow ray.
-BHRT_HD V3 illuminate(const SceneView &s, const bhrt_light &L, V3 p, Rng *rng, RayCounters &rc)
+// Light::Illuminate (PointLight.cpp:7-18, lights.h:33,50), split around its one shadow ray:
+// illuminate_begin builds the shadow query (returns false when the light needs none and the
+// irradiance is already known), illuminate_end turns the any-hit answer into irradiance.
+BHRT_HD bool illuminate_begin(const bhrt_light &L, V3 p, Rng *rng, Query &q, V3 &irrad)
 {
     V3 I = ld3(L.intensity);
-    if (L.kind == BHRT_LIGHT_AMBIENT) return I;
-    if (L.kind == BHRT_LIGHT_DIRECT) {
-        Ray r; r.p = p; r.dir = -ld3(L.v);
-        rc.shadow++;
-        float sh = scene_shadow(s, r, BHRT_BIGFLOAT) ? 0.f : 1.f;
-        return sh * I;
-    }
+    if (L.kind == BHRT_LIGHT_AMBIENT) { irrad = I; return false; }
+    q.kind = Q_SHADOW; q.hitSide = HIT_FRONT; q.ray.p = p;
+    if (L.kind == BHRT_LIGHT_DIRECT) { q.ray.dir = -ld3(L.v); q.t_max = BHRT_BIGFLOAT; return true; }
     V3 centerDir = ld3(L.v) - p;
     float r = length(centerDir);
     float rr = r * r;
-    if (rr == 0) return V3(1, 1, 1) * BHRT_BIGFLOAT;
-    Ray sr; sr.p = p;
-    if (L.size > 0 && rng) sr.dir = sample_along_normal(centerDir, L.size, *rng);
-    else sr.dir = centerDir;
-    rc.shadow++;
-    float sh = scene_shadow(s, sr, 1.f) ? 0.f : 1.f;
+    if (rr == 0) { irrad = V3(1, 1, 1) * BHRT_BIGFLOAT; return false; }
+    if (L.size > 0 && rng) q.ray.dir = sample_along_normal(centerDir, L.size, *rng);
+    else q.ray.dir = centerDir;
+    q.t_max = 1.f;
+    return true;
+}
+BHRT_HD V3 illuminate_end(const bhrt_light &L, V3 p, bool shadowed)
+{
+    V3 I = ld3(L.intensity);
+    float sh = shadowed ? 0.f : 1.f;
+    if (L.kind == BHRT_LIGHT_DIRECT) return sh * I;
+    V3 centerDir = ld3(L.v) - p;
+    float r = length(centerDir);
+    float rr = r * r;
     return (sh * I) / rr;
 }
 // Light::Direction (lights.h:34,51,69)
@@ -717,8 +742,12 @@ BHRT_HD Ray handle_refraction_out(const Ray &inRay, const Hit &ih, float ior, bo
 
 // ------------------------------------------------------------------------------------------
 // The estimator.  MtlBlinn::Shade (MtlBlinn.cpp:89-138) is a recursion TREE with a clamp and
-// an early-out at every level, not a linear path, so it is evaluated here
-// with an explicit frame stack and a post-order resolve.
+// an early-out at every level, not a linear path, so it is evaluated with an
+// explicit frame stack and a post-order resolve.  It is written as a coroutine around ONE ray
+// query: sample_advance() runs until the estimator needs a ray, leaves it in Lane::q and
+// returns; the caller traces it (scene_trace) and calls sample_advance() again.  In the kernel
+// every lane of a warp therefore meets the traversal code together, whatever stage of whatever
+// recursion level its sample is in.
 struct Frame {
     V3 p, vN, vV, uvw, duvw0, duvw1;    // shading point
     V3 out;                              // colour accumulated so far at this level
@@ -727,9 +756,9 @@ struct Frame {
     int mtl, bounce, gi;
     int stage;
     bool useSpec;                        // lobe chosen by the GI sample
-    bool z_ok;
 };
-enum { ST_REFR = 0, ST_REFR_WAIT = 1, ST_GI = 2, ST_GI_WAIT = 3, ST_DIRECT = 4 };
+enum { ST_REFR = 0, ST_REFR_IN_WAIT = 1, ST_REFR_OUT_WAIT = 2, ST_REFR_WAIT = 3, ST_GI = 4, ST_GI_TRACE_WAIT = 5, ST_GI_WAIT = 6,
+       ST_DIRECT = 7, ST_SHADOW_WAIT = 8 };
 #define BHRT_MAX_FRAMES 24
 
 struct ShadeCfg {
@@ -737,43 +766,90 @@ struct ShadeCfg {
     int gi_depth, tir_budget;
 };
 
-BHRT_HD void frame_begin(Frame &f, const SceneView &s, const Ray &ray, const Hit &h, int bounce, int gi)
+struct Lane {
+    Frame fr[BHRT_MAX_FRAMES];
+    int sp;                 // frames in use; 0 = waiting for the primary ray
+    Query q;                // the pending ray query
+    Hit hit;                // its answer (closest) ...
+    bool hit_ok;            // ... and whether anything was hit / the shadow ray is blocked
+    Rng rng;
+    V3 ret;                 // value returned by the child frame that just completed
+    // scratch of the top frame's wait states (a child frame runs to completion in between, so
+    // one set per lane is enough)
+    V3 sv;                  // refraction: (1-F)*refraction      direct: colour summed over lights
+    V3 sw;                  // direct: the sampled light direction vL
+    float sf;               // refraction: glossiness of the refraction lobe
+    int si;                 // refraction: remaining internal-reflection budget      direct: light index
+    int hit_id; float hit_z;    // primary AOVs of this sample
+};
+
+BHRT_HD void frame_begin(Frame &f, const SceneView &s, V3 ray_p, const Hit &h, int bounce, int gi)
 {
     f.p = h.p; f.uvw = h.uvw; f.duvw0 = h.duvw0; f.duvw1 = h.duvw1;
     f.vN = normalized(h.N);
-    f.vV = normalized(ray.p - h.p);
+    f.vV = normalized(ray_p - h.p);
     f.mtl = s.nodes[h.node].material;
     f.bounce = bounce; f.gi = gi;
     f.out = V3(0, 0, 0);
     f.stage = ST_REFR;
 }
 
-// One camera sample (the body of the loop in PathTracing(), Main.cpp:150-169).
-// Returns the sample's colour; fills the primary hit id / z.
-BHRT_HD_NOINLINE V3 trace_sample(const SceneView &s, const ShadeCfg &cfg, const PhotonGather &pg, const Ray &primary, float bgu, float bgv,
-                                 Rng &rng, RayCounters &rc, int &hit_id, float &hit_z)
+BHRT_HD void issue_closest(Lane &L, const Ray &r, int hitSide, RayCounters &rc)
+{
+    L.q.ray = r; L.q.kind = Q_CLOSEST; L.q.hitSide = hitSide; L.q.t_max = 0;
+    rc.closest++;
+}
+
+// Start one camera sample (the body of the loop in PathTracing(), Main.cpp:150-169)
+BHRT_HD void sample_begin(Lane &L, const Ray &primary, RayCounters &rc)
+{
+    L.sp = 0;
+    issue_closest(L, primary, HIT_FRONT, rc);
+}
+
+// Shade epilogue shared by the two ways the direct term ends (MtlBlinn.cpp:343-350,131-136)
+BHRT_HD void direct_finish(Frame &f, V3 D)
+{
+    clamp_white(D);
+    if (is_nan(D.x)) D = V3(0, 0, 0);
+    f.out = f.out + D;
+    if (!saturated(f.out) && is_nan(f.out.x)) f.out = V3(1.0f, 0.0f, 1.0f);
+}
+
+// Blinn BRDF * cos of the direct term (MtlBlinn.cpp:319-327) for light direction vL
+BHRT_HD V3 direct_brdf(const SceneView &s, const Frame &f, const bhrt_material &M, V3 vL)
+{
+    float cosTheta = dot(vL, f.vN);
+    V3 vH = normalized(vL + f.vV);
+    V3 kdT = texcolor_sample_filtered(s, ld3(M.diffuse.color), M.diffuse.texmap, f.uvw, f.duvw0, f.duvw1);
+    V3 ksT = texcolor_sample_filtered(s, f.newSpec, M.specular.texmap, f.uvw, f.duvw0, f.duvw1);
+    return kdT * cosTheta + ksT * powf(dot(vH, f.vN), M.glossiness);
+}
+
+// Consume the answer to L.q (L.hit / L.hit_ok) and run the estimator until it needs the next
+// ray (returns false, query in L.q) or the sample is finished (returns true, colour in `color`).
+BHRT_HD_NOINLINE bool sample_advance(Lane &L, const SceneView &s, const ShadeCfg &cfg, const PhotonGather &pg, float bgu, float bgv,
+                                     RayCounters &rc, V3 &color)
 {
     const bool det = (cfg.mode == BHRT_MODE_DET);
-    Hit h; h.init();
-    rc.closest++;
-    bool bHit = scene_closest(s, primary, h, HIT_FRONT);
-    hit_id = bHit ? h.node : -1;
-    hit_z = h.z;
-    if (!bHit) return texcolor_sample(s, s.background, V3(bgu, bgv, 0.0f));   // Main.cpp:166-167
-
-    Frame fr[BHRT_MAX_FRAMES];
-    int sp = 1;
-    frame_begin(fr[0], s, primary, h, cfg.tir_budget, cfg.gi_depth);
-    V3 ret(0, 0, 0);        // value returned by the child that just completed
-    bool have_ret = false;
-
+    Rng &rng = L.rng;
+    if (L.sp == 0) {
+        L.hit_id = L.hit_ok ? L.hit.node : -1;
+        L.hit_z = L.hit.z;
+        if (!L.hit_ok) { color = texcolor_sample(s, s.background, V3(bgu, bgv, 0.0f)); return true; }   // Main.cpp:166-167
+        frame_begin(L.fr[0], s, L.q.ray.p, L.hit, cfg.tir_budget, cfg.gi_depth);
+        L.sp = 1;
+    }
     for (;;) {
-        Frame &f = fr[sp - 1];
+        Frame &f = L.fr[L.sp - 1];
         const bhrt_material &M = s.materials[f.mtl];
         bool push_child = false;    // a child frame was pushed at fr[sp]
         bool done = false;          // this frame finished, value in f.out
+        bool refr_resolved = false; V3 R(0, 0, 0);      // refraction term known
+        bool gi_resolved = false; V3 G(0, 0, 0);        // GI term known
 
-        if (f.stage == ST_REFR) {
+        switch (f.stage) {
+        case ST_REFR: {
             // ---- Shade prologue (MtlBlinn.cpp:91-117)
             float cosPhi1 = dot(f.vN, f.vV);
             if (cosPhi1 > 1) cosPhi1 = 1;
@@ -788,8 +864,6 @@ BHRT_HD_NOINLINE V3 trace_sample(const SceneView &s, const ShadeCfg &cfg, const 
             if (!det && M.glossiness > 50) rgloss = M.glossiness;
             V3 refrC = (1 - F) * refr;
             // ---- PathTracing_Refraction (MtlBlinn.cpp:437-473)
-            V3 R(0, 0, 0);
-            bool resolved = true;
             if (f.bounce > 0 && !is_zero(refrC)) {
                 float sinPhi1 = sqrtf(1 - cosPhi1 * cosPhi1);
                 float sinPhi2 = sinPhi1 / M.ior;
@@ -803,175 +877,205 @@ BHRT_HD_NOINLINE V3 trace_sample(const SceneView &s, const ShadeCfg &cfg, const 
                     float ds = 0; int guard = 0;
                     while (ds >= 0 && guard++ < 64) { float th = 0; vTs = sample_along_direction(vT, rgloss, th, rng); ds = dot(vTs, f.vN); }
                 }
-                // ---- RefractionRecusive (MtlBlinn.cpp:476-519); the TIR recursion is a loop
-                V3 cur_p = f.p, cur_N = f.vN, dir = normalized(vTs);
-                int b = f.bounce;
-                for (;;) {
-                    Ray rin; rin.dir = dir; rin.p = cur_p - cur_N * BHRT_BIAS;
-                    Hit hin; hin.init();
-                    rc.closest++;
-                    bool hitIn = scene_closest(s, rin, hin, HIT_FRONT_AND_BACK);
-                    if (!hitIn) { R = V3(1.0f, 0.0f, 1.0f); break; }           // NANPurple (:517)
-                    if (!hin.front) {
-                        bool goingOut;
-                        Ray nx = handle_refraction_out(rin, hin, M.ior, goingOut, rgloss, det ? (Rng *)0 : &rng);
-                        if (goingOut) {
-                            // ---- RefractionOut (MtlBlinn.cpp:521-541)
-                            Hit ho; ho.init();
-                            rc.closest++;
-                            bool hitOut = scene_closest(s, nx, ho, HIT_FRONT);
-                            if (hitOut) {
-                                V3 ab = ld3(M.absorption);
-                                V3 af(powf(BHRT_EULER, -ab.x * ho.z), powf(BHRT_EULER, -ab.y * ho.z), powf(BHRT_EULER, -ab.z * ho.z));
-                                f.mult = refrC * af;
-                                if (sp < BHRT_MAX_FRAMES) {
-                                    frame_begin(fr[sp], s, nx, ho, b, f.gi - 1);
-                                    push_child = true; resolved = false;
-                                } else R = V3(0, 0, 0);
-                            } else {
-                                R = refrC * sample_environment(s, nx.dir);
-                                clamp_white(R);
-                            }
-                            break;
-                        } else {
-                            if (b <= 0) { R = V3(0, 0, 0); break; }
-                            b--;
-                            cur_p = hin.p; cur_N = hin.N; dir = nx.dir;
-                            continue;
-                        }
-                    } else {
-                        f.mult = V3(1, 1, 1);
-                        if (sp < BHRT_MAX_FRAMES) {
-                            frame_begin(fr[sp], s, rin, hin, b, f.gi - 1);
-                            push_child = true; resolved = false;
-                        } else R = V3(0, 0, 0);
-                        break;
-                    }
-                }
+                // ---- RefractionRecusive (MtlBlinn.cpp:476-519); its TIR recursion is the loop
+                // ST_REFR_IN_WAIT -> ST_REFR_IN_WAIT below
+                L.sv = refrC; L.sf = rgloss; L.si = f.bounce;
+                Ray rin; rin.dir = normalized(vTs); rin.p = f.p - f.vN * BHRT_BIAS;
+                issue_closest(L, rin, HIT_FRONT_AND_BACK, rc);
+                f.stage = ST_REFR_IN_WAIT;
+                return false;
             }
-            if (resolved) {
+            refr_resolved = true;
+            break;
+        }
+        case ST_REFR_IN_WAIT: {
+            const Ray rin = L.q.ray;
+            if (!L.hit_ok) { R = V3(1.0f, 0.0f, 1.0f); refr_resolved = true; break; }            // NANPurple (:517)
+            if (!L.hit.front) {
+                bool goingOut;
+                Ray nx = handle_refraction_out(rin, L.hit, M.ior, goingOut, L.sf, det ? (Rng *)0 : &rng);
+                if (goingOut) {
+                    // ---- RefractionOut (MtlBlinn.cpp:521-541)
+                    issue_closest(L, nx, HIT_FRONT, rc);
+                    f.stage = ST_REFR_OUT_WAIT;
+                    return false;
+                }
+                if (L.si <= 0) { refr_resolved = true; break; }
+                L.si--;
+                Ray r2; r2.dir = nx.dir; r2.p = L.hit.p - L.hit.N * BHRT_BIAS;
+                issue_closest(L, r2, HIT_FRONT_AND_BACK, rc);
+                return false;
+            }
+            f.mult = V3(1, 1, 1);
+            if (L.sp < BHRT_MAX_FRAMES) {
+                frame_begin(L.fr[L.sp], s, rin.p, L.hit, L.si, f.gi - 1);
+                push_child = true;
+                f.stage = ST_REFR_WAIT;
+            } else refr_resolved = true;
+            break;
+        }
+        case ST_REFR_OUT_WAIT: {
+            const Ray nx = L.q.ray;
+            if (L.hit_ok) {
+                V3 ab = ld3(M.absorption);
+                float hz = L.hit.z;
+                V3 af(powf(BHRT_EULER, -ab.x * hz), powf(BHRT_EULER, -ab.y * hz), powf(BHRT_EULER, -ab.z * hz));
+                f.mult = L.sv * af;
+                if (L.sp < BHRT_MAX_FRAMES) {
+                    frame_begin(L.fr[L.sp], s, nx.p, L.hit, L.si, f.gi - 1);
+                    push_child = true;
+                    f.stage = ST_REFR_WAIT;
+                } else refr_resolved = true;
+            } else {
+                R = L.sv * sample_environment(s, nx.dir);
                 clamp_white(R);
-                f.out = f.out + R;
-                if (saturated(f.out)) done = true; else f.stage = ST_GI;
-            } else f.stage = ST_REFR_WAIT;
-        } else if (f.stage == ST_REFR_WAIT) {
-            V3 R = f.mult * ret;        // refraction*absorption*Shade(...) (:533) or Shade (:509)
-            clamp_white(R);
-            f.out = f.out + R;
-            have_ret = false;
-            if (saturated(f.out)) done = true; else f.stage = ST_GI;
-        } else if (f.stage == ST_GI) {
-            // ---- PathTracing_GlobalIllumination (MtlBlinn.cpp:383-433)
-            if (det || f.gi < 0) f.stage = ST_DIRECT;
-            else {
-                // GIUseSpecularDirOrDiffuseDir (:354-378)
-                V3 dcol = ld3(M.diffuse.color);
-                float kd = fmaxr(fmaxr(dcol.x, dcol.y), dcol.z);
-                float ks = fmaxr(fmaxr(f.newSpec.x, f.newSpec.y), f.newSpec.z);
-                float dTheta = 0;
-                V3 ddir = normalized(sample_semisphere(f.vN, dTheta, rng));
-                float p_d = sinf(2 * dTheta);
-                float sTheta = 0;
-                float cvn = dot(f.vN, f.vV);
-                V3 vR = 2 * cvn * f.vN - f.vV;
-                V3 sdir = sample_along_direction(vR, M.glossiness, sTheta, rng);
-                float p_s = powf(cosf(sTheta), M.glossiness);
-                float P_d = kd * p_d;
-                float P_sum = P_d + ks * p_s;
-                float P_dn = P_d / P_sum;
-                float rnd = rng.rnd01();
-                f.useSpec = rnd >= P_dn;
-                Ray g; g.dir = f.useSpec ? sdir : ddir; g.p = f.p + f.vN * BHRT_BIAS;
-                Hit hg; hg.init();
-                rc.closest++;
-                bool hitG = scene_closest(s, g, hg, HIT_FRONT);
-                V3 G(0, 0, 0);
-                bool resolved = true;
-                if (hitG) {
-                    if (fabsf(hg.z) > BHRT_BIAS && sp < BHRT_MAX_FRAMES) {
-                        frame_begin(fr[sp], s, g, hg, f.bounce, f.gi - 1);
-                        push_child = true; resolved = false;
-                    }
-                    // else: indirect = black, black * albedo = black
-                } else {
-                    if (g.dir.x == g.dir.y && g.dir.x == 0) G = V3(1.0f, 0.0f, 1.0f);
-                    else {
-                        V3 alb = f.useSpec ? texcolor_sample_filtered(s, f.newSpec, M.specular.texmap, f.uvw, f.duvw0, f.duvw1)
-                                           : texcolor_sample_filtered(s, ld3(M.diffuse.color), M.diffuse.texmap, f.uvw, f.duvw0, f.duvw1);
-                        V3 env = sample_environment(s, g.dir) * alb;
-                        if (!(is_nan(env.x) || is_nan(env.y) || is_nan(env.z))) G = env;
-                    }
-                }
-                if (resolved) {
-                    if (is_nan(G.x)) G = V3(1.0f, 0.0f, 1.0f);
-                    clamp_white(G);
-                    f.out = f.out + G;
-                    if (saturated(f.out)) done = true; else f.stage = ST_DIRECT;
-                } else f.stage = ST_GI_WAIT;
+                refr_resolved = true;
             }
-        } else if (f.stage == ST_GI_WAIT) {
+            break;
+        }
+        case ST_REFR_WAIT:
+            R = f.mult * L.ret;         // refraction*absorption*Shade(...) (:533) or Shade (:509)
+            refr_resolved = true;
+            break;
+        case ST_GI: {
+            // ---- PathTracing_GlobalIllumination (MtlBlinn.cpp:383-433)
+            if (det || f.gi < 0) { f.stage = ST_DIRECT; L.si = 0; L.sv = V3(0, 0, 0); break; }
+            // GIUseSpecularDirOrDiffuseDir (:354-378)
+            V3 dcol = ld3(M.diffuse.color);
+            float kd = fmaxr(fmaxr(dcol.x, dcol.y), dcol.z);
+            float ks = fmaxr(fmaxr(f.newSpec.x, f.newSpec.y), f.newSpec.z);
+            float dTheta = 0;
+            V3 ddir = normalized(sample_semisphere(f.vN, dTheta, rng));
+            float p_d = sinf(2 * dTheta);
+            float sTheta = 0;
+            float cvn = dot(f.vN, f.vV);
+            V3 vR = 2 * cvn * f.vN - f.vV;
+            V3 sdir = sample_along_direction(vR, M.glossiness, sTheta, rng);
+            float p_s = powf(cosf(sTheta), M.glossiness);
+            float P_d = kd * p_d;
+            float P_sum = P_d + ks * p_s;
+            float P_dn = P_d / P_sum;
+            float rnd = rng.rnd01();
+            f.useSpec = rnd >= P_dn;
+            Ray g; g.dir = f.useSpec ? sdir : ddir; g.p = f.p + f.vN * BHRT_BIAS;
+            issue_closest(L, g, HIT_FRONT, rc);
+            f.stage = ST_GI_TRACE_WAIT;
+            return false;
+        }
+        case ST_GI_TRACE_WAIT: {
+            const Ray g = L.q.ray;
+            if (L.hit_ok) {
+                if (fabsf(L.hit.z) > BHRT_BIAS && L.sp < BHRT_MAX_FRAMES) {
+                    frame_begin(L.fr[L.sp], s, g.p, L.hit, f.bounce, f.gi - 1);
+                    push_child = true;
+                    f.stage = ST_GI_WAIT;
+                } else gi_resolved = true;      // indirect = black, black * albedo = black
+            } else {
+                if (g.dir.x == g.dir.y && g.dir.x == 0) G = V3(1.0f, 0.0f, 1.0f);
+                else {
+                    V3 alb = f.useSpec ? texcolor_sample_filtered(s, f.newSpec, M.specular.texmap, f.uvw, f.duvw0, f.duvw1)
+                                       : texcolor_sample_filtered(s, ld3(M.diffuse.color), M.diffuse.texmap, f.uvw, f.duvw0, f.duvw1);
+                    V3 env = sample_environment(s, g.dir) * alb;
+                    if (!(is_nan(env.x) || is_nan(env.y) || is_nan(env.z))) G = env;
+                }
+                gi_resolved = true;
+            }
+            break;
+        }
+        case ST_GI_WAIT: {
             V3 alb = f.useSpec ? texcolor_sample_filtered(s, f.newSpec, M.specular.texmap, f.uvw, f.duvw0, f.duvw1)
                                : texcolor_sample_filtered(s, ld3(M.diffuse.color), M.diffuse.texmap, f.uvw, f.duvw0, f.duvw1);
-            V3 G = ret * alb;
-            have_ret = false;
+            G = L.ret * alb;
+            gi_resolved = true;
+            break;
+        }
+        case ST_DIRECT: {
+            // ---- PathTracing_DiffuseNSpecular (MtlBlinn.cpp:304-351); L.si / L.sv were reset on entry
+            if (det) {
+                // D-3 of SURVEY.md 8(c): every light, exact direction
+                bool issued = false;
+                while (L.si < s.n_lights) {
+                    const bhrt_light &Lt = s.lights[L.si];
+                    V3 vL = -normalized(light_direction(Lt, f.p));
+                    float cosTheta = dot(vL, f.vN);
+                    if (cosTheta > 0) {
+                        V3 irrad;
+                        L.sw = vL;
+                        if (illuminate_begin(Lt, f.p, (Rng *)0, L.q, irrad)) { rc.shadow++; f.stage = ST_SHADOW_WAIT; issued = true; break; }
+                        L.sv = L.sv + irrad * direct_brdf(s, f, M, vL);
+                    }
+                    L.si++;
+                }
+                if (issued) return false;
+                direct_finish(f, L.sv);
+                done = true;
+            } else {
+                if (s.n_lights > 0) {
+                    float rnd = rng.rnd01();
+                    int i = 0;
+                    while (rnd > gray(ld3(s.lights[i].intensity)) / s.all_light_intensity && i < s.n_lights - 1) i++;
+                    const bhrt_light &Lt = s.lights[i];
+                    V3 dcol = ld3(M.diffuse.color);
+                    float kd = fmaxr(fmaxr(dcol.x, dcol.y), dcol.z);
+                    float ks = fmaxr(fmaxr(f.newSpec.x, f.newSpec.y), f.newSpec.z);
+                    V3 vL = sample_in_light(Lt, f.p, kd, ks, M.glossiness, rng);
+                    float cosTheta = dot(vL, f.vN);
+                    if (cosTheta > 0) {
+                        V3 irrad;
+                        L.sw = vL; L.si = i;
+                        if (illuminate_begin(Lt, f.p, &rng, L.q, irrad)) { rc.shadow++; f.stage = ST_SHADOW_WAIT; return false; }
+                        L.sv = L.sv + irrad * direct_brdf(s, f, M, vL);
+                    }
+                }
+                direct_finish(f, L.sv);
+                done = true;
+            }
+            break;
+        }
+        case ST_SHADOW_WAIT: {
+            const bhrt_light &Lt = s.lights[L.si];
+            V3 irrad = illuminate_end(Lt, f.p, L.hit_ok);
+            L.sv = L.sv + irrad * direct_brdf(s, f, M, L.sw);
+            if (det) { L.si++; f.stage = ST_DIRECT; }
+            else { direct_finish(f, L.sv); done = true; }
+            break;
+        }
+        }
+
+        if (refr_resolved) {
+            clamp_white(R);
+            f.out = f.out + R;
+            if (saturated(f.out)) done = true; else f.stage = ST_GI;
+        }
+        if (gi_resolved) {
             if (is_nan(G.x)) G = V3(1.0f, 0.0f, 1.0f);
             clamp_white(G);
             f.out = f.out + G;
-            if (saturated(f.out)) done = true; else f.stage = ST_DIRECT;
-        } else {
-            // ---- PathTracing_DiffuseNSpecular (MtlBlinn.cpp:304-351)
-            V3 D(0, 0, 0);
-            V3 dcol = ld3(M.diffuse.color);
-            if (det) {
-                // D-3 of SURVEY.md 8(c): every light, exact direction
-                for (int li = 0; li < s.n_lights; li++) {
-                    const bhrt_light &L = s.lights[li];
-                    V3 vL = -normalized(light_direction(L, f.p));
-                    float cosTheta = dot(vL, f.vN);
-                    if (cosTheta > 0) {
-                        V3 vH = normalized(vL + f.vV);
-                        V3 irrad = illuminate(s, L, f.p, (Rng *)0, rc);
-                        V3 kdT = texcolor_sample_filtered(s, dcol, M.diffuse.texmap, f.uvw, f.duvw0, f.duvw1);
-                        V3 ksT = texcolor_sample_filtered(s, f.newSpec, M.specular.texmap, f.uvw, f.duvw0, f.duvw1);
-                        V3 brdf = kdT * cosTheta + ksT * powf(dot(vH, f.vN), M.glossiness);
-                        D = D + irrad * brdf;
-                    }
-                }
-            } else if (s.n_lights > 0) {
-                float rnd = rng.rnd01();
-                int i = 0;
-                while (rnd > gray(ld3(s.lights[i].intensity)) / s.all_light_intensity && i < s.n_lights - 1) i++;
-                const bhrt_light &L = s.lights[i];
-                float kd = fmaxr(fmaxr(dcol.x, dcol.y), dcol.z);
-                float ks = fmaxr(fmaxr(f.newSpec.x, f.newSpec.y), f.newSpec.z);
-                V3 vL = sample_in_light(L, f.p, kd, ks, M.glossiness, rng);
-                float cosTheta = dot(vL, f.vN);
-                if (cosTheta > 0) {
-                    V3 vH = normalized(vL + f.vV);
-                    V3 irrad = illuminate(s, L, f.p, &rng, rc);
-                    V3 kdT = texcolor_sample_filtered(s, dcol, M.diffuse.texmap, f.uvw, f.duvw0, f.duvw1);
-                    V3 ksT = texcolor_sample_filtered(s, f.newSpec, M.specular.texmap, f.uvw, f.duvw0, f.duvw1);
-                    V3 brdf = kdT * cosTheta + ksT * powf(dot(vH, f.vN), M.glossiness);
-                    D = D + irrad * brdf;
-                }
-            }
-            clamp_white(D);
-            if (is_nan(D.x)) D = V3(0, 0, 0);
-            f.out = f.out + D;
-            if (!saturated(f.out) && is_nan(f.out.x)) f.out = V3(1.0f, 0.0f, 1.0f);   // Shade epilogue (:131-136)
-            done = true;
+            if (saturated(f.out)) done = true;
+            else { f.stage = ST_DIRECT; L.si = 0; L.sv = V3(0, 0, 0); }
         }
-
-        if (push_child) { sp++; continue; }
+        if (push_child) { L.sp++; continue; }
         if (done) {
-            ret = fr[sp - 1].out;
-            have_ret = true;
-            sp--;
-            if (sp == 0) break;
+            L.ret = f.out;
+            L.sp--;
+            if (L.sp == 0) { color = L.ret; return true; }
         }
     }
-    (void)have_ret;
-    return ret;
+}
+
+// One camera sample, synchronously: the reference's PathTracing() loop body.  Used by the CPU
+// harness (tests/emu); the kernel interleaves the same two calls across a warp.
+BHRT_HD V3 trace_sample(Lane &L, const SceneView &s, const ShadeCfg &cfg, const PhotonGather &pg, const Ray &primary, float bgu, float bgv,
+                        RayCounters &rc, int &hit_id, float &hit_z)
+{
+    V3 color(0, 0, 0);
+    sample_begin(L, primary, rc);
+    for (;;) {
+        L.hit_ok = scene_trace(s, L.q, L.hit);
+        if (sample_advance(L, s, cfg, pg, bgu, bgv, rc, color)) break;
+    }
+    hit_id = L.hit_id; hit_z = L.hit_z;
+    return color;
 }
 
 // RandomPositionInPixel (Main.cpp:132-139) + the primary ray of PathTracing (Main.cpp:145-153)

@@ -14,6 +14,7 @@
 #include <vector>
 #include "core.cuh"
 #include "setup.hpp"
+#include "accel.hpp"
 #include "photon.cuh"
 
 using namespace bhrt;
@@ -50,6 +51,10 @@ struct bhrt_ctx {
     DevBuf accum, hit_id, z, rgb8, linear, counters;
     PhotonState photons;
     int rendered_spp = 0;
+    int n_materials = 0;
+    DevBuf accels, accel_data;
+    bool kernel_ready = false;
+    int kernel_smem = 0, blocks_per_sm = 1;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -57,49 +62,114 @@ struct RenderArgs {
     ShadeCfg cfg;
     unsigned long long seed;
     int sample_begin, sample_end;
-    int row_begin, row_end, row_stride;
+    int row_begin, row_stride;
     int n_rows;              // number of rows this launch covers
-    int accumulate;          // add to the accumulation buffer instead of overwriting it
+    int tiles_x;             // 8x8 pixel tiles per row of tiles
+    unsigned int n_work;     // work items = tiles * 64 (items outside the image are skipped)
     PhotonGather gather;     // caustic photon map (use = 0 when disabled)
+    int smem_nodes, smem_materials, smem_lights, smem_offsets;   // byte offsets of the staged tables
 };
 
-// One warp = one 8x4 pixel tile; block = 4 warps = a 16x8 tile.
-#define BHRT_TILE_W 16
-#define BHRT_TILE_H 8
+#define BHRT_BLOCK 128
+#define BHRT_FULL 0xffffffffu
 
-__global__ void __launch_bounds__(128)
+// Persistent-thread renderer.  The grid is sized to fill the machine once (SMs x resident CTAs);
+// every lane owns ONE pixel at a time and evaluates its samples in order (so a pixel's sum is
+// independent of launch geometry and GPU count), then pulls the next pixel from a global counter
+// -- one warp-aggregated atomic per refill.  Pixels are numbered in 8x8 tiles so the lanes of a
+// warp start on neighbouring primary rays.
+//
+// Each loop iteration has exactly one traversal (scene_trace) that all lanes with work enter
+// together, whatever their sample's recursion level or stage; sample_advance() then runs each
+// lane's estimator coroutine to its next ray.  The scene-graph node table, materials, lights and
+// the texture-filter taps are staged in shared memory once per CTA: the node loop of scene_trace
+// reads them at warp-uniform addresses (one broadcast per access).
+__global__ void __launch_bounds__(BHRT_BLOCK)
 render_kernel(SceneView s, RenderArgs a, float4 *__restrict__ accum, int *__restrict__ hit_id, float *__restrict__ zbuf,
               unsigned long long *__restrict__ counters)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tx = blockIdx.x * BHRT_TILE_W + (warp & 1) * 8 + (lane & 7);
-    const int trow = blockIdx.y * BHRT_TILE_H + (warp >> 1) * 4 + (lane >> 3);    // index into this launch's row list
+    extern __shared__ __align__(16) unsigned char smem[];
+    {
+        // cooperative 32-bit copies of the small tables (all sizes are multiples of 4)
+        const uint32_t *src; uint32_t *dst; int n;
+        src = (const uint32_t *)s.nodes; dst = (uint32_t *)(smem + a.smem_nodes); n = s.n_nodes * (int)(sizeof(bhrt_node) / 4);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        src = (const uint32_t *)s.materials; dst = (uint32_t *)(smem + a.smem_materials); n = s.n_materials * (int)(sizeof(bhrt_material) / 4);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        src = (const uint32_t *)s.lights; dst = (uint32_t *)(smem + a.smem_lights); n = s.n_lights * (int)(sizeof(bhrt_light) / 4);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        src = (const uint32_t *)s.tex_offsets; dst = (uint32_t *)(smem + a.smem_offsets); n = 2 * (BHRT_TEX_SAMPLES - 1);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        s.nodes = (const bhrt_node *)(smem + a.smem_nodes);
+        s.materials = (const bhrt_material *)(smem + a.smem_materials);
+        s.lights = (const bhrt_light *)(smem + a.smem_lights);
+        s.tex_offsets = (const float *)(smem + a.smem_offsets);
+    }
+    const int lane = threadIdx.x & 31;
+    const bool det = a.cfg.mode == BHRT_MODE_DET;
     RayCounters rc; rc.closest = 0; rc.shadow = 0;
-    if (tx < s.width && trow < a.n_rows) {
-        const int j = a.row_begin + trow * a.row_stride;
-        const int i = tx;
-        V3 sum(0, 0, 0);
-        int id0 = -1; float z0 = BHRT_BIGFLOAT;
-        const bool det = a.cfg.mode == BHRT_MODE_DET;
-        for (int sidx = a.sample_begin; sidx < a.sample_end; sidx++) {
-            Rng rng; rng.seed(a.seed, (uint64_t)j * s.width + i, (uint64_t)sidx);
-            Ray pr = primary_ray(s, i, j, !det, rng);
-            int id; float zz;
-            V3 c = trace_sample(s, a.cfg, a.gather, pr, (float)i / s.width, (float)j / s.height, rng, rc, id, zz);
-            if (sidx == 0) { id0 = id; z0 = zz; }
-            sum = sum + c;
+    Lane L;
+    int pi = 0, pj = 0;             // the lane's pixel
+    bool have_pixel = false, in_sample = false, exhausted = false;
+    int sidx = 0, id0 = -1;
+    float z0 = BHRT_BIGFLOAT;
+    V3 sum(0, 0, 0);
+    for (;;) {
+        // ---- refill idle lanes (warp-aggregated fetch)
+        const bool need = !have_pixel && !exhausted;
+        const unsigned nm = __ballot_sync(BHRT_FULL, need);
+        if (nm) {
+            const int leader = __ffs(nm) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd((unsigned int *)&counters[2], (unsigned)__popc(nm));
+            base = __shfl_sync(BHRT_FULL, base, leader);
+            if (need) {
+                const unsigned idx = base + __popc(nm & ((1u << lane) - 1u));
+                if (idx >= a.n_work) exhausted = true;
+                else {
+                    const unsigned tile = idx >> 6, w = idx & 63u;
+                    const int tx = (int)(tile % (unsigned)a.tiles_x), ty = (int)(tile / (unsigned)a.tiles_x);
+                    const int i = tx * 8 + (int)(w & 7u), trow = ty * 8 + (int)(w >> 3);
+                    if (i < s.width && trow < a.n_rows) {
+                        pi = i; pj = a.row_begin + trow * a.row_stride;
+                        have_pixel = true; in_sample = false;
+                        sidx = a.sample_begin; sum = V3(0, 0, 0);
+                    }
+                }
+            }
         }
-        const size_t p = (size_t)j * s.width + i;
-        float4 v = make_float4(sum.x, sum.y, sum.z, (float)(a.sample_end - a.sample_begin));
-        if (a.accumulate) { float4 o = accum[p]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-        accum[p] = v;
-        if (a.sample_begin == 0) { hit_id[p] = id0; zbuf[p] = z0; }
+        if (!__any_sync(BHRT_FULL, have_pixel)) {
+            if (!__any_sync(BHRT_FULL, !exhausted)) break;
+            continue;
+        }
+        if (have_pixel) {
+            if (!in_sample) {
+                L.rng.seed(a.seed, (uint64_t)pj * s.width + pi, (uint64_t)sidx);
+                Ray pr = primary_ray(s, pi, pj, !det, L.rng);
+                sample_begin(L, pr, rc);
+                in_sample = true;
+            }
+            L.hit_ok = scene_trace(s, L.q, L.hit);
+            V3 c;
+            if (sample_advance(L, s, a.cfg, a.gather, (float)pi / s.width, (float)pj / s.height, rc, c)) {
+                if (sidx == 0) { id0 = L.hit_id; z0 = L.hit_z; }
+                sum = sum + c;
+                in_sample = false;
+                if (++sidx == a.sample_end) {
+                    const size_t p = (size_t)pj * s.width + pi;
+                    accum[p] = make_float4(sum.x, sum.y, sum.z, (float)(a.sample_end - a.sample_begin));
+                    if (a.sample_begin == 0) { hit_id[p] = id0; zbuf[p] = z0; }
+                    have_pixel = false;
+                }
+            }
+        }
     }
     // ray counters: warp-reduce, one atomic per warp
     unsigned long long c0 = rc.closest, c1 = rc.shadow;
     for (int o = 16; o > 0; o >>= 1) {
-        c0 += __shfl_down_sync(0xffffffffu, c0, o);
-        c1 += __shfl_down_sync(0xffffffffu, c1, o);
+        c0 += __shfl_down_sync(BHRT_FULL, c0, o);
+        c1 += __shfl_down_sync(BHRT_FULL, c1, o);
     }
     if (lane == 0 && (c0 | c1)) { atomicAdd(&counters[0], c0); atomicAdd(&counters[1], c1); }
 }
@@ -154,7 +224,7 @@ int bhrt_destroy(bhrt_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = { &c->nodes, &c->materials, &c->lights, &c->texmaps, &c->textures, &c->texels, &c->meshes, &c->mesh_data,
-                       &c->tex_offsets, &c->accum, &c->hit_id, &c->z, &c->rgb8, &c->linear, &c->counters };
+                       &c->tex_offsets, &c->accels, &c->accel_data, &c->accum, &c->hit_id, &c->z, &c->rgb8, &c->linear, &c->counters };
     for (auto b : bufs) b->release();
     c->photons.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -209,12 +279,17 @@ int bhrt_upload_scene(bhrt_ctx *c, const bhrt_scene_desc *d)
     if ((r = upload(c, c->meshes, d->meshes, sizeof(bhrt_mesh) * d->n_meshes))) return r;
     if ((r = upload(c, c->mesh_data, d->mesh_data, d->mesh_bytes))) return r;
     if ((r = upload(c, c->tex_offsets, offs.data(), sizeof(float) * offs.size()))) return r;
+    AccelBlob accel;
+    std::string aerr;
+    if (!build_accel(*d, accel, &aerr)) return set_err(BHRT_ERR_ARG, "bhrt_upload_scene: " + aerr);
+    if ((r = upload(c, c->accels, accel.meshes.data(), sizeof(MeshAccel) * accel.meshes.size()))) return r;
+    if ((r = upload(c, c->accel_data, accel.data.data(), accel.data.size()))) return r;
     CU(cudaStreamSynchronize(c->stream));      // the staging vectors above die with this scope
 
     FrameConstants fc = camera_setup(d->camera);
     SceneView &s = c->view;
     memset(&s, 0, sizeof(s));
-    s.n_nodes = d->n_nodes; s.n_lights = d->n_lights; s.max_depth = max_depth;
+    s.n_nodes = d->n_nodes; s.n_lights = d->n_lights; s.max_depth = max_depth; s.n_materials = d->n_materials;
     s.nodes = (const bhrt_node *)c->nodes.p;
     s.materials = (const bhrt_material *)c->materials.p;
     s.lights = (const bhrt_light *)c->lights.p;
@@ -224,6 +299,9 @@ int bhrt_upload_scene(bhrt_ctx *c, const bhrt_scene_desc *d)
     s.meshes = (const bhrt_mesh *)c->meshes.p;
     s.mesh_data = (const uint8_t *)c->mesh_data.p;
     s.tex_offsets = (const float *)c->tex_offsets.p;
+    s.accels = (const MeshAccel *)c->accels.p;
+    s.accel_data = (const uint8_t *)c->accel_data.p;
+    c->n_materials = d->n_materials;
     s.background = d->background; s.environment = d->environment;
     s.all_light_intensity = allI;
     s.cam_pos = fc.cam_pos; s.top_left = fc.top_left; s.dd_x = fc.dd_x; s.dd_y = fc.dd_y;
@@ -254,31 +332,53 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     a.sample_begin = p->sample_begin; a.sample_end = p->sample_end;
     if (a.sample_begin == 0 && a.sample_end == 0) a.sample_end = spp;
     if (a.sample_begin < 0 || a.sample_end > spp || a.sample_begin > a.sample_end) return set_err(BHRT_ERR_ARG, "bhrt_render: bad sample range");
-    a.row_begin = p->row_begin; a.row_end = p->row_end;
-    if (a.row_begin == 0 && a.row_end == 0) a.row_end = c->height;
-    if (a.row_begin < 0 || a.row_end > c->height || a.row_begin > a.row_end) return set_err(BHRT_ERR_ARG, "bhrt_render: bad row range");
+    int row_begin = p->row_begin, row_end = p->row_end;
+    if (row_begin == 0 && row_end == 0) row_end = c->height;
+    if (row_begin < 0 || row_end > c->height || row_begin > row_end) return set_err(BHRT_ERR_ARG, "bhrt_render: bad row range");
+    a.row_begin = row_begin;
     a.row_stride = p->row_stride > 1 ? p->row_stride : 1;
-    a.n_rows = (a.row_end - a.row_begin + a.row_stride - 1) / a.row_stride;
-    a.accumulate = 0;
+    a.n_rows = (row_end - row_begin + a.row_stride - 1) / a.row_stride;
+    a.tiles_x = (c->width + 7) / 8;
+    a.n_work = (unsigned)a.tiles_x * (unsigned)((a.n_rows + 7) / 8) * 64u;
     a.gather.use = 0;
     if (p->use_photon_map) {
         if (!c->photons.built) return set_err(BHRT_ERR_STATE, "bhrt_render: use_photon_map set but no photon map built");
         a.gather = c->photons.gather_view(p->photon_k > 0 ? p->photon_k : 1000, p->photon_radius > 0 ? p->photon_radius : 0.5f);
     }
-    CU(cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(unsigned long long), c->stream));
-    // rows outside this launch's share must read as zero for the multi-GPU sum
-    if (a.n_rows != c->height || a.sample_begin != 0)
+    // shared-memory staging of the small scene tables
+    auto al16 = [](int v) { return (v + 15) & ~15; };
+    a.smem_nodes = 0;
+    a.smem_materials = al16(a.smem_nodes + c->view.n_nodes * (int)sizeof(bhrt_node));
+    a.smem_lights = al16(a.smem_materials + c->n_materials * (int)sizeof(bhrt_material));
+    a.smem_offsets = al16(a.smem_lights + c->view.n_lights * (int)sizeof(bhrt_light));
+    const int smem_bytes = al16(a.smem_offsets + 2 * (BHRT_TEX_SAMPLES - 1) * (int)sizeof(float));
+    if (!c->kernel_ready || c->kernel_smem < smem_bytes) {
+        CU(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel, BHRT_BLOCK, smem_bytes));
+        if (per_sm < 1) return set_err(BHRT_ERR_LIMIT, "bhrt_render: scene tables do not fit in shared memory");
+        c->blocks_per_sm = per_sm;
+        c->kernel_smem = smem_bytes;
+        c->kernel_ready = true;
+    }
+    CU(cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    // rows / samples outside this launch's share must read as zero for the multi-GPU sum
+    if (a.n_rows != c->height || a.sample_begin != 0 || a.sample_end == a.sample_begin)
         CU(cudaMemsetAsync(c->accum.p, 0, (size_t)c->width * c->height * sizeof(float4), c->stream));
-    if (a.sample_begin != 0) {
+    if (a.n_rows != c->height || a.sample_begin != 0) {
         CU(cudaMemsetAsync(c->hit_id.p, 0, (size_t)c->width * c->height * 4, c->stream));
         CU(cudaMemsetAsync(c->z.p, 0, (size_t)c->width * c->height * 4, c->stream));
     }
-    dim3 block(128);
-    dim3 grid((c->width + BHRT_TILE_W - 1) / BHRT_TILE_W, (a.n_rows + BHRT_TILE_H - 1) / BHRT_TILE_H);
+    // persistent grid: fill the machine once; never more CTAs than there is work for
+    unsigned grid = (unsigned)(c->sm_count * c->blocks_per_sm);
+    const unsigned need_blocks = (a.n_work + BHRT_BLOCK - 1) / BHRT_BLOCK;
+    if (grid > need_blocks) grid = need_blocks;
     CU(cudaEventRecord(c->ev0, c->stream));
-    if (a.n_rows > 0 && a.sample_end > a.sample_begin)
-        render_kernel<<<grid, block, 0, c->stream>>>(c->view, a, (float4 *)c->accum.p, (int *)c->hit_id.p, (float *)c->z.p,
-                                                     (unsigned long long *)c->counters.p), c->launches++;
+    if (a.n_rows > 0 && a.sample_end > a.sample_begin && grid > 0) {
+        render_kernel<<<grid, BHRT_BLOCK, smem_bytes, c->stream>>>(c->view, a, (float4 *)c->accum.p, (int *)c->hit_id.p, (float *)c->z.p,
+                                                                    (unsigned long long *)c->counters.p);
+        c->launches++;
+    }
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev1, c->stream));
     c->rendered_spp = a.sample_end - a.sample_begin;

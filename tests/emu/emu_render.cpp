@@ -16,6 +16,7 @@
 #include <vector>
 #include "../../bhraytracer_b200/csrc/device/core.cuh"
 #include "../../bhraytracer_b200/csrc/device/setup.hpp"
+#include "../../bhraytracer_b200/csrc/device/accel.hpp"
 #include "../../bhraytracer_b200/csrc/host/scene.hpp"
 
 using namespace bhrt;
@@ -61,6 +62,9 @@ int main(int argc, char **argv)
     s.nodes = D.nodes; s.materials = D.materials; s.lights = lights.data();
     s.texmaps = D.texmaps; s.textures = D.textures; s.texels = D.texels;
     s.meshes = D.meshes; s.mesh_data = D.mesh_data; s.tex_offsets = offs.data();
+    AccelBlob accel;
+    if (!build_accel(D, accel, &err)) { fprintf(stderr, "accel: %s\n", err.c_str()); return 3; }
+    s.accels = accel.meshes.data(); s.accel_data = accel.data.data();
     s.background = D.background; s.environment = D.environment;
     s.all_light_intensity = allI;
     s.cam_pos = fc.cam_pos; s.top_left = fc.top_left; s.dd_x = fc.dd_x; s.dd_y = fc.dd_y;
@@ -82,11 +86,12 @@ int main(int argc, char **argv)
             RayCounters rc; rc.closest = 0; rc.shadow = 0;
             V3 sum(0, 0, 0);
             int id0 = -1; float z0 = BHRT_BIGFLOAT;
+            Lane L;
             for (int sidx = smp_b; sidx < smp_e; sidx++) {
-                Rng rng; rng.seed(seed, (uint64_t)j * W + i, sidx);
-                Ray pr = primary_ray(s, i, j, !det, rng);
+                L.rng.seed(seed, (uint64_t)j * W + i, sidx);
+                Ray pr = primary_ray(s, i, j, !det, L.rng);
                 int id; float zz;
-                V3 c = trace_sample(s, cfg, pg, pr, (float)i / W, (float)j / H, rng, rc, id, zz);
+                V3 c = trace_sample(L, s, cfg, pg, pr, (float)i / W, (float)j / H, rc, id, zz);
                 if (sidx == 0) { id0 = id; z0 = zz; }
                 sum = sum + c;
             }

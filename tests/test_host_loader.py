@@ -91,7 +91,7 @@ def test_mesh_tables_and_bvh_topology(built):
             data = int(bvh[n, 6])
             if data & 0x80000000:
                 cnt, off = ((data >> 28) & 7) + 1, data & 0x0FFFFFFF
-                assert cnt <= 4
+                assert cnt <= 8      # MeanSplit may fail to split coincident centroids (cyBVH.h:295-328); 3-bit count
                 seen[elems[off:off + cnt]] += 1
             else:
                 c = data & 0x7FFFFFFF
