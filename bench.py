@@ -138,7 +138,7 @@ def scene_bytes(desc):
     """Bytes bhrt_upload_scene copies host -> device for this description."""
     import bhraytracer_b200 as b
     d = desc.contents
-    sz = {"node": 104, "material": 68, "light": 32, "texmap": 88, "texture": 48, "mesh": 88}
+    sz = {"node": 104, "material": 72, "light": 32, "texmap": 88, "texture": 48, "mesh": 88}
     return (d.n_nodes * sz["node"] + d.n_materials * sz["material"] + d.n_lights * sz["light"] + d.n_texmaps * sz["texmap"] +
             d.n_textures * sz["texture"] + d.n_meshes * sz["mesh"] + d.texel_bytes + d.mesh_bytes + 31 * 8)
 
@@ -356,7 +356,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU legs (profiling runs)")
+    ap.add_argument("--size", default=None, help="WxH override for ncu runs (marks the line as a profile run; not a bench value)")
+    ap.add_argument("--spp", type=int, default=None, help="samples per pixel override for ncu runs")
     args = ap.parse_args()
+    global WIDTH, HEIGHT, SPP, WORKLOAD
+    if args.size or args.spp:
+        if args.size:
+            WIDTH, HEIGHT = (int(x) for x in args.size.lower().split("x"))
+        if args.spp:
+            SPP = args.spp
+        WORKLOAD = "PROFILE RUN (not a bench value): cfg2_mesh_refract %dx%d %dspp H-mode gi3" % (WIDTH, HEIGHT, SPP)
     if args.impl == "reference":
         bench_reference(args)
     else:

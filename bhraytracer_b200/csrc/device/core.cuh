@@ -84,7 +84,7 @@ BHRT_HD V3 xf_vec_from(const bhrt_xform &t, V3 d) { return mat_tmul(t.itm, d); }
 
 struct Ray { V3 p, dir; };
 
-struct Hit {                // reference scene.h:62-75 (HitInfo)
+struct alignas(16) Hit {    // reference scene.h:62-75 (HitInfo)
     float z;
     V3 p, N, uvw, duvw0, duvw1;
     int node;               // index into nodes, -1 = none
@@ -106,6 +106,7 @@ BHRT_HD Ray to_node(const bhrt_xform &t, const Ray &r)
     return o;
 }
 
+#define BHRT_MESH_MASK_BITS 32
 // ---- device traversal tables (built at upload by accel.hpp from the bhrt_mesh tables) --------
 struct alignas(16) F4 { float x, y, z, w; };
 BHRT_HD F4 ld4(const F4 *p)
@@ -116,6 +117,14 @@ BHRT_HD F4 ld4(const F4 *p)
     return r;
 #else
     return *p;
+#endif
+}
+BHRT_HD float u2f(uint32_t u)
+{
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
 #endif
 }
 BHRT_HD uint32_t f2u(float f)
@@ -153,6 +162,8 @@ struct SceneView {
     const uint8_t *mesh_data;
     const MeshAccel *accels;            // one per mesh
     const uint8_t *accel_data;
+    int mesh_nodes[BHRT_MESH_MASK_BITS]; // node indices of the first 32 mesh nodes in DFS order
+    int n_mesh_nodes;                   // all mesh nodes of the scene graph
     const float *tex_offsets;           // 31 (x,y) pairs of the elliptical Halton filter (scene.h:322-329)
     bhrt_texcolor background, environment;
     float all_light_intensity;          // Main.cpp:119-122
@@ -172,19 +183,102 @@ struct PhotonRecord {
     int16_t dirX, dirY;
 };
 
-// Read-only view of the gather structure (photon.cuh builds it): photons sorted by the cell
-// of a uniform grid whose cell edge is the gather radius, so a query touches 27 cells.
+// Gather-side photon: 32 bytes, two 128-bit loads.  a = (position, max-channel power);
+// b = (direction as Photon::GetDirection decodes it -- including its dirX*dirX + dirY - dirY
+// slip, cyPhotonMap.h:196 -- and the 8-bit colour ratio in the bits of b.w).
+struct alignas(16) GatherRec { F4 a, b; };
+
+#define BHRT_PM_LEVELS 5            // grid levels: cell, cell/2, ... cell/16
+#define BHRT_PM_FINE_BITS 12        // 4 octree levels below a coarse cell -> 12 Morton bits
+// Read-only view of the gather structure (photon_build.hpp / photon.cuh build it): photons sorted
+// by key = coarse cell << 12 | Morton code of the 1/16 sub-cell.  Every cell of every level is a
+// contiguous key range, so ONE sorted array serves all five resolutions; a query picks the level
+// at which the k nearest photons fit in its 3x3x3 block (cyPhotonMap's kd-tree adapts to the
+// density the same way, cyPhotonMap.h:421-498).
 struct PhotonGather {
     int use;                    // 0 = no caustic term (reference built without USE_PhotonMap)
     int k;                      // MAX_PhotonCountInArea (MtlBlinn.cpp:28)
     float radius;               // MAX_Area (MtlBlinn.cpp:29)
     int n_photons;
-    const PhotonRecord *photons;
-    const uint32_t *cell_start; // [n_cells + 1]
+    const GatherRec *recs;      // sorted by key
+    const uint32_t *keys;       // sorted keys
+    const uint32_t *coarse_start;   // [dim.x*dim.y*dim.z + 1]
     float origin[3];
-    float inv_cell;
+    float cell;                 // coarse cell edge (>= radius)
     int dim[3];
 };
+
+// Photon::SetDirection / SetPower (cyPhotonMap.h:172-191) and the Color24 conversion (cyColor.h:271)
+BHRT_HD void photon_pack(PhotonRecord &r, V3 pos, V3 dir, V3 power)
+{
+    r.pos[0] = pos.x; r.pos[1] = pos.y; r.pos[2] = pos.z;
+    r.dirX = (int16_t)(dir.x * 0x7FFF);
+    r.dirY = (int16_t)(dir.y * 0x7FFF);
+    r.planeAndDirZ = dir.z > 0 ? 0 : 0x8;
+    float pw = power.x;
+    if (pw < power.y) pw = power.y;
+    if (pw < power.z) pw = power.z;
+    r.power = pw;
+    V3 c = power / pw;
+    int v;
+    v = (int)(c.x * 255 + 0.5f); r.rgb[0] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    v = (int)(c.y * 255 + 0.5f); r.rgb[1] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    v = (int)(c.z * 255 + 0.5f); r.rgb[2] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+// Photon::GetDirection (cyPhotonMap.h:193-214), integer square root and all
+BHRT_HD V3 photon_direction(const PhotonRecord &r)
+{
+    V3 dir;
+    dir.x = float(r.dirX) / float(0x7FFF);
+    dir.y = float(r.dirY) / float(0x7FFF);
+    int dirXY2 = r.dirX * r.dirX + r.dirY - r.dirY;
+    if (dirXY2 > 0x3FFF0001) dirXY2 = 0x3FFF0001;
+    int dirZ2 = 0x3FFF0001 - dirXY2;
+    int dirZ = 0;
+    int place = 0x40000000;
+    int remainder = dirZ2;
+    while (place > remainder) place = place >> 2;
+    while (place) {
+        if (remainder >= dirZ + place) {
+            remainder = remainder - dirZ - place;
+            dirZ = dirZ + (place << 1);
+        }
+        dirZ = dirZ >> 1;
+        place = place >> 2;
+    }
+    dir.z = float(dirZ) / float(0x7FFF);
+    if (r.planeAndDirZ & 0x8) dir.z = -dir.z;
+    return dir;
+}
+BHRT_HD GatherRec photon_gather_rec(const PhotonRecord &r, float power_scale)
+{
+    GatherRec g;
+    V3 d = photon_direction(r);
+    g.a.x = r.pos[0]; g.a.y = r.pos[1]; g.a.z = r.pos[2]; g.a.w = r.power * power_scale;      // ScalePhotonPowers (Main.cpp:380)
+    g.b.x = d.x; g.b.y = d.y; g.b.z = d.z;
+    uint32_t rgb = (uint32_t)r.rgb[0] | ((uint32_t)r.rgb[1] << 8) | ((uint32_t)r.rgb[2] << 16);
+    memcpy(&g.b.w, &rgb, 4);
+    return g;
+}
+// Morton code (x,y,z interleaved, most significant level first) of a 4-bit sub-cell coordinate
+BHRT_HD uint32_t photon_morton12(uint32_t x, uint32_t y, uint32_t z)
+{
+    uint32_t m = 0;
+    for (int j = 3; j >= 0; j--) m = (m << 3) | (((x >> j) & 1u) << 2) | (((y >> j) & 1u) << 1) | ((z >> j) & 1u);
+    return m;
+}
+// Sort key of a position (shared by the host and the device builder); false = outside the grid
+BHRT_HD bool photon_key(const float *origin, float cell, const int *dim, V3 p, uint32_t &key)
+{
+    float fx = (p.x - origin[0]) / cell, fy = (p.y - origin[1]) / cell, fz = (p.z - origin[2]) / cell;
+    int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= dim[0] || cy >= dim[1] || cz >= dim[2]) return false;
+    int sx = (int)((fx - cx) * 16.f), sy = (int)((fy - cy) * 16.f), sz = (int)((fz - cz) * 16.f);
+    sx = sx < 0 ? 0 : (sx > 15 ? 15 : sx); sy = sy < 0 ? 0 : (sy > 15 ? 15 : sy); sz = sz < 0 ? 0 : (sz > 15 ? 15 : sz);
+    uint32_t coarse = (uint32_t)cx + (uint32_t)dim[0] * ((uint32_t)cy + (uint32_t)dim[1] * (uint32_t)cz);
+    key = (coarse << BHRT_PM_FINE_BITS) | photon_morton12((uint32_t)sx, (uint32_t)sy, (uint32_t)sz);
+    return true;
+}
 
 // ------------------------------------------------------------------------------------------
 // Box::IntersectRay (reference Objects/Box/Box.cpp:3-46)
@@ -274,8 +368,10 @@ BHRT_HD void intersect_pair(const PairNode *pn, const Ray &r, float t_max, bool 
 #define BHRT_BVH_CHILD(d) ((d) & 0x7fffffffu)
 #define BHRT_BVH_STACK 64
 
-// One traversal loop for both query kinds (the two heavy parts -- pair slab tests and triangle
-// tests -- are shared, so a warp whose lanes mix closest-hit and shadow queries stays converged):
+// One traversal for both query kinds (the two heavy parts -- pair slab tests and triangle tests --
+// are shared, so a warp whose lanes mix closest-hit and shadow queries stays converged), written
+// as a STEPPER (one BVH node per step) so that the mesh kernel can hand a finished lane its next
+// ray while its warp neighbours are still traversing:
 //
 //  closest (any_hit == false): TriObj::IntersectRay + TraceBVHNode (reference TriObj.cpp:17-39,
 //    192-270) made iterative.  The visiting order, the near/far rule, "the far child is skipped
@@ -285,62 +381,90 @@ BHRT_HD void intersect_pair(const PairNode *pn, const Ray &r, float t_max, bool 
 //    child 1 before child 2, both visited when EITHER box is hit (boxes tested against BIGFLOAT),
 //    stop at the FIRST leaf containing any front-face hit and range-check only that leaf's t.
 //
-// Returns: closest -> number of accepted triangles > 0 (z, front, mh updated);
-//          shadow  -> the reference's bool.
-BHRT_HD bool mesh_trace(const SceneView &s, const MeshAccel &A, const Ray &ray, bool any_hit, float t_max_shadow,
-                        float &z, bool &front, int hitSide, MeshHit &mh)
-{
-    float tmin = -1;
-    if (!intersect_box(A.root_box, ray, any_hit ? BHRT_BIGFLOAT : z, tmin)) return false;
-    const PairNode *pairs = (const PairNode *)(s.accel_data + A.pairs_off);
-    const TriRec *tris = (const TriRec *)(s.accel_data + A.tris_off);
-    const float len_dir = length(ray.dir);
+// Result: closest -> number of accepted triangles > 0 (z, front, mh updated);
+//         shadow  -> the reference's bool.
+struct MeshTrav {
+    Ray ray;
+    float len_dir;
+    const PairNode *pairs;
+    const TriRec *tris;
+    uint32_t cur;
+    int sp, hits;
+    float z; bool front; MeshHit mh;        // running closest hit (in/out)
+    float t_max_shadow;
+    int hitSide;
+    bool any_hit;
+    bool done, result;
     uint32_t st_word[BHRT_BVH_STACK];
     float st_tmin[BHRT_BVH_STACK];
     int st_hits[BHRT_BVH_STACK];
-    int sp = 0, hits = 0;
-    uint32_t cur = A.root_word;
-    for (;;) {
-        bool descend = false;
-        if (BHRT_BVH_LEAF(cur)) {
-            uint32_t cnt = BHRT_BVH_COUNT(cur), off = BHRT_BVH_OFFSET(cur);
-            if (any_hit) {
-                float lz = BHRT_BIGFLOAT; bool lf; MeshHit lm;
-                bool any = false;
-                for (uint32_t i = 0; i < cnt; i++)
-                    if (intersect_trirec(tris + off + i, ray, len_dir, lz, lf, HIT_FRONT, lm)) any = true;
-                if (any) return lz > BHRT_BIAS && lz < t_max_shadow;
-            } else {
-                for (uint32_t i = 0; i < cnt; i++)
-                    if (intersect_trirec(tris + off + i, ray, len_dir, z, front, hitSide, mh)) hits++;
-            }
+};
+
+BHRT_HD void mesh_trav_begin(MeshTrav &T, const SceneView &s, const MeshAccel &A, const Ray &ray, bool any_hit, float t_max_shadow,
+                             float z, bool front, int hitSide)
+{
+    T.ray = ray; T.any_hit = any_hit; T.t_max_shadow = t_max_shadow; T.z = z; T.front = front; T.hitSide = hitSide;
+    T.mh.face = 0; T.mh.a0 = T.mh.a1 = T.mh.a2 = 0;
+    T.sp = 0; T.hits = 0; T.result = false;
+    float tmin = -1;
+    if (!intersect_box(A.root_box, ray, any_hit ? BHRT_BIGFLOAT : z, tmin)) { T.done = true; return; }
+    T.pairs = (const PairNode *)(s.accel_data + A.pairs_off);
+    T.tris = (const TriRec *)(s.accel_data + A.tris_off);
+    T.len_dir = length(ray.dir);
+    T.cur = A.root_word;
+    T.done = false;
+}
+
+BHRT_HD void mesh_trav_step(MeshTrav &T)
+{
+    bool descend = false;
+    const uint32_t cur = T.cur;
+    if (BHRT_BVH_LEAF(cur)) {
+        uint32_t cnt = BHRT_BVH_COUNT(cur), off = BHRT_BVH_OFFSET(cur);
+        if (T.any_hit) {
+            float lz = BHRT_BIGFLOAT; bool lf; MeshHit lm;
+            bool any = false;
+            for (uint32_t i = 0; i < cnt; i++)
+                if (intersect_trirec(T.tris + off + i, T.ray, T.len_dir, lz, lf, HIT_FRONT, lm)) any = true;
+            if (any) { T.result = lz > BHRT_BIAS && lz < T.t_max_shadow; T.done = true; return; }
         } else {
-            bool h1, h2; float t1, t2; uint32_t w1, w2;
-            intersect_pair(pairs + cur, ray, any_hit ? BHRT_BIGFLOAT : z, h1, t1, h2, t2, w1, w2);
-            if (h1 || h2) {
-                uint32_t first, second; float tsecond;
-                if (any_hit || t1 < t2) { first = w1; second = w2; tsecond = t2; }
-                else { first = w2; second = w1; tsecond = t1; }
-                if (sp < BHRT_BVH_STACK) { st_word[sp] = second; st_tmin[sp] = tsecond; st_hits[sp] = hits; sp++; }
-                cur = first;
-                descend = true;
-            }
+            for (uint32_t i = 0; i < cnt; i++)
+                if (intersect_trirec(T.tris + off + i, T.ray, T.len_dir, T.z, T.front, T.hitSide, T.mh)) T.hits++;
         }
-        if (descend) continue;
-        bool found = false;
-        while (sp > 0) {
-            sp--;
-            if (!any_hit) {
-                bool nearHit = (hits != st_hits[sp]);
-                if (nearHit && !(z > st_tmin[sp])) continue;
-            }
-            cur = st_word[sp];
-            found = true;
-            break;
+    } else {
+        bool h1, h2; float t1, t2; uint32_t w1, w2;
+        intersect_pair(T.pairs + cur, T.ray, T.any_hit ? BHRT_BIGFLOAT : T.z, h1, t1, h2, t2, w1, w2);
+        if (h1 || h2) {
+            uint32_t first, second; float tsecond;
+            if (T.any_hit || t1 < t2) { first = w1; second = w2; tsecond = t2; }
+            else { first = w2; second = w1; tsecond = t1; }
+            if (T.sp < BHRT_BVH_STACK) { T.st_word[T.sp] = second; T.st_tmin[T.sp] = tsecond; T.st_hits[T.sp] = T.hits; T.sp++; }
+            T.cur = first;
+            descend = true;
         }
-        if (!found) break;
     }
-    return hits > 0;
+    if (descend) return;
+    while (T.sp > 0) {
+        T.sp--;
+        if (!T.any_hit) {
+            bool nearHit = (T.hits != T.st_hits[T.sp]);
+            if (nearHit && !(T.z > T.st_tmin[T.sp])) continue;
+        }
+        T.cur = T.st_word[T.sp];
+        return;
+    }
+    T.result = T.hits > 0;
+    T.done = true;
+}
+
+BHRT_HD bool mesh_trace(const SceneView &s, const MeshAccel &A, const Ray &ray, bool any_hit, float t_max_shadow,
+                        float &z, bool &front, int hitSide, MeshHit &mh)
+{
+    MeshTrav T;
+    mesh_trav_begin(T, s, A, ray, any_hit, t_max_shadow, z, front, hitSide);
+    while (!T.done) mesh_trav_step(T);
+    if (!any_hit && T.result) { z = T.z; front = T.front; mh = T.mh; }
+    return T.result;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -349,28 +473,41 @@ BHRT_HD bool mesh_trace(const SceneView &s, const MeshAccel &A, const Ray &ray, 
 // ShadowRayRecursive (reference Lights/GenLight.cpp:10-69, any-hit; the result is the OR over
 // all nodes of the node's own test, so DFS pre-order is as good as the reference's post-order).
 enum { Q_NONE = 0, Q_CLOSEST = 1, Q_SHADOW = 2 };
-struct Query {
+struct alignas(16) Query {
     Ray ray;
     int kind;
     int hitSide;        // CLOSEST
     float t_max;        // SHADOW
 };
 
+// The query is answered in three phases so that the wavefront can give each its own, converged,
+// kernel (wavefront.cuh); scene_trace() below simply runs them back to back.
+//
+//  1 scene_trace_graph   the node loop: ray transform + analytic object per node (warp-uniform
+//                        control flow: every lane visits node k at the same time).  A mesh node is
+//                        only tested against its root box; hits are recorded in `mesh_mask` (bit i
+//                        = i-th mesh node of the DFS order, SceneView::mesh_nodes).
+//  2 scene_trace_meshes  BVH traversal of the recorded mesh nodes -- only lanes that need it.
+//  3 scene_trace_finish  winner-only work: sphere uv (atan2/asin), plane ray differentials (pow),
+//                        mesh normal/uv interpolation, Node::FromNodeCoords.
+//
+// Equivalence with recursive() (Main.cpp:389-413), which tests the nodes strictly in DFS order
+// with one running HitInfo: every candidate's t is computed by the same expression whatever the
+// running z is (z only rejects), so the winner is the candidate with the smallest t and, between
+// equal t, the LATER node (the reference rejects only t > z).  Phase 2 therefore starts each mesh
+// with the best z found so far and applies that tie rule explicitly (`strict`).
 // nodes[] is in DFS pre-order; rs[d] is the ray in the space of the current node at depth d.
 // Shadow quirks kept: sphere ignored when the origin is inside (GenLight.cpp:36-37), plane
 // bounds tested with the PARENT-space ray (:54), no rayDz == 0 test (:50).
-// Closest: per-candidate HitInfo fields that only the winner needs (sphere uv with atan2/asin,
-// plane ray differentials with pow, mesh normals/uv) are derived once after the loop from the
-// winner's local ray -- the same expressions on the same inputs as the reference evaluates at
-// accept time.
-BHRT_HD bool scene_trace(const SceneView &s, const Query &q, Hit &h)
+// returns true when a SHADOW query is already answered "blocked"
+BHRT_HD bool scene_trace_graph(const SceneView &s, const Query &q, Hit &h, uint32_t &mesh_mask)
 {
     const bool shadow = (q.kind == Q_SHADOW);
     Ray rs[BHRT_MAX_DEPTH + 1];
     rs[0] = q.ray;
     h.init();
-    Ray wr; wr.p = V3(0, 0, 0); wr.dir = V3(0, 0, 0);   // winner's local ray
-    MeshHit mh; mh.face = 0; mh.a0 = mh.a1 = mh.a2 = 0;
+    mesh_mask = 0;
+    int mesh_ordinal = 0;
     for (int k = 0; k < s.n_nodes; k++) {
         const bhrt_node &nd = s.nodes[k];
         const int d = nd.depth;
@@ -424,18 +561,118 @@ BHRT_HD bool scene_trace(const SceneView &s, const Query &q, Hit &h)
                 }
             }
         } else if (nd.kind == BHRT_OBJ_MESH) {
-            bool r_ = mesh_trace(s, s.accels[nd.mesh], r, shadow, q.t_max, h.z, h.front, q.hitSide, mh);
-            if (shadow) { if (r_) return true; }
-            else hit = r_;
+            const MeshAccel &A = s.accels[nd.mesh];
+            // only the root box here; nodes beyond the mask are picked up by scene_trace_meshes
+            if (mesh_ordinal < BHRT_MESH_MASK_BITS) {
+                float tmin = -1;
+                if (intersect_box(A.root_box, r, shadow ? BHRT_BIGFLOAT : h.z, tmin)) mesh_mask |= 1u << mesh_ordinal;
+            }
+            mesh_ordinal++;
         }
-        if (hit) { h.node = k; wr = r; }
+        if (hit) h.node = k;
     }
-    if (shadow || h.node < 0) return false;
+    return false;
+}
 
-    // ---- finish the winner's HitInfo in its local space
+// The ray in the local space of node k: Node::ToNodeCoords down the ancestor chain (what rs[] held)
+BHRT_HD Ray node_local_ray(const SceneView &s, int k, const Ray &world)
+{
+    int chain[BHRT_MAX_DEPTH + 1];
+    int n = 0;
+    for (int i = k; i >= 0 && n <= BHRT_MAX_DEPTH; i = s.nodes[i].parent) chain[n++] = i;
+    Ray r = world;
+    for (int i = n - 1; i >= 0; i--) r = to_node(s.nodes[chain[i]].xf, r);
+    return r;
+}
+
+BHRT_HD float prev_float(float z)     // the next float below a positive finite z
+{
+    uint32_t u; memcpy(&u, &z, 4); u -= 1u;
+    float r; memcpy(&r, &u, 4);
+    return r;
+}
+
+// Phase 2 as a stepper: one BVH node (or one "pick the next mesh node" action) per step, so the
+// mesh kernel can refill a finished lane while its warp neighbours still traverse.  On completion
+// `blocked` answers a SHADOW query; for CLOSEST h holds z, front, node and the winning triangle in
+// h.uvw (a0,a1,a2) / h.duvw0.x (face bits) for phase 3.
+struct MeshJob {
+    Query q;
+    Hit h;
+    uint32_t mask;
+    int extra;              // next node index to scan for mesh nodes beyond the mask
+    int k;                  // mesh node being traversed
+    bool in_trav, strict, blocked;
+    MeshTrav T;
+};
+
+BHRT_HD void mesh_job_begin(MeshJob &J, const SceneView &s, const Query &q, float z, int node, bool front, uint32_t mask)
+{
+    J.q = q;
+    J.h.init();
+    J.h.z = z; J.h.node = node; J.h.front = front;
+    J.mask = mask;
+    // mesh nodes beyond the 32 the mask covers (s.n_mesh_nodes > 32) are visited unconditionally:
+    // mesh_trav_begin tests the root box itself
+    J.extra = s.n_mesh_nodes > BHRT_MESH_MASK_BITS ? s.mesh_nodes[BHRT_MESH_MASK_BITS - 1] + 1 : s.n_nodes;
+    J.in_trav = false; J.blocked = false; J.strict = false; J.k = -1;
+}
+
+// returns true when the job is finished
+BHRT_HD bool mesh_job_step(MeshJob &J, const SceneView &s)
+{
+    const bool shadow = (J.q.kind == Q_SHADOW);
+    if (!J.in_trav) {
+        int k;
+        if (J.mask) {
+            int bit = 0;
+            while (!((J.mask >> bit) & 1u)) bit++;
+            J.mask &= J.mask - 1u;
+            k = s.mesh_nodes[bit];
+        } else {
+            while (J.extra < s.n_nodes && s.nodes[J.extra].kind != BHRT_OBJ_MESH) J.extra++;
+            if (J.extra >= s.n_nodes) return true;
+            k = J.extra++;
+        }
+        J.k = k;
+        const bhrt_node &nd = s.nodes[k];
+        Ray r = node_local_ray(s, k, J.q.ray);
+        if (shadow) mesh_trav_begin(J.T, s, s.accels[nd.mesh], r, true, J.q.t_max, BHRT_BIGFLOAT, true, J.q.hitSide);
+        else {
+            // an equal-t candidate of an EARLIER node loses against the current winner
+            J.strict = J.h.node > k;
+            mesh_trav_begin(J.T, s, s.accels[nd.mesh], r, false, 0.f, J.strict ? prev_float(J.h.z) : J.h.z, J.h.front, J.q.hitSide);
+        }
+        J.in_trav = true;
+    } else mesh_trav_step(J.T);
+    if (J.T.done) {
+        J.in_trav = false;
+        if (J.T.result) {
+            if (shadow) { J.blocked = true; return true; }
+            J.h.z = J.T.z; J.h.front = J.T.front; J.h.node = J.k;
+            J.h.uvw = V3(J.T.mh.a0, J.T.mh.a1, J.T.mh.a2); J.h.duvw0.x = u2f(J.T.mh.face);
+        }
+    }
+    return false;
+}
+
+BHRT_HD bool scene_trace_meshes(const SceneView &s, const Query &q, Hit &h, uint32_t mesh_mask)
+{
+    MeshJob J;
+    mesh_job_begin(J, s, q, h.z, h.node, h.front, mesh_mask);
+    while (!mesh_job_step(J, s)) {}
+    if (J.blocked) return true;
+    h = J.h;
+    return false;
+}
+
+// Winner-only part of the closest hit: complete HitInfo in local space, then FromNodeCoords
+BHRT_HD bool scene_trace_finish(const SceneView &s, const Query &q, Hit &h)
+{
+    if (h.node < 0) return false;
     const bhrt_node &nd = s.nodes[h.node];
+    const Ray wr = node_local_ray(s, h.node, q.ray);
     V3 lp, lN;
-    h.duvw0 = V3(0, 0, 0); h.duvw1 = V3(0, 0, 0);
     if (nd.kind == BHRT_OBJ_SPHERE) {
         lp = wr.p + h.z * wr.dir;                           // Sphere.cpp:52-54
         lN = lp;
@@ -446,6 +683,7 @@ BHRT_HD bool scene_trace(const SceneView &s, const Query &q, Hit &h)
         // uvw.z keeps whatever the default-constructed Vec3f held in the reference (uninitialised
         // there; never read by 2-D textures).  We define it as 0.
         h.uvw.z = 0.f;
+        h.duvw0 = V3(0, 0, 0); h.duvw1 = V3(0, 0, 0);
     } else if (nd.kind == BHRT_OBJ_PLANE) {
         const float t = h.z;
         lp = wr.p + t * wr.dir;
@@ -468,7 +706,10 @@ BHRT_HD bool scene_trace(const SceneView &s, const Query &q, Hit &h)
         h.duvw1 = hy / 2.f;
     } else {
         lp = wr.p + h.z * wr.dir;                           // TriObj.cpp:107
-        mesh_attributes(s, s.accels[nd.mesh], mh.face, mh.a0, mh.a1, mh.a2, lN, h.uvw);
+        const float a0 = h.uvw.x, a1 = h.uvw.y, a2 = h.uvw.z;
+        const uint32_t face = f2u(h.duvw0.x);
+        mesh_attributes(s, s.accels[nd.mesh], face, a0, a1, a2, lN, h.uvw);
+        h.duvw0 = V3(0, 0, 0); h.duvw1 = V3(0, 0, 0);
     }
     // Node::FromNodeCoords of the hit node (Main.cpp:401) and then of its parent
     // (Main.cpp:407-412; the rootNode's identity transform for depth-1 nodes).  Deeper
@@ -485,6 +726,16 @@ BHRT_HD bool scene_trace(const SceneView &s, const Query &q, Hit &h)
         h.N = normalized(V3(1.f * h.N.x + 0.f * h.N.y + 0.f * h.N.z, 0.f * h.N.x + 1.f * h.N.y + 0.f * h.N.z, 0.f * h.N.x + 0.f * h.N.y + 1.f * h.N.z));
     }
     return true;
+}
+
+// All three phases for one ray (CPU harness, photon emission)
+BHRT_HD bool scene_trace(const SceneView &s, const Query &q, Hit &h)
+{
+    uint32_t mask;
+    if (scene_trace_graph(s, q, h, mask)) return true;
+    if ((mask || s.n_mesh_nodes > BHRT_MESH_MASK_BITS) && scene_trace_meshes(s, q, h, mask)) return true;
+    if (q.kind == Q_SHADOW) return false;
+    return scene_trace_finish(s, q, h);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -587,13 +838,15 @@ struct Rng {
         uint32_t rot = (uint32_t)(old >> 59u);
         return (xs >> rot) | (xs << ((32u - rot) & 31u));
     }
-    // (double)rand()/RAND_MAX with glibc's RAND_MAX = 2^31-1 (Main.cpp:136)
-    BHRT_HD double unit() { return (double)(next() >> 1) / 2147483647.0; }
+    // (double)rand()/RAND_MAX (Main.cpp:136) is a uniform variate on a 2^31-point lattice; parity with
+    // the reference's stream is statistical, so this is a uniform variate on the 2^24-point lattice
+    // every float in [0,1) can hold, with no double-precision division.
+    BHRT_HD float unit() { return (float)(next() >> 8) * (1.0f / 16777216.0f); }
     // Rnd01 (MtlBlinn.cpp:42-49): float, redrawn while exactly 0 or 1
     BHRT_HD float rnd01()
     {
-        float r = (float)unit();
-        while (r == 0.0f || r == 1.0f) r = (float)unit();
+        float r = unit();
+        while (r == 0.0f) r = unit();
         return r;
     }
 };
@@ -741,6 +994,191 @@ BHRT_HD Ray handle_refraction_out(const Ray &inRay, const Hit &ih, float ior, bo
 }
 
 // ------------------------------------------------------------------------------------------
+// PhotonMap::EstimateIrradiance<k> + LocatePhotons (reference cyPhotonMap.h:332-382,421-498),
+// FILTER_TYPE_CONSTANT, ellipticity 1.  With the constant filter the result depends only on the
+// SET of photons the max-heap ends up holding: the k nearest photons within `radius` whose
+// direction satisfies dir.N < 0; irrad = sum(power) / (pi * r2), r2 = radius^2 when at most k
+// qualified, else the k-th smallest squared distance; direction = normalize(sum(dir * maxpower)).
+// A 1000-entry heap per thread is hopeless on a GPU, so the set is found by
+// selection instead: pick the finest grid level whose 3x3x3 block holds more than k qualifying
+// photons within one cell edge, then a 32-bin histogram of squared distances, a 32-bin histogram
+// of the crossing bin, and an exact selection among the handful of photons of the crossing sub-bin.
+struct PmRange { uint32_t b[27], e[27]; };
+
+BHRT_HD uint32_t pm_lower_bound(const uint32_t *keys, uint32_t lo, uint32_t hi, uint32_t key)
+{
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// key ranges of the 27 level-`level` cells around (coarse cell c, sub-cell s)
+BHRT_HD void pm_ranges(const PhotonGather &pg, int level, const int *c, const int *sub, PmRange &R)
+{
+    const int sh = 4 - level;                         // sub-cell bits dropped at this level
+    const int span = 1 << level;                      // level cells per coarse cell edge
+    int g[3] = { (c[0] << level) | (sub[0] >> sh), (c[1] << level) | (sub[1] >> sh), (c[2] << level) | (sub[2] >> sh) };
+    int n = 0;
+    for (int dz = -1; dz <= 1; dz++)
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++, n++) {
+                int x = g[0] + dx, y = g[1] + dy, z = g[2] + dz;
+                R.b[n] = 0; R.e[n] = 0;
+                if (x < 0 || y < 0 || z < 0 || x >= pg.dim[0] * span || y >= pg.dim[1] * span || z >= pg.dim[2] * span) continue;
+                uint32_t cx = (uint32_t)(x >> level), cy = (uint32_t)(y >> level), cz = (uint32_t)(z >> level);
+                uint32_t coarse = cx + (uint32_t)pg.dim[0] * (cy + (uint32_t)pg.dim[1] * cz);
+                uint32_t lo = pg.coarse_start[coarse], hi = pg.coarse_start[coarse + 1];
+                if (lo == hi) continue;
+                if (level == 0) { R.b[n] = lo; R.e[n] = hi; continue; }
+                uint32_t m = photon_morton12((uint32_t)(x & (span - 1)) << sh, (uint32_t)(y & (span - 1)) << sh, (uint32_t)(z & (span - 1)) << sh);
+                uint32_t k0 = (coarse << BHRT_PM_FINE_BITS) | m;
+                uint32_t k1 = k0 + (1u << (3 * sh));
+                R.b[n] = pm_lower_bound(pg.keys, lo, hi, k0);
+                R.e[n] = pm_lower_bound(pg.keys, R.b[n], hi, k1);
+            }
+}
+
+BHRT_HD V3 pm_power(const GatherRec *rec, float maxpower)
+{
+    uint32_t rgb = f2u(ld4(&rec->b).w);
+    // Photon::GetPower: color.ToColor() * power (cyPhotonMap.h:83, cyColor.h:236)
+    return V3((float)(rgb & 255u) / 255.0f, (float)((rgb >> 8) & 255u) / 255.0f, (float)((rgb >> 16) & 255u) / 255.0f) * maxpower;
+}
+
+#define BHRT_PM_CAND 48
+BHRT_HD void estimate_irradiance(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction)
+{
+    irrad = V3(0, 0, 0); direction = V3(0, 0, 0);
+    if (pg.n_photons <= 0) return;
+    const float r2 = pg.radius * pg.radius;
+    // the query's coarse cell and 1/16 sub-cell, computed like photon_key does
+    float f[3] = { (pos.x - pg.origin[0]) / pg.cell, (pos.y - pg.origin[1]) / pg.cell, (pos.z - pg.origin[2]) / pg.cell };
+    int c[3], sub[3];
+    bool inside = true;
+    for (int a = 0; a < 3; a++) {
+        c[a] = (int)floorf(f[a]);
+        if (c[a] < -1 || c[a] > pg.dim[a]) return;          // farther than one cell from the grid: nothing in range
+        int s_ = (int)((f[a] - c[a]) * 16.f);
+        sub[a] = s_ < 0 ? 0 : (s_ > 15 ? 15 : s_);
+        if (c[a] < 0 || c[a] >= pg.dim[a]) inside = false;
+    }
+    // starting level from the population of the query's coarse cell (surface density guess):
+    // expect ~ n_c * pi / 16^l qualifying photons within one level-l cell edge
+    int level = 0;
+    if (inside) {
+        uint32_t coarse = (uint32_t)c[0] + (uint32_t)pg.dim[0] * ((uint32_t)c[1] + (uint32_t)pg.dim[1] * (uint32_t)c[2]);
+        float n_c = (float)(pg.coarse_start[coarse + 1] - pg.coarse_start[coarse]) * 3.14159265f;
+        float need = 2.f * pg.k * 16.f;
+        while (level < BHRT_PM_LEVELS - 1 && n_c > need) { level++; need *= 16.f; }
+    }
+    PmRange R;
+    int hist[32];
+    for (;;) {
+        pm_ranges(pg, level, c, sub, R);
+        const float cell_l = pg.cell / (float)(1 << level);
+        float bound2 = 0.998f * cell_l * cell_l;            // every photon this close lies in the 3x3x3 block
+        if (bound2 > r2) bound2 = r2;
+        const float scale = 32.f / bound2;
+        // ---- pass A: 32-bin histogram of squared distances (and, at level 0, the plain sums)
+        for (int i = 0; i < 32; i++) hist[i] = 0;
+        int total = 0;
+        V3 sumP(0, 0, 0), sumD(0, 0, 0);
+        for (int n = 0; n < 27; n++)
+            for (uint32_t i = R.b[n]; i < R.e[n]; i++) {
+                F4 A = ld4(&pg.recs[i].a);
+                V3 dif(A.x - pos.x, A.y - pos.y, A.z - pos.z);
+                float d2 = length2(dif);
+                if (!(d2 < bound2)) continue;
+                F4 B = ld4(&pg.recs[i].b);
+                if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;       // cyPhotonMap.h:450
+                int bin = (int)(d2 * scale); if (bin > 31) bin = 31;
+                hist[bin]++; total++;
+                if (level == 0) { sumP = sumP + pm_power(&pg.recs[i], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w; }
+            }
+        if (total <= pg.k) {
+            if (level > 0) { level--; continue; }           // the k nearest do not fit in this block: one level up
+            if (total == 0) return;
+            // at most k photons qualified within the radius: area = pi * radius^2 (dist2[0] never shrank)
+            float area = 3.14159265358979323846f * r2;
+            irrad = sumP * (1.0f / area);
+            direction = normalized(sumD);
+            return;
+        }
+        // ---- more than k qualify: find the k-th smallest squared distance
+        int cum = 0, b0 = 0;
+        for (; b0 < 32; b0++) { if (cum + hist[b0] >= pg.k) break; cum += hist[b0]; }
+        const int rank_in_bin = pg.k - cum;                 // 1-based rank inside bin b0
+        // ---- pass B: 32 sub-bins of bin b0
+        for (int i = 0; i < 32; i++) hist[i] = 0;
+        for (int n = 0; n < 27; n++)
+            for (uint32_t i = R.b[n]; i < R.e[n]; i++) {
+                F4 A = ld4(&pg.recs[i].a);
+                V3 dif(A.x - pos.x, A.y - pos.y, A.z - pos.z);
+                float d2 = length2(dif);
+                if (!(d2 < bound2)) continue;
+                float t = d2 * scale;
+                int bin = (int)t; if (bin > 31) bin = 31;
+                if (bin != b0) continue;
+                F4 B = ld4(&pg.recs[i].b);
+                if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;
+                int sb = (int)((t - (float)bin) * 32.f); if (sb > 31) sb = 31; if (sb < 0) sb = 0;
+                hist[sb]++;
+            }
+        int cum2 = 0, s0 = 0;
+        for (; s0 < 32; s0++) { if (cum2 + hist[s0] >= rank_in_bin) break; cum2 += hist[s0]; }
+        const int rank_in_sub = rank_in_bin - cum2;         // 1-based rank inside sub-bin s0
+        // ---- pass C: sum everything below the crossing sub-bin, collect the sub-bin's photons
+        sumP = V3(0, 0, 0); sumD = V3(0, 0, 0);
+        float cd2[BHRT_PM_CAND]; uint32_t cidx[BHRT_PM_CAND];
+        int ncand = 0;
+        bool overflow = false;
+        V3 subP(0, 0, 0), subD(0, 0, 0);
+        float kth2 = 0;
+        for (int n = 0; n < 27; n++)
+            for (uint32_t i = R.b[n]; i < R.e[n]; i++) {
+                F4 A = ld4(&pg.recs[i].a);
+                V3 dif(A.x - pos.x, A.y - pos.y, A.z - pos.z);
+                float d2 = length2(dif);
+                if (!(d2 < bound2)) continue;
+                float t = d2 * scale;
+                int bin = (int)t; if (bin > 31) bin = 31;
+                if (bin > b0) continue;
+                int sb = 0;
+                if (bin == b0) { sb = (int)((t - (float)bin) * 32.f); if (sb > 31) sb = 31; if (sb < 0) sb = 0; if (sb > s0) continue; }
+                F4 B = ld4(&pg.recs[i].b);
+                if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;
+                if (bin < b0 || sb < s0) {
+                    sumP = sumP + pm_power(&pg.recs[i], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w;
+                    if (d2 > kth2) kth2 = d2;
+                } else {
+                    subP = subP + pm_power(&pg.recs[i], A.w); subD = subD + V3(B.x, B.y, B.z) * A.w;
+                    if (ncand < BHRT_PM_CAND) { cd2[ncand] = d2; cidx[ncand] = i; ncand++; } else overflow = true;
+                }
+            }
+        if (overflow) {
+            // (practically unreachable: > 48 photons inside 1/1024 of the search area) keep the whole sub-bin
+            sumP = sumP + subP; sumD = sumD + subD;
+            kth2 = ((float)b0 + (float)(s0 + 1) / 32.f) / scale;
+        } else {
+            // exact: the rank_in_sub nearest photons of the crossing sub-bin (insertion sort, <= 48 entries)
+            for (int i = 1; i < ncand; i++) {
+                float d = cd2[i]; uint32_t ix = cidx[i]; int j = i - 1;
+                while (j >= 0 && cd2[j] > d) { cd2[j + 1] = cd2[j]; cidx[j + 1] = cidx[j]; j--; }
+                cd2[j + 1] = d; cidx[j + 1] = ix;
+            }
+            for (int i = 0; i < rank_in_sub && i < ncand; i++) {
+                F4 A = ld4(&pg.recs[cidx[i]].a); F4 B = ld4(&pg.recs[cidx[i]].b);
+                sumP = sumP + pm_power(&pg.recs[cidx[i]], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w;
+                kth2 = cd2[i];
+            }
+        }
+        float area = 3.14159265358979323846f * kth2;        // (float)M_PI * np.dist2[0]
+        if (area > 0) irrad = sumP * (1.0f / area); else irrad = sumP;
+        direction = normalized(sumD);
+        return;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // The estimator.  MtlBlinn::Shade (MtlBlinn.cpp:89-138) is a recursion TREE with a clamp and
 // an early-out at every level, not a linear path, so it is evaluated with an
 // explicit frame stack and a post-order resolve.  It is written as a coroutine around ONE ray
@@ -748,26 +1186,29 @@ BHRT_HD Ray handle_refraction_out(const Ray &inRay, const Hit &ih, float ior, bo
 // returns; the caller traces it (scene_trace) and calls sample_advance() again.  In the kernel
 // every lane of a warp therefore meets the traversal code together, whatever stage of whatever
 // recursion level its sample is in.
-struct Frame {
+struct alignas(128) Frame {              // one 128-byte line per recursion level
     V3 p, vN, vV, uvw, duvw0, duvw1;    // shading point
     V3 out;                              // colour accumulated so far at this level
     V3 mult;                             // factor for the pending child's value
     V3 newSpec;                          // Fresnel-boosted specular colour (MtlBlinn.cpp:110-113)
     int mtl, bounce, gi;
-    int stage;
-    bool useSpec;                        // lobe chosen by the GI sample
+    int useSpec;                         // lobe chosen by the GI sample
+    int pad_;
 };
 enum { ST_REFR = 0, ST_REFR_IN_WAIT = 1, ST_REFR_OUT_WAIT = 2, ST_REFR_WAIT = 3, ST_GI = 4, ST_GI_TRACE_WAIT = 5, ST_GI_WAIT = 6,
        ST_DIRECT = 7, ST_SHADOW_WAIT = 8 };
-#define BHRT_MAX_FRAMES 24
+#define BHRT_MAX_FRAMES 16
 
 struct ShadeCfg {
     int mode;           // BHRT_MODE_*
     int gi_depth, tir_budget;
 };
 
-struct Lane {
-    Frame fr[BHRT_MAX_FRAMES];
+struct alignas(16) Lane {
+    // camera sample this lane is evaluating (wavefront bookkeeping; unused by the estimator)
+    unsigned long long work;
+    int pi, pj, sidx;
+    float bgu, bgv;
     int sp;                 // frames in use; 0 = waiting for the primary ray
     Query q;                // the pending ray query
     Hit hit;                // its answer (closest) ...
@@ -781,7 +1222,12 @@ struct Lane {
     float sf;               // refraction: glossiness of the refraction lobe
     int si;                 // refraction: remaining internal-reflection budget      direct: light index
     int hit_id; float hit_z;    // primary AOVs of this sample
+    uint32_t mesh_mask;         // wavefront: mesh nodes whose root box the pending ray entered
+    uint8_t stage[BHRT_MAX_FRAMES];     // stage of every live recursion level (the frames themselves live apart)
 };
+// The recursion levels of one lane: the estimator only ever touches the top frame and, when it
+// recurses, the slot above it.
+struct LaneStack { Frame fr[BHRT_MAX_FRAMES]; };
 
 BHRT_HD void frame_begin(Frame &f, const SceneView &s, V3 ray_p, const Hit &h, int bounce, int gi)
 {
@@ -791,7 +1237,6 @@ BHRT_HD void frame_begin(Frame &f, const SceneView &s, V3 ray_p, const Hit &h, i
     f.mtl = s.nodes[h.node].material;
     f.bounce = bounce; f.gi = gi;
     f.out = V3(0, 0, 0);
-    f.stage = ST_REFR;
 }
 
 BHRT_HD void issue_closest(Lane &L, const Ray &r, int hitSide, RayCounters &rc)
@@ -807,15 +1252,6 @@ BHRT_HD void sample_begin(Lane &L, const Ray &primary, RayCounters &rc)
     issue_closest(L, primary, HIT_FRONT, rc);
 }
 
-// Shade epilogue shared by the two ways the direct term ends (MtlBlinn.cpp:343-350,131-136)
-BHRT_HD void direct_finish(Frame &f, V3 D)
-{
-    clamp_white(D);
-    if (is_nan(D.x)) D = V3(0, 0, 0);
-    f.out = f.out + D;
-    if (!saturated(f.out) && is_nan(f.out.x)) f.out = V3(1.0f, 0.0f, 1.0f);
-}
-
 // Blinn BRDF * cos of the direct term (MtlBlinn.cpp:319-327) for light direction vL
 BHRT_HD V3 direct_brdf(const SceneView &s, const Frame &f, const bhrt_material &M, V3 vL)
 {
@@ -826,36 +1262,72 @@ BHRT_HD V3 direct_brdf(const SceneView &s, const Frame &f, const bhrt_material &
     return kdT * cosTheta + ksT * powf(dot(vH, f.vN), M.glossiness);
 }
 
-// Consume the answer to L.q (L.hit / L.hit_ok) and run the estimator until it needs the next
-// ray (returns false, query in L.q) or the sample is finished (returns true, colour in `color`).
-BHRT_HD_NOINLINE bool sample_advance(Lane &L, const SceneView &s, const ShadeCfg &cfg, const PhotonGather &pg, float bgu, float bgv,
-                                     RayCounters &rc, V3 &color)
+// End of PathTracing_DiffuseNSpecular: the caustic gather term (MtlBlinn.cpp:329-342, only when a
+// photon map is in use), then the clamp / NaN epilogue (MtlBlinn.cpp:343-350,131-136)
+BHRT_HD void direct_finish(const SceneView &s, const PhotonGather &pg, Frame &f, const bhrt_material &M, V3 D)
+{
+    if (pg.use) {
+        V3 irr, vL;
+        estimate_irradiance(pg, f.p, f.vN, irr, vL);
+        float cosTheta = -dot(vL, f.vN);
+        if (cosTheta > 0) {
+            V3 vH = normalized(vL + f.vV);
+            V3 kdT = texcolor_sample_filtered(s, ld3(M.diffuse.color), M.diffuse.texmap, f.uvw, f.duvw0, f.duvw1);
+            V3 ksT = texcolor_sample_filtered(s, f.newSpec, M.specular.texmap, f.uvw, f.duvw0, f.duvw1);
+            V3 brdf = kdT + ksT * powf(dot(vH, f.vN), M.glossiness) / cosTheta;
+            D = D + brdf * irr;
+        }
+    }
+    clamp_white(D);
+    if (is_nan(D.x)) D = V3(0, 0, 0);
+    f.out = f.out + D;
+    if (!saturated(f.out) && is_nan(f.out.x)) f.out = V3(1.0f, 0.0f, 1.0f);
+}
+
+// ONE step of the estimator coroutine: the case of the top frame's stage (or the consumption of
+// the primary hit when no frame exists yet).  STEP_RAY: a query was left in L.q and the stage that
+// consumes its answer is on top; STEP_CONT: no ray needed, call again; STEP_DONE: the sample is
+// finished, colour in `color`.  Stages that consume a ray answer read L.hit / L.hit_ok.
+// The wavefront sorts lanes by the stage they are about to run, so a warp executes one case.
+enum { STEP_CONT = 0, STEP_RAY = 1, STEP_DONE = 2 };
+// `f` = the top frame (fr[sp-1]; unused while sp == 0), `child` = the slot above it (fr[sp]).
+BHRT_HD int sample_step(Lane &L, Frame &f, Frame &child, const SceneView &s, const ShadeCfg &cfg, const PhotonGather &pg, float bgu, float bgv,
+                        RayCounters &rc, V3 &color)
 {
     const bool det = (cfg.mode == BHRT_MODE_DET);
     Rng &rng = L.rng;
     if (L.sp == 0) {
         L.hit_id = L.hit_ok ? L.hit.node : -1;
         L.hit_z = L.hit.z;
-        if (!L.hit_ok) { color = texcolor_sample(s, s.background, V3(bgu, bgv, 0.0f)); return true; }   // Main.cpp:166-167
-        frame_begin(L.fr[0], s, L.q.ray.p, L.hit, cfg.tir_budget, cfg.gi_depth);
+        if (!L.hit_ok) { color = texcolor_sample(s, s.background, V3(bgu, bgv, 0.0f)); return STEP_DONE; }   // Main.cpp:166-167
+        frame_begin(child, s, L.q.ray.p, L.hit, cfg.tir_budget, cfg.gi_depth);
+        L.stage[0] = ST_REFR;
         L.sp = 1;
+        return STEP_CONT;
     }
-    for (;;) {
-        Frame &f = L.fr[L.sp - 1];
+    {
+        uint8_t &stage = L.stage[L.sp - 1];
         const bhrt_material &M = s.materials[f.mtl];
         bool push_child = false;    // a child frame was pushed at fr[sp]
         bool done = false;          // this frame finished, value in f.out
         bool refr_resolved = false; V3 R(0, 0, 0);      // refraction term known
         bool gi_resolved = false; V3 G(0, 0, 0);        // GI term known
 
-        switch (f.stage) {
+        switch (stage) {
         case ST_REFR: {
             // ---- Shade prologue (MtlBlinn.cpp:91-117)
             float cosPhi1 = dot(f.vN, f.vV);
             if (cosPhi1 > 1) cosPhi1 = 1;
             if (cosPhi1 <= 0) cosPhi1 = 0;
-            float R0 = (float)pow((double)((1 - M.ior) / (1 + M.ior)), 2.0);
-            float F = (float)(R0 + (1 - R0) * pow((double)(1 - cosPhi1), 5.0));
+            // float R0 = pow((1-ior)/(1+ior), 2); F = R0 + (1-R0)*pow(1-cosPhi1, 5): double pow() in the
+            // reference (MtlBlinn.cpp:107-109).  x*x of a float is exact in double; x^5 by three double
+            // products is within 1 double-ulp of the correctly rounded power, i.e. the same float
+            // except on ~2^-28 of the inputs (shading only, never a hit decision).
+            const double r0d = (double)((1 - M.ior) / (1 + M.ior));
+            float R0 = (float)(r0d * r0d);
+            const double omc = (double)(1 - cosPhi1);
+            const double omc2 = omc * omc;
+            float F = (float)(R0 + (1 - R0) * (omc2 * omc2 * omc));
             V3 refr = ld3(M.refraction);
             V3 fs = ld3(M.specular.color) + F * refr;
             clamp_white(fs);
@@ -882,8 +1354,8 @@ BHRT_HD_NOINLINE bool sample_advance(Lane &L, const SceneView &s, const ShadeCfg
                 L.sv = refrC; L.sf = rgloss; L.si = f.bounce;
                 Ray rin; rin.dir = normalized(vTs); rin.p = f.p - f.vN * BHRT_BIAS;
                 issue_closest(L, rin, HIT_FRONT_AND_BACK, rc);
-                f.stage = ST_REFR_IN_WAIT;
-                return false;
+                stage = ST_REFR_IN_WAIT;
+                return STEP_RAY;
             }
             refr_resolved = true;
             break;
@@ -897,20 +1369,20 @@ BHRT_HD_NOINLINE bool sample_advance(Lane &L, const SceneView &s, const ShadeCfg
                 if (goingOut) {
                     // ---- RefractionOut (MtlBlinn.cpp:521-541)
                     issue_closest(L, nx, HIT_FRONT, rc);
-                    f.stage = ST_REFR_OUT_WAIT;
-                    return false;
+                    stage = ST_REFR_OUT_WAIT;
+                    return STEP_RAY;
                 }
                 if (L.si <= 0) { refr_resolved = true; break; }
                 L.si--;
                 Ray r2; r2.dir = nx.dir; r2.p = L.hit.p - L.hit.N * BHRT_BIAS;
                 issue_closest(L, r2, HIT_FRONT_AND_BACK, rc);
-                return false;
+                return STEP_RAY;
             }
             f.mult = V3(1, 1, 1);
             if (L.sp < BHRT_MAX_FRAMES) {
-                frame_begin(L.fr[L.sp], s, rin.p, L.hit, L.si, f.gi - 1);
+                frame_begin(child, s, rin.p, L.hit, L.si, f.gi - 1);
                 push_child = true;
-                f.stage = ST_REFR_WAIT;
+                stage = ST_REFR_WAIT;
             } else refr_resolved = true;
             break;
         }
@@ -922,9 +1394,9 @@ BHRT_HD_NOINLINE bool sample_advance(Lane &L, const SceneView &s, const ShadeCfg
                 V3 af(powf(BHRT_EULER, -ab.x * hz), powf(BHRT_EULER, -ab.y * hz), powf(BHRT_EULER, -ab.z * hz));
                 f.mult = L.sv * af;
                 if (L.sp < BHRT_MAX_FRAMES) {
-                    frame_begin(L.fr[L.sp], s, nx.p, L.hit, L.si, f.gi - 1);
+                    frame_begin(child, s, nx.p, L.hit, L.si, f.gi - 1);
                     push_child = true;
-                    f.stage = ST_REFR_WAIT;
+                    stage = ST_REFR_WAIT;
                 } else refr_resolved = true;
             } else {
                 R = L.sv * sample_environment(s, nx.dir);
@@ -939,7 +1411,7 @@ BHRT_HD_NOINLINE bool sample_advance(Lane &L, const SceneView &s, const ShadeCfg
             break;
         case ST_GI: {
             // ---- PathTracing_GlobalIllumination (MtlBlinn.cpp:383-433)
-            if (det || f.gi < 0) { f.stage = ST_DIRECT; L.si = 0; L.sv = V3(0, 0, 0); break; }
+            if (det || f.gi < 0) { stage = ST_DIRECT; L.si = 0; L.sv = V3(0, 0, 0); break; }
             // GIUseSpecularDirOrDiffuseDir (:354-378)
             V3 dcol = ld3(M.diffuse.color);
             float kd = fmaxr(fmaxr(dcol.x, dcol.y), dcol.z);
@@ -956,19 +1428,19 @@ BHRT_HD_NOINLINE bool sample_advance(Lane &L, const SceneView &s, const ShadeCfg
             float P_sum = P_d + ks * p_s;
             float P_dn = P_d / P_sum;
             float rnd = rng.rnd01();
-            f.useSpec = rnd >= P_dn;
+            f.useSpec = rnd >= P_dn ? 1 : 0;
             Ray g; g.dir = f.useSpec ? sdir : ddir; g.p = f.p + f.vN * BHRT_BIAS;
             issue_closest(L, g, HIT_FRONT, rc);
-            f.stage = ST_GI_TRACE_WAIT;
-            return false;
+            stage = ST_GI_TRACE_WAIT;
+            return STEP_RAY;
         }
         case ST_GI_TRACE_WAIT: {
             const Ray g = L.q.ray;
             if (L.hit_ok) {
                 if (fabsf(L.hit.z) > BHRT_BIAS && L.sp < BHRT_MAX_FRAMES) {
-                    frame_begin(L.fr[L.sp], s, g.p, L.hit, f.bounce, f.gi - 1);
+                    frame_begin(child, s, g.p, L.hit, f.bounce, f.gi - 1);
                     push_child = true;
-                    f.stage = ST_GI_WAIT;
+                    stage = ST_GI_WAIT;
                 } else gi_resolved = true;      // indirect = black, black * albedo = black
             } else {
                 if (g.dir.x == g.dir.y && g.dir.x == 0) G = V3(1.0f, 0.0f, 1.0f);
@@ -1001,13 +1473,13 @@ BHRT_HD_NOINLINE bool sample_advance(Lane &L, const SceneView &s, const ShadeCfg
                     if (cosTheta > 0) {
                         V3 irrad;
                         L.sw = vL;
-                        if (illuminate_begin(Lt, f.p, (Rng *)0, L.q, irrad)) { rc.shadow++; f.stage = ST_SHADOW_WAIT; issued = true; break; }
+                        if (illuminate_begin(Lt, f.p, (Rng *)0, L.q, irrad)) { rc.shadow++; stage = ST_SHADOW_WAIT; issued = true; break; }
                         L.sv = L.sv + irrad * direct_brdf(s, f, M, vL);
                     }
                     L.si++;
                 }
-                if (issued) return false;
-                direct_finish(f, L.sv);
+                if (issued) return STEP_RAY;
+                direct_finish(s, pg, f, M, L.sv);
                 done = true;
             } else {
                 if (s.n_lights > 0) {
@@ -1023,11 +1495,11 @@ BHRT_HD_NOINLINE bool sample_advance(Lane &L, const SceneView &s, const ShadeCfg
                     if (cosTheta > 0) {
                         V3 irrad;
                         L.sw = vL; L.si = i;
-                        if (illuminate_begin(Lt, f.p, &rng, L.q, irrad)) { rc.shadow++; f.stage = ST_SHADOW_WAIT; return false; }
+                        if (illuminate_begin(Lt, f.p, &rng, L.q, irrad)) { rc.shadow++; stage = ST_SHADOW_WAIT; return STEP_RAY; }
                         L.sv = L.sv + irrad * direct_brdf(s, f, M, vL);
                     }
                 }
-                direct_finish(f, L.sv);
+                direct_finish(s, pg, f, M, L.sv);
                 done = true;
             }
             break;
@@ -1036,8 +1508,8 @@ BHRT_HD_NOINLINE bool sample_advance(Lane &L, const SceneView &s, const ShadeCfg
             const bhrt_light &Lt = s.lights[L.si];
             V3 irrad = illuminate_end(Lt, f.p, L.hit_ok);
             L.sv = L.sv + irrad * direct_brdf(s, f, M, L.sw);
-            if (det) { L.si++; f.stage = ST_DIRECT; }
-            else { direct_finish(f, L.sv); done = true; }
+            if (det) { L.si++; stage = ST_DIRECT; }
+            else { direct_finish(s, pg, f, M, L.sv); done = true; }
             break;
         }
         }
@@ -1045,37 +1517,169 @@ BHRT_HD_NOINLINE bool sample_advance(Lane &L, const SceneView &s, const ShadeCfg
         if (refr_resolved) {
             clamp_white(R);
             f.out = f.out + R;
-            if (saturated(f.out)) done = true; else f.stage = ST_GI;
+            if (saturated(f.out)) done = true; else stage = ST_GI;
         }
         if (gi_resolved) {
             if (is_nan(G.x)) G = V3(1.0f, 0.0f, 1.0f);
             clamp_white(G);
             f.out = f.out + G;
             if (saturated(f.out)) done = true;
-            else { f.stage = ST_DIRECT; L.si = 0; L.sv = V3(0, 0, 0); }
+            else { stage = ST_DIRECT; L.si = 0; L.sv = V3(0, 0, 0); }
         }
-        if (push_child) { L.sp++; continue; }
+        if (push_child) { L.stage[L.sp] = ST_REFR; L.sp++; return STEP_CONT; }
         if (done) {
             L.ret = f.out;
             L.sp--;
-            if (L.sp == 0) { color = L.ret; return true; }
+            if (L.sp == 0) { color = L.ret; return STEP_DONE; }
         }
+    }
+    return STEP_CONT;
+}
+
+// Runs steps until the estimator needs a ray (false, query in L.q) or the sample is finished (true)
+BHRT_HD bool sample_advance(Lane &L, LaneStack &S, const SceneView &s, const ShadeCfg &cfg, const PhotonGather &pg, float bgu, float bgv,
+                            RayCounters &rc, V3 &color)
+{
+    for (;;) {
+        const int top = L.sp > 0 ? L.sp - 1 : 0, up = L.sp < BHRT_MAX_FRAMES ? L.sp : BHRT_MAX_FRAMES - 1;
+        int r = sample_step(L, S.fr[top], S.fr[up], s, cfg, pg, bgu, bgv, rc, color);
+        if (r == STEP_RAY) return false;
+        if (r == STEP_DONE) return true;
     }
 }
 
+
 // One camera sample, synchronously: the reference's PathTracing() loop body.  Used by the CPU
 // harness (tests/emu); the kernel interleaves the same two calls across a warp.
-BHRT_HD V3 trace_sample(Lane &L, const SceneView &s, const ShadeCfg &cfg, const PhotonGather &pg, const Ray &primary, float bgu, float bgv,
+BHRT_HD V3 trace_sample(Lane &L, LaneStack &S, const SceneView &s, const ShadeCfg &cfg, const PhotonGather &pg, const Ray &primary, float bgu, float bgv,
                         RayCounters &rc, int &hit_id, float &hit_z)
 {
     V3 color(0, 0, 0);
     sample_begin(L, primary, rc);
     for (;;) {
         L.hit_ok = scene_trace(s, L.q, L.hit);
-        if (sample_advance(L, s, cfg, pg, bgu, bgv, rc, color)) break;
+        if (sample_advance(L, S, s, cfg, pg, bgu, bgv, rc, color)) break;
     }
     hit_id = L.hit_id; hit_z = L.hit_z;
     return color;
+}
+
+// ------------------------------------------------------------------------------------------
+// Caustic photon emission: BuildCausticPhotonMap / TraceCausticPhotonRay (reference Main.cpp:319-386),
+// PointLight::RandomPhoton (PointLight.cpp:20-34), MtlBlinn::RandomPhotonBounceForCaustic
+// (MtlBlinn.cpp:203-303) -- again a coroutine around one ray query per step.
+struct PhotonEmitCfg {
+    int n_lights;               // point lights only (the reference reinterpret_casts every light to
+                                // PointLight, Main.cpp:350 -- undefined for the others), sorted like
+                                // ComparePointLight (Main.cpp:247): ascending intensity.Gray() * int(size)
+    int light[BHRT_MAX_LIGHTS]; // indices into SceneView::lights
+    float sum;                  // sum of Gray() * int(size)  (Main.cpp:357-361)
+};
+enum { PH_TRACE_WAIT = 0, PH_REFR_IN_WAIT = 1 };
+#define BHRT_PHOTON_ABSORB 0.3f     // Photon_AbsorbChance (MtlBlinn.cpp:27)
+struct PhotonLane {
+    Query q;
+    Hit hit;
+    bool hit_ok;
+    Rng rng;
+    V3 c;                       // photon power carried along the path
+    int stage;
+    bool first;                 // no bounce yet (direct light is not stored, Main.cpp:328)
+    int mtl;                    // material of the refractive object being crossed
+};
+
+BHRT_HD void photon_begin(PhotonLane &P, const SceneView &s, const PhotonEmitCfg &cfg, unsigned long long &rays)
+{
+    Rng &rng = P.rng;
+    float rnd = rng.rnd01();
+    int i = 0;
+    // PointLight::GetProbability: Gray() * size (the float) / sum (Lights/lights.h:81)
+    while (i < cfg.n_lights - 1 && rnd > gray(ld3(s.lights[cfg.light[i]].intensity)) * s.lights[cfg.light[i]].size / cfg.sum) i++;
+    const bhrt_light &Lt = s.lights[cfg.light[i]];
+    float phi = (float)(rng.rnd01() * 2 * BHRT_PI_D);
+    float theta = acos_safe(1 - 2 * rng.rnd01());
+    Ray r;
+    r.dir = sinf(theta) * (V3(1, 0, 0) * cosf(phi) + V3(0, 1, 0) * sinf(phi)) + V3(0, 0, 1) * cosf(theta);
+    r.p = ld3(Lt.v);
+    P.c = ld3(Lt.intensity);
+    P.first = true;
+    P.stage = PH_TRACE_WAIT;
+    P.q.ray = r; P.q.kind = Q_CLOSEST; P.q.hitSide = HIT_FRONT; P.q.t_max = 0;
+    rays++;
+}
+
+// Consumes the answer to P.q.  Returns true when the path ended; `store` tells the caller to
+// append `rec` to the photon map (PhotonMap::AddPhoton, cyPhotonMap.h:218-232).
+BHRT_HD bool photon_advance(PhotonLane &P, const SceneView &s, PhotonRecord &rec, bool &store, unsigned long long &rays)
+{
+    Rng &rng = P.rng;
+    store = false;
+    if (P.stage == PH_REFR_IN_WAIT) {
+        // inside a refractive object (MtlBlinn.cpp:232-248)
+        if (!(P.hit_ok && P.hit.node >= 0)) return true;
+        const bhrt_material &M = s.materials[P.mtl];
+        bool goingOut;
+        Ray nx = handle_refraction_out(P.q.ray, P.hit, M.ior, goingOut, M.refraction_glossiness, &rng);
+        if (!goingOut) return true;
+        P.first = false;
+        P.stage = PH_TRACE_WAIT;
+        P.q.ray = nx; P.q.kind = Q_CLOSEST; P.q.hitSide = HIT_FRONT;
+        rays++;
+        return false;
+    }
+    if (!P.hit_ok) return true;                                             // Main.cpp:337-339
+    const Ray ray = P.q.ray;
+    const Hit &h = P.hit;
+    const int mtl = s.nodes[h.node].material;
+    const bhrt_material &M = s.materials[mtl];
+    if (!P.first && gray(ld3(M.diffuse.color)) > 0) {                       // IsPhotonSurface (materials.h:49)
+        photon_pack(rec, h.p, normalized(ray.dir), P.c);
+        store = true;
+    }
+    // ---- RandomPhotonBounceForCaustic (MtlBlinn.cpp:203-303)
+    float rnd = rng.rnd01();
+    V3 vN = normalized(h.N);
+    V3 vV = -normalized(ray.dir);
+    if (gray(ld3(M.refraction)) > 0) {
+        float cosPhi1 = dot(vN, vV);
+        float sinPhi1 = sqrtf(1 - cosPhi1 * cosPhi1);
+        float sinPhi2 = sinPhi1 / M.ior;
+        float cosPhi2 = sqrtf(1 - sinPhi2 * sinPhi2);
+        V3 vTn = -cosPhi2 * vN;
+        V3 vNxV = cross(vN, vV);
+        V3 vTp = normalized(cross(vN, vNxV)) * sinPhi2;
+        Ray rin; rin.dir = vTn + vTp; rin.p = h.p - vN * BHRT_BIAS;
+        P.mtl = mtl;
+        P.stage = PH_REFR_IN_WAIT;
+        P.q.ray = rin; P.q.kind = Q_CLOSEST; P.q.hitSide = HIT_BACK;
+        rays++;
+        return false;
+    }
+    if (rnd < BHRT_PHOTON_ABSORB) return true;
+    V3 dcol = ld3(M.diffuse.color), scol = ld3(M.specular.color);
+    float kd = fmaxr(fmaxr(dcol.x, dcol.y), dcol.z);
+    float ks = fmaxr(fmaxr(scol.x, scol.y), scol.z);
+    float dTheta = 0;
+    V3 ddir = normalized(sample_semisphere(vN, dTheta, rng));
+    (void)ddir;
+    float p_d = sinf(2 * dTheta);
+    float sTheta = 0;
+    float cvn = dot(vN, vV);
+    V3 vR = 2 * cvn * vN - vV;
+    V3 sdir = sample_along_direction(vR, M.glossiness, sTheta, rng);
+    float p_s = powf(cosf(sTheta), M.glossiness);
+    float P_d = kd * p_d;
+    float P_sum = P_d + ks * p_s;
+    float p_Diff = (P_d / P_sum) * (1 - BHRT_PHOTON_ABSORB) + BHRT_PHOTON_ABSORB;
+    float p_Spec = (1 - p_Diff) * (1 - BHRT_PHOTON_ABSORB) + BHRT_PHOTON_ABSORB;
+    if (!(rnd >= p_Diff)) return true;                                      // a diffuse bounce ends a caustic path
+    P.c = P.c * (scol / p_Spec);
+    Ray nr; nr.dir = sdir; nr.p = h.p + h.N * BHRT_BIAS;
+    P.first = false;
+    P.stage = PH_TRACE_WAIT;
+    P.q.ray = nr; P.q.kind = Q_CLOSEST; P.q.hitSide = HIT_FRONT;
+    rays++;
+    return false;
 }
 
 // RandomPositionInPixel (Main.cpp:132-139) + the primary ray of PathTracing (Main.cpp:145-153)
@@ -1085,9 +1689,9 @@ BHRT_HD Ray primary_ray(const SceneView &s, int i, int j, bool jitter, Rng &rng)
     if (jitter) {
         float pixelLen = length(s.dd_x);
         V3 ux = normalized(s.dd_x), uy = normalized(s.dd_y);
-        float a = (float)(rng.unit() * 2 - 1);
+        float a = rng.unit() * 2 - 1;
         pc = pc + ux * a * pixelLen / 2;
-        float b = (float)(rng.unit() * 2 - 1);
+        float b = rng.unit() * 2 - 1;
         pc = pc + uy * b * pixelLen / 2;
     }
     Ray r; r.p = s.cam_pos; r.dir = pc - s.cam_pos;

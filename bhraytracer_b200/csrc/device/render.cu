@@ -10,12 +10,14 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "core.cuh"
 #include "setup.hpp"
 #include "accel.hpp"
 #include "photon.cuh"
+#include "wavefront.cuh"
 
 using namespace bhrt;
 
@@ -50,129 +52,15 @@ struct bhrt_ctx {
     DevBuf nodes, materials, lights, texmaps, textures, texels, meshes, mesh_data, tex_offsets;
     DevBuf accum, hit_id, z, rgb8, linear, counters;
     PhotonState photons;
+    std::vector<bhrt_light> sorted_lights;      // host copy of the device light table (photon emission setup)
     int rendered_spp = 0;
     int n_materials = 0;
     DevBuf accels, accel_data;
     bool kernel_ready = false;
-    int kernel_smem = 0, blocks_per_sm = 1;
+    int kernel_smem = 0, trace_blocks = 1, mesh_blocks = 1, finish_blocks = 1, advance_blocks = 1, scatter_blocks = 1;
+    size_t pool_lanes = (size_t)1 << 20;        // live camera samples (2.3 KB of state each)
+    DevBuf lanes, frames, list0, list1, mesh_queue, keys, samples, wave_counters;
 };
-
-// ------------------------------------------------------------------------------------------
-struct RenderArgs {
-    ShadeCfg cfg;
-    unsigned long long seed;
-    int sample_begin, sample_end;
-    int row_begin, row_stride;
-    int n_rows;              // number of rows this launch covers
-    int tiles_x;             // 8x8 pixel tiles per row of tiles
-    unsigned int n_work;     // work items = tiles * 64 (items outside the image are skipped)
-    PhotonGather gather;     // caustic photon map (use = 0 when disabled)
-    int smem_nodes, smem_materials, smem_lights, smem_offsets;   // byte offsets of the staged tables
-};
-
-#define BHRT_BLOCK 128
-#define BHRT_FULL 0xffffffffu
-
-// Persistent-thread renderer.  The grid is sized to fill the machine once (SMs x resident CTAs);
-// every lane owns ONE pixel at a time and evaluates its samples in order (so a pixel's sum is
-// independent of launch geometry and GPU count), then pulls the next pixel from a global counter
-// -- one warp-aggregated atomic per refill.  Pixels are numbered in 8x8 tiles so the lanes of a
-// warp start on neighbouring primary rays.
-//
-// Each loop iteration has exactly one traversal (scene_trace) that all lanes with work enter
-// together, whatever their sample's recursion level or stage; sample_advance() then runs each
-// lane's estimator coroutine to its next ray.  The scene-graph node table, materials, lights and
-// the texture-filter taps are staged in shared memory once per CTA: the node loop of scene_trace
-// reads them at warp-uniform addresses (one broadcast per access).
-__global__ void __launch_bounds__(BHRT_BLOCK)
-render_kernel(SceneView s, RenderArgs a, float4 *__restrict__ accum, int *__restrict__ hit_id, float *__restrict__ zbuf,
-              unsigned long long *__restrict__ counters)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    {
-        // cooperative 32-bit copies of the small tables (all sizes are multiples of 4)
-        const uint32_t *src; uint32_t *dst; int n;
-        src = (const uint32_t *)s.nodes; dst = (uint32_t *)(smem + a.smem_nodes); n = s.n_nodes * (int)(sizeof(bhrt_node) / 4);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-        src = (const uint32_t *)s.materials; dst = (uint32_t *)(smem + a.smem_materials); n = s.n_materials * (int)(sizeof(bhrt_material) / 4);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-        src = (const uint32_t *)s.lights; dst = (uint32_t *)(smem + a.smem_lights); n = s.n_lights * (int)(sizeof(bhrt_light) / 4);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-        src = (const uint32_t *)s.tex_offsets; dst = (uint32_t *)(smem + a.smem_offsets); n = 2 * (BHRT_TEX_SAMPLES - 1);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-        __syncthreads();
-        s.nodes = (const bhrt_node *)(smem + a.smem_nodes);
-        s.materials = (const bhrt_material *)(smem + a.smem_materials);
-        s.lights = (const bhrt_light *)(smem + a.smem_lights);
-        s.tex_offsets = (const float *)(smem + a.smem_offsets);
-    }
-    const int lane = threadIdx.x & 31;
-    const bool det = a.cfg.mode == BHRT_MODE_DET;
-    RayCounters rc; rc.closest = 0; rc.shadow = 0;
-    Lane L;
-    int pi = 0, pj = 0;             // the lane's pixel
-    bool have_pixel = false, in_sample = false, exhausted = false;
-    int sidx = 0, id0 = -1;
-    float z0 = BHRT_BIGFLOAT;
-    V3 sum(0, 0, 0);
-    for (;;) {
-        // ---- refill idle lanes (warp-aggregated fetch)
-        const bool need = !have_pixel && !exhausted;
-        const unsigned nm = __ballot_sync(BHRT_FULL, need);
-        if (nm) {
-            const int leader = __ffs(nm) - 1;
-            unsigned base = 0;
-            if (lane == leader) base = atomicAdd((unsigned int *)&counters[2], (unsigned)__popc(nm));
-            base = __shfl_sync(BHRT_FULL, base, leader);
-            if (need) {
-                const unsigned idx = base + __popc(nm & ((1u << lane) - 1u));
-                if (idx >= a.n_work) exhausted = true;
-                else {
-                    const unsigned tile = idx >> 6, w = idx & 63u;
-                    const int tx = (int)(tile % (unsigned)a.tiles_x), ty = (int)(tile / (unsigned)a.tiles_x);
-                    const int i = tx * 8 + (int)(w & 7u), trow = ty * 8 + (int)(w >> 3);
-                    if (i < s.width && trow < a.n_rows) {
-                        pi = i; pj = a.row_begin + trow * a.row_stride;
-                        have_pixel = true; in_sample = false;
-                        sidx = a.sample_begin; sum = V3(0, 0, 0);
-                    }
-                }
-            }
-        }
-        if (!__any_sync(BHRT_FULL, have_pixel)) {
-            if (!__any_sync(BHRT_FULL, !exhausted)) break;
-            continue;
-        }
-        if (have_pixel) {
-            if (!in_sample) {
-                L.rng.seed(a.seed, (uint64_t)pj * s.width + pi, (uint64_t)sidx);
-                Ray pr = primary_ray(s, pi, pj, !det, L.rng);
-                sample_begin(L, pr, rc);
-                in_sample = true;
-            }
-            L.hit_ok = scene_trace(s, L.q, L.hit);
-            V3 c;
-            if (sample_advance(L, s, a.cfg, a.gather, (float)pi / s.width, (float)pj / s.height, rc, c)) {
-                if (sidx == 0) { id0 = L.hit_id; z0 = L.hit_z; }
-                sum = sum + c;
-                in_sample = false;
-                if (++sidx == a.sample_end) {
-                    const size_t p = (size_t)pj * s.width + pi;
-                    accum[p] = make_float4(sum.x, sum.y, sum.z, (float)(a.sample_end - a.sample_begin));
-                    if (a.sample_begin == 0) { hit_id[p] = id0; zbuf[p] = z0; }
-                    have_pixel = false;
-                }
-            }
-        }
-    }
-    // ray counters: warp-reduce, one atomic per warp
-    unsigned long long c0 = rc.closest, c1 = rc.shadow;
-    for (int o = 16; o > 0; o >>= 1) {
-        c0 += __shfl_down_sync(BHRT_FULL, c0, o);
-        c1 += __shfl_down_sync(BHRT_FULL, c1, o);
-    }
-    if (lane == 0 && (c0 | c1)) { atomicAdd(&counters[0], c0); atomicAdd(&counters[1], c1); }
-}
 
 // sum/spp (Main.cpp:170), gamma (Main.cpp:220-227), Color24 (Main.cpp:230)
 __global__ void resolve_kernel(const float4 *__restrict__ accum, int n, float inv_is_div_by, float *__restrict__ linear, uint8_t *__restrict__ rgb8)
@@ -212,8 +100,7 @@ int bhrt_create(int device, bhrt_ctx **out)
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     if (c->counters.ensure(8 * sizeof(unsigned long long))) { delete c; return set_err(BHRT_ERR_CUDA, "cudaMalloc(counters)"); }
-    // the estimator keeps a frame stack + BVH stacks in local memory
-    cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024);
+    if (const char *e = getenv("BHRT_POOL_LANES")) { long v = atol(e); if (v >= 1024) c->pool_lanes = (size_t)v; }   // tuning knob
     *out = c;
     return BHRT_OK;
 }
@@ -224,7 +111,7 @@ int bhrt_destroy(bhrt_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = { &c->nodes, &c->materials, &c->lights, &c->texmaps, &c->textures, &c->texels, &c->meshes, &c->mesh_data,
-                       &c->tex_offsets, &c->accels, &c->accel_data, &c->accum, &c->hit_id, &c->z, &c->rgb8, &c->linear, &c->counters };
+                       &c->tex_offsets, &c->accels, &c->accel_data, &c->lanes, &c->frames, &c->list0, &c->list1, &c->mesh_queue, &c->keys, &c->samples, &c->wave_counters, &c->accum, &c->hit_id, &c->z, &c->rgb8, &c->linear, &c->counters };
     for (auto b : bufs) b->release();
     c->photons.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -273,6 +160,8 @@ int bhrt_upload_scene(bhrt_ctx *c, const bhrt_scene_desc *d)
     if ((r = upload(c, c->nodes, d->nodes, sizeof(bhrt_node) * d->n_nodes))) return r;
     if ((r = upload(c, c->materials, d->materials, sizeof(bhrt_material) * d->n_materials))) return r;
     if ((r = upload(c, c->lights, lights.data(), sizeof(bhrt_light) * lights.size()))) return r;
+    c->sorted_lights = lights;
+    c->photons.count = 0; c->photons.built = false;     // a photon map belongs to the scene it was traced in
     if ((r = upload(c, c->texmaps, d->texmaps, sizeof(bhrt_texmap) * d->n_texmaps))) return r;
     if ((r = upload(c, c->textures, d->textures, sizeof(bhrt_texture) * d->n_textures))) return r;
     if ((r = upload(c, c->texels, d->texels, d->texel_bytes))) return r;
@@ -302,6 +191,7 @@ int bhrt_upload_scene(bhrt_ctx *c, const bhrt_scene_desc *d)
     s.accels = (const MeshAccel *)c->accels.p;
     s.accel_data = (const uint8_t *)c->accel_data.p;
     c->n_materials = d->n_materials;
+    fill_mesh_nodes(s, d->nodes, d->n_nodes);
     s.background = d->background; s.environment = d->environment;
     s.all_light_intensity = allI;
     s.cam_pos = fc.cam_pos; s.top_left = fc.top_left; s.dd_x = fc.dd_x; s.dd_y = fc.dd_y;
@@ -315,13 +205,14 @@ int bhrt_upload_scene(bhrt_ctx *c, const bhrt_scene_desc *d)
     return BHRT_OK;
 }
 
+// One frame (or one rank's share of it) through the wavefront kernels of wavefront.cuh.
 static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
 {
     if (!c || !p) return set_err(BHRT_ERR_ARG, "bhrt_render: null argument");
     if (!c->have_scene) return set_err(BHRT_ERR_STATE, "bhrt_render: no scene uploaded");
     if (p->mode != BHRT_MODE_PATH && p->mode != BHRT_MODE_DET) return set_err(BHRT_ERR_ARG, "bhrt_render: bad mode");
     CU(cudaSetDevice(c->device));
-    RenderArgs a;
+    WaveArgs a;
     memset(&a, 0, sizeof(a));
     a.cfg.mode = p->mode;
     a.cfg.gi_depth = p->gi_depth;
@@ -329,9 +220,9 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     a.seed = p->seed;
     int spp = p->mode == BHRT_MODE_DET ? 1 : p->spp;
     if (spp <= 0) return set_err(BHRT_ERR_ARG, "bhrt_render: spp must be > 0");
-    a.sample_begin = p->sample_begin; a.sample_end = p->sample_end;
-    if (a.sample_begin == 0 && a.sample_end == 0) a.sample_end = spp;
-    if (a.sample_begin < 0 || a.sample_end > spp || a.sample_begin > a.sample_end) return set_err(BHRT_ERR_ARG, "bhrt_render: bad sample range");
+    int sample_begin = p->sample_begin, sample_end = p->sample_end;
+    if (sample_begin == 0 && sample_end == 0) sample_end = spp;
+    if (sample_begin < 0 || sample_end > spp || sample_begin > sample_end) return set_err(BHRT_ERR_ARG, "bhrt_render: bad sample range");
     int row_begin = p->row_begin, row_end = p->row_end;
     if (row_begin == 0 && row_end == 0) row_end = c->height;
     if (row_begin < 0 || row_end > c->height || row_begin > row_end) return set_err(BHRT_ERR_ARG, "bhrt_render: bad row range");
@@ -339,57 +230,118 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     a.row_stride = p->row_stride > 1 ? p->row_stride : 1;
     a.n_rows = (row_end - row_begin + a.row_stride - 1) / a.row_stride;
     a.tiles_x = (c->width + 7) / 8;
-    a.n_work = (unsigned)a.tiles_x * (unsigned)((a.n_rows + 7) / 8) * 64u;
+    a.n_pix_work = (unsigned)a.tiles_x * (unsigned)((a.n_rows + 7) / 8) * 64u;
     a.gather.use = 0;
     if (p->use_photon_map) {
         if (!c->photons.built) return set_err(BHRT_ERR_STATE, "bhrt_render: use_photon_map set but no photon map built");
-        a.gather = c->photons.gather_view(p->photon_k > 0 ? p->photon_k : 1000, p->photon_radius > 0 ? p->photon_radius : 0.5f);
+        const float radius = p->photon_radius > 0 ? p->photon_radius : 0.5f;
+        if (radius != c->photons.built_radius) {            // the grid cell follows the gather radius
+            std::string perr;
+            int pr = c->photons.build(c->photons.built_total, radius, c->stream, c->launches, perr);
+            if (pr) return set_err(pr, perr);
+        }
+        a.gather = c->photons.gather_view(p->photon_k > 0 ? p->photon_k : 1000, radius);
     }
     // shared-memory staging of the small scene tables
     auto al16 = [](int v) { return (v + 15) & ~15; };
     a.smem_nodes = 0;
     a.smem_materials = al16(a.smem_nodes + c->view.n_nodes * (int)sizeof(bhrt_node));
-    a.smem_lights = al16(a.smem_materials + c->n_materials * (int)sizeof(bhrt_material));
+    a.smem_lights = al16(a.smem_materials + c->view.n_materials * (int)sizeof(bhrt_material));
     a.smem_offsets = al16(a.smem_lights + c->view.n_lights * (int)sizeof(bhrt_light));
     const int smem_bytes = al16(a.smem_offsets + 2 * (BHRT_TEX_SAMPLES - 1) * (int)sizeof(float));
     if (!c->kernel_ready || c->kernel_smem < smem_bytes) {
-        CU(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel, BHRT_BLOCK, smem_bytes));
-        if (per_sm < 1) return set_err(BHRT_ERR_LIMIT, "bhrt_render: scene tables do not fit in shared memory");
-        c->blocks_per_sm = per_sm;
+        CU(cudaFuncSetAttribute(wf_trace_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        CU(cudaFuncSetAttribute(wf_trace_mesh, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        CU(cudaFuncSetAttribute(wf_step, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        CU(cudaFuncSetAttribute(wf_trace_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        int t_sm = 0, m_sm = 0, a_sm = 0, s_sm = 0, f_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f_sm, wf_trace_finish, WF_BLOCK, smem_bytes));
+        if (f_sm < 1) return set_err(BHRT_ERR_LIMIT, "bhrt_render: scene tables do not fit in shared memory");
+        c->finish_blocks = f_sm;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t_sm, wf_trace_graph, WF_BLOCK, smem_bytes));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m_sm, wf_trace_mesh, WF_BLOCK, smem_bytes));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a_sm, wf_step, WF_BLOCK, smem_bytes));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_sm, wf_scatter, WF_BLOCK, 0));
+        if (t_sm < 1 || m_sm < 1 || a_sm < 1 || s_sm < 1) return set_err(BHRT_ERR_LIMIT, "bhrt_render: scene tables do not fit in shared memory");
+        c->trace_blocks = t_sm; c->mesh_blocks = m_sm; c->advance_blocks = a_sm; c->scatter_blocks = s_sm;
         c->kernel_smem = smem_bytes;
         c->kernel_ready = true;
     }
-    CU(cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    // ---- lane pool and per-chunk sample buffer
+    const size_t n_pix_share = (size_t)a.n_pix_work;
+    const int n_spp_share = sample_end - sample_begin;
+    int chunk = n_spp_share;
+    const size_t max_samples = (size_t)1 << 27;                 // 2 GiB of float4 sample colours per chunk
+    if (chunk > 0 && n_pix_share * (size_t)chunk > max_samples) chunk = (int)(max_samples / n_pix_share);
+    if (chunk < 1) chunk = 1;
+    size_t pool = c->pool_lanes;
+    if (n_pix_share * (size_t)chunk < pool) pool = n_pix_share * (size_t)chunk;
+    if (pool < 1) pool = 1;
+    if (c->lanes.ensure(pool * sizeof(Lane)) || c->frames.ensure(pool * sizeof(Frame) * BHRT_MAX_FRAMES) || c->list0.ensure(pool * 4) || c->list1.ensure(pool * 4) || c->mesh_queue.ensure(pool * 4) || c->keys.ensure(pool) ||
+        c->samples.ensure(n_pix_share * (size_t)chunk * sizeof(float4)) || c->wave_counters.ensure(sizeof(WaveCounters)))
+        return set_err(BHRT_ERR_CUDA, "cudaMalloc(wavefront buffers) failed");
+    a.lanes = (Lane *)c->lanes.p; a.frames = (Frame *)c->frames.p; a.list[0] = (unsigned *)c->list0.p; a.list[1] = (unsigned *)c->list1.p;
+    a.keys = (unsigned char *)c->keys.p; a.mesh_queue = (unsigned *)c->mesh_queue.p; a.samples = (float4 *)c->samples.p;
+    a.hit_id = (int *)c->hit_id.p; a.zbuf = (float *)c->z.p;
+    a.cnt = (WaveCounters *)c->wave_counters.p;
+    a.pool = (unsigned)pool;
+
     // rows / samples outside this launch's share must read as zero for the multi-GPU sum
-    if (a.n_rows != c->height || a.sample_begin != 0 || a.sample_end == a.sample_begin)
+    const bool partial_rows = a.n_rows != c->height;
+    if (partial_rows || n_spp_share == 0)
         CU(cudaMemsetAsync(c->accum.p, 0, (size_t)c->width * c->height * sizeof(float4), c->stream));
-    if (a.n_rows != c->height || a.sample_begin != 0) {
+    if (partial_rows || sample_begin != 0) {
         CU(cudaMemsetAsync(c->hit_id.p, 0, (size_t)c->width * c->height * 4, c->stream));
         CU(cudaMemsetAsync(c->z.p, 0, (size_t)c->width * c->height * 4, c->stream));
     }
-    // persistent grid: fill the machine once; never more CTAs than there is work for
-    unsigned grid = (unsigned)(c->sm_count * c->blocks_per_sm);
-    const unsigned need_blocks = (a.n_work + BHRT_BLOCK - 1) / BHRT_BLOCK;
-    if (grid > need_blocks) grid = need_blocks;
+    unsigned long long rays[2] = { 0, 0 };
     CU(cudaEventRecord(c->ev0, c->stream));
-    if (a.n_rows > 0 && a.sample_end > a.sample_begin && grid > 0) {
-        render_kernel<<<grid, BHRT_BLOCK, smem_bytes, c->stream>>>(c->view, a, (float4 *)c->accum.p, (int *)c->hit_id.p, (float *)c->z.p,
-                                                                    (unsigned long long *)c->counters.p);
+    const unsigned tg = (unsigned)(c->sm_count * c->trace_blocks), mg = (unsigned)(c->sm_count * c->mesh_blocks),
+                   ag = (unsigned)(c->sm_count * c->advance_blocks), sg = (unsigned)(c->sm_count * c->scatter_blocks),
+                   fg = (unsigned)(c->sm_count * c->finish_blocks);
+    for (int s0 = sample_begin; s0 < sample_end && a.n_rows > 0; s0 += chunk) {
+        a.sample_first = s0;
+        a.chunk_spp = (sample_end - s0 < chunk) ? (sample_end - s0) : chunk;
+        a.n_work = (unsigned long long)a.n_pix_work * (unsigned long long)a.chunk_spp;
+        CU(cudaMemsetAsync(c->wave_counters.p, 0, sizeof(WaveCounters), c->stream));
+        // fill the pool: every lane fetches a camera sample; live list 0 = sorted pool
+        wf_step<<<ag, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a, 1, 1);
+        wf_scatter<<<sg, WF_BLOCK, 0, c->stream>>>(a, 1, 1);
+        c->launches += 2;
+        int parity = 0;
+        for (;;) {
+            const int burst = 16;                                // iterations between live-count checks
+            for (int k = 0; k < burst; k++) {
+                wf_trace_graph<<<tg, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a, parity);
+                wf_trace_mesh<<<mg, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a, parity);
+                wf_trace_finish<<<fg, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a, parity);
+                wf_step<<<ag, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a, parity, 0);
+                wf_scatter<<<sg, WF_BLOCK, 0, c->stream>>>(a, parity, 0);
+                c->launches += 5;
+                parity ^= 1;
+            }
+            CU(cudaGetLastError());
+            unsigned live[2];
+            CU(cudaMemcpyAsync(live, &a.cnt->n_active[0], sizeof(live), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            if (live[parity] == 0) break;
+        }
+        wf_reduce<<<(a.n_pix_work + 255) / 256, 256, 0, c->stream>>>(c->view, a, (float4 *)c->accum.p, s0 == sample_begin ? 1 : 0);
         c->launches++;
+        unsigned long long r2[2];
+        CU(cudaMemcpyAsync(r2, &a.cnt->rays_closest, sizeof(r2), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        rays[0] += r2[0]; rays[1] += r2[1];
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev1, c->stream));
-    c->rendered_spp = a.sample_end - a.sample_begin;
+    CU(cudaStreamSynchronize(c->stream));
+    c->rendered_spp = n_spp_share;
     if (out) {
-        unsigned long long cnt[2];
-        CU(cudaMemcpyAsync(cnt, c->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-        out->rays_closest = cnt[0]; out->rays_shadow = cnt[1]; out->kernel_ms = ms;
-    } else CU(cudaStreamSynchronize(c->stream));
+        out->rays_closest = rays[0]; out->rays_shadow = rays[1]; out->kernel_ms = ms;
+    }
     return BHRT_OK;
 }
 
@@ -460,7 +412,7 @@ int bhrt_photons_emit(bhrt_ctx *c, int32_t target_stored, uint64_t seed, int32_t
     if (!c || !c->have_scene) return set_err(BHRT_ERR_STATE, "bhrt_photons_emit: no scene uploaded");
     CU(cudaSetDevice(c->device));
     std::string err;
-    int r = c->photons.emit(c->view, c->stream, c->sm_count, target_stored, seed, stored, (unsigned long long *)photon_rays, err);
+    int r = c->photons.emit(c->view, c->sorted_lights, c->stream, c->sm_count, target_stored, seed, stored, (unsigned long long *)photon_rays, c->launches, err);
     if (r) return set_err(r, err);
     return BHRT_OK;
 }
@@ -494,7 +446,7 @@ int bhrt_photons_build(bhrt_ctx *c, int32_t total_stored)
     if (!c) return set_err(BHRT_ERR_ARG, "null ctx");
     CU(cudaSetDevice(c->device));
     std::string err;
-    int r = c->photons.build(total_stored, c->stream, err);
+    int r = c->photons.build(total_stored, 0.5f /* MAX_Area, MtlBlinn.cpp:29; rebuilt if bhrt_params asks for another radius */, c->stream, c->launches, err);
     if (r) return set_err(r, err);
     return BHRT_OK;
 }

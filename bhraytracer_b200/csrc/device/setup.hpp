@@ -56,6 +56,35 @@ inline void sort_lights(std::vector<bhrt_light> &lights, float &all_intensity)
     for (auto &l : lights) all_intensity += gray(ld3(l.intensity));
 }
 
+// SceneView::mesh_nodes: node indices of the first BHRT_MESH_MASK_BITS mesh nodes in DFS order
+inline void fill_mesh_nodes(SceneView &s, const bhrt_node *host_nodes, int n_nodes)
+{
+    int n = 0;
+    for (int i = 0; i < BHRT_MESH_MASK_BITS; i++) s.mesh_nodes[i] = 0;
+    s.n_mesh_nodes = 0;
+    for (int k = 0; k < n_nodes; k++)
+        if (host_nodes[k].kind == BHRT_OBJ_MESH) { if (n < BHRT_MESH_MASK_BITS) s.mesh_nodes[n++] = k; s.n_mesh_nodes++; }
+}
+
+// Point lights in the order BuildCausticPhotonMap uses them (reference Main.cpp:347-361): sorted
+// ascending by Gray() * GetSize(), GetSize() returning int (Lights/lights.h:76); `lights` must be
+// the already intensity-sorted device table.
+inline PhotonEmitCfg photon_emit_cfg(const std::vector<bhrt_light> &lights)
+{
+    PhotonEmitCfg cfg;
+    cfg.n_lights = 0; cfg.sum = 0;
+    for (size_t i = 0; i < lights.size() && cfg.n_lights < BHRT_MAX_LIGHTS; i++)
+        if (lights[i].kind == BHRT_LIGHT_POINT) cfg.light[cfg.n_lights++] = (int)i;
+    auto w = [&](int li) { return gray(ld3(lights[li].intensity)) * (float)(int)lights[li].size; };
+    for (int i = 1; i < cfg.n_lights; i++) {           // insertion sort = std::sort for <= 16 elements
+        int v = cfg.light[i]; int k = i;
+        while (k > 0 && w(v) < w(cfg.light[k - 1])) { cfg.light[k] = cfg.light[k - 1]; k--; }
+        cfg.light[k] = v;
+    }
+    for (int i = 0; i < cfg.n_lights; i++) cfg.sum += w(cfg.light[i]);
+    return cfg;
+}
+
 // Halton(i,2), Halton(i,3) mapped to the elliptical footprint (scene.h:137-146,322-329)
 inline float halton(int index, int base)
 {

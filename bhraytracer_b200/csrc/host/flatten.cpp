@@ -72,6 +72,7 @@ struct Flattener {
         d.refraction[0] = b.refraction.color.r; d.refraction[1] = b.refraction.color.g; d.refraction[2] = b.refraction.color.b;
         d.absorption[0] = b.absorption.r; d.absorption[1] = b.absorption.g; d.absorption[2] = b.absorption.b;
         d.glossiness = b.glossiness;
+        d.refraction_glossiness = b.refractionGlossiness;
         d.ior = b.ior;
         d.flags = flags;
         out.materials.push_back(d);

@@ -91,8 +91,10 @@ typedef struct bhrt_texture {
 enum { BHRT_MTL_MULTI = 1 };   /* flattened from a MultiMtl: sub-material 0 (mtlID is never set, TriObj.cpp:68-189) */
 
 /* reference Materials/materials.h:20-61 (MtlBlinn).  emission / reflection /
- * reflectionGlossiness / refractionGlossiness are parsed by the reference loader but never
- * read by its renderer (MtlBlinn.cpp:89-138), so they are not part of the device table. */
+ * reflectionGlossiness are parsed by the reference loader but never read by its renderer
+ * (MtlBlinn.cpp:89-138), so they are not part of the device table.  refractionGlossiness is
+ * ignored by Shade() too (MtlBlinn.cpp:115-116) but IS used where a caustic photon leaves a
+ * refractive object (MtlBlinn.cpp:236). */
 typedef struct bhrt_material {
     bhrt_texcolor diffuse;
     bhrt_texcolor specular;
@@ -101,6 +103,7 @@ typedef struct bhrt_material {
     float glossiness;
     float ior;
     int32_t flags;
+    float refraction_glossiness;
 } bhrt_material;
 
 enum { BHRT_LIGHT_AMBIENT = 0, BHRT_LIGHT_DIRECT = 1, BHRT_LIGHT_POINT = 2 };

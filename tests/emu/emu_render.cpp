@@ -5,6 +5,9 @@
 //
 // usage: emu_render <scene.xml> <out_prefix> [--det] [--spp N] [--gi N] [--seed S] [--size W H]
 //                   [--rows B E STRIDE] [--samples B E]
+//                   [--emit N FILE]                 emit N caustic photons (unscaled power) into FILE and exit
+//                   [--photons FILE TOTAL K RADIUS] render with the caustic gather term over the
+//                                                   24-byte records of FILE, powers scaled by 1/TOTAL
 // writes <out_prefix>.aov in the layout of oracle/ref_build/driver.cpp and <out_prefix>.acc, the
 // float4 accumulation buffer (r,g,b sums + sample count; zeros outside the rendered share) a
 // GPU rank would hold after bhrt_render_device with the same row / sample share.
@@ -17,6 +20,7 @@
 #include "../../bhraytracer_b200/csrc/device/core.cuh"
 #include "../../bhraytracer_b200/csrc/device/setup.hpp"
 #include "../../bhraytracer_b200/csrc/device/accel.hpp"
+#include "../../bhraytracer_b200/csrc/device/photon_build.hpp"
 #include "../../bhraytracer_b200/csrc/host/scene.hpp"
 
 using namespace bhrt;
@@ -26,6 +30,8 @@ int main(int argc, char **argv)
     if (argc < 3) { fprintf(stderr, "usage: %s scene.xml out_prefix [--det] [--spp N] [--gi N] [--seed S] [--size W H]\n", argv[0]); return 2; }
     int det = 0, spp = 32, gi = 3, W = 0, H = 0;
     int row_b = 0, row_e = 0, row_s = 1, smp_b = 0, smp_e = 0;
+    int emit_n = 0; const char *emit_file = nullptr;
+    const char *photon_file = nullptr; int photon_total = 1, photon_k = 1000; float photon_radius = 0.5f;
     unsigned long long seed = 1;
     for (int a = 3; a < argc; a++) {
         if (!strcmp(argv[a], "--det")) det = 1;
@@ -35,6 +41,8 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[a], "--size") && a + 2 < argc) { W = atoi(argv[++a]); H = atoi(argv[++a]); }
         else if (!strcmp(argv[a], "--rows") && a + 3 < argc) { row_b = atoi(argv[++a]); row_e = atoi(argv[++a]); row_s = atoi(argv[++a]); }
         else if (!strcmp(argv[a], "--samples") && a + 2 < argc) { smp_b = atoi(argv[++a]); smp_e = atoi(argv[++a]); }
+        else if (!strcmp(argv[a], "--emit") && a + 2 < argc) { emit_n = atoi(argv[++a]); emit_file = argv[++a]; }
+        else if (!strcmp(argv[a], "--photons") && a + 4 < argc) { photon_file = argv[++a]; photon_total = atoi(argv[++a]); photon_k = atoi(argv[++a]); photon_radius = (float)atof(argv[++a]); }
         else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
     }
     if (det) spp = 1;
@@ -69,8 +77,47 @@ int main(int argc, char **argv)
     s.all_light_intensity = allI;
     s.cam_pos = fc.cam_pos; s.top_left = fc.top_left; s.dd_x = fc.dd_x; s.dd_y = fc.dd_y;
     s.width = W; s.height = H;
+    fill_mesh_nodes(s, D.nodes, D.n_nodes);
 
+    if (emit_n > 0) {
+        // BuildCausticPhotonMap's serial while loop (reference Main.cpp:363-379) over the same coroutine
+        // the emission kernel runs
+        PhotonEmitCfg ecfg = photon_emit_cfg(lights);
+        if (ecfg.n_lights == 0) { fprintf(stderr, "no point light\n"); return 3; }
+        std::vector<PhotonRecord> recs;
+        unsigned long long rays = 0, paths = 0;
+        PhotonLane P;
+        while ((int)recs.size() < emit_n) {
+            P.rng.seed(seed, paths, 0x50484f54u);
+            paths++;
+            photon_begin(P, s, ecfg, rays);
+            for (;;) {
+                P.hit_ok = scene_trace(s, P.q, P.hit);
+                PhotonRecord r; bool store;
+                bool ended = photon_advance(P, s, r, store, rays);
+                if (store && (int)recs.size() < emit_n) recs.push_back(r);
+                if (ended) break;
+            }
+        }
+        FILE *fp = fopen(emit_file, "wb");
+        if (!fp) return 4;
+        fwrite(recs.data(), sizeof(PhotonRecord), recs.size(), fp);
+        fclose(fp);
+        printf("{\"emu\": true, \"photons\": %d, \"paths\": %llu, \"photon_rays\": %llu}\n", (int)recs.size(), paths, rays);
+        return 0;
+    }
     PhotonGather pg; memset(&pg, 0, sizeof(pg));
+    HostPhotonMap pmap;
+    if (photon_file) {
+        FILE *fp = fopen(photon_file, "rb");
+        if (!fp) { fprintf(stderr, "cannot read %s\n", photon_file); return 3; }
+        std::vector<PhotonRecord> recs;
+        PhotonRecord r;
+        while (fread(&r, sizeof(r), 1, fp) == 1) recs.push_back(r);
+        fclose(fp);
+        build_photon_map_host(recs.data(), (int)recs.size(), photon_total, photon_radius, pmap);
+        pg = pmap.view(photon_k, photon_radius);
+    }
     ShadeCfg cfg; cfg.mode = det ? BHRT_MODE_DET : BHRT_MODE_PATH; cfg.gi_depth = gi; cfg.tir_budget = 16;
     if (row_e == 0) row_e = H;
     if (row_s < 1) row_s = 1;
@@ -86,12 +133,12 @@ int main(int argc, char **argv)
             RayCounters rc; rc.closest = 0; rc.shadow = 0;
             V3 sum(0, 0, 0);
             int id0 = -1; float z0 = BHRT_BIGFLOAT;
-            Lane L;
+            Lane L; LaneStack S;
             for (int sidx = smp_b; sidx < smp_e; sidx++) {
                 L.rng.seed(seed, (uint64_t)j * W + i, sidx);
                 Ray pr = primary_ray(s, i, j, !det, L.rng);
                 int id; float zz;
-                V3 c = trace_sample(L, s, cfg, pg, pr, (float)i / W, (float)j / H, rc, id, zz);
+                V3 c = trace_sample(L, S, s, cfg, pg, pr, (float)i / W, (float)j / H, rc, id, zz);
                 if (sidx == 0) { id0 = id; z0 = zz; }
                 sum = sum + c;
             }

@@ -52,9 +52,38 @@ def sized_scene(name, w, h, tmp):
     return path
 
 
+def sized_scene_keep(path, w, h):
+    import re
+    src = open(path).read()
+    src = re.sub(r'<width value="\d+"/>', '<width value="%d"/>' % w, src)
+    src = re.sub(r'<height value="\d+"/>', '<height value="%d"/>' % h, src)
+    p2 = path + ".small.xml"
+    open(p2, "w").write(src)
+    return p2
+
+
 def run_ref(scene_path, prefix, *args):
     out = subprocess.check_output([REF, scene_path, prefix] + list(args), cwd=ROOT)
     return json.loads(out.decode().strip().splitlines()[-1]), read_aov(prefix + ".aov")
+
+
+# (scene, width, height, photons) D-mode WITH the caustic photon map (bhrt_ref_pm): the fixture keeps
+# the reference's own photons (its .dat: 24-byte records, power already scaled by 1/N) so that the
+# gather can be compared deterministically, plus summary statistics of the emission.
+PHOTON = [("det_caustics", 200, 150, 40000)]
+REF_PM = os.path.join(ROOT, "oracle", "_ref", "bhrt_ref_pm")
+PHOTON_DT = np.dtype([("pos", "<f4", 3), ("power", "<f4"), ("rgb", "u1", 3), ("flag", "u1"), ("dx", "<i2"), ("dy", "<i2")])
+
+
+def photon_stats(rec, scaled_by):
+    """Distribution summary used by the emission tests (positions on the floor, axis histograms, power)."""
+    pos = rec["pos"]
+    floor = rec[np.abs(pos[:, 2]) < 1e-3]
+    h2, _, _ = np.histogram2d(floor["pos"][:, 0], floor["pos"][:, 1], bins=24, range=[[-15, 15], [-30, 20]])
+    ax = [np.histogram(pos[:, a], bins=16, range=(-16, 25))[0] / float(len(rec)) for a in range(3)]
+    return dict(floor_hist=(h2 / max(1, len(rec))).astype(np.float32), axis_hist=np.array(ax, np.float32),
+                floor_frac=len(floor) / float(len(rec)), mean_power=float((rec["power"].astype(np.float64) * scaled_by).mean()),
+                dirz_neg_frac=float(((rec["flag"] & 8) != 0).mean()))
 
 
 def main():
@@ -74,6 +103,30 @@ def main():
             np.savez_compressed(out, hit_id=a["hit_id"].astype(np.int16), rgb8=a["rgb8"], z_bits=a["z"].view(np.uint32),
                                 rays_closest=info["rays_closest"], rays_shadow=info["rays_shadow"], width=w, height=h)
             print("%-28s %dx%d rays %d+%d -> %d bytes" % (name, w, h, info["rays_closest"], info["rays_shadow"], os.path.getsize(out)))
+        for name, w, h, nph in PHOTON:
+            if only and name not in only:
+                continue
+            sp = sized_scene(name, w, h, tmp)
+            try:
+                prefix = os.path.join(tmp, name + "_pm")
+                out = subprocess.check_output([REF_PM, sp, prefix, "--det", "--photons", str(nph), "--seed", "3"], cwd=ROOT)
+                info = json.loads(out.decode().strip().splitlines()[-1])
+                a = read_aov(prefix + ".aov")
+                rec = np.fromfile(prefix + ".photons.dat", dtype=PHOTON_DT)
+                # a larger, independent emission only for the statistics
+                prefix2 = os.path.join(tmp, name + "_pm2")
+                subprocess.check_output([REF_PM, sized_scene_keep(sp, 16, 12), prefix2, "--det", "--photons", "300000", "--seed", "5"], cwd=ROOT)
+                big = np.fromfile(prefix2 + ".photons.dat", dtype=PHOTON_DT)
+            finally:
+                os.remove(sp)
+                if os.path.exists(sp + ".small.xml"):
+                    os.remove(sp + ".small.xml")
+            assert len(rec) == nph
+            st = photon_stats(big, len(big))
+            outp = os.path.join(ROOT, "tests", "golden", name + "_pm.npz")
+            np.savez_compressed(outp, photons=rec.view(np.uint8).reshape(-1, 24), hit_id=a["hit_id"].astype(np.int16), rgb8=a["rgb8"],
+                                width=w, height=h, k=1000, radius=0.5, stats_photons=len(big), **st)
+            print("%-28s %dx%d photon map %d photons -> %d bytes" % (name, w, h, nph, os.path.getsize(outp)))
         for name, w, h, spp, ref_spp in STOCH:
             if only and name not in only:
                 continue

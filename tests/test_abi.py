@@ -49,7 +49,7 @@ def test_struct_sizes_match_the_header(built, tmp_path):
     assert sizes[1] == C.sizeof(b.Params)
     assert sizes[2] == C.sizeof(b.Outputs)
     assert sizes[3] == C.sizeof(b._Node)
-    assert sizes[4:] == [68, 32, 88, 48, 88, 32]
+    assert sizes[4:] == [72, 32, 88, 48, 88, 32]
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="this is the no-GPU behaviour")

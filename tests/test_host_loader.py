@@ -46,7 +46,7 @@ def test_defaults_and_case_insensitive_tags(built, tmp_path):
     assert (d.camera.width, d.camera.height) == (200, 150)
     assert abs(d.camera.fov - 40) < 1e-6
     assert list(d.camera.dir) == [0, 0, -1]
-    mats = (C.c_float * 17).from_address(d.materials)
+    mats = (C.c_float * 18).from_address(d.materials)
     assert np.allclose(list(mats[0:3]), [0.25, 0.5, 0.5])       # diffuse * value
     assert np.allclose(list(mats[4:7]), [0.7, 0.7, 0.7])        # default specular
     assert abs(mats[14] - 20) < 1e-6 and abs(mats[15] - 1) < 1e-6   # glossiness 20, ior 1
