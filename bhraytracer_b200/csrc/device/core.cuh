@@ -21,8 +21,12 @@
 #define BHRT_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define BHRT_HD inline
-#define BHRT_HD_NOINLINE
+#define BHRT_HD_NOINLINE inline
 #endif
+// BHRT_FN: a function kept OUT OF LINE in the kernels.  The estimator calls the samplers, the
+// texture filter and the libm-grade transcendentals from dozens of sites; inlined everywhere the
+// render kernel was 935 KB of SASS and spent most issue slots waiting for instruction fetch.
+#define BHRT_FN BHRT_HD_NOINLINE
 
 namespace bhrt {
 
@@ -63,6 +67,14 @@ BHRT_HD float gray(V3 c) { return (c.x + c.y + c.z) / 3.0f; }     // cyColor.h:8
 BHRT_HD void clamp_white(V3 &c) { if (c.x > 1) c.x = 1.f; if (c.y > 1) c.y = 1.f; if (c.z > 1) c.z = 1.f; }  // MtlBlinn.cpp:79-83
 BHRT_HD bool saturated(V3 c) { return c.x >= 1 && c.y >= 1 && c.z >= 1; }
 BHRT_HD bool is_nan(float v) { return v != v; }
+// one out-of-line copy of each libm-grade transcendental (never --use_fast_math)
+BHRT_FN float m_pow(float a, float b) { return powf(a, b); }
+BHRT_FN float m_sin(float a) { return sinf(a); }
+BHRT_FN float m_cos(float a) { return cosf(a); }
+BHRT_FN float m_tan(float a) { return tanf(a); }
+BHRT_FN float m_acos(float a) { return acosf(a); }
+BHRT_FN float m_asin(float a) { return asinf(a); }
+BHRT_FN float m_atan2(float a, float b) { return atan2f(a, b); }
 
 // Matrix3f * Vec3f (reference cyMatrix.h:297-302), column-major cells
 BHRT_HD V3 mat_mul(const float *m, V3 p)
@@ -415,10 +427,14 @@ BHRT_HD void mesh_trav_begin(MeshTrav &T, const SceneView &s, const MeshAccel &A
     T.done = false;
 }
 
+#ifndef BHRT_TRAV_HOOK
+#define BHRT_TRAV_HOOK(is_leaf, is_shadow)
+#endif
 BHRT_HD void mesh_trav_step(MeshTrav &T)
 {
     bool descend = false;
     const uint32_t cur = T.cur;
+    BHRT_TRAV_HOOK(BHRT_BVH_LEAF(cur), T.any_hit);
     if (BHRT_BVH_LEAF(cur)) {
         uint32_t cnt = BHRT_BVH_COUNT(cur), off = BHRT_BVH_OFFSET(cur);
         if (T.any_hit) {
@@ -606,7 +622,7 @@ struct MeshJob {
     MeshTrav T;
 };
 
-BHRT_HD void mesh_job_begin(MeshJob &J, const SceneView &s, const Query &q, float z, int node, bool front, uint32_t mask)
+BHRT_FN void mesh_job_begin(MeshJob &J, const SceneView &s, const Query &q, float z, int node, bool front, uint32_t mask)
 {
     J.q = q;
     J.h.init();
@@ -667,7 +683,7 @@ BHRT_HD bool scene_trace_meshes(const SceneView &s, const Query &q, Hit &h, uint
 }
 
 // Winner-only part of the closest hit: complete HitInfo in local space, then FromNodeCoords
-BHRT_HD bool scene_trace_finish(const SceneView &s, const Query &q, Hit &h)
+BHRT_FN bool scene_trace_finish(const SceneView &s, const Query &q, Hit &h)
 {
     if (h.node < 0) return false;
     const bhrt_node &nd = s.nodes[h.node];
@@ -678,8 +694,8 @@ BHRT_HD bool scene_trace_finish(const SceneView &s, const Query &q, Hit &h)
         lN = lp;
         V3 d = normalized(lN);
         // 0.5f + atan2(d.y,d.x)/(2*PI): float atan2f promoted to double, PI is a double literal
-        h.uvw.x = (float)(0.5f + atan2f(d.y, d.x) / (2 * BHRT_PI_D));
-        h.uvw.y = (float)(0.5f - asinf(d.z) / (BHRT_PI_D));
+        h.uvw.x = (float)(0.5f + m_atan2(d.y, d.x) / (2 * BHRT_PI_D));
+        h.uvw.y = (float)(0.5f - m_asin(d.z) / (BHRT_PI_D));
         // uvw.z keeps whatever the default-constructed Vec3f held in the reference (uninitialised
         // there; never read by 2-D textures).  We define it as 0.
         h.uvw.z = 0.f;
@@ -693,7 +709,7 @@ BHRT_HD bool scene_trace_finish(const SceneView &s, const Query &q, Hit &h)
         V3 nd_ = normalized(wr.dir);
         float scaled_t = length(t * wr.dir);
         float ndnd = dot(nd_, nd_);
-        float den = powf(ndnd, 1.5f);
+        float den = m_pow(ndnd, 1.5f);
         V3 dDX = (ndnd * s.dd_x - dot(nd_, s.dd_x) * nd_) / den;
         V3 dDY = (ndnd * s.dd_y - dot(nd_, s.dd_y) * nd_) / den;
         float ndN = dot(nd_, lN);
@@ -729,11 +745,16 @@ BHRT_HD bool scene_trace_finish(const SceneView &s, const Query &q, Hit &h)
 }
 
 // All three phases for one ray (CPU harness, photon emission)
+#ifndef BHRT_QUERY_HOOK
+#define BHRT_QUERY_HOOK(kind)
+#endif
 BHRT_HD bool scene_trace(const SceneView &s, const Query &q, Hit &h)
 {
     uint32_t mask;
-    if (scene_trace_graph(s, q, h, mask)) return true;
-    if ((mask || s.n_mesh_nodes > BHRT_MESH_MASK_BITS) && scene_trace_meshes(s, q, h, mask)) return true;
+    if (scene_trace_graph(s, q, h, mask)) { BHRT_QUERY_HOOK(q.kind); return true; }
+    const bool blocked = (mask || s.n_mesh_nodes > BHRT_MESH_MASK_BITS) && scene_trace_meshes(s, q, h, mask);
+    BHRT_QUERY_HOOK(q.kind);
+    if (blocked) return true;
     if (q.kind == Q_SHADOW) return false;
     return scene_trace_finish(s, q, h);
 }
@@ -750,7 +771,7 @@ BHRT_HD V3 tile_clamp(V3 uvw)
 }
 BHRT_HD V3 texel(const uint8_t *p) { return V3(p[0] / 255.0f, p[1] / 255.0f, p[2] / 255.0f); }
 
-BHRT_HD V3 texture_sample(const SceneView &s, const bhrt_texture &t, V3 uvw)
+BHRT_FN V3 texture_sample(const SceneView &s, const bhrt_texture &t, V3 uvw)
 {
     V3 u = tile_clamp(uvw);
     if (t.kind == BHRT_TEX_CHECKER) {
@@ -776,7 +797,7 @@ BHRT_HD V3 texture_sample(const SceneView &s, const bhrt_texture &t, V3 uvw)
 }
 
 // Texture::Sample(uvw, duvw) (scene.h:318-337): 32-tap elliptical Halton filter when duvw != 0
-BHRT_HD V3 texture_sample_filtered(const SceneView &s, const bhrt_texture &t, V3 uvw, V3 d0, V3 d1)
+BHRT_FN V3 texture_sample_filtered(const SceneView &s, const bhrt_texture &t, V3 uvw, V3 d0, V3 d1)
 {
     V3 c = texture_sample(s, t, uvw);
     if (length2(d0) + length2(d1) == 0) return c;
@@ -797,7 +818,7 @@ BHRT_HD V3 texcolor_sample(const SceneView &s, const bhrt_texcolor &tc, V3 uvw)
     return color * texture_sample(s, s.textures[m.texture], xf_to(m.xf, uvw));
 }
 // TexturedColor::Sample(uvw,duvw) (scene.h:411) -> TextureMap::Sample(uvw,duvw) (:372-380)
-BHRT_HD V3 texcolor_sample_filtered(const SceneView &s, V3 color, int texmap, V3 uvw, V3 d0, V3 d1)
+BHRT_FN V3 texcolor_sample_filtered(const SceneView &s, V3 color, int texmap, V3 uvw, V3 d0, V3 d1)
 {
     if (texmap < 0) return color;
     const bhrt_texmap &m = s.texmaps[texmap];
@@ -808,9 +829,9 @@ BHRT_HD V3 texcolor_sample_filtered(const SceneView &s, V3 color, int texmap, V3
     return color * texture_sample_filtered(s, s.textures[m.texture], u, e0, e1);
 }
 // TexturedColor::SampleEnvironment (scene.h:414-420); dir is NOT normalised by the callers
-BHRT_HD V3 sample_environment(const SceneView &s, V3 dir)
+BHRT_FN V3 sample_environment(const SceneView &s, V3 dir)
 {
-    float z = asinf(-dir.z) / 3.14159265358979323846f + 0.5f;
+    float z = m_asin(-dir.z) / 3.14159265358979323846f + 0.5f;
     float x = dir.x / (fabsf(dir.x) + fabsf(dir.y));
     float y = dir.y / (fabsf(dir.x) + fabsf(dir.y));
     V3 uvw = V3(0.5f, 0.5f, 0.0f) + z * (x * V3(0.5f, 0.5f, 0) + y * V3(-0.5f, 0.5f, 0));
@@ -851,7 +872,7 @@ struct Rng {
     }
 };
 
-BHRT_HD float acos_safe(float v) { return acosf(fminr(1.f, fmaxr(-1.f, v))); }   // cyCore.h:193
+BHRT_HD float acos_safe(float v) { return m_acos(fminr(1.f, fmaxr(-1.f, v))); }   // cyCore.h:193
 
 // GetRandomCrossingVector (MtlBlinn.cpp:591-600)
 BHRT_HD V3 random_crossing_vector(V3 v, Rng &rng)
@@ -861,30 +882,30 @@ BHRT_HD V3 random_crossing_vector(V3 v, Rng &rng)
     return r;
 }
 // GetSampleAlongNormal (MtlBlinn.cpp:602-617): uniform disk of radius R at the tip of N
-BHRT_HD V3 sample_along_normal(V3 N, float R, Rng &rng)
+BHRT_FN V3 sample_along_normal(V3 N, float R, Rng &rng)
 {
     float r = rng.rnd01();
     r = sqrtf(r) * R;
     float theta = (float)(rng.rnd01() * 2 * BHRT_PI_D);
-    float x = r * cosf(theta), y = r * sinf(theta);
+    float x = r * m_cos(theta), y = r * m_sin(theta);
     V3 a1 = cross(random_crossing_vector(N, rng), N);
     V3 a2 = cross(a1, N);
     return N + normalized(a1) * x + normalized(a2) * y;
 }
 // GetSampleAlongLightDirection (MtlBlinn.cpp:619-635): Phong lobe about N, unnormalised result
-BHRT_HD V3 sample_along_direction(V3 N, float gloss, float &theta_out, Rng &rng)
+BHRT_FN V3 sample_along_direction(V3 N, float gloss, float &theta_out, Rng &rng)
 {
-    float wt = acos_safe(powf(rng.rnd01(), 1.f / (gloss + 1.f)));
+    float wt = acos_safe(m_pow(rng.rnd01(), 1.f / (gloss + 1.f)));
     theta_out = wt;
-    float R = tanf(wt);
+    float R = m_tan(wt);
     float phi = (float)(rng.rnd01() * 2 * BHRT_PI_D);
-    float x = R * cosf(phi), y = R * sinf(phi);
+    float x = R * m_cos(phi), y = R * m_sin(phi);
     V3 a1 = cross(random_crossing_vector(N, rng), N);
     V3 a2 = cross(a1, N);
     return N + normalized(a1) * x + normalized(a2) * y;
 }
 // GetSampleInSemiSphere (MtlBlinn.cpp:697-716): cosine-weighted hemisphere, retried while N.d <= 0
-BHRT_HD V3 sample_semisphere(V3 N, float &theta_out, Rng &rng)
+BHRT_FN V3 sample_semisphere(V3 N, float &theta_out, Rng &rng)
 {
     for (int guard = 0; guard < 64; guard++) {
         V3 axisY = normalized(cross(N, random_crossing_vector(N, rng)));
@@ -893,8 +914,8 @@ BHRT_HD V3 sample_semisphere(V3 N, float &theta_out, Rng &rng)
         float rnd = rng.rnd01();
         float theta = 0.5f * acos_safe(1 - 2 * rnd);
         theta_out = theta;
-        float st = sinf(theta);
-        V3 ret = st * cosf(phi) * axisX + st * sinf(phi) * axisY + cosf(theta) * N;
+        float st = m_sin(theta);
+        V3 ret = st * m_cos(phi) * axisX + st * m_sin(phi) * axisY + m_cos(theta) * N;
         if (dot(N, ret) > 0) return ret;
     }
     return N;
@@ -938,18 +959,18 @@ BHRT_HD V3 light_direction(const bhrt_light &L, V3 p)
 }
 
 // GetSampleInLight (MtlBlinn.cpp:637-695)
-BHRT_HD V3 sample_in_light(const bhrt_light &L, V3 p, float kd, float ks, float gloss, Rng &rng)
+BHRT_FN V3 sample_in_light(const bhrt_light &L, V3 p, float kd, float ks, float gloss, Rng &rng)
 {
     if (L.kind != BHRT_LIGHT_POINT) return -normalized(light_direction(L, p));
     V3 vL = ld3(L.v) - p;
     float dtheta = 0;
     V3 diffuse_vL = sample_along_direction(normalized(vL), gloss, dtheta, rng);
-    float p_diffuse = powf(cosf(dtheta), gloss);
+    float p_diffuse = m_pow(m_cos(dtheta), gloss);
     if (ks == 0 && kd != 0) return normalized(diffuse_vL);
     float r = rng.rnd01();
     float R = sqrtf(r) * (float)(int)L.size;         // PointLight::GetSize() returns int (lights.h:76)
     float st = (float)(rng.rnd01() * 2 * BHRT_PI_D);
-    float x = R * cosf(st), y = R * sinf(st);
+    float x = R * m_cos(st), y = R * m_sin(st);
     V3 a1 = cross(random_crossing_vector(vL, rng), vL);
     V3 a2 = cross(a1, vL);
     V3 specular_vL = vL + normalized(a1) * x + normalized(a2) * y;
@@ -963,7 +984,7 @@ BHRT_HD V3 sample_in_light(const bhrt_light &L, V3 p, float kd, float ks, float 
 }
 
 // HandleRayWhenRefractionRayOut (MtlBlinn.cpp:543-589)
-BHRT_HD Ray handle_refraction_out(const Ray &inRay, const Hit &ih, float ior, bool &toOut, float rgloss, Rng *rng)
+BHRT_FN Ray handle_refraction_out(const Ray &inRay, const Hit &ih, float ior, bool &toOut, float rgloss, Rng *rng)
 {
     V3 vN = ih.N;
     V3 vV = -inRay.dir;
@@ -1045,7 +1066,7 @@ BHRT_HD V3 pm_power(const GatherRec *rec, float maxpower)
 }
 
 #define BHRT_PM_CAND 48
-BHRT_HD void estimate_irradiance(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction)
+BHRT_FN void estimate_irradiance(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction)
 {
     irrad = V3(0, 0, 0); direction = V3(0, 0, 0);
     if (pg.n_photons <= 0) return;
@@ -1253,18 +1274,18 @@ BHRT_HD void sample_begin(Lane &L, const Ray &primary, RayCounters &rc)
 }
 
 // Blinn BRDF * cos of the direct term (MtlBlinn.cpp:319-327) for light direction vL
-BHRT_HD V3 direct_brdf(const SceneView &s, const Frame &f, const bhrt_material &M, V3 vL)
+BHRT_FN V3 direct_brdf(const SceneView &s, const Frame &f, const bhrt_material &M, V3 vL)
 {
     float cosTheta = dot(vL, f.vN);
     V3 vH = normalized(vL + f.vV);
     V3 kdT = texcolor_sample_filtered(s, ld3(M.diffuse.color), M.diffuse.texmap, f.uvw, f.duvw0, f.duvw1);
     V3 ksT = texcolor_sample_filtered(s, f.newSpec, M.specular.texmap, f.uvw, f.duvw0, f.duvw1);
-    return kdT * cosTheta + ksT * powf(dot(vH, f.vN), M.glossiness);
+    return kdT * cosTheta + ksT * m_pow(dot(vH, f.vN), M.glossiness);
 }
 
 // End of PathTracing_DiffuseNSpecular: the caustic gather term (MtlBlinn.cpp:329-342, only when a
 // photon map is in use), then the clamp / NaN epilogue (MtlBlinn.cpp:343-350,131-136)
-BHRT_HD void direct_finish(const SceneView &s, const PhotonGather &pg, Frame &f, const bhrt_material &M, V3 D)
+BHRT_FN void direct_finish(const SceneView &s, const PhotonGather &pg, Frame &f, const bhrt_material &M, V3 D)
 {
     if (pg.use) {
         V3 irr, vL;
@@ -1274,7 +1295,7 @@ BHRT_HD void direct_finish(const SceneView &s, const PhotonGather &pg, Frame &f,
             V3 vH = normalized(vL + f.vV);
             V3 kdT = texcolor_sample_filtered(s, ld3(M.diffuse.color), M.diffuse.texmap, f.uvw, f.duvw0, f.duvw1);
             V3 ksT = texcolor_sample_filtered(s, f.newSpec, M.specular.texmap, f.uvw, f.duvw0, f.duvw1);
-            V3 brdf = kdT + ksT * powf(dot(vH, f.vN), M.glossiness) / cosTheta;
+            V3 brdf = kdT + ksT * m_pow(dot(vH, f.vN), M.glossiness) / cosTheta;
             D = D + brdf * irr;
         }
     }
@@ -1391,7 +1412,7 @@ BHRT_HD int sample_step(Lane &L, Frame &f, Frame &child, const SceneView &s, con
             if (L.hit_ok) {
                 V3 ab = ld3(M.absorption);
                 float hz = L.hit.z;
-                V3 af(powf(BHRT_EULER, -ab.x * hz), powf(BHRT_EULER, -ab.y * hz), powf(BHRT_EULER, -ab.z * hz));
+                V3 af(m_pow(BHRT_EULER, -ab.x * hz), m_pow(BHRT_EULER, -ab.y * hz), m_pow(BHRT_EULER, -ab.z * hz));
                 f.mult = L.sv * af;
                 if (L.sp < BHRT_MAX_FRAMES) {
                     frame_begin(child, s, nx.p, L.hit, L.si, f.gi - 1);
@@ -1418,12 +1439,12 @@ BHRT_HD int sample_step(Lane &L, Frame &f, Frame &child, const SceneView &s, con
             float ks = fmaxr(fmaxr(f.newSpec.x, f.newSpec.y), f.newSpec.z);
             float dTheta = 0;
             V3 ddir = normalized(sample_semisphere(f.vN, dTheta, rng));
-            float p_d = sinf(2 * dTheta);
+            float p_d = m_sin(2 * dTheta);
             float sTheta = 0;
             float cvn = dot(f.vN, f.vV);
             V3 vR = 2 * cvn * f.vN - f.vV;
             V3 sdir = sample_along_direction(vR, M.glossiness, sTheta, rng);
-            float p_s = powf(cosf(sTheta), M.glossiness);
+            float p_s = m_pow(m_cos(sTheta), M.glossiness);
             float P_d = kd * p_d;
             float P_sum = P_d + ks * p_s;
             float P_dn = P_d / P_sum;
@@ -1599,7 +1620,7 @@ BHRT_HD void photon_begin(PhotonLane &P, const SceneView &s, const PhotonEmitCfg
     float phi = (float)(rng.rnd01() * 2 * BHRT_PI_D);
     float theta = acos_safe(1 - 2 * rng.rnd01());
     Ray r;
-    r.dir = sinf(theta) * (V3(1, 0, 0) * cosf(phi) + V3(0, 1, 0) * sinf(phi)) + V3(0, 0, 1) * cosf(theta);
+    r.dir = m_sin(theta) * (V3(1, 0, 0) * m_cos(phi) + V3(0, 1, 0) * m_sin(phi)) + V3(0, 0, 1) * m_cos(theta);
     r.p = ld3(Lt.v);
     P.c = ld3(Lt.intensity);
     P.first = true;
@@ -1662,12 +1683,12 @@ BHRT_HD bool photon_advance(PhotonLane &P, const SceneView &s, PhotonRecord &rec
     float dTheta = 0;
     V3 ddir = normalized(sample_semisphere(vN, dTheta, rng));
     (void)ddir;
-    float p_d = sinf(2 * dTheta);
+    float p_d = m_sin(2 * dTheta);
     float sTheta = 0;
     float cvn = dot(vN, vV);
     V3 vR = 2 * cvn * vN - vV;
     V3 sdir = sample_along_direction(vR, M.glossiness, sTheta, rng);
-    float p_s = powf(cosf(sTheta), M.glossiness);
+    float p_s = m_pow(m_cos(sTheta), M.glossiness);
     float P_d = kd * p_d;
     float P_sum = P_d + ks * p_s;
     float p_Diff = (P_d / P_sum) * (1 - BHRT_PHOTON_ABSORB) + BHRT_PHOTON_ABSORB;
@@ -1707,7 +1728,7 @@ BHRT_HD uint8_t float_to_byte(float r)
 BHRT_HD V3 gamma_correct(V3 c)
 {
     const float ig = 1 / 2.2f;
-    return V3(powf(c.x, ig), powf(c.y, ig), powf(c.z, ig));
+    return V3(m_pow(c.x, ig), m_pow(c.y, ig), m_pow(c.z, ig));
 }
 
 }  // namespace bhrt

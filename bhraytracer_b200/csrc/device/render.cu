@@ -57,9 +57,11 @@ struct bhrt_ctx {
     int n_materials = 0;
     DevBuf accels, accel_data;
     bool kernel_ready = false;
-    int kernel_smem = 0, trace_blocks = 1, mesh_blocks = 1, finish_blocks = 1, advance_blocks = 1, scatter_blocks = 1;
-    size_t pool_lanes = (size_t)1 << 20;        // live camera samples (2.3 KB of state each)
-    DevBuf lanes, frames, list0, list1, mesh_queue, keys, samples, wave_counters;
+    int kernel_smem = 0, render_blocks = 1;
+    unsigned pool_lanes = 4096;                 // lanes (camera samples in flight) per CTA, 2.3 KB of state each
+    int mesh_budget = WF_MESH_BUDGET;
+    unsigned mesh_batch = 2 * WF_BLOCK;
+    DevBuf lanes, frames, samples, wave_counters;
 };
 
 // sum/spp (Main.cpp:170), gamma (Main.cpp:220-227), Color24 (Main.cpp:230)
@@ -100,7 +102,10 @@ int bhrt_create(int device, bhrt_ctx **out)
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     if (c->counters.ensure(8 * sizeof(unsigned long long))) { delete c; return set_err(BHRT_ERR_CUDA, "cudaMalloc(counters)"); }
-    if (const char *e = getenv("BHRT_POOL_LANES")) { long v = atol(e); if (v >= 1024) c->pool_lanes = (size_t)v; }   // tuning knob
+    // tuning knobs
+    if (const char *e = getenv("BHRT_POOL_LANES")) { long v = atol(e); if (v >= 32 && v <= 32768) c->pool_lanes = (unsigned)v; }
+    if (const char *e = getenv("BHRT_MESH_BUDGET")) { long v = atol(e); if (v >= 1) c->mesh_budget = (int)v; }
+    if (const char *e = getenv("BHRT_MESH_BATCH")) { long v = atol(e); if (v >= 1) c->mesh_batch = (unsigned)v; }
     *out = c;
     return BHRT_OK;
 }
@@ -111,7 +116,7 @@ int bhrt_destroy(bhrt_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = { &c->nodes, &c->materials, &c->lights, &c->texmaps, &c->textures, &c->texels, &c->meshes, &c->mesh_data,
-                       &c->tex_offsets, &c->accels, &c->accel_data, &c->lanes, &c->frames, &c->list0, &c->list1, &c->mesh_queue, &c->keys, &c->samples, &c->wave_counters, &c->accum, &c->hit_id, &c->z, &c->rgb8, &c->linear, &c->counters };
+                       &c->tex_offsets, &c->accels, &c->accel_data, &c->lanes, &c->frames, &c->samples, &c->wave_counters, &c->accum, &c->hit_id, &c->z, &c->rgb8, &c->linear, &c->counters };
     for (auto b : bufs) b->release();
     c->photons.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -242,49 +247,46 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
         }
         a.gather = c->photons.gather_view(p->photon_k > 0 ? p->photon_k : 1000, radius);
     }
-    // shared-memory staging of the small scene tables
-    auto al16 = [](int v) { return (v + 15) & ~15; };
-    a.smem_nodes = 0;
-    a.smem_materials = al16(a.smem_nodes + c->view.n_nodes * (int)sizeof(bhrt_node));
-    a.smem_lights = al16(a.smem_materials + c->view.n_materials * (int)sizeof(bhrt_material));
-    a.smem_offsets = al16(a.smem_lights + c->view.n_lights * (int)sizeof(bhrt_light));
-    const int smem_bytes = al16(a.smem_offsets + 2 * (BHRT_TEX_SAMPLES - 1) * (int)sizeof(float));
-    if (!c->kernel_ready || c->kernel_smem < smem_bytes) {
-        CU(cudaFuncSetAttribute(wf_trace_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        CU(cudaFuncSetAttribute(wf_trace_mesh, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        CU(cudaFuncSetAttribute(wf_step, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        CU(cudaFuncSetAttribute(wf_trace_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        int t_sm = 0, m_sm = 0, a_sm = 0, s_sm = 0, f_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f_sm, wf_trace_finish, WF_BLOCK, smem_bytes));
-        if (f_sm < 1) return set_err(BHRT_ERR_LIMIT, "bhrt_render: scene tables do not fit in shared memory");
-        c->finish_blocks = f_sm;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t_sm, wf_trace_graph, WF_BLOCK, smem_bytes));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m_sm, wf_trace_mesh, WF_BLOCK, smem_bytes));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a_sm, wf_step, WF_BLOCK, smem_bytes));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_sm, wf_scatter, WF_BLOCK, 0));
-        if (t_sm < 1 || m_sm < 1 || a_sm < 1 || s_sm < 1) return set_err(BHRT_ERR_LIMIT, "bhrt_render: scene tables do not fit in shared memory");
-        c->trace_blocks = t_sm; c->mesh_blocks = m_sm; c->advance_blocks = a_sm; c->scatter_blocks = s_sm;
-        c->kernel_smem = smem_bytes;
-        c->kernel_ready = true;
-    }
-    // ---- lane pool and per-chunk sample buffer
+    // ---- lane pools (one per CTA) and the shared-memory layout
     const size_t n_pix_share = (size_t)a.n_pix_work;
     const int n_spp_share = sample_end - sample_begin;
     int chunk = n_spp_share;
     const size_t max_samples = (size_t)1 << 27;                 // 2 GiB of float4 sample colours per chunk
     if (chunk > 0 && n_pix_share * (size_t)chunk > max_samples) chunk = (int)(max_samples / n_pix_share);
     if (chunk < 1) chunk = 1;
-    size_t pool = c->pool_lanes;
-    if (n_pix_share * (size_t)chunk < pool) pool = n_pix_share * (size_t)chunk;
-    if (pool < 1) pool = 1;
-    if (c->lanes.ensure(pool * sizeof(Lane)) || c->frames.ensure(pool * sizeof(Frame) * BHRT_MAX_FRAMES) || c->list0.ensure(pool * 4) || c->list1.ensure(pool * 4) || c->mesh_queue.ensure(pool * 4) || c->keys.ensure(pool) ||
+    a.pool = c->pool_lanes;
+    a.mesh_budget = c->mesh_budget;
+    a.mesh_batch = c->mesh_batch;
+    auto al16 = [](int v) { return (v + 15) & ~15; };
+    a.smem_nodes = 0;
+    a.smem_materials = al16(a.smem_nodes + c->view.n_nodes * (int)sizeof(bhrt_node));
+    a.smem_lights = al16(a.smem_materials + c->view.n_materials * (int)sizeof(bhrt_material));
+    a.smem_offsets = al16(a.smem_lights + c->view.n_lights * (int)sizeof(bhrt_light));
+    a.smem_wave = al16(a.smem_offsets + 2 * (BHRT_TEX_SAMPLES - 1) * (int)sizeof(float));
+    const int smem_bytes = al16(a.smem_wave + wf_wave_smem_bytes(a.pool));
+    if (!c->kernel_ready || c->kernel_smem != smem_bytes) {
+        CU(cudaFuncSetAttribute(wf_render, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_render, WF_BLOCK, smem_bytes));
+        if (per_sm < 1) return set_err(BHRT_ERR_LIMIT, "bhrt_render: scene tables do not fit in shared memory");
+        c->render_blocks = per_sm;
+        c->kernel_smem = smem_bytes;
+        c->kernel_ready = true;
+    }
+    // grid: one resident CTA per slot, but no more CTAs than there is work for their pools
+    unsigned grid = (unsigned)(c->sm_count * c->render_blocks);
+    {
+        const unsigned long long work = (unsigned long long)n_pix_share * (unsigned long long)chunk;
+        const unsigned long long need = (work + a.pool - 1) / a.pool;
+        if (need < grid) grid = need < 1 ? 1u : (unsigned)need;
+    }
+    const size_t lanes_total = (size_t)grid * a.pool;
+    if (c->lanes.ensure(lanes_total * sizeof(Lane)) || c->frames.ensure(lanes_total * sizeof(Frame) * BHRT_MAX_FRAMES) ||
         c->samples.ensure(n_pix_share * (size_t)chunk * sizeof(float4)) || c->wave_counters.ensure(sizeof(WaveCounters)))
         return set_err(BHRT_ERR_CUDA, "cudaMalloc(wavefront buffers) failed");
-    a.lanes = (Lane *)c->lanes.p; a.frames = (Frame *)c->frames.p; a.list[0] = (unsigned *)c->list0.p; a.list[1] = (unsigned *)c->list1.p;
-    a.keys = (unsigned char *)c->keys.p; a.mesh_queue = (unsigned *)c->mesh_queue.p; a.samples = (float4 *)c->samples.p;
+    a.lanes = (Lane *)c->lanes.p; a.frames = (Frame *)c->frames.p; a.samples = (float4 *)c->samples.p;
     a.hit_id = (int *)c->hit_id.p; a.zbuf = (float *)c->z.p;
     a.cnt = (WaveCounters *)c->wave_counters.p;
-    a.pool = (unsigned)pool;
 
     // rows / samples outside this launch's share must read as zero for the multi-GPU sum
     const bool partial_rows = a.n_rows != c->height;
@@ -294,45 +296,19 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
         CU(cudaMemsetAsync(c->hit_id.p, 0, (size_t)c->width * c->height * 4, c->stream));
         CU(cudaMemsetAsync(c->z.p, 0, (size_t)c->width * c->height * 4, c->stream));
     }
-    unsigned long long rays[2] = { 0, 0 };
     CU(cudaEventRecord(c->ev0, c->stream));
-    const unsigned tg = (unsigned)(c->sm_count * c->trace_blocks), mg = (unsigned)(c->sm_count * c->mesh_blocks),
-                   ag = (unsigned)(c->sm_count * c->advance_blocks), sg = (unsigned)(c->sm_count * c->scatter_blocks),
-                   fg = (unsigned)(c->sm_count * c->finish_blocks);
+    CU(cudaMemsetAsync(c->wave_counters.p, 0, sizeof(WaveCounters), c->stream));
     for (int s0 = sample_begin; s0 < sample_end && a.n_rows > 0; s0 += chunk) {
         a.sample_first = s0;
         a.chunk_spp = (sample_end - s0 < chunk) ? (sample_end - s0) : chunk;
         a.n_work = (unsigned long long)a.n_pix_work * (unsigned long long)a.chunk_spp;
-        CU(cudaMemsetAsync(c->wave_counters.p, 0, sizeof(WaveCounters), c->stream));
-        // fill the pool: every lane fetches a camera sample; live list 0 = sorted pool
-        wf_step<<<ag, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a, 1, 1);
-        wf_scatter<<<sg, WF_BLOCK, 0, c->stream>>>(a, 1, 1);
-        c->launches += 2;
-        int parity = 0;
-        for (;;) {
-            const int burst = 16;                                // iterations between live-count checks
-            for (int k = 0; k < burst; k++) {
-                wf_trace_graph<<<tg, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a, parity);
-                wf_trace_mesh<<<mg, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a, parity);
-                wf_trace_finish<<<fg, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a, parity);
-                wf_step<<<ag, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a, parity, 0);
-                wf_scatter<<<sg, WF_BLOCK, 0, c->stream>>>(a, parity, 0);
-                c->launches += 5;
-                parity ^= 1;
-            }
-            CU(cudaGetLastError());
-            unsigned live[2];
-            CU(cudaMemcpyAsync(live, &a.cnt->n_active[0], sizeof(live), cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-            if (live[parity] == 0) break;
-        }
+        CU(cudaMemsetAsync(&((WaveCounters *)c->wave_counters.p)->next_work, 0, sizeof(unsigned long long), c->stream));
+        wf_render<<<grid, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a);
         wf_reduce<<<(a.n_pix_work + 255) / 256, 256, 0, c->stream>>>(c->view, a, (float4 *)c->accum.p, s0 == sample_begin ? 1 : 0);
-        c->launches++;
-        unsigned long long r2[2];
-        CU(cudaMemcpyAsync(r2, &a.cnt->rays_closest, sizeof(r2), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        rays[0] += r2[0]; rays[1] += r2[1];
+        c->launches += 2;
     }
+    unsigned long long rays[2] = { 0, 0 };
+    CU(cudaMemcpyAsync(rays, &((WaveCounters *)c->wave_counters.p)->rays_closest, sizeof(rays), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaStreamSynchronize(c->stream));

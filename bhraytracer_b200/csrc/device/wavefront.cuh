@@ -1,48 +1,50 @@
-// wavefront.cuh -- the headless wavefront renderer that replaces the pixel loop of BeginRender()
+// wavefront.cuh -- the headless renderer that replaces the pixel loop of BeginRender()
 // (reference Main.cpp:204-234: `#pragma omp parallel for` over image columns, PathTracing(i,j)
-// per pixel).
+// per pixel): ONE persistent kernel in which every CTA runs its own small wavefront.
 //
-// Why a wavefront: the estimator (MtlBlinn::Shade, reference MtlBlinn.cpp:89-138) is a clamped
-// recursion tree with nine distinct stages.  Run as one big per-pixel kernel it executed with
-// ~3 of 32 lanes active per issued instruction and spent most issue slots waiting on instruction
-// fetch (profiles/r1a_*, r1b_*: 64 KB of hot code, stall_no_instruction dominant).  Here every
-// camera sample is a LANE whose state (core.cuh `Lane`: query, hit, frame stack, RNG) lives in
-// HBM, and five small kernels advance all live lanes:
+// Why this shape (profiles/r1a..r1d document the three designs tried before it):
+//  * the estimator (MtlBlinn::Shade, reference MtlBlinn.cpp:89-138) is a clamped recursion tree
+//    with nine distinct stages.  One thread per pixel executed it with ~3 of 32 lanes active per
+//    issued instruction and starved on instruction fetch (r1a, r1b);
+//  * a device-wide wavefront (five kernels per iteration over a lane pool in HBM, r1c/r1d) fixed
+//    the divergence but paid a device-wide barrier per iteration: BVH traversal lengths are
+//    heavily skewed (88 % of the rays of config 2 never enter the mesh, 1 % need > 256 node steps,
+//    a few need thousands), so every launch ended in a long, almost empty tail, and the lane
+//    state made five round trips to HBM per ray.
 //
-//   wf_trace_graph  the scene-graph node loop for the lanes that wait for a ray (warp-uniform control
-//                   flow, analytic objects, mesh root boxes); lanes whose ray entered a mesh are
-//                   compacted into a queue (warp-aggregated atomic), the rest are finished;
-//   wf_trace_mesh   BVH traversal for the queued lanes only, persistent lanes with per-lane refill:
-//                   every lane of every warp steps through BVH nodes; closest-hit and shadow
-//                   queries share the stepper (core.cuh mesh_trav_step);
-//   wf_trace_finish winner-only work of the closest hits (uv with atan2/asin, ray differentials,
-//                   normal interpolation, FromNodeCoords);
-//   wf_step         ONE step of the estimator coroutine (sample_step) per live lane, lanes sorted BY
-//                   the step they run, so a warp executes one case of the state machine and a CTA's
-//                   instruction footprint is one or two cases; a lane whose sample finished writes
-//                   the sample colour and immediately starts the next camera sample (regeneration,
-//                   one warp-aggregated atomic per refill), so the pool stays full until the frame
-//                   runs out of samples;
-//   wf_scatter      counting sort of the live lanes by next step into the next live list
-//                   (ray-waiting steps first; dead lanes dropped); warp-aggregated with
-//                   __match_any_sync.
+// Here a CTA owns a private pool of lanes (camera samples in flight; state in global memory, but
+// touched by this CTA only, so it lives in L1/L2) and loops over three phases separated by
+// __syncthreads() -- the only synchronisation there is:
+//
+//   P1 lanes   one pass over the CTA's live lanes, SORTED BY THE STAGE THEY RUN NEXT (a warp
+//              executes one case of the estimator; the whole CTA walks the cases in step, which
+//              keeps its instruction footprint small): complete the pending closest hit
+//              (winner-only transcendental work), run the estimator coroutine up to its next ray,
+//              write finished samples and start the next camera sample (warp-aggregated fetch
+//              from the global work counter), then answer the new ray against the scene graph
+//              (warp-uniform node loop, analytic objects, mesh root boxes).  Rays that entered a
+//              mesh are queued; everything else is already answered.
+//   P2 meshes  BVH traversal of the queued rays.  Each THREAD keeps its traversal (stack
+//              included) across iterations and may spend at most WF_MESH_BUDGET node steps per
+//              iteration, so a ray that needs thousands of steps occupies one thread for many
+//              iterations while its lane simply stays out of the live list -- nobody waits for it.
+//   P3 sort    counting sort of the live lanes by next stage (shared memory).
 //
 // Sample colours go to a per-chunk buffer and are added to the accumulation buffer IN SAMPLE ORDER
 // by wf_reduce, so a pixel's sum is bit-identical whatever the pool size, launch geometry or GPU
-// count (same guarantee the first, per-pixel kernel gave).
+// count.
 #pragma once
 #include <cuda_runtime.h>
 #include "core.cuh"
 
 namespace bhrt {
 
-#define WF_BLOCK 256
+#define WF_BLOCK 512
 #define WF_NKEYS 16
-// Sort keys = the step a lane runs next, ordered so that the lanes that need a ray first come
-// first: [0, n_trace) of the sorted live list is exactly the input of the trace kernels.
+#define WF_MESH_BUDGET 48
+// Sort keys = the step a lane runs next
 enum { WF_KEY_PRIMARY = 0, WF_KEY_REFR_IN = 1, WF_KEY_REFR_OUT = 2, WF_KEY_GI_TRACE = 3, WF_KEY_SHADOW = 4,
-       WF_KEY_REFR = 5, WF_KEY_REFR_RET = 6, WF_KEY_GI = 7, WF_KEY_GI_RET = 8, WF_KEY_DIRECT = 9, WF_KEY_DEAD = 10,
-       WF_N_TRACE_KEYS = 5 };
+       WF_KEY_REFR = 5, WF_KEY_REFR_RET = 6, WF_KEY_GI = 7, WF_KEY_GI_RET = 8, WF_KEY_DIRECT = 9, WF_KEY_DEAD = 10 };
 __device__ __forceinline__ unsigned wf_key_of_stage(int stage)
 {
     // ST_REFR 0, ST_REFR_IN_WAIT 1, ST_REFR_OUT_WAIT 2, ST_REFR_WAIT 3, ST_GI 4, ST_GI_TRACE_WAIT 5, ST_GI_WAIT 6, ST_DIRECT 7, ST_SHADOW_WAIT 8
@@ -54,12 +56,6 @@ struct WaveCounters {
     unsigned long long rays_closest, rays_shadow;
     unsigned long long next_work;           // next camera-sample work item of the chunk
     unsigned long long pad;
-    unsigned n_active[2];                   // live lanes of each parity's list
-    unsigned n_trace[2];                    // ... of which the first n_trace wait for a ray
-    unsigned n_mesh[2];                     // lanes queued for BVH traversal this iteration
-    unsigned mesh_cursor[2];                // ... and how many of them the mesh kernel has taken
-    unsigned key_count[2][WF_NKEYS];
-    unsigned key_cursor[2][WF_NKEYS];
 };
 
 struct WaveArgs {
@@ -71,29 +67,19 @@ struct WaveArgs {
     unsigned n_pix_work;        // tiles * 64 (work items outside the image are skipped)
     unsigned long long n_work;  // n_pix_work * chunk_spp
     PhotonGather gather;
-    Lane *lanes;                // [pool] lane headers
-    Frame *frames;              // [pool][BHRT_MAX_FRAMES] recursion levels
-    unsigned *list[2];          // live lists
-    unsigned *mesh_queue;       // lanes whose ray entered a mesh's root box
-    unsigned char *keys;        // key of live-list slot i after wf_step
+    Lane *lanes;                // [gridDim.x][pool] lane headers
+    Frame *frames;              // [gridDim.x][pool][BHRT_MAX_FRAMES] recursion levels
     float4 *samples;            // [chunk_spp][n_pix_work]
     int *hit_id; float *zbuf;
     WaveCounters *cnt;
-    unsigned pool;              // number of lanes
-    int smem_nodes, smem_materials, smem_lights, smem_offsets;   // byte offsets of the staged tables
+    unsigned pool;              // lanes per CTA (<= 65535)
+    int mesh_budget;            // BVH node steps a thread may run on after the mesh queue drained
+    unsigned mesh_batch;        // queue length that triggers a traversal phase
+    int smem_nodes, smem_materials, smem_lights, smem_offsets, smem_wave;   // byte offsets into dynamic shared memory
 };
 
-// Contiguous, warp-uniform partition of [0,n) over the grid: block b owns one range (so it stays
-// inside one or two sort keys -- one case of the estimator -- and its instruction footprint
-// stays small), every thread of a warp runs the same number of trips.
-struct WfRange { unsigned begin, trips; };
-__device__ __forceinline__ WfRange wf_block_range(unsigned n)
-{
-    unsigned per = (n + gridDim.x - 1) / gridDim.x;
-    per = (per + blockDim.x - 1) / blockDim.x * blockDim.x;
-    WfRange r; r.begin = blockIdx.x * per; r.trips = per / blockDim.x;
-    return r;
-}
+// dynamic shared memory needed by the CTA-local wavefront for `pool` lanes
+static inline int wf_wave_smem_bytes(unsigned pool) { return (int)(pool * 2 /*list*/ + pool * 2 /*mesh queue*/ + pool /*key*/ + pool /*pending*/ + 16); }
 
 // Stage the small, uniformly-read scene tables in shared memory (node table, materials, lights,
 // texture-filter taps) and redirect the view to them.
@@ -115,9 +101,9 @@ __device__ __forceinline__ void stage_tables(SceneView &s, const WaveArgs &a, un
     s.tex_offsets = (const float *)(smem + a.smem_offsets);
 }
 
-// 128-bit copies between a lane's records in HBM and the thread's own copy.  All loads of a record
-// are issued back to back (memory-level parallelism) instead of one dependent scalar load per
-// field; the thread-local copy is interleaved across the warp by the hardware, i.e. coalesced.
+// 128-bit copies between a lane's records in global memory and the thread's own copy.  All loads
+// of a record are issued back to back (memory-level parallelism) instead of one dependent scalar
+// load per field.
 template <typename T>
 __device__ __forceinline__ void wf_load(T &dst, const T *src)
 {
@@ -136,121 +122,6 @@ __device__ __forceinline__ void wf_store(T *dst, const T &src)
     for (int i = 0; i < (int)(sizeof(T) / 16); i++) d4[i] = s4[i];
 }
 
-// ---- wf_trace_graph / wf_trace_mesh / wf_trace_finish ----------------------------------------------
-// Phase 1 of scene_trace for the lanes that wait for a ray: the warp-uniform node loop.  Shadow rays
-// blocked by an analytic object are answered here; lanes whose ray entered a mesh's root box are
-// appended to the mesh queue (warp-aggregated atomic).
-__global__ void __launch_bounds__(WF_BLOCK)
-wf_trace_graph(SceneView s, WaveArgs a, int parity)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    stage_tables(s, a, smem);
-    const unsigned n = a.cnt->n_trace[parity];
-    const unsigned *list = a.list[parity];
-    const unsigned lane = threadIdx.x & 31u;
-    const WfRange R = wf_block_range(n);
-    for (unsigned t = 0; t < R.trips; t++) {
-        const unsigned i = R.begin + t * blockDim.x + threadIdx.x;
-        const bool valid = i < n;
-        bool to_mesh = false;
-        unsigned id = 0;
-        if (valid) {
-            id = list[i];
-            Lane &L = a.lanes[id];
-            Query q;
-            wf_load(q, &L.q);
-            Hit h;
-            uint32_t mask;
-            const bool blocked = scene_trace_graph(s, q, h, mask);
-            L.hit_ok = blocked;
-            L.hit.z = h.z; L.hit.node = h.node; L.hit.front = h.front;
-            L.mesh_mask = 0;
-            if (!blocked && (mask || s.n_mesh_nodes > BHRT_MESH_MASK_BITS)) { L.mesh_mask = mask; to_mesh = true; }
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, to_mesh);
-        if (m) {
-            const int leader = __ffs(m) - 1;
-            unsigned base = 0;
-            if ((int)lane == leader) base = atomicAdd(&a.cnt->n_mesh[parity], (unsigned)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (to_mesh) a.mesh_queue[base + __popc(m & ((1u << lane) - 1u))] = id;
-        }
-    }
-}
-
-// Phase 2: BVH traversal for the queued lanes only.  Persistent lanes with PER-LANE refill: a lane
-// whose traversal finished takes the next queued ray at once (one warp-aggregated atomic per
-// refill) instead of idling until the longest traversal of its warp ends, so the warp keeps ~all
-// lanes stepping through BVH nodes (traversal lengths are heavily skewed: most rays leave the
-// mesh after a few nodes, a few visit hundreds).
-__global__ void __launch_bounds__(WF_BLOCK)
-wf_trace_mesh(SceneView s, WaveArgs a, int parity)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    stage_tables(s, a, smem);
-    const unsigned n = a.cnt->n_mesh[parity];
-    const unsigned lane = threadIdx.x & 31u;
-    MeshJob J;
-    bool have = false, exhausted = false;
-    unsigned id = 0;
-    for (;;) {
-        const bool need = !have && !exhausted;
-        const unsigned nm = __ballot_sync(0xffffffffu, need);
-        if (nm) {
-            const int leader = __ffs(nm) - 1;
-            unsigned base = 0;
-            if ((int)lane == leader) base = atomicAdd(&a.cnt->mesh_cursor[parity], (unsigned)__popc(nm));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (need) {
-                const unsigned i = base + __popc(nm & ((1u << lane) - 1u));
-                if (i >= n) exhausted = true;
-                else {
-                    id = a.mesh_queue[i];
-                    const Lane &L = a.lanes[id];
-                    Query q;
-                    wf_load(q, &L.q);
-                    mesh_job_begin(J, s, q, L.hit.z, L.hit.node, L.hit.front, L.mesh_mask);
-                    have = true;
-                }
-            }
-        }
-        if (!__any_sync(0xffffffffu, have)) {
-            if (!__any_sync(0xffffffffu, !exhausted)) break;
-            continue;
-        }
-        if (have && mesh_job_step(J, s)) {
-            Lane &L = a.lanes[id];
-            if (J.blocked) L.hit_ok = true;
-            else if (J.q.kind == Q_CLOSEST) {
-                L.hit.z = J.h.z; L.hit.node = J.h.node; L.hit.front = J.h.front;
-                L.hit.uvw = J.h.uvw; L.hit.duvw0.x = J.h.duvw0.x;
-            }
-            have = false;
-        }
-    }
-}
-
-// Phase 3: complete the closest hits (winner-only transcendental work, FromNodeCoords)
-__global__ void __launch_bounds__(WF_BLOCK)
-wf_trace_finish(SceneView s, WaveArgs a, int parity)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    stage_tables(s, a, smem);
-    const unsigned n = a.cnt->n_trace[parity];
-    const unsigned *list = a.list[parity];
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        Lane &L = a.lanes[list[i]];
-        Query q;
-        wf_load(q, &L.q);
-        if (q.kind != Q_CLOSEST) continue;
-        Hit h;
-        wf_load(h, &L.hit);
-        L.hit_ok = scene_trace_finish(s, q, h);
-        wf_store(&L.hit, h);
-    }
-}
-
-// ---- wf_step --------------------------------------------------------------------------------------
 // Work item g of the chunk -> (pixel, sample).  Sample-major: consecutive items are the pixels of
 // one 8x8 tile, so the lanes of a warp start on neighbouring primary rays.
 __device__ __forceinline__ bool work_to_pixel(const SceneView &s, const WaveArgs &a, unsigned long long g, int &pi, int &pj, int &sidx)
@@ -265,88 +136,216 @@ __device__ __forceinline__ bool work_to_pixel(const SceneView &s, const WaveArgs
     return true;
 }
 
-// One estimator step per live lane (sample_step): lanes arrive sorted by the step they run, so a
-// warp executes one case.  The lane header and the top frame are copied in with 128-bit loads,
-// stepped in the thread's own copy and written back (plus the child frame when the step
-// recursed).  A finished sample is written out and the lane immediately starts the next camera
-// sample of the chunk (warp-aggregated fetch).  `first` = fill the pool.
-__global__ void __launch_bounds__(WF_BLOCK)
-wf_step(SceneView s, WaveArgs a, int parity, int first)
+// ---- the persistent kernel ------------------------------------------------------------------------
+__global__ void __launch_bounds__(WF_BLOCK, 1)
+wf_render(SceneView s, WaveArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     stage_tables(s, a, smem);
-    const unsigned n = first ? a.pool : a.cnt->n_active[parity];
-    const unsigned *list = a.list[parity];
+    const unsigned P = a.pool;
+    unsigned short *list = (unsigned short *)(smem + a.smem_wave);         // [P] live lanes sorted by key
+    unsigned short *mq = list + P;                                         // [P] mesh queue (ring)
+    unsigned char *lkey = (unsigned char *)(mq + P);                       // [P] key of lane id
+    unsigned char *pend = lkey + P;                                        // [P] lane id is queued / being traversed
+    __shared__ unsigned key_count[WF_NKEYS], key_base[WF_NKEYS];
+    __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s;
+
+    Lane *const lanes = a.lanes + (size_t)blockIdx.x * P;
+    Frame *const frames_all = a.frames + (size_t)blockIdx.x * P * BHRT_MAX_FRAMES;
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
     const bool det = a.cfg.mode == BHRT_MODE_DET;
-    const unsigned lane = threadIdx.x & 31u;
-    // the counters of this parity were consumed by the previous iteration's wf_scatter / trace
-    // kernels and are filled again by the next iteration: clear them here
-    if (!first && blockIdx.x == 0 && threadIdx.x < WF_NKEYS) {
-        a.cnt->key_count[parity][threadIdx.x] = 0; a.cnt->key_cursor[parity][threadIdx.x] = 0;
-        if (threadIdx.x == 0) { a.cnt->n_mesh[parity] = 0; a.cnt->mesh_cursor[parity] = 0; }
-    }
+
+    for (unsigned i = tid; i < P; i += WF_BLOCK) { list[i] = (unsigned short)i; lkey[i] = WF_KEY_DEAD; pend[i] = 0; }
+    if (tid < WF_NKEYS) key_count[tid] = 0;
+    if (tid == 0) { n_live_s = P; n_pending_s = 0; mq_head = 0; mq_tail = 0; }
+    __syncthreads();
+
     RayCounters rc; rc.closest = 0; rc.shadow = 0;
-    const WfRange R = wf_block_range(n);
-    for (unsigned t = 0; t < R.trips; t++) {
-        const unsigned i = R.begin + t * blockDim.x + threadIdx.x;
-        const bool valid = i < n;
-        const unsigned id = valid ? (first ? i : list[i]) : 0u;
-        Lane L;
-        Frame top, child;
-        Frame *frames = a.frames + (size_t)id * BHRT_MAX_FRAMES;
-        bool want_new = valid && first;
-        int sp_in = 0;
-        if (valid && !first) {
-            wf_load(L, &a.lanes[id]);
-            sp_in = L.sp;
-            if (sp_in > 0) wf_load(top, &frames[sp_in - 1]);
-            V3 c;
-            if (sample_step(L, top, child, s, a.cfg, a.gather, L.bgu, L.bgv, rc, c) == STEP_DONE) {
-                a.samples[L.work] = make_float4(c.x, c.y, c.z, 1.f);
-                if (L.sidx == 0) { const size_t p = (size_t)L.pj * s.width + L.pi; a.hit_id[p] = L.hit_id; a.zbuf[p] = L.hit_z; }
-                want_new = true;
-            } else {
-                if (sp_in > 0 && L.sp >= sp_in) wf_store(&frames[sp_in - 1], top);    // (a popped frame is dead)
-                if (L.sp > sp_in) wf_store(&frames[sp_in], child);
+    MeshJob J;                      // this thread's BVH traversal, kept across iterations
+    bool have = false;
+    unsigned jid = 0;
+    bool first = true;
+
+    for (;;) {
+        // ================= P1: one pass over the live lanes =================
+        const unsigned n_live = n_live_s;
+        const unsigned trips = (n_live + WF_BLOCK - 1) / WF_BLOCK;
+        for (unsigned t = 0; t < trips; t++) {
+            const unsigned idx = t * WF_BLOCK + tid;
+            const bool valid = idx < n_live;
+            const unsigned id = valid ? (unsigned)list[idx] : 0u;
+            Lane L;
+            Frame top, par, child;
+            Frame *const frames = frames_all + (size_t)id * BHRT_MAX_FRAMES;
+            bool want_new = valid && first;
+            bool par_valid = false;
+            if (valid && !first) {
+                wf_load(L, &lanes[id]);
+                int sp = L.sp;
+                if (sp > 0) wf_load(top, &frames[sp - 1]);
+                if (sp > 1) { wf_load(par, &frames[sp - 2]); par_valid = true; }
+                // the answer of the pending query: winner-only work of a closest hit
+                if (L.q.kind == Q_CLOSEST) L.hit_ok = scene_trace_finish(s, L.q, L.hit);
+                for (;;) {
+                    V3 c;
+                    const int r = sample_step(L, top, child, s, a.cfg, a.gather, L.bgu, L.bgv, rc, c);
+                    if (r == STEP_RAY) break;
+                    if (r == STEP_DONE) {
+                        a.samples[L.work] = make_float4(c.x, c.y, c.z, 1.f);
+                        if (L.sidx == 0) { const size_t p = (size_t)L.pj * s.width + L.pi; a.hit_id[p] = L.hit_id; a.zbuf[p] = L.hit_z; }
+                        want_new = true;
+                        break;
+                    }
+                    if (L.sp > sp) {                    // recursed: `top` becomes the parent (saved), `child` the top
+                        if (sp > 0) { wf_store(&frames[sp - 1], top); par = top; par_valid = true; }
+                        top = child;
+                    } else if (L.sp < sp) {             // returned: the popped frame is dead
+                        if (par_valid) { top = par; par_valid = false; }
+                        else wf_load(top, &frames[L.sp - 1]);
+                    }
+                    sp = L.sp;
+                }
             }
-        }
-        // ---- regeneration: warp-aggregated fetch of new camera samples
-        bool dead = false;
-        for (;;) {
-            const unsigned m = __ballot_sync(0xffffffffu, want_new);
-            if (!m) break;
-            const int leader = __ffs(m) - 1;
-            unsigned long long base = 0;
-            if ((int)lane == leader) base = atomicAdd(&a.cnt->next_work, (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (want_new) {
-                const unsigned long long g = base + __popc(m & ((1u << lane) - 1u));
-                if (g >= a.n_work) { dead = true; want_new = false; }
-                else {
-                    int pi, pj, sidx;
-                    if (work_to_pixel(s, a, g, pi, pj, sidx)) {
-                        L.work = g; L.pi = pi; L.pj = pj; L.sidx = sidx;
-                        L.bgu = (float)pi / s.width; L.bgv = (float)pj / s.height;
-                        L.rng.seed(a.seed, (uint64_t)pj * s.width + pi, (uint64_t)sidx);
-                        Ray pr = primary_ray(s, pi, pj, !det, L.rng);
-                        sample_begin(L, pr, rc);
-                        want_new = false;
+            // ---- regeneration: warp-aggregated fetch of new camera samples
+            bool dead = false;
+            for (;;) {
+                const unsigned m = __ballot_sync(0xffffffffu, want_new);
+                if (!m) break;
+                const int leader = __ffs(m) - 1;
+                unsigned long long base = 0;
+                if ((int)lane == leader) base = atomicAdd(&a.cnt->next_work, (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (want_new) {
+                    const unsigned long long g = base + __popc(m & ((1u << lane) - 1u));
+                    if (g >= a.n_work) { dead = true; want_new = false; }
+                    else {
+                        int pi, pj, sidx;
+                        if (work_to_pixel(s, a, g, pi, pj, sidx)) {
+                            L.work = g; L.pi = pi; L.pj = pj; L.sidx = sidx;
+                            L.bgu = (float)pi / s.width; L.bgv = (float)pj / s.height;
+                            L.rng.seed(a.seed, (uint64_t)pj * s.width + pi, (uint64_t)sidx);
+                            Ray pr = primary_ray(s, pi, pj, !det, L.rng);
+                            sample_begin(L, pr, rc);
+                            want_new = false;
+                        }
                     }
                 }
             }
+            // ---- the new ray against the scene graph (every surviving lane has one)
+            const bool alive = valid && !dead;
+            bool to_mesh = false;
+            if (alive) {
+                Hit h;
+                uint32_t mask;
+                const bool blocked = scene_trace_graph(s, L.q, h, mask);
+                L.hit_ok = blocked;
+                L.hit.z = h.z; L.hit.node = h.node; L.hit.front = h.front;
+                L.mesh_mask = 0;
+                if (!blocked && (mask || s.n_mesh_nodes > BHRT_MESH_MASK_BITS)) { L.mesh_mask = mask; to_mesh = true; }
+                wf_store(&lanes[id], L);
+                if (L.sp > 0) wf_store(&frames[L.sp - 1], top);
+                lkey[id] = (unsigned char)((L.sp == 0) ? (unsigned)WF_KEY_PRIMARY : wf_key_of_stage(L.stage[L.sp - 1]));
+            } else if (valid) lkey[id] = WF_KEY_DEAD;
+            const unsigned mm = __ballot_sync(0xffffffffu, to_mesh);
+            if (mm) {
+                const int leader = __ffs(mm) - 1;
+                unsigned base = 0;
+                if ((int)lane == leader) { base = atomicAdd(&mq_tail, (unsigned)__popc(mm)); atomicAdd(&n_pending_s, (unsigned)__popc(mm)); }
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (to_mesh) { mq[(base + __popc(mm & ((1u << lane) - 1u))) % P] = (unsigned short)id; pend[id] = 1; }
+            }
         }
-        // ---- key of this slot for the counting sort
-        unsigned key = WF_KEY_DEAD;
-        if (valid && !dead) {
-            key = (L.sp == 0) ? (unsigned)WF_KEY_PRIMARY : wf_key_of_stage(L.stage[L.sp - 1]);
-            wf_store(&a.lanes[id], L);
+        first = false;
+        __syncthreads();
+
+        // P3 first: the lanes that did not go to a mesh are sorted for the next pass; P2 runs only
+        // when it has enough rays to fill the CTA (or the live list has run low), then sorts again
+        for (int round = 0; round < 2; round++) {
+            // ================= P3: counting sort of the live lanes by key =================
+            for (unsigned i0 = 0; i0 < P; i0 += WF_BLOCK) {
+                const unsigned i = i0 + tid;
+                const unsigned k = (i < P && !pend[i]) ? (unsigned)lkey[i] : (unsigned)WF_KEY_DEAD;
+                const bool live = k != WF_KEY_DEAD;
+                const unsigned lm = __ballot_sync(0xffffffffu, live);
+                if (live) {
+                    const unsigned peers = __match_any_sync(lm, k);
+                    if ((int)lane == __ffs(peers) - 1) atomicAdd(&key_count[k], (unsigned)__popc(peers));
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned acc = 0;
+                for (int k = 0; k < WF_NKEYS; k++) { key_base[k] = acc; acc += key_count[k]; key_count[k] = 0; }
+                n_live_s = acc;
+                // decisions every thread must agree on, taken while nobody changes their inputs
+                run_mesh_s = round == 0 && n_pending_s > 0 && (mq_tail - mq_head >= a.mesh_batch || acc < WF_BLOCK);
+                done_s = acc == 0 && n_pending_s == 0;
+            }
+            __syncthreads();
+            for (unsigned i0 = 0; i0 < P; i0 += WF_BLOCK) {
+                const unsigned i = i0 + tid;
+                const unsigned k = (i < P && !pend[i]) ? (unsigned)lkey[i] : (unsigned)WF_KEY_DEAD;
+                const bool live = k != WF_KEY_DEAD;
+                const unsigned lm = __ballot_sync(0xffffffffu, live);
+                if (live) {
+                    const unsigned peers = __match_any_sync(lm, k);
+                    const int leader = __ffs(peers) - 1;
+                    unsigned base = 0;
+                    if ((int)lane == leader) base = atomicAdd(&key_base[k], (unsigned)__popc(peers));
+                    base = __shfl_sync(peers, base, leader);
+                    list[base + __popc(peers & ((1u << lane) - 1u))] = (unsigned short)i;
+                }
+            }
+            __syncthreads();
+            if (!run_mesh_s) break;
+            const unsigned tail = mq_tail;
+
+            // ================= P2: BVH traversal of the queued rays =================
+            // per-lane refill while the queue lasts, then at most `mesh_budget` more steps: what
+            // is still running after that stays in its thread until the next traversal phase
+            int budget = a.mesh_budget;
+            for (;;) {
+                const bool need = !have;
+                const unsigned nm = __ballot_sync(0xffffffffu, need);
+                unsigned head = 0;
+                if (lane == 0) head = *(volatile unsigned *)&mq_head;
+                head = __shfl_sync(0xffffffffu, head, 0);
+                const bool drained = head >= tail;
+                if (nm && !drained) {
+                    const int leader = __ffs(nm) - 1;
+                    unsigned base = 0;
+                    if ((int)lane == leader) base = atomicAdd(&mq_head, (unsigned)__popc(nm));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (need) {
+                        const unsigned i = base + __popc(nm & ((1u << lane) - 1u));
+                        if (i < tail) {
+                            jid = mq[i % P];
+                            const Lane &Lg = lanes[jid];
+                            Query q;
+                            wf_load(q, &Lg.q);
+                            mesh_job_begin(J, s, q, Lg.hit.z, Lg.hit.node, Lg.hit.front, Lg.mesh_mask);
+                            have = true;
+                        }
+                    }
+                }
+                if (!__any_sync(0xffffffffu, have)) break;
+                if (have && mesh_job_step(J, s)) {
+                    Lane &Lg = lanes[jid];
+                    if (J.blocked) Lg.hit_ok = true;
+                    else if (J.q.kind == Q_CLOSEST) {
+                        Lg.hit.z = J.h.z; Lg.hit.node = J.h.node; Lg.hit.front = J.h.front;
+                        Lg.hit.uvw = J.h.uvw; Lg.hit.duvw0.x = J.h.duvw0.x;
+                    }
+                    pend[jid] = 0;
+                    atomicSub(&n_pending_s, 1u);
+                    have = false;
+                }
+                if (drained && --budget <= 0) break;
+            }
+            __syncthreads();
+            if (tid == 0 && mq_head > mq_tail) mq_head = mq_tail;       // over-claimed pops of an empty queue
         }
-        if (valid) a.keys[i] = (unsigned char)key;
-        const unsigned vm = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const unsigned peers = __match_any_sync(vm, key);
-            if ((int)lane == __ffs(peers) - 1) atomicAdd(&a.cnt->key_count[parity ^ 1][key], (unsigned)__popc(peers));
-        }
+        if (done_s) break;
     }
     unsigned long long c0 = rc.closest, c1 = rc.shadow;
     for (int o = 16; o > 0; o >>= 1) {
@@ -354,42 +353,6 @@ wf_step(SceneView s, WaveArgs a, int parity, int first)
         c1 += __shfl_down_sync(0xffffffffu, c1, o);
     }
     if (lane == 0 && (c0 | c1)) { atomicAdd(&a.cnt->rays_closest, c0); atomicAdd(&a.cnt->rays_shadow, c1); }
-}
-
-// ---- wf_scatter -----------------------------------------------------------------------------------
-// Counting sort of the slots of list[parity] (keys[] from wf_advance) into list[parity^1]; dead
-// lanes are dropped.  Also publishes n_active[parity^1].
-__global__ void __launch_bounds__(WF_BLOCK)
-wf_scatter(WaveArgs a, int parity, int first)
-{
-    const unsigned n = first ? a.pool : a.cnt->n_active[parity];
-    const unsigned *list = a.list[parity];
-    unsigned *out = a.list[parity ^ 1];
-    const unsigned *count = a.cnt->key_count[parity ^ 1];
-    unsigned *cursor = a.cnt->key_cursor[parity ^ 1];
-    __shared__ unsigned offs[WF_NKEYS];
-    if (threadIdx.x == 0) {
-        unsigned acc = 0, ntr = 0;
-        for (int k = 0; k < WF_NKEYS; k++) { offs[k] = acc; if (k != WF_KEY_DEAD) acc += count[k]; if (k == WF_N_TRACE_KEYS - 1) ntr = acc; }
-        if (blockIdx.x == 0) { a.cnt->n_active[parity ^ 1] = acc; a.cnt->n_trace[parity ^ 1] = ntr; }
-    }
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned n_round = (n + 31u) & ~31u;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        const bool valid = i < n;
-        const unsigned key = valid ? a.keys[i] : (unsigned)WF_KEY_DEAD;
-        const bool live = valid && key != WF_KEY_DEAD;
-        const unsigned lm = __ballot_sync(0xffffffffu, live);
-        if (live) {
-            const unsigned peers = __match_any_sync(lm, key);
-            const int leader = __ffs(peers) - 1;
-            unsigned base = 0;
-            if ((int)lane == leader) base = atomicAdd(&cursor[key], (unsigned)__popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            out[offs[key] + base + __popc(peers & ((1u << lane) - 1u))] = first ? i : list[i];
-        }
-    }
 }
 
 // ---- wf_reduce ------------------------------------------------------------------------------------

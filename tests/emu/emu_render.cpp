@@ -17,6 +17,28 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#ifdef BHRT_EMU_STATS
+static thread_local unsigned long long g_trav[4];
+#define BHRT_TRAV_HOOK(is_leaf, is_shadow) g_trav[((is_shadow) ? 2 : 0) + ((is_leaf) ? 1 : 0)]++
+// per-query histogram of BVH steps (log2 buckets), [kind-1][bucket]; merged at exit
+static unsigned long long g_hist[2][24], g_sum[2][2], g_nq[2];
+static inline void emu_query_done(int kind)
+{
+    const int k = kind - 1;
+    unsigned long long n = g_trav[2 * k] + g_trav[2 * k + 1];
+    int b = 0; while ((1ull << b) <= n && b < 23) b++;
+#pragma omp atomic
+    g_hist[k][b]++;
+#pragma omp atomic
+    g_sum[k][0] += g_trav[2 * k];
+#pragma omp atomic
+    g_sum[k][1] += g_trav[2 * k + 1];
+#pragma omp atomic
+    g_nq[k]++;
+    g_trav[0] = g_trav[1] = g_trav[2] = g_trav[3] = 0;
+}
+#define BHRT_QUERY_HOOK(kind) emu_query_done(kind)
+#endif
 #include "../../bhraytracer_b200/csrc/device/core.cuh"
 #include "../../bhraytracer_b200/csrc/device/setup.hpp"
 #include "../../bhraytracer_b200/csrc/device/accel.hpp"
@@ -153,6 +175,14 @@ int main(int argc, char **argv)
         }
     }
     double ms = (omp_get_wtime() - t0) * 1e3;
+#ifdef BHRT_EMU_STATS
+    for (int k = 0; k < 2; k++) {
+        fprintf(stderr, "%s queries %llu  internal steps %.2f  leaf steps %.2f per query\n  hist(steps < 2^b):", k ? "shadow" : "closest", g_nq[k],
+                (double)g_sum[k][0] / g_nq[k], (double)g_sum[k][1] / g_nq[k]);
+        for (int b = 0; b < 24; b++) fprintf(stderr, " %llu", g_hist[k][b]);
+        fprintf(stderr, "\n");
+    }
+#endif
     std::string path = std::string(argv[2]) + ".aov";
     FILE *fp = fopen(path.c_str(), "wb");
     if (!fp) return 4;
