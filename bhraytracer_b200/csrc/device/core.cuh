@@ -430,36 +430,9 @@ BHRT_HD void mesh_trav_begin(MeshTrav &T, const SceneView &s, const MeshAccel &A
 #ifndef BHRT_TRAV_HOOK
 #define BHRT_TRAV_HOOK(is_leaf, is_shadow)
 #endif
-BHRT_HD void mesh_trav_step(MeshTrav &T)
+// after a leaf, or an internal node neither of whose boxes was hit: resume at the deferred child
+BHRT_HD void mesh_trav_pop(MeshTrav &T)
 {
-    bool descend = false;
-    const uint32_t cur = T.cur;
-    BHRT_TRAV_HOOK(BHRT_BVH_LEAF(cur), T.any_hit);
-    if (BHRT_BVH_LEAF(cur)) {
-        uint32_t cnt = BHRT_BVH_COUNT(cur), off = BHRT_BVH_OFFSET(cur);
-        if (T.any_hit) {
-            float lz = BHRT_BIGFLOAT; bool lf; MeshHit lm;
-            bool any = false;
-            for (uint32_t i = 0; i < cnt; i++)
-                if (intersect_trirec(T.tris + off + i, T.ray, T.len_dir, lz, lf, HIT_FRONT, lm)) any = true;
-            if (any) { T.result = lz > BHRT_BIAS && lz < T.t_max_shadow; T.done = true; return; }
-        } else {
-            for (uint32_t i = 0; i < cnt; i++)
-                if (intersect_trirec(T.tris + off + i, T.ray, T.len_dir, T.z, T.front, T.hitSide, T.mh)) T.hits++;
-        }
-    } else {
-        bool h1, h2; float t1, t2; uint32_t w1, w2;
-        intersect_pair(T.pairs + cur, T.ray, T.any_hit ? BHRT_BIGFLOAT : T.z, h1, t1, h2, t2, w1, w2);
-        if (h1 || h2) {
-            uint32_t first, second; float tsecond;
-            if (T.any_hit || t1 < t2) { first = w1; second = w2; tsecond = t2; }
-            else { first = w2; second = w1; tsecond = t1; }
-            if (T.sp < BHRT_BVH_STACK) { T.st_word[T.sp] = second; T.st_tmin[T.sp] = tsecond; T.st_hits[T.sp] = T.hits; T.sp++; }
-            T.cur = first;
-            descend = true;
-        }
-    }
-    if (descend) return;
     while (T.sp > 0) {
         T.sp--;
         if (!T.any_hit) {
@@ -471,6 +444,44 @@ BHRT_HD void mesh_trav_step(MeshTrav &T)
     }
     T.result = T.hits > 0;
     T.done = true;
+}
+// T.cur is an internal node: both child boxes, near child first
+BHRT_HD void mesh_trav_internal(MeshTrav &T)
+{
+    BHRT_TRAV_HOOK(false, T.any_hit);
+    bool h1, h2; float t1, t2; uint32_t w1, w2;
+    intersect_pair(T.pairs + T.cur, T.ray, T.any_hit ? BHRT_BIGFLOAT : T.z, h1, t1, h2, t2, w1, w2);
+    if (h1 || h2) {
+        uint32_t first, second; float tsecond;
+        if (T.any_hit || t1 < t2) { first = w1; second = w2; tsecond = t2; }
+        else { first = w2; second = w1; tsecond = t1; }
+        if (T.sp < BHRT_BVH_STACK) { T.st_word[T.sp] = second; T.st_tmin[T.sp] = tsecond; T.st_hits[T.sp] = T.hits; T.sp++; }
+        T.cur = first;
+        return;
+    }
+    mesh_trav_pop(T);
+}
+// T.cur is a leaf: its triangles
+BHRT_HD void mesh_trav_leaf(MeshTrav &T)
+{
+    BHRT_TRAV_HOOK(true, T.any_hit);
+    const uint32_t cur = T.cur;
+    const uint32_t cnt = BHRT_BVH_COUNT(cur), off = BHRT_BVH_OFFSET(cur);
+    if (T.any_hit) {
+        float lz = BHRT_BIGFLOAT; bool lf; MeshHit lm;
+        bool any = false;
+        for (uint32_t i = 0; i < cnt; i++)
+            if (intersect_trirec(T.tris + off + i, T.ray, T.len_dir, lz, lf, HIT_FRONT, lm)) any = true;
+        if (any) { T.result = lz > BHRT_BIAS && lz < T.t_max_shadow; T.done = true; return; }
+    } else {
+        for (uint32_t i = 0; i < cnt; i++)
+            if (intersect_trirec(T.tris + off + i, T.ray, T.len_dir, T.z, T.front, T.hitSide, T.mh)) T.hits++;
+    }
+    mesh_trav_pop(T);
+}
+BHRT_HD void mesh_trav_step(MeshTrav &T)
+{
+    if (BHRT_BVH_LEAF(T.cur)) mesh_trav_leaf(T); else mesh_trav_internal(T);
 }
 
 BHRT_HD bool mesh_trace(const SceneView &s, const MeshAccel &A, const Ray &ray, bool any_hit, float t_max_shadow,
@@ -622,7 +633,7 @@ struct MeshJob {
     MeshTrav T;
 };
 
-BHRT_FN void mesh_job_begin(MeshJob &J, const SceneView &s, const Query &q, float z, int node, bool front, uint32_t mask)
+BHRT_HD void mesh_job_begin(MeshJob &J, const SceneView &s, const Query &q, float z, int node, bool front, uint32_t mask)
 {
     J.q = q;
     J.h.init();
@@ -634,41 +645,51 @@ BHRT_FN void mesh_job_begin(MeshJob &J, const SceneView &s, const Query &q, floa
     J.in_trav = false; J.blocked = false; J.strict = false; J.k = -1;
 }
 
-// returns true when the job is finished
-BHRT_HD bool mesh_job_step(MeshJob &J, const SceneView &s)
+// Pick the next mesh node the ray has to visit and start its traversal (root box included).
+// false = no mesh node left: the job is finished.
+BHRT_HD bool mesh_job_next(MeshJob &J, const SceneView &s)
 {
     const bool shadow = (J.q.kind == Q_SHADOW);
-    if (!J.in_trav) {
-        int k;
-        if (J.mask) {
-            int bit = 0;
-            while (!((J.mask >> bit) & 1u)) bit++;
-            J.mask &= J.mask - 1u;
-            k = s.mesh_nodes[bit];
-        } else {
-            while (J.extra < s.n_nodes && s.nodes[J.extra].kind != BHRT_OBJ_MESH) J.extra++;
-            if (J.extra >= s.n_nodes) return true;
-            k = J.extra++;
-        }
-        J.k = k;
-        const bhrt_node &nd = s.nodes[k];
-        Ray r = node_local_ray(s, k, J.q.ray);
-        if (shadow) mesh_trav_begin(J.T, s, s.accels[nd.mesh], r, true, J.q.t_max, BHRT_BIGFLOAT, true, J.q.hitSide);
-        else {
-            // an equal-t candidate of an EARLIER node loses against the current winner
-            J.strict = J.h.node > k;
-            mesh_trav_begin(J.T, s, s.accels[nd.mesh], r, false, 0.f, J.strict ? prev_float(J.h.z) : J.h.z, J.h.front, J.q.hitSide);
-        }
-        J.in_trav = true;
-    } else mesh_trav_step(J.T);
-    if (J.T.done) {
-        J.in_trav = false;
-        if (J.T.result) {
-            if (shadow) { J.blocked = true; return true; }
-            J.h.z = J.T.z; J.h.front = J.T.front; J.h.node = J.k;
-            J.h.uvw = V3(J.T.mh.a0, J.T.mh.a1, J.T.mh.a2); J.h.duvw0.x = u2f(J.T.mh.face);
-        }
+    int k;
+    if (J.mask) {
+        int bit = 0;
+        while (!((J.mask >> bit) & 1u)) bit++;
+        J.mask &= J.mask - 1u;
+        k = s.mesh_nodes[bit];
+    } else {
+        while (J.extra < s.n_nodes && s.nodes[J.extra].kind != BHRT_OBJ_MESH) J.extra++;
+        if (J.extra >= s.n_nodes) return false;
+        k = J.extra++;
     }
+    J.k = k;
+    const bhrt_node &nd = s.nodes[k];
+    Ray r = node_local_ray(s, k, J.q.ray);
+    if (shadow) mesh_trav_begin(J.T, s, s.accels[nd.mesh], r, true, J.q.t_max, BHRT_BIGFLOAT, true, J.q.hitSide);
+    else {
+        // an equal-t candidate of an EARLIER node loses against the current winner
+        J.strict = J.h.node > k;
+        mesh_trav_begin(J.T, s, s.accels[nd.mesh], r, false, 0.f, J.strict ? prev_float(J.h.z) : J.h.z, J.h.front, J.q.hitSide);
+    }
+    J.in_trav = true;
+    return true;
+}
+// Collect a finished traversal (J.T.done).  true = the job is finished (shadow ray blocked).
+BHRT_HD bool mesh_job_harvest(MeshJob &J)
+{
+    J.in_trav = false;
+    if (J.T.result) {
+        if (J.q.kind == Q_SHADOW) { J.blocked = true; return true; }
+        J.h.z = J.T.z; J.h.front = J.T.front; J.h.node = J.k;
+        J.h.uvw = V3(J.T.mh.a0, J.T.mh.a1, J.T.mh.a2); J.h.duvw0.x = u2f(J.T.mh.face);
+    }
+    return false;
+}
+// one action per call; returns true when the job is finished
+BHRT_HD bool mesh_job_step(MeshJob &J, const SceneView &s)
+{
+    if (!J.in_trav) { if (!mesh_job_next(J, s)) return true; }
+    else mesh_trav_step(J.T);
+    if (J.T.done) return mesh_job_harvest(J);
     return false;
 }
 
@@ -689,7 +710,15 @@ BHRT_FN bool scene_trace_finish(const SceneView &s, const Query &q, Hit &h)
     const bhrt_node &nd = s.nodes[h.node];
     const Ray wr = node_local_ray(s, h.node, q.ray);
     V3 lp, lN;
-    if (nd.kind == BHRT_OBJ_SPHERE) {
+    // uvw / duvw are read by texture lookups only (scene.h:371-380): an untextured material never
+    // looks at them, so the atan2/asin/pow work is skipped there (they are defined as 0)
+    const bhrt_material &hm = s.materials[nd.material];
+    const bool textured = hm.diffuse.texmap >= 0 || hm.specular.texmap >= 0;
+    if (!textured && nd.kind != BHRT_OBJ_MESH) {
+        lp = wr.p + h.z * wr.dir;
+        lN = nd.kind == BHRT_OBJ_SPHERE ? lp : V3(0, 0, 1);
+        h.uvw = V3(0, 0, 0); h.duvw0 = V3(0, 0, 0); h.duvw1 = V3(0, 0, 0);
+    } else if (nd.kind == BHRT_OBJ_SPHERE) {
         lp = wr.p + h.z * wr.dir;                           // Sphere.cpp:52-54
         lN = lp;
         V3 d = normalized(lN);

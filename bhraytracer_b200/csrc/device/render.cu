@@ -58,9 +58,9 @@ struct bhrt_ctx {
     DevBuf accels, accel_data;
     bool kernel_ready = false;
     int kernel_smem = 0, render_blocks = 1;
-    unsigned pool_lanes = 4096;                 // lanes (camera samples in flight) per CTA, 2.3 KB of state each
+    unsigned pool_lanes = 2048;                 // lanes (camera samples in flight) per CTA, 2.3 KB of state each
     int mesh_budget = WF_MESH_BUDGET;
-    unsigned mesh_batch = 2 * WF_BLOCK;
+    unsigned mesh_batch = WF_BLOCK;
     DevBuf lanes, frames, samples, wave_counters;
 };
 
@@ -254,7 +254,7 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     const size_t max_samples = (size_t)1 << 27;                 // 2 GiB of float4 sample colours per chunk
     if (chunk > 0 && n_pix_share * (size_t)chunk > max_samples) chunk = (int)(max_samples / n_pix_share);
     if (chunk < 1) chunk = 1;
-    a.pool = c->pool_lanes;
+    a.pool = (c->pool_lanes + 31u) & ~31u;
     a.mesh_budget = c->mesh_budget;
     a.mesh_batch = c->mesh_batch;
     auto al16 = [](int v) { return (v + 15) & ~15; };
@@ -313,6 +313,13 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->rendered_spp = n_spp_share;
+    if (getenv("BHRT_DEBUG")) {
+        WaveCounters h;
+        CU(cudaMemcpy(&h, c->wave_counters.p, sizeof(h), cudaMemcpyDeviceToHost));
+        const double tot = (double)(h.prof[0] + h.prof[1] + h.prof[2]);
+        fprintf(stderr, "[bhrt] grid %u pool %u: lanes pass %.1f%%  sort %.1f%%  traversal %.1f%%  | %.0f iterations, %.0f kcycles per CTA\n", grid, a.pool,
+                100.0 * h.prof[0] / tot, 100.0 * h.prof[1] / tot, 100.0 * h.prof[2] / tot, (double)h.prof[3] / grid, tot / grid / 1e3);
+    }
     if (out) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));

@@ -39,9 +39,9 @@
 
 namespace bhrt {
 
-#define WF_BLOCK 512
+#define WF_BLOCK 1024
 #define WF_NKEYS 16
-#define WF_MESH_BUDGET 48
+#define WF_MESH_BUDGET 4
 // Sort keys = the step a lane runs next
 enum { WF_KEY_PRIMARY = 0, WF_KEY_REFR_IN = 1, WF_KEY_REFR_OUT = 2, WF_KEY_GI_TRACE = 3, WF_KEY_SHADOW = 4,
        WF_KEY_REFR = 5, WF_KEY_REFR_RET = 6, WF_KEY_GI = 7, WF_KEY_GI_RET = 8, WF_KEY_DIRECT = 9, WF_KEY_DEAD = 10 };
@@ -56,6 +56,8 @@ struct WaveCounters {
     unsigned long long rays_closest, rays_shadow;
     unsigned long long next_work;           // next camera-sample work item of the chunk
     unsigned long long pad;
+    // clock64() cycles summed over the CTAs (warp 0): lanes pass, sort, BVH traversal; iterations, traversal phases
+    unsigned long long prof[6];
 };
 
 struct WaveArgs {
@@ -73,13 +75,13 @@ struct WaveArgs {
     int *hit_id; float *zbuf;
     WaveCounters *cnt;
     unsigned pool;              // lanes per CTA (<= 65535)
-    int mesh_budget;            // BVH node steps a thread may run on after the mesh queue drained
-    unsigned mesh_batch;        // queue length that triggers a traversal phase
+    int mesh_budget;            // traversal trips a thread may still run after the last warp left the lanes pass
+    unsigned mesh_batch;        // queued rays that switch the traversal phase on
     int smem_nodes, smem_materials, smem_lights, smem_offsets, smem_wave;   // byte offsets into dynamic shared memory
 };
 
 // dynamic shared memory needed by the CTA-local wavefront for `pool` lanes
-static inline int wf_wave_smem_bytes(unsigned pool) { return (int)(pool * 2 /*list*/ + pool * 2 /*mesh queue*/ + pool /*key*/ + pool /*pending*/ + 16); }
+static inline int wf_wave_smem_bytes(unsigned pool) { return (int)(pool * 2 /*list*/ + pool * 2 /*mesh queue*/ + pool /*key*/ + pool /*pending*/ + (pool / 32 + 1) * WF_NKEYS * 2 /*group counts*/ + 16); }
 
 // Stage the small, uniformly-read scene tables in shared memory (node table, materials, lights,
 // texture-filter taps) and redirect the view to them.
@@ -147,8 +149,9 @@ wf_render(SceneView s, WaveArgs a)
     unsigned short *mq = list + P;                                         // [P] mesh queue (ring)
     unsigned char *lkey = (unsigned char *)(mq + P);                       // [P] key of lane id
     unsigned char *pend = lkey + P;                                        // [P] lane id is queued / being traversed
+    unsigned short *gcount = (unsigned short *)(pend + P);                 // [P/32][WF_NKEYS] per-group key counts / offsets (P is a multiple of 32)
     __shared__ unsigned key_count[WF_NKEYS], key_base[WF_NKEYS];
-    __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s;
+    __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor;
 
     Lane *const lanes = a.lanes + (size_t)blockIdx.x * P;
     Frame *const frames_all = a.frames + (size_t)blockIdx.x * P * BHRT_MAX_FRAMES;
@@ -157,7 +160,7 @@ wf_render(SceneView s, WaveArgs a)
 
     for (unsigned i = tid; i < P; i += WF_BLOCK) { list[i] = (unsigned short)i; lkey[i] = WF_KEY_DEAD; pend[i] = 0; }
     if (tid < WF_NKEYS) key_count[tid] = 0;
-    if (tid == 0) { n_live_s = P; n_pending_s = 0; mq_head = 0; mq_tail = 0; }
+    if (tid == 0) { n_live_s = P; n_pending_s = 0; mq_head = 0; mq_tail = 0; p1_cursor = 0; run_mesh_s = 0; done_s = 0; }
     __syncthreads();
 
     RayCounters rc; rc.closest = 0; rc.shadow = 0;
@@ -166,12 +169,20 @@ wf_render(SceneView s, WaveArgs a)
     unsigned jid = 0;
     bool first = true;
 
+    long long t_p1 = 0, t_sort = 0, t_mesh = 0, n_iter = 0;
     for (;;) {
+        const long long c_begin = clock64();
+        n_iter++;
         // ================= P1: one pass over the live lanes =================
+        // Warps take 32-lane chunks of the sorted list in order (shared cursor): the CTA walks the
+        // stages together and no warp waits at the barrier for a slower one's fixed share.
         const unsigned n_live = n_live_s;
-        const unsigned trips = (n_live + WF_BLOCK - 1) / WF_BLOCK;
-        for (unsigned t = 0; t < trips; t++) {
-            const unsigned idx = t * WF_BLOCK + tid;
+        for (;;) {
+            unsigned chunk = 0;
+            if (lane == 0) chunk = atomicAdd(&p1_cursor, 32u);
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+            if (chunk >= n_live) break;
+            const unsigned idx = chunk + lane;
             const bool valid = idx < n_live;
             const unsigned id = valid ? (unsigned)list[idx] : 0u;
             Lane L;
@@ -179,32 +190,43 @@ wf_render(SceneView s, WaveArgs a)
             Frame *const frames = frames_all + (size_t)id * BHRT_MAX_FRAMES;
             bool want_new = valid && first;
             bool par_valid = false;
-            if (valid && !first) {
+            bool running = valid && !first;
+            int sp = 0;
+            if (running) {
                 wf_load(L, &lanes[id]);
-                int sp = L.sp;
+                sp = L.sp;
                 if (sp > 0) wf_load(top, &frames[sp - 1]);
                 if (sp > 1) { wf_load(par, &frames[sp - 2]); par_valid = true; }
                 // the answer of the pending query: winner-only work of a closest hit
                 if (L.q.kind == Q_CLOSEST) L.hit_ok = scene_trace_finish(s, L.q, L.hit);
-                for (;;) {
-                    V3 c;
-                    const int r = sample_step(L, top, child, s, a.cfg, a.gather, L.bgu, L.bgv, rc, c);
-                    if (r == STEP_RAY) break;
-                    if (r == STEP_DONE) {
-                        a.samples[L.work] = make_float4(c.x, c.y, c.z, 1.f);
-                        if (L.sidx == 0) { const size_t p = (size_t)L.pj * s.width + L.pi; a.hit_id[p] = L.hit_id; a.zbuf[p] = L.hit_z; }
-                        want_new = true;
-                        break;
-                    }
-                    if (L.sp > sp) {                    // recursed: `top` becomes the parent (saved), `child` the top
-                        if (sp > 0) { wf_store(&frames[sp - 1], top); par = top; par_valid = true; }
-                        top = child;
-                    } else if (L.sp < sp) {             // returned: the popped frame is dead
-                        if (par_valid) { top = par; par_valid = false; }
-                        else wf_load(top, &frames[L.sp - 1]);
-                    }
-                    sp = L.sp;
+            }
+            // The estimator coroutine up to its next ray.  Lanes of a warp may be in different
+            // stages (and reach a stage after different numbers of steps): each trip runs ONE
+            // stage -- the earliest any lane is in -- for all lanes that are in it, so later
+            // stages wait until the stragglers have caught up and then run together.
+            for (;;) {
+                const int st = running ? (L.sp == 0 ? -1 : (int)L.stage[L.sp - 1]) : 127;
+                const int mn = __reduce_min_sync(0xffffffffu, st);
+                if (mn == 127) break;
+                if (st != mn) continue;
+                V3 c;
+                const int r = sample_step(L, top, child, s, a.cfg, a.gather, L.bgu, L.bgv, rc, c);
+                if (r == STEP_RAY) { running = false; continue; }
+                if (r == STEP_DONE) {
+                    a.samples[L.work] = make_float4(c.x, c.y, c.z, 1.f);
+                    if (L.sidx == 0) { const size_t p = (size_t)L.pj * s.width + L.pi; a.hit_id[p] = L.hit_id; a.zbuf[p] = L.hit_z; }
+                    want_new = true;
+                    running = false;
+                    continue;
                 }
+                if (L.sp > sp) {                    // recursed: `top` becomes the parent (saved), `child` the top
+                    if (sp > 0) { wf_store(&frames[sp - 1], top); par = top; par_valid = true; }
+                    top = child;
+                } else if (L.sp < sp) {             // returned: the popped frame is dead
+                    if (par_valid) { top = par; par_valid = false; }
+                    else wf_load(top, &frames[L.sp - 1]);
+                }
+                sp = L.sp;
             }
             // ---- regeneration: warp-aggregated fetch of new camera samples
             bool dead = false;
@@ -246,6 +268,7 @@ wf_render(SceneView s, WaveArgs a)
                 if (L.sp > 0) wf_store(&frames[L.sp - 1], top);
                 lkey[id] = (unsigned char)((L.sp == 0) ? (unsigned)WF_KEY_PRIMARY : wf_key_of_stage(L.stage[L.sp - 1]));
             } else if (valid) lkey[id] = WF_KEY_DEAD;
+            // queue the rays that entered a mesh
             const unsigned mm = __ballot_sync(0xffffffffu, to_mesh);
             if (mm) {
                 const int leader = __ffs(mm) - 1;
@@ -257,53 +280,61 @@ wf_render(SceneView s, WaveArgs a)
         }
         first = false;
         __syncthreads();
+        long long c_mark = clock64();
+        t_p1 += c_mark - c_begin;
 
-        // P3 first: the lanes that did not go to a mesh are sorted for the next pass; P2 runs only
-        // when it has enough rays to fill the CTA (or the live list has run low), then sorts again
+        // Sort first: the lanes that did not go to a mesh are ready for the next pass.  The traversal
+        // phase runs only when it has enough rays to keep every thread busy (or the live list has run
+        // low); the lanes it completes are merged by a second sort.
         for (int round = 0; round < 2; round++) {
             // ================= P3: counting sort of the live lanes by key =================
-            for (unsigned i0 = 0; i0 < P; i0 += WF_BLOCK) {
-                const unsigned i = i0 + tid;
+            // No atomics: per 32-lane group, ballots give each key's count (lane k keeps key k's);
+            // one thread per key scans its column over the groups; a lane's slot is then
+            // key base + its group's offset + its rank among the group's lanes of that key.
+            const unsigned n_groups = (P + 31u) / 32u;
+            for (unsigned g = tid >> 5; g < n_groups; g += WF_BLOCK / 32) {
+                const unsigned i = g * 32u + lane;
                 const unsigned k = (i < P && !pend[i]) ? (unsigned)lkey[i] : (unsigned)WF_KEY_DEAD;
-                const bool live = k != WF_KEY_DEAD;
-                const unsigned lm = __ballot_sync(0xffffffffu, live);
-                if (live) {
-                    const unsigned peers = __match_any_sync(lm, k);
-                    if ((int)lane == __ffs(peers) - 1) atomicAdd(&key_count[k], (unsigned)__popc(peers));
+                unsigned mine = 0;
+#pragma unroll
+                for (unsigned j = 0; j < WF_KEY_DEAD; j++) {
+                    const unsigned m = __ballot_sync(0xffffffffu, k == j);
+                    if (lane == j) mine = (unsigned)__popc(m);
                 }
+                if (lane < WF_NKEYS) gcount[g * WF_NKEYS + lane] = (unsigned short)mine;
+            }
+            __syncthreads();
+            if (tid < WF_NKEYS) {
+                unsigned run = 0;
+                for (unsigned g = 0; g < n_groups; g++) { const unsigned t = gcount[g * WF_NKEYS + tid]; gcount[g * WF_NKEYS + tid] = (unsigned short)run; run += t; }
+                key_count[tid] = run;
             }
             __syncthreads();
             if (tid == 0) {
                 unsigned acc = 0;
-                for (int k = 0; k < WF_NKEYS; k++) { key_base[k] = acc; acc += key_count[k]; key_count[k] = 0; }
+                for (int k = 0; k < WF_NKEYS; k++) { key_base[k] = acc; acc += key_count[k]; }
                 n_live_s = acc;
+                p1_cursor = 0;
                 // decisions every thread must agree on, taken while nobody changes their inputs
                 run_mesh_s = round == 0 && n_pending_s > 0 && (mq_tail - mq_head >= a.mesh_batch || acc < WF_BLOCK);
                 done_s = acc == 0 && n_pending_s == 0;
             }
             __syncthreads();
-            for (unsigned i0 = 0; i0 < P; i0 += WF_BLOCK) {
-                const unsigned i = i0 + tid;
+            for (unsigned g = tid >> 5; g < n_groups; g += WF_BLOCK / 32) {
+                const unsigned i = g * 32u + lane;
                 const unsigned k = (i < P && !pend[i]) ? (unsigned)lkey[i] : (unsigned)WF_KEY_DEAD;
-                const bool live = k != WF_KEY_DEAD;
-                const unsigned lm = __ballot_sync(0xffffffffu, live);
-                if (live) {
-                    const unsigned peers = __match_any_sync(lm, k);
-                    const int leader = __ffs(peers) - 1;
-                    unsigned base = 0;
-                    if ((int)lane == leader) base = atomicAdd(&key_base[k], (unsigned)__popc(peers));
-                    base = __shfl_sync(peers, base, leader);
-                    list[base + __popc(peers & ((1u << lane) - 1u))] = (unsigned short)i;
-                }
+                const unsigned peers = __match_any_sync(0xffffffffu, k);
+                if (k != WF_KEY_DEAD) list[key_base[k] + gcount[g * WF_NKEYS + k] + __popc(peers & ((1u << lane) - 1u))] = (unsigned short)i;
             }
             __syncthreads();
+            { const long long c = clock64(); t_sort += c - c_mark; c_mark = c; }
             if (!run_mesh_s) break;
-            const unsigned tail = mq_tail;
 
             // ================= P2: BVH traversal of the queued rays =================
-            // per-lane refill while the queue lasts, then at most `mesh_budget` more steps: what
+            // per-lane refill while the queue lasts, then at most `mesh_budget` more trips: what
             // is still running after that stays in its thread until the next traversal phase
-            int budget = a.mesh_budget;
+            const unsigned tail = mq_tail;
+            int budget = n_live_s == 0 ? 64 : a.mesh_budget;    // nothing else to do: stay in the traversal
             for (;;) {
                 const bool need = !have;
                 const unsigned nm = __ballot_sync(0xffffffffu, need);
@@ -329,7 +360,19 @@ wf_render(SceneView s, WaveArgs a)
                     }
                 }
                 if (!__any_sync(0xffffffffu, have)) break;
-                if (have && mesh_job_step(J, s)) {
+                // job control: next mesh node of the ray (or none left: finished)
+                bool finished = false;
+                if (have && !J.in_trav) finished = !mesh_job_next(J, s);
+                // internal nodes: lanes that reach a leaf wait here for the others (a few trips),
+                // then all leaves are processed together -- the triangle tests run converged
+                for (int r = 0; r < 4; r++) {
+                    const bool go = have && !finished && !J.T.done && !BHRT_BVH_LEAF(J.T.cur);
+                    if (!__any_sync(0xffffffffu, go)) break;
+                    if (go) mesh_trav_internal(J.T);
+                }
+                if (have && !finished && !J.T.done && BHRT_BVH_LEAF(J.T.cur)) mesh_trav_leaf(J.T);
+                if (have && !finished && J.T.done) finished = mesh_job_harvest(J);
+                if (finished) {
                     Lane &Lg = lanes[jid];
                     if (J.blocked) Lg.hit_ok = true;
                     else if (J.q.kind == Q_CLOSEST) {
@@ -344,6 +387,7 @@ wf_render(SceneView s, WaveArgs a)
             }
             __syncthreads();
             if (tid == 0 && mq_head > mq_tail) mq_head = mq_tail;       // over-claimed pops of an empty queue
+            { const long long c = clock64(); t_mesh += c - c_mark; c_mark = c; }
         }
         if (done_s) break;
     }
@@ -353,6 +397,10 @@ wf_render(SceneView s, WaveArgs a)
         c1 += __shfl_down_sync(0xffffffffu, c1, o);
     }
     if (lane == 0 && (c0 | c1)) { atomicAdd(&a.cnt->rays_closest, c0); atomicAdd(&a.cnt->rays_shadow, c1); }
+    if (tid == 0) {
+        atomicAdd(&a.cnt->prof[0], (unsigned long long)t_p1); atomicAdd(&a.cnt->prof[1], (unsigned long long)t_sort);
+        atomicAdd(&a.cnt->prof[2], (unsigned long long)t_mesh); atomicAdd(&a.cnt->prof[3], (unsigned long long)n_iter);
+    }
 }
 
 // ---- wf_reduce ------------------------------------------------------------------------------------
