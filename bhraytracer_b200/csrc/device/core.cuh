@@ -1050,9 +1050,10 @@ BHRT_FN Ray handle_refraction_out(const Ray &inRay, const Hit &ih, float ior, bo
 // direction satisfies dir.N < 0; irrad = sum(power) / (pi * r2), r2 = radius^2 when at most k
 // qualified, else the k-th smallest squared distance; direction = normalize(sum(dir * maxpower)).
 // A 1000-entry heap per thread is hopeless on a GPU, so the set is found by
-// selection instead: pick the finest grid level whose 3x3x3 block holds more than k qualifying
-// photons within one cell edge, then a 32-bin histogram of squared distances, a 32-bin histogram
-// of the crossing bin, and an exact selection among the handful of photons of the crossing sub-bin.
+// selection instead: pick a grid level whose 3x3x3 block holds more than k qualifying photons
+// within one cell edge, then a radix-32 select of the k-th smallest squared distance (32-bin
+// histograms of a 20-bit distance key, narrowing to the crossing bin until it holds a handful of
+// photons) and an exact selection among those.
 struct PmRange { uint32_t b[27], e[27]; };
 
 BHRT_HD uint32_t pm_lower_bound(const uint32_t *keys, uint32_t lo, uint32_t hi, uint32_t key)
@@ -1140,8 +1141,8 @@ BHRT_FN void estimate_irradiance(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad
                 if (!(d2 < bound2)) continue;
                 F4 B = ld4(&pg.recs[i].b);
                 if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;       // cyPhotonMap.h:450
-                int bin = (int)(d2 * scale); if (bin > 31) bin = 31;
-                hist[bin]++; total++;
+                uint32_t u = (uint32_t)((d2 * scale) * 32768.f); if (u > 0xfffffu) u = 0xfffffu;
+                hist[u >> 15]++; total++;
                 if (level == 0) { sumP = sumP + pm_power(&pg.recs[i], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w; }
             }
         if (total <= pg.k) {
@@ -1153,69 +1154,73 @@ BHRT_FN void estimate_irradiance(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad
             direction = normalized(sumD);
             return;
         }
-        // ---- more than k qualify: find the k-th smallest squared distance
-        int cum = 0, b0 = 0;
-        for (; b0 < 32; b0++) { if (cum + hist[b0] >= pg.k) break; cum += hist[b0]; }
-        const int rank_in_bin = pg.k - cum;                 // 1-based rank inside bin b0
-        // ---- pass B: 32 sub-bins of bin b0
-        for (int i = 0; i < 32; i++) hist[i] = 0;
-        for (int n = 0; n < 27; n++)
-            for (uint32_t i = R.b[n]; i < R.e[n]; i++) {
-                F4 A = ld4(&pg.recs[i].a);
-                V3 dif(A.x - pos.x, A.y - pos.y, A.z - pos.z);
-                float d2 = length2(dif);
-                if (!(d2 < bound2)) continue;
-                float t = d2 * scale;
-                int bin = (int)t; if (bin > 31) bin = 31;
-                if (bin != b0) continue;
-                F4 B = ld4(&pg.recs[i].b);
-                if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;
-                int sb = (int)((t - (float)bin) * 32.f); if (sb > 31) sb = 31; if (sb < 0) sb = 0;
-                hist[sb]++;
-            }
-        int cum2 = 0, s0 = 0;
-        for (; s0 < 32; s0++) { if (cum2 + hist[s0] >= rank_in_bin) break; cum2 += hist[s0]; }
-        const int rank_in_sub = rank_in_bin - cum2;         // 1-based rank inside sub-bin s0
-        // ---- pass C: sum everything below the crossing sub-bin, collect the sub-bin's photons
+        // ---- more than k qualify: find the k-th smallest squared distance by a radix-32 select on
+        // u = (int)(d2 * scale * 2^15), a 20-bit key whose top digit is the bin of pass A (the
+        // products are exact scalings by powers of two, so every pass sees the same digits)
+        const float qscale = 32768.f;
+        uint32_t prefix = 0;            // digits of the crossing bin found so far
+        int shift = 15;                 // position of the digit `hist` currently holds
+        int need = pg.k;                // 1-based rank of the k-th photon among those matching `prefix`
+        for (;;) {
+            int cum = 0, b = 0;
+            for (; b < 31; b++) { if (cum + hist[b] >= need) break; cum += hist[b]; }
+            need -= cum;
+            prefix = (prefix << 5) | (uint32_t)b;
+            if (hist[b] <= BHRT_PM_CAND || shift == 0) break;
+            shift -= 5;
+            for (int i = 0; i < 32; i++) hist[i] = 0;
+            for (int n = 0; n < 27; n++)
+                for (uint32_t i = R.b[n]; i < R.e[n]; i++) {
+                    F4 A = ld4(&pg.recs[i].a);
+                    V3 dif(A.x - pos.x, A.y - pos.y, A.z - pos.z);
+                    float d2 = length2(dif);
+                    if (!(d2 < bound2)) continue;
+                    uint32_t u = (uint32_t)((d2 * scale) * qscale); if (u > 0xfffffu) u = 0xfffffu;
+                    if ((u >> (shift + 5)) != prefix) continue;
+                    F4 B = ld4(&pg.recs[i].b);
+                    if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;
+                    hist[(u >> shift) & 31u]++;
+                }
+        }
+        // ---- last pass: sum everything below the crossing bin, collect the crossing bin's photons
         sumP = V3(0, 0, 0); sumD = V3(0, 0, 0);
         float cd2[BHRT_PM_CAND]; uint32_t cidx[BHRT_PM_CAND];
         int ncand = 0;
         bool overflow = false;
         V3 subP(0, 0, 0), subD(0, 0, 0);
-        float kth2 = 0;
+        float kth2 = 0, sub_max = 0;
         for (int n = 0; n < 27; n++)
             for (uint32_t i = R.b[n]; i < R.e[n]; i++) {
                 F4 A = ld4(&pg.recs[i].a);
                 V3 dif(A.x - pos.x, A.y - pos.y, A.z - pos.z);
                 float d2 = length2(dif);
                 if (!(d2 < bound2)) continue;
-                float t = d2 * scale;
-                int bin = (int)t; if (bin > 31) bin = 31;
-                if (bin > b0) continue;
-                int sb = 0;
-                if (bin == b0) { sb = (int)((t - (float)bin) * 32.f); if (sb > 31) sb = 31; if (sb < 0) sb = 0; if (sb > s0) continue; }
+                uint32_t u = (uint32_t)((d2 * scale) * qscale); if (u > 0xfffffu) u = 0xfffffu;
+                const uint32_t top = u >> shift;
+                if (top > prefix) continue;
                 F4 B = ld4(&pg.recs[i].b);
                 if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;
-                if (bin < b0 || sb < s0) {
+                if (top < prefix) {
                     sumP = sumP + pm_power(&pg.recs[i], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w;
                     if (d2 > kth2) kth2 = d2;
                 } else {
                     subP = subP + pm_power(&pg.recs[i], A.w); subD = subD + V3(B.x, B.y, B.z) * A.w;
+                    if (d2 > sub_max) sub_max = d2;
                     if (ncand < BHRT_PM_CAND) { cd2[ncand] = d2; cidx[ncand] = i; ncand++; } else overflow = true;
                 }
             }
         if (overflow) {
-            // (practically unreachable: > 48 photons inside 1/1024 of the search area) keep the whole sub-bin
+            // more than 48 photons share all 20 key bits (coincident positions): keep them all
             sumP = sumP + subP; sumD = sumD + subD;
-            kth2 = ((float)b0 + (float)(s0 + 1) / 32.f) / scale;
+            kth2 = sub_max;
         } else {
-            // exact: the rank_in_sub nearest photons of the crossing sub-bin (insertion sort, <= 48 entries)
+            // exact: the `need` nearest photons of the crossing bin (insertion sort, <= 48 entries)
             for (int i = 1; i < ncand; i++) {
                 float d = cd2[i]; uint32_t ix = cidx[i]; int j = i - 1;
                 while (j >= 0 && cd2[j] > d) { cd2[j + 1] = cd2[j]; cidx[j + 1] = cidx[j]; j--; }
                 cd2[j + 1] = d; cidx[j + 1] = ix;
             }
-            for (int i = 0; i < rank_in_sub && i < ncand; i++) {
+            for (int i = 0; i < need && i < ncand; i++) {
                 F4 A = ld4(&pg.recs[cidx[i]].a); F4 B = ld4(&pg.recs[cidx[i]].b);
                 sumP = sumP + pm_power(&pg.recs[cidx[i]], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w;
                 kth2 = cd2[i];

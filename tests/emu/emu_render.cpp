@@ -8,6 +8,9 @@
 //                   [--emit N FILE]                 emit N caustic photons (unscaled power) into FILE and exit
 //                   [--photons FILE TOTAL K RADIUS] render with the caustic gather term over the
 //                                                   24-byte records of FILE, powers scaled by 1/TOTAL
+//                   [--queries IN OUT]              with --photons: evaluate the irradiance estimate at the
+//                                                   (pos, normal) float[6] records of IN, write float[6]
+//                                                   (irradiance rgb, mean direction) per query to OUT, exit
 // writes <out_prefix>.aov in the layout of oracle/ref_build/driver.cpp and <out_prefix>.acc, the
 // float4 accumulation buffer (r,g,b sums + sample count; zeros outside the rendered share) a
 // GPU rank would hold after bhrt_render_device with the same row / sample share.
@@ -16,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <vector>
 #ifdef BHRT_EMU_STATS
 static thread_local unsigned long long g_trav[4];
@@ -54,6 +58,7 @@ int main(int argc, char **argv)
     int row_b = 0, row_e = 0, row_s = 1, smp_b = 0, smp_e = 0;
     int emit_n = 0; const char *emit_file = nullptr;
     const char *photon_file = nullptr; int photon_total = 1, photon_k = 1000; float photon_radius = 0.5f;
+    const char *query_in = nullptr, *query_out = nullptr;
     unsigned long long seed = 1;
     for (int a = 3; a < argc; a++) {
         if (!strcmp(argv[a], "--det")) det = 1;
@@ -65,6 +70,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[a], "--samples") && a + 2 < argc) { smp_b = atoi(argv[++a]); smp_e = atoi(argv[++a]); }
         else if (!strcmp(argv[a], "--emit") && a + 2 < argc) { emit_n = atoi(argv[++a]); emit_file = argv[++a]; }
         else if (!strcmp(argv[a], "--photons") && a + 4 < argc) { photon_file = argv[++a]; photon_total = atoi(argv[++a]); photon_k = atoi(argv[++a]); photon_radius = (float)atof(argv[++a]); }
+        else if (!strcmp(argv[a], "--queries") && a + 2 < argc) { query_in = argv[++a]; query_out = argv[++a]; }
         else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
     }
     if (det) spp = 1;
@@ -139,6 +145,45 @@ int main(int argc, char **argv)
         fclose(fp);
         build_photon_map_host(recs.data(), (int)recs.size(), photon_total, photon_radius, pmap);
         pg = pmap.view(photon_k, photon_radius);
+        if (query_in) {
+            FILE *fq = fopen(query_in, "rb");
+            if (!fq) { fprintf(stderr, "cannot read %s\n", query_in); return 3; }
+            std::vector<float> q;
+            float rec6[6];
+            while (fread(rec6, sizeof(float), 6, fq) == 6) q.insert(q.end(), rec6, rec6 + 6);
+            fclose(fq);
+            // per query: the estimator's (irradiance, direction), then the same from a plain scan of all
+            // gather records (same arithmetic, std::sort instead of the grid + histogram selection)
+            std::vector<float> res(q.size() * 2);
+            for (size_t i = 0, o = 0; i + 6 <= q.size(); i += 6, o += 12) {
+                V3 irr, dir;
+                const V3 qp(q[i], q[i + 1], q[i + 2]), qn(q[i + 3], q[i + 4], q[i + 5]);
+                estimate_irradiance(pg, qp, qn, irr, dir);
+                res[o] = irr.x; res[o + 1] = irr.y; res[o + 2] = irr.z; res[o + 3] = dir.x; res[o + 4] = dir.y; res[o + 5] = dir.z;
+                std::vector<std::pair<float, int>> cand;
+                for (int j = 0; j < pg.n_photons; j++) {
+                    const GatherRec &g = pg.recs[j];
+                    V3 dif(g.a.x - qp.x, g.a.y - qp.y, g.a.z - qp.z);
+                    float d2 = length2(dif);
+                    if (!(d2 < pg.radius * pg.radius)) continue;
+                    if (dot(V3(g.b.x, g.b.y, g.b.z), qn) >= 0) continue;
+                    cand.push_back(std::make_pair(d2, j));
+                }
+                std::sort(cand.begin(), cand.end());
+                float r2 = pg.radius * pg.radius;
+                if ((int)cand.size() > pg.k) { cand.resize(pg.k); r2 = cand.back().first; }
+                V3 sp(0, 0, 0), sd(0, 0, 0);
+                for (auto &c : cand) { const GatherRec &g = pg.recs[c.second]; sp = sp + pm_power(&g, g.a.w); sd = sd + V3(g.b.x, g.b.y, g.b.z) * g.a.w; }
+                if (!cand.empty()) { sp = sp * (1.0f / (3.14159265358979323846f * r2)); sd = normalized(sd); }
+                res[o + 6] = sp.x; res[o + 7] = sp.y; res[o + 8] = sp.z; res[o + 9] = sd.x; res[o + 10] = sd.y; res[o + 11] = sd.z;
+            }
+            FILE *fo = fopen(query_out, "wb");
+            if (!fo) return 4;
+            fwrite(res.data(), sizeof(float), res.size(), fo);
+            fclose(fo);
+            printf("{\"emu\": true, \"queries\": %d}\n", (int)(q.size() / 6));
+            return 0;
+        }
     }
     ShadeCfg cfg; cfg.mode = det ? BHRT_MODE_DET : BHRT_MODE_PATH; cfg.gi_depth = gi; cfg.tir_budget = 16;
     if (row_e == 0) row_e = H;

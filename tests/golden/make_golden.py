@@ -72,18 +72,7 @@ def run_ref(scene_path, prefix, *args):
 # gather can be compared deterministically, plus summary statistics of the emission.
 PHOTON = [("det_caustics", 200, 150, 40000)]
 REF_PM = os.path.join(ROOT, "oracle", "_ref", "bhrt_ref_pm")
-PHOTON_DT = np.dtype([("pos", "<f4", 3), ("power", "<f4"), ("rgb", "u1", 3), ("flag", "u1"), ("dx", "<i2"), ("dy", "<i2")])
-
-
-def photon_stats(rec, scaled_by):
-    """Distribution summary used by the emission tests (positions on the floor, axis histograms, power)."""
-    pos = rec["pos"]
-    floor = rec[np.abs(pos[:, 2]) < 1e-3]
-    h2, _, _ = np.histogram2d(floor["pos"][:, 0], floor["pos"][:, 1], bins=24, range=[[-15, 15], [-30, 20]])
-    ax = [np.histogram(pos[:, a], bins=16, range=(-16, 25))[0] / float(len(rec)) for a in range(3)]
-    return dict(floor_hist=(h2 / max(1, len(rec))).astype(np.float32), axis_hist=np.array(ax, np.float32),
-                floor_frac=len(floor) / float(len(rec)), mean_power=float((rec["power"].astype(np.float64) * scaled_by).mean()),
-                dirz_neg_frac=float(((rec["flag"] & 8) != 0).mean()))
+from photon_util import PHOTON_DT, photon_stats  # noqa: E402
 
 
 def main():
