@@ -83,6 +83,24 @@ class GpuEngine:
     def resolve(self, total_spp, want):
         return self.r.resolve(total_spp, want=want)
 
+    # ---- caustic photon map
+    def photons_emit(self, quota, seed):
+        return self.r.photons_emit(quota, seed)
+
+    def photon_records(self):
+        """uint8 view [count * 24] of this rank's records in device memory (zero-copy)."""
+        ptr, n = self.r.photons_buffer()
+        dev = self.torch.device("cuda", self.r.device)
+        if n == 0:
+            return self.torch.zeros(0, dtype=self.torch.uint8, device=dev)
+        return self.torch.as_tensor(_CudaArray(ptr, n * 24, "|u1"), device=dev)
+
+    def photons_set(self, records, count):
+        self.r.photons_set(records.data_ptr(), from_device=True, count=count)
+
+    def photons_build(self, total_stored):
+        self.r.photons_build(total_stored)
+
     def close(self):
         self.r.close()
 
