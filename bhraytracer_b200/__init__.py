@@ -61,6 +61,9 @@ class SceneDesc(C.Structure):
                 ("camera", _Camera)]
 
 
+FLAG_EXACT_MATH = 1      # BHRT_FLAG_EXACT_MATH
+
+
 class Params(C.Structure):
     """bhrt_params (include/bhrt.h)."""
     _fields_ = [("mode", C.c_int32), ("spp", C.c_int32), ("gi_depth", C.c_int32), ("tir_budget", C.c_int32),
@@ -68,7 +71,7 @@ class Params(C.Structure):
                 ("sample_begin", C.c_int32), ("sample_end", C.c_int32),
                 ("row_begin", C.c_int32), ("row_end", C.c_int32), ("row_stride", C.c_int32),
                 ("use_photon_map", C.c_int32), ("photon_k", C.c_int32), ("photon_radius", C.c_float),
-                ("quirks", C.c_uint32)]
+                ("flags", C.c_uint32)]
 
 
 class Outputs(C.Structure):
@@ -223,7 +226,7 @@ class Renderer:
 
     @staticmethod
     def params(mode=MODE_PATH, spp=32, gi_depth=3, tir_budget=16, seed=1, sample_range=None, rows=None,
-               row_stride=1, use_photon_map=False, photon_k=1000, photon_radius=0.5):
+               row_stride=1, use_photon_map=False, photon_k=1000, photon_radius=0.5, exact_math=False):
         p = Params()
         p.mode, p.spp, p.gi_depth, p.tir_budget, p.seed = mode, spp, gi_depth, tir_budget, seed
         if sample_range:
@@ -232,6 +235,7 @@ class Renderer:
             p.row_begin, p.row_end = rows
         p.row_stride = row_stride
         p.use_photon_map, p.photon_k, p.photon_radius = int(use_photon_map), photon_k, photon_radius
+        p.flags = FLAG_EXACT_MATH if exact_math else 0
         return p
 
     def _alloc_outputs(self, want):

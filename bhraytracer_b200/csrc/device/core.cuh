@@ -28,7 +28,13 @@
 // render kernel was 935 KB of SASS and spent most issue slots waiting for instruction fetch.
 #define BHRT_FN BHRT_HD_NOINLINE
 
-namespace bhrt {
+// The whole device code lives in namespace BHRT_NS: `bhrt` in the exact build (render.cu, tests/emu)
+// and `bhrt_fast` in render_fast.cu, which compiles the same source with --use_fast_math for the
+// stochastic mode (see render_fast.cu).
+#ifndef BHRT_NS
+#define BHRT_NS bhrt
+#endif
+namespace BHRT_NS {
 
 #define BHRT_BIGFLOAT 1.0e30f          // reference Scenes/scene.h:38
 #define BHRT_BIAS 0.0001f              // reference MtlBlinn.cpp:10, TriObj.cpp:9
@@ -1765,4 +1771,4 @@ BHRT_HD V3 gamma_correct(V3 c)
     return V3(m_pow(c.x, ig), m_pow(c.y, ig), m_pow(c.z, ig));
 }
 
-}  // namespace bhrt
+}  // namespace BHRT_NS

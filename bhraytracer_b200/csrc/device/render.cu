@@ -21,6 +21,10 @@
 
 using namespace bhrt;
 
+// render_fast.cu: the same render kernel built with --use_fast_math (stochastic mode)
+extern "C" int bhrt_fast_prepare(int smem_bytes, int *blocks_per_sm);
+extern "C" int bhrt_fast_launch(const void *view, size_t view_bytes, const void *args, size_t args_bytes, unsigned grid, int smem_bytes, cudaStream_t stream);
+
 static thread_local std::string g_err;
 static int set_err(int code, const std::string &m) { g_err = m; return code; }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err(BHRT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
@@ -264,10 +268,14 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     a.smem_offsets = al16(a.smem_lights + c->view.n_lights * (int)sizeof(bhrt_light));
     a.smem_wave = al16(a.smem_offsets + 2 * (BHRT_TEX_SAMPLES - 1) * (int)sizeof(float));
     const int smem_bytes = al16(a.smem_wave + wf_wave_smem_bytes(a.pool));
+    // stochastic frames run the fast-math build of the kernel unless the caller asks for the exact one
+    const bool fast = p->mode == BHRT_MODE_PATH && !(p->flags & BHRT_FLAG_EXACT_MATH);
     if (!c->kernel_ready || c->kernel_smem != smem_bytes) {
         CU(cudaFuncSetAttribute(wf_render, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        int per_sm = 0;
+        int per_sm = 0, per_sm_fast = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_render, WF_BLOCK, smem_bytes));
+        if (int e = bhrt_fast_prepare(smem_bytes, &per_sm_fast)) return set_err(BHRT_ERR_CUDA, std::string("bhrt_render: ") + cudaGetErrorString((cudaError_t)e));
+        if (per_sm_fast < per_sm) per_sm = per_sm_fast;
         if (per_sm < 1) return set_err(BHRT_ERR_LIMIT, "bhrt_render: scene tables do not fit in shared memory");
         c->render_blocks = per_sm;
         c->kernel_smem = smem_bytes;
@@ -303,7 +311,10 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
         a.chunk_spp = (sample_end - s0 < chunk) ? (sample_end - s0) : chunk;
         a.n_work = (unsigned long long)a.n_pix_work * (unsigned long long)a.chunk_spp;
         CU(cudaMemsetAsync(&((WaveCounters *)c->wave_counters.p)->next_work, 0, sizeof(unsigned long long), c->stream));
-        wf_render<<<grid, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a);
+        if (fast) {
+            if (int e = bhrt_fast_launch(&c->view, sizeof(c->view), &a, sizeof(a), grid, smem_bytes, c->stream))
+                return set_err(BHRT_ERR_CUDA, std::string("wf_render (fast-math build): ") + cudaGetErrorString((cudaError_t)e));
+        } else wf_render<<<grid, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a);
         wf_reduce<<<(a.n_pix_work + 255) / 256, 256, 0, c->stream>>>(c->view, a, (float4 *)c->accum.p, s0 == sample_begin ? 1 : 0);
         c->launches += 2;
     }

@@ -37,7 +37,7 @@
 #include <cuda_runtime.h>
 #include "core.cuh"
 
-namespace bhrt {
+namespace BHRT_NS {
 
 #define WF_BLOCK 1024
 #define WF_NKEYS 16
@@ -420,4 +420,4 @@ __global__ void wf_reduce(SceneView s, WaveArgs a, float4 *__restrict__ accum, i
     accum[p] = v;
 }
 
-}  // namespace bhrt
+}  // namespace BHRT_NS

@@ -181,8 +181,14 @@ typedef struct bhrt_params {
     int32_t use_photon_map; /* add the caustic gather term (MtlBlinn.cpp:329-342) */
     int32_t photon_k;       /* MAX_PhotonCountInArea, default 1000 */
     float photon_radius;    /* MAX_Area, default 0.5 */
-    uint32_t quirks;        /* reserved, 0 = reproduce every reference quirk */
+    uint32_t flags;         /* BHRT_FLAG_*; 0 = defaults */
 } bhrt_params;
+
+/* The stochastic mode (BHRT_MODE_PATH) is judged statistically (RMSE against the reference's
+ * high-spp render), so by default it runs a build of the kernels with approximate division, square
+ * root and transcendentals and with FMA contraction.  This flag selects the exact build (IEEE
+ * operations in the reference's order) for it as well.  The deterministic mode is always exact. */
+#define BHRT_FLAG_EXACT_MATH 1u
 
 /* Any pointer may be NULL to skip that output.  Layouts follow the reference's
  * colorArray / RenderImage (Main.cpp:202,229-230): row-major, j*W+i, row 0 at the top. */
