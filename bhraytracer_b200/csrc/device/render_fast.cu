@@ -10,6 +10,7 @@
 // Same source, same data layout: the launcher in render.cu hands over its SceneView / WaveArgs as
 // plain bytes.
 #define BHRT_NS bhrt_fast
+#define BHRT_FAST 1
 #include <cuda_runtime.h>
 #include <cstring>
 #include "wavefront.cuh"

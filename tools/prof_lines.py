@@ -18,8 +18,9 @@ import tempfile
 def line_table(so, kernel):
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
-    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    dis = subprocess.check_output(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)]).decode(errors="replace")
+    dis = ""
+    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+        dis += subprocess.check_output(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)]).decode(errors="replace") + "\n"
     table = {}
     in_kernel = False
     fn = None
