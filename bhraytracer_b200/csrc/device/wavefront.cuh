@@ -40,16 +40,43 @@
 namespace BHRT_NS {
 
 #define WF_BLOCK 1024
-#define WF_NKEYS 16
+#define WF_NKEYS 128
 #define WF_MESH_BUDGET 4
-// Sort keys = the step a lane runs next
-enum { WF_KEY_PRIMARY = 0, WF_KEY_REFR_IN = 1, WF_KEY_REFR_OUT = 2, WF_KEY_GI_TRACE = 3, WF_KEY_SHADOW = 4,
-       WF_KEY_REFR = 5, WF_KEY_REFR_RET = 6, WF_KEY_GI = 7, WF_KEY_GI_RET = 8, WF_KEY_DIRECT = 9, WF_KEY_DEAD = 10 };
-__device__ __forceinline__ unsigned wf_key_of_stage(int stage)
+// Sort keys.  A lane's key says what its next pass through the estimator will execute, as far as that
+// is known when the lanes are sorted:
+//   bits 6..4  the stage that consumes the pending ray's answer (5 in use)
+//   bits 3..1  class of the answer: closest-hit stages -> 0 = miss, else 1 + material of the hit node
+//              (capped); shadow stage -> material of the shading point
+//   bit  0     the GI budget of the frame is used up (the next level shades direct light only)
+// so a warp's 32 lanes not only run the same case of the state machine, they take the same branches
+// inside it (refractive / glossy / diffuse material, miss -> environment, ...).
+enum { WF_ST_PRIMARY = 0, WF_ST_REFR_IN = 1, WF_ST_REFR_OUT = 2, WF_ST_GI_TRACE = 3, WF_ST_SHADOW = 4, WF_ST_OTHER = 5, WF_KEY_DEAD = 127 };
+__device__ __forceinline__ unsigned wf_stage_slot(int stage)
 {
     // ST_REFR 0, ST_REFR_IN_WAIT 1, ST_REFR_OUT_WAIT 2, ST_REFR_WAIT 3, ST_GI 4, ST_GI_TRACE_WAIT 5, ST_GI_WAIT 6, ST_DIRECT 7, ST_SHADOW_WAIT 8
-    const unsigned long long table = 0x498376215ull;       // nibble i = key of stage i
+    const unsigned long long table = 0x455355215ull;       // nibble i = slot of stage i
     return (unsigned)((table >> (4 * stage)) & 15ull);
+}
+// key of a lane whose pending ray has been answered (hit_ok / hit node known)
+__device__ __forceinline__ unsigned wf_key(const SceneView &s, const Lane &L, const Frame &top)
+{
+    if (L.sp == 0) {
+        const unsigned cls = (L.hit.node >= 0) ? 1u + min((unsigned)s.nodes[L.hit.node].material, 6u) : 0u;
+        return (WF_ST_PRIMARY << 4) | (cls << 1);
+    }
+    const unsigned slot = wf_stage_slot(L.stage[L.sp - 1]);
+    unsigned cls;
+    if (slot == WF_ST_SHADOW || slot == WF_ST_OTHER) cls = min((unsigned)top.mtl, 7u);
+    else cls = (L.q.kind == Q_CLOSEST && L.hit.node >= 0) ? 1u + min((unsigned)s.nodes[L.hit.node].material, 6u) : 0u;
+    return (slot << 4) | (cls << 1) | (top.gi <= 0 ? 1u : 0u);
+}
+// the same after a BVH traversal changed the answer: only the class bits of a closest-hit stage move
+__device__ __forceinline__ unsigned wf_key_patch(const SceneView &s, unsigned key, int hit_node)
+{
+    const unsigned slot = key >> 4;
+    if (slot == WF_ST_SHADOW || slot == WF_ST_OTHER) return key;
+    const unsigned cls = hit_node >= 0 ? 1u + min((unsigned)s.nodes[hit_node].material, 6u) : 0u;
+    return (key & ~0xeu) | (cls << 1);
 }
 
 struct WaveCounters {
@@ -266,7 +293,7 @@ wf_render(SceneView s, WaveArgs a)
                 if (!blocked && (mask || s.n_mesh_nodes > BHRT_MESH_MASK_BITS)) { L.mesh_mask = mask; to_mesh = true; }
                 wf_store(&lanes[id], L);
                 if (L.sp > 0) wf_store(&frames[L.sp - 1], top);
-                lkey[id] = (unsigned char)((L.sp == 0) ? (unsigned)WF_KEY_PRIMARY : wf_key_of_stage(L.stage[L.sp - 1]));
+                lkey[id] = (unsigned char)wf_key(s, L, top);
             } else if (valid) lkey[id] = WF_KEY_DEAD;
             // queue the rays that entered a mesh
             const unsigned mm = __ballot_sync(0xffffffffu, to_mesh);
@@ -288,20 +315,18 @@ wf_render(SceneView s, WaveArgs a)
         // low); the lanes it completes are merged by a second sort.
         for (int round = 0; round < 2; round++) {
             // ================= P3: counting sort of the live lanes by key =================
-            // No atomics: per 32-lane group, ballots give each key's count (lane k keeps key k's);
+            // No atomics: per 32-lane group, __match_any_sync gives each key's count;
             // one thread per key scans its column over the groups; a lane's slot is then
             // key base + its group's offset + its rank among the group's lanes of that key.
             const unsigned n_groups = (P + 31u) / 32u;
             for (unsigned g = tid >> 5; g < n_groups; g += WF_BLOCK / 32) {
                 const unsigned i = g * 32u + lane;
                 const unsigned k = (i < P && !pend[i]) ? (unsigned)lkey[i] : (unsigned)WF_KEY_DEAD;
-                unsigned mine = 0;
-#pragma unroll
-                for (unsigned j = 0; j < WF_KEY_DEAD; j++) {
-                    const unsigned m = __ballot_sync(0xffffffffu, k == j);
-                    if (lane == j) mine = (unsigned)__popc(m);
-                }
-                if (lane < WF_NKEYS) gcount[g * WF_NKEYS + lane] = (unsigned short)mine;
+                unsigned short *row = gcount + g * WF_NKEYS;
+                for (unsigned j = lane; j < WF_NKEYS; j += 32u) row[j] = 0;
+                __syncwarp();
+                const unsigned peers = __match_any_sync(0xffffffffu, k);
+                if ((int)lane == __ffs(peers) - 1) row[k] = (unsigned short)__popc(peers);
             }
             __syncthreads();
             if (tid < WF_NKEYS) {
@@ -312,7 +337,7 @@ wf_render(SceneView s, WaveArgs a)
             __syncthreads();
             if (tid == 0) {
                 unsigned acc = 0;
-                for (int k = 0; k < WF_NKEYS; k++) { key_base[k] = acc; acc += key_count[k]; }
+                for (int k = 0; k < WF_KEY_DEAD; k++) { key_base[k] = acc; acc += key_count[k]; }
                 n_live_s = acc;
                 p1_cursor = 0;
                 // decisions every thread must agree on, taken while nobody changes their inputs
@@ -378,6 +403,7 @@ wf_render(SceneView s, WaveArgs a)
                     else if (J.q.kind == Q_CLOSEST) {
                         Lg.hit.z = J.h.z; Lg.hit.node = J.h.node; Lg.hit.front = J.h.front;
                         Lg.hit.uvw = J.h.uvw; Lg.hit.duvw0.x = J.h.duvw0.x;
+                        lkey[jid] = (unsigned char)wf_key_patch(s, lkey[jid], J.h.node);
                     }
                     pend[jid] = 0;
                     atomicSub(&n_pending_s, 1u);
