@@ -213,17 +213,13 @@ wf_render(SceneView s, WaveArgs a)
             const bool valid = idx < n_live;
             const unsigned id = valid ? (unsigned)list[idx] : 0u;
             Lane L;
-            Frame top, par, child;
+            // the recursion levels are used in place (global memory, cached in L1 while this lane is
+            // being stepped): a step touches the top frame and, when it recurses, the slot above it
             Frame *const frames = frames_all + (size_t)id * BHRT_MAX_FRAMES;
             bool want_new = valid && first;
-            bool par_valid = false;
             bool running = valid && !first;
-            int sp = 0;
             if (running) {
                 wf_load(L, &lanes[id]);
-                sp = L.sp;
-                if (sp > 0) wf_load(top, &frames[sp - 1]);
-                if (sp > 1) { wf_load(par, &frames[sp - 2]); par_valid = true; }
                 // the answer of the pending query: winner-only work of a closest hit
                 if (L.q.kind == Q_CLOSEST) L.hit_ok = scene_trace_finish(s, L.q, L.hit);
             }
@@ -237,23 +233,15 @@ wf_render(SceneView s, WaveArgs a)
                 if (mn == 127) break;
                 if (st != mn) continue;
                 V3 c;
-                const int r = sample_step(L, top, child, s, a.cfg, a.gather, L.bgu, L.bgv, rc, c);
+                const int r = sample_step(L, frames[L.sp > 0 ? L.sp - 1 : 0], frames[L.sp < BHRT_MAX_FRAMES ? L.sp : BHRT_MAX_FRAMES - 1],
+                                          s, a.cfg, a.gather, L.bgu, L.bgv, rc, c);
                 if (r == STEP_RAY) { running = false; continue; }
                 if (r == STEP_DONE) {
                     a.samples[L.work] = make_float4(c.x, c.y, c.z, 1.f);
                     if (L.sidx == 0) { const size_t p = (size_t)L.pj * s.width + L.pi; a.hit_id[p] = L.hit_id; a.zbuf[p] = L.hit_z; }
                     want_new = true;
                     running = false;
-                    continue;
                 }
-                if (L.sp > sp) {                    // recursed: `top` becomes the parent (saved), `child` the top
-                    if (sp > 0) { wf_store(&frames[sp - 1], top); par = top; par_valid = true; }
-                    top = child;
-                } else if (L.sp < sp) {             // returned: the popped frame is dead
-                    if (par_valid) { top = par; par_valid = false; }
-                    else wf_load(top, &frames[L.sp - 1]);
-                }
-                sp = L.sp;
             }
             // ---- regeneration: warp-aggregated fetch of new camera samples
             bool dead = false;
@@ -292,8 +280,7 @@ wf_render(SceneView s, WaveArgs a)
                 L.mesh_mask = 0;
                 if (!blocked && (mask || s.n_mesh_nodes > BHRT_MESH_MASK_BITS)) { L.mesh_mask = mask; to_mesh = true; }
                 wf_store(&lanes[id], L);
-                if (L.sp > 0) wf_store(&frames[L.sp - 1], top);
-                lkey[id] = (unsigned char)wf_key(s, L, top);
+                lkey[id] = (unsigned char)wf_key(s, L, frames[L.sp > 0 ? L.sp - 1 : 0]);
             } else if (valid) lkey[id] = WF_KEY_DEAD;
             // queue the rays that entered a mesh
             const unsigned mm = __ballot_sync(0xffffffffu, to_mesh);
