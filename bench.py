@@ -272,7 +272,7 @@ def bench_ours(args):
             "gpu_launches": total_launches,
             "clocks": clocks,
         }
-        # ---- roofline of the dominant kernel (render_kernel), algorithmic bytes per SURVEY.md 8(d)
+        # ---- roofline of the dominant kernel (wf_render), algorithmic bytes per SURVEY.md 8(d)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -295,14 +295,14 @@ def bench_ours(args):
         achieved = bytes_per_ray * rays_per_launch / (kernel_ms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("render_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("wf_render_dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
-        line["roofline"] = {"bound": "hbm", "kernel": "render_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+        line["roofline"] = {"bound": "hbm", "kernel": "wf_render (one persistent launch per frame)", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                             "frac": round(achieved / peak, 4), "traffic": traffic, "peak_kind": peak_kind,
                             "algorithmic_bytes_per_ray": round(bytes_per_ray, 1), "bytes_source": src,
                             "kernel_ms_per_launch": round(kernel_ms, 3), "rays_per_launch": int(rays_per_launch),
-                            "note": "scene (<= 20 MB) is L2-resident: HBM traffic << algorithmic bytes by design (SURVEY.md H6)"}
+                            "note": "algorithmic bytes are defined on the reference's data structures (SURVEY.md 8d); the scene (<= 20 MB) is L2-resident, the measured DRAM traffic is the kernel's own lane state (profiles/r1k_wf_render_ncu_summary.json)"}
         # ---- CPU baseline: the reference itself on this box's host cores, bounded sample
         if world == 1 and os.path.exists(REF_BIN) and not args.no_cpu:
             info = run_reference(REF_BIN, CPU_W, CPU_H, SPP)
