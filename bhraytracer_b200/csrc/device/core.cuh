@@ -1267,7 +1267,7 @@ struct alignas(128) Frame {              // one 128-byte line per recursion leve
     int pad_;
 };
 enum { ST_REFR = 0, ST_REFR_IN_WAIT = 1, ST_REFR_OUT_WAIT = 2, ST_REFR_WAIT = 3, ST_GI = 4, ST_GI_TRACE_WAIT = 5, ST_GI_WAIT = 6,
-       ST_DIRECT = 7, ST_SHADOW_WAIT = 8 };
+       ST_DIRECT = 7, ST_SHADOW_WAIT = 8, ST_GATHER_WAIT = 9 };
 #define BHRT_MAX_FRAMES 16
 
 struct ShadeCfg {
@@ -1335,11 +1335,9 @@ BHRT_FN V3 direct_brdf(const SceneView &s, const Frame &f, const bhrt_material &
 
 // End of PathTracing_DiffuseNSpecular: the caustic gather term (MtlBlinn.cpp:329-342, only when a
 // photon map is in use), then the clamp / NaN epilogue (MtlBlinn.cpp:343-350,131-136)
-BHRT_FN void direct_finish(const SceneView &s, const PhotonGather &pg, Frame &f, const bhrt_material &M, V3 D)
+BHRT_FN void direct_finish(const SceneView &s, bool have_gather, V3 irr, V3 vL, Frame &f, const bhrt_material &M, V3 D)
 {
-    if (pg.use) {
-        V3 irr, vL;
-        estimate_irradiance(pg, f.p, f.vN, irr, vL);
+    if (have_gather) {
         float cosTheta = -dot(vL, f.vN);
         if (cosTheta > 0) {
             V3 vH = normalized(vL + f.vV);
@@ -1360,7 +1358,10 @@ BHRT_FN void direct_finish(const SceneView &s, const PhotonGather &pg, Frame &f,
 // consumes its answer is on top; STEP_CONT: no ray needed, call again; STEP_DONE: the sample is
 // finished, colour in `color`.  Stages that consume a ray answer read L.hit / L.hit_ok.
 // The wavefront sorts lanes by the stage they are about to run, so a warp executes one case.
-enum { STEP_CONT = 0, STEP_RAY = 1, STEP_DONE = 2 };
+// STEP_GATHER: the estimator needs the caustic irradiance estimate at the top frame's (p, vN): the
+// caller evaluates it (estimate_irradiance; a whole warp per query in the kernel), leaves the
+// irradiance in L.hit.p and the mean photon direction in L.sw, and calls again.
+enum { STEP_CONT = 0, STEP_RAY = 1, STEP_DONE = 2, STEP_GATHER = 3 };
 // `f` = the top frame (fr[sp-1]; unused while sp == 0), `child` = the slot above it (fr[sp]).
 BHRT_HD int sample_step(Lane &L, Frame &f, Frame &child, const SceneView &s, const ShadeCfg &cfg, const PhotonGather &pg, float bgu, float bgv,
                         RayCounters &rc, V3 &color)
@@ -1550,7 +1551,8 @@ BHRT_HD int sample_step(Lane &L, Frame &f, Frame &child, const SceneView &s, con
                     L.si++;
                 }
                 if (issued) return STEP_RAY;
-                direct_finish(s, pg, f, M, L.sv);
+                if (pg.use) { stage = ST_GATHER_WAIT; return STEP_GATHER; }
+                direct_finish(s, false, V3(0, 0, 0), V3(0, 0, 0), f, M, L.sv);
                 done = true;
             } else {
                 if (s.n_lights > 0) {
@@ -1570,7 +1572,8 @@ BHRT_HD int sample_step(Lane &L, Frame &f, Frame &child, const SceneView &s, con
                         L.sv = L.sv + irrad * direct_brdf(s, f, M, vL);
                     }
                 }
-                direct_finish(s, pg, f, M, L.sv);
+                if (pg.use) { stage = ST_GATHER_WAIT; return STEP_GATHER; }
+                direct_finish(s, false, V3(0, 0, 0), V3(0, 0, 0), f, M, L.sv);
                 done = true;
             }
             break;
@@ -1580,9 +1583,15 @@ BHRT_HD int sample_step(Lane &L, Frame &f, Frame &child, const SceneView &s, con
             V3 irrad = illuminate_end(Lt, f.p, L.hit_ok);
             L.sv = L.sv + irrad * direct_brdf(s, f, M, L.sw);
             if (det) { L.si++; stage = ST_DIRECT; }
-            else { direct_finish(s, pg, f, M, L.sv); done = true; }
+            else if (pg.use) { stage = ST_GATHER_WAIT; return STEP_GATHER; }
+            else { direct_finish(s, false, V3(0, 0, 0), V3(0, 0, 0), f, M, L.sv); done = true; }
             break;
         }
+        case ST_GATHER_WAIT:
+            // the caustic term (MtlBlinn.cpp:329-342) with the estimate the caller left in L.hit.p / L.sw
+            direct_finish(s, true, L.hit.p, L.sw, f, M, L.sv);
+            done = true;
+            break;
         }
 
         if (refr_resolved) {
@@ -1614,6 +1623,7 @@ BHRT_HD bool sample_advance(Lane &L, LaneStack &S, const SceneView &s, const Sha
     for (;;) {
         const int top = L.sp > 0 ? L.sp - 1 : 0, up = L.sp < BHRT_MAX_FRAMES ? L.sp : BHRT_MAX_FRAMES - 1;
         int r = sample_step(L, S.fr[top], S.fr[up], s, cfg, pg, bgu, bgv, rc, color);
+        if (r == STEP_GATHER) { estimate_irradiance(pg, S.fr[top].p, S.fr[top].vN, L.hit.p, L.sw); continue; }
         if (r == STEP_RAY) return false;
         if (r == STEP_DONE) return true;
     }

@@ -267,7 +267,8 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     a.smem_lights = al16(a.smem_materials + c->view.n_materials * (int)sizeof(bhrt_material));
     a.smem_offsets = al16(a.smem_lights + c->view.n_lights * (int)sizeof(bhrt_light));
     a.smem_wave = al16(a.smem_offsets + 2 * (BHRT_TEX_SAMPLES - 1) * (int)sizeof(float));
-    const int smem_bytes = al16(a.smem_wave + wf_wave_smem_bytes(a.pool));
+    a.smem_gather = al16(a.smem_wave + wf_wave_smem_bytes(a.pool));
+    const int smem_bytes = al16(a.smem_gather + (WF_BLOCK / 32) * (int)sizeof(PmWarpScratch));
     // stochastic frames run the fast-math build of the kernel unless the caller asks for the exact one
     const bool fast = p->mode == BHRT_MODE_PATH && !(p->flags & BHRT_FLAG_EXACT_MATH);
     if (!c->kernel_ready || c->kernel_smem != smem_bytes) {

@@ -54,7 +54,7 @@ enum { WF_ST_PRIMARY = 0, WF_ST_REFR_IN = 1, WF_ST_REFR_OUT = 2, WF_ST_GI_TRACE 
 __device__ __forceinline__ unsigned wf_stage_slot(int stage)
 {
     // ST_REFR 0, ST_REFR_IN_WAIT 1, ST_REFR_OUT_WAIT 2, ST_REFR_WAIT 3, ST_GI 4, ST_GI_TRACE_WAIT 5, ST_GI_WAIT 6, ST_DIRECT 7, ST_SHADOW_WAIT 8
-    const unsigned long long table = 0x455355215ull;       // nibble i = slot of stage i
+    const unsigned long long table = 0x5455355215ull;      // nibble i = slot of stage i (ST_GATHER_WAIT 9 never waits across a sort)
     return (unsigned)((table >> (4 * stage)) & 15ull);
 }
 // key of a lane whose pending ray has been answered (hit_ok / hit node known)
@@ -104,7 +104,7 @@ struct WaveArgs {
     unsigned pool;              // lanes per CTA (<= 65535)
     int mesh_budget;            // traversal trips a thread may still run after the last warp left the lanes pass
     unsigned mesh_batch;        // queued rays that switch the traversal phase on
-    int smem_nodes, smem_materials, smem_lights, smem_offsets, smem_wave;   // byte offsets into dynamic shared memory
+    int smem_nodes, smem_materials, smem_lights, smem_offsets, smem_wave, smem_gather;   // byte offsets into dynamic shared memory
 };
 
 // dynamic shared memory needed by the CTA-local wavefront for `pool` lanes
@@ -165,6 +165,190 @@ __device__ __forceinline__ bool work_to_pixel(const SceneView &s, const WaveArgs
     return true;
 }
 
+// ---- caustic irradiance estimate, one query per WARP ------------------------------------------------
+// estimate_irradiance (core.cuh) restated for 32 cooperating lanes: the same selection -- the k nearest
+// photons within the radius with dir.N < 0, constant filter (cyPhotonMap.h:332-382,421-498) -- but the
+// lanes stride together over the photons of the 27 cells (32-byte records, coalesced), the 32-bin
+// histograms of the radix select live in shared memory, and the sums are warp reductions.  A thread
+// running the scalar version visits the same tens of thousands of photons alone, with its histogram
+// in thread-local memory; the reference spends 85 % of a photon-mapped render here.
+// All arguments are warp-uniform; every lane returns the same result.  `wsm` = this warp's scratch.
+struct PmWarpScratch { int hist[32]; float cd2[BHRT_PM_CAND]; uint32_t cidx[BHRT_PM_CAND]; int ncand; int pad[3]; };
+
+__device__ __forceinline__ float wf_sum(float v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+__device__ __forceinline__ float wf_max(float v) { for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+__device__ __forceinline__ V3 wf_sum3(V3 v) { return V3(wf_sum(v.x), wf_sum(v.y), wf_sum(v.z)); }
+
+__device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction, PmWarpScratch *wsm)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    irrad = V3(0, 0, 0); direction = V3(0, 0, 0);
+    if (pg.n_photons <= 0) return;
+    const float r2 = pg.radius * pg.radius;
+    float f[3] = { (pos.x - pg.origin[0]) / pg.cell, (pos.y - pg.origin[1]) / pg.cell, (pos.z - pg.origin[2]) / pg.cell };
+    int c[3], sub[3];
+    bool inside = true;
+    for (int a = 0; a < 3; a++) {
+        c[a] = (int)floorf(f[a]);
+        if (c[a] < -1 || c[a] > pg.dim[a]) return;
+        int s_ = (int)((f[a] - c[a]) * 16.f);
+        sub[a] = s_ < 0 ? 0 : (s_ > 15 ? 15 : s_);
+        if (c[a] < 0 || c[a] >= pg.dim[a]) inside = false;
+    }
+    int level = 0;
+    if (inside) {
+        uint32_t coarse = (uint32_t)c[0] + (uint32_t)pg.dim[0] * ((uint32_t)c[1] + (uint32_t)pg.dim[1] * (uint32_t)c[2]);
+        float n_c = (float)(pg.coarse_start[coarse + 1] - pg.coarse_start[coarse]) * 3.14159265f;
+        float need = 2.f * pg.k * 16.f;
+        while (level < BHRT_PM_LEVELS - 1 && n_c > need) { level++; need *= 16.f; }
+    }
+    for (;;) {
+        // lane n < 27 owns the key range of cell n of the 3x3x3 block (pm_ranges, one cell per lane)
+        uint32_t my_b = 0, my_e = 0;
+        if (lane < 27u) {
+            const int sh = 4 - level, span = 1 << level;
+            const int dz = (int)lane / 9 - 1, dy = ((int)lane / 3) % 3 - 1, dx = (int)lane % 3 - 1;
+            const int x = ((c[0] << level) | (sub[0] >> sh)) + dx, y = ((c[1] << level) | (sub[1] >> sh)) + dy, z = ((c[2] << level) | (sub[2] >> sh)) + dz;
+            if (!(x < 0 || y < 0 || z < 0 || x >= pg.dim[0] * span || y >= pg.dim[1] * span || z >= pg.dim[2] * span)) {
+                const uint32_t cx = (uint32_t)(x >> level), cy = (uint32_t)(y >> level), cz = (uint32_t)(z >> level);
+                const uint32_t coarse = cx + (uint32_t)pg.dim[0] * (cy + (uint32_t)pg.dim[1] * cz);
+                const uint32_t lo = pg.coarse_start[coarse], hi = pg.coarse_start[coarse + 1];
+                if (lo != hi) {
+                    if (level == 0) { my_b = lo; my_e = hi; }
+                    else {
+                        const uint32_t m = photon_morton12((uint32_t)(x & (span - 1)) << sh, (uint32_t)(y & (span - 1)) << sh, (uint32_t)(z & (span - 1)) << sh);
+                        const uint32_t k0 = (coarse << BHRT_PM_FINE_BITS) | m, k1 = k0 + (1u << (3 * sh));
+                        my_b = pm_lower_bound(pg.keys, lo, hi, k0);
+                        my_e = pm_lower_bound(pg.keys, my_b, hi, k1);
+                    }
+                }
+            }
+        }
+        const float cell_l = pg.cell / (float)(1 << level);
+        float bound2 = 0.998f * cell_l * cell_l;
+        if (bound2 > r2) bound2 = r2;
+        const float scale = 32.f / bound2;
+        // ---- pass A
+        wsm->hist[lane] = 0;
+        __syncwarp();
+        int total = 0;
+        V3 sumP(0, 0, 0), sumD(0, 0, 0);
+        for (int n = 0; n < 27; n++) {
+            const uint32_t b = __shfl_sync(0xffffffffu, my_b, n), e = __shfl_sync(0xffffffffu, my_e, n);
+            for (uint32_t i = b + lane; i < e; i += 32u) {
+                F4 A = ld4(&pg.recs[i].a);
+                V3 dif(A.x - pos.x, A.y - pos.y, A.z - pos.z);
+                float d2 = length2(dif);
+                if (!(d2 < bound2)) continue;
+                F4 B = ld4(&pg.recs[i].b);
+                if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;
+                uint32_t u = (uint32_t)((d2 * scale) * 32768.f); if (u > 0xfffffu) u = 0xfffffu;
+                atomicAdd(&wsm->hist[u >> 15], 1);
+                total++;
+                if (level == 0) { sumP = sumP + pm_power(&pg.recs[i], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w; }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        __syncwarp();
+        if (total <= pg.k) {
+            if (level > 0) { level--; continue; }
+            if (total == 0) return;
+            sumP = wf_sum3(sumP); sumD = wf_sum3(sumD);
+            irrad = sumP * (1.0f / (3.14159265358979323846f * r2));
+            direction = normalized(sumD);
+            return;
+        }
+        // ---- radix-32 select of the k-th smallest squared distance
+        uint32_t prefix = 0;
+        int shift = 15, need = pg.k;
+        for (;;) {
+            const int h = wsm->hist[lane];
+            int incl = h;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+            const unsigned m = __ballot_sync(0xffffffffu, incl >= need);
+            const int b = m ? __ffs(m) - 1 : 31;
+            const int cum = __shfl_sync(0xffffffffu, incl - h, b), hb = __shfl_sync(0xffffffffu, h, b);
+            need -= cum;
+            prefix = (prefix << 5) | (uint32_t)b;
+            if (hb <= BHRT_PM_CAND || shift == 0) break;
+            shift -= 5;
+            __syncwarp();
+            wsm->hist[lane] = 0;
+            __syncwarp();
+            for (int n = 0; n < 27; n++) {
+                const uint32_t bb = __shfl_sync(0xffffffffu, my_b, n), e = __shfl_sync(0xffffffffu, my_e, n);
+                for (uint32_t i = bb + lane; i < e; i += 32u) {
+                    F4 A = ld4(&pg.recs[i].a);
+                    V3 dif(A.x - pos.x, A.y - pos.y, A.z - pos.z);
+                    float d2 = length2(dif);
+                    if (!(d2 < bound2)) continue;
+                    uint32_t u = (uint32_t)((d2 * scale) * 32768.f); if (u > 0xfffffu) u = 0xfffffu;
+                    if ((u >> (shift + 5)) != prefix) continue;
+                    F4 B = ld4(&pg.recs[i].b);
+                    if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;
+                    atomicAdd(&wsm->hist[(u >> shift) & 31u], 1);
+                }
+            }
+            __syncwarp();
+        }
+        // ---- last pass: everything below the crossing bin is in; the crossing bin's photons are candidates
+        if (lane == 0) wsm->ncand = 0;
+        __syncwarp();
+        sumP = V3(0, 0, 0); sumD = V3(0, 0, 0);
+        V3 subP(0, 0, 0), subD(0, 0, 0);
+        float kth2 = 0, sub_max = 0;
+        for (int n = 0; n < 27; n++) {
+            const uint32_t bb = __shfl_sync(0xffffffffu, my_b, n), e = __shfl_sync(0xffffffffu, my_e, n);
+            for (uint32_t i = bb + lane; i < e; i += 32u) {
+                F4 A = ld4(&pg.recs[i].a);
+                V3 dif(A.x - pos.x, A.y - pos.y, A.z - pos.z);
+                float d2 = length2(dif);
+                if (!(d2 < bound2)) continue;
+                uint32_t u = (uint32_t)((d2 * scale) * 32768.f); if (u > 0xfffffu) u = 0xfffffu;
+                const uint32_t top = u >> shift;
+                if (top > prefix) continue;
+                F4 B = ld4(&pg.recs[i].b);
+                if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;
+                if (top < prefix) {
+                    sumP = sumP + pm_power(&pg.recs[i], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w;
+                    kth2 = fmaxf(kth2, d2);
+                } else {
+                    subP = subP + pm_power(&pg.recs[i], A.w); subD = subD + V3(B.x, B.y, B.z) * A.w;
+                    sub_max = fmaxf(sub_max, d2);
+                    const int slot = atomicAdd(&wsm->ncand, 1);
+                    if (slot < BHRT_PM_CAND) { wsm->cd2[slot] = d2; wsm->cidx[slot] = i; }
+                }
+            }
+        }
+        __syncwarp();
+        const int ncand = wsm->ncand;
+        if (ncand > BHRT_PM_CAND) {
+            // more than 48 photons share all 20 key bits (coincident positions): keep them all
+            sumP = sumP + subP; sumD = sumD + subD;
+            kth2 = fmaxf(kth2, sub_max);
+        } else {
+            // exact: candidate j is in iff fewer than `need` candidates are nearer (ties by slot)
+            for (int j = (int)lane; j < ncand; j += 32) {
+                const float dj = wsm->cd2[j];
+                int rank = 0;
+                for (int i = 0; i < ncand; i++) { const float di = wsm->cd2[i]; rank += (di < dj || (di == dj && i < j)) ? 1 : 0; }
+                if (rank < need) {
+                    const uint32_t ix = wsm->cidx[j];
+                    F4 A = ld4(&pg.recs[ix].a); F4 B = ld4(&pg.recs[ix].b);
+                    sumP = sumP + pm_power(&pg.recs[ix], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w;
+                    kth2 = fmaxf(kth2, dj);
+                }
+            }
+        }
+        sumP = wf_sum3(sumP); sumD = wf_sum3(sumD); kth2 = wf_max(kth2);
+        __syncwarp();
+        const float area = 3.14159265358979323846f * kth2;
+        irrad = area > 0 ? sumP * (1.0f / area) : sumP;
+        direction = normalized(sumD);
+        return;
+    }
+}
+
 // ---- the persistent kernel ------------------------------------------------------------------------
 __global__ void __launch_bounds__(WF_BLOCK, 1)
 wf_render(SceneView s, WaveArgs a)
@@ -176,6 +360,7 @@ wf_render(SceneView s, WaveArgs a)
     unsigned short *mq = list + P;                                         // [P] mesh queue (ring)
     unsigned char *lkey = (unsigned char *)(mq + P);                       // [P] key of lane id
     unsigned char *pend = lkey + P;                                        // [P] lane id is queued / being traversed
+    PmWarpScratch *pm_scratch = (PmWarpScratch *)(smem + a.smem_gather);   // [WF_BLOCK / 32]
     unsigned short *gcount = (unsigned short *)(pend + P);                 // [P/32][WF_NKEYS] per-group key counts / offsets (P is a multiple of 32)
     __shared__ unsigned key_count[WF_NKEYS], key_base[WF_NKEYS];
     __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor;
@@ -227,7 +412,19 @@ wf_render(SceneView s, WaveArgs a)
             // stages (and reach a stage after different numbers of steps): each trip runs ONE
             // stage -- the earliest any lane is in -- for all lanes that are in it, so later
             // stages wait until the stragglers have caught up and then run together.
+            bool want_gather = false;
             for (;;) {
+                // caustic gathers asked for in the last trip: the whole warp evaluates them, one query at a time
+                for (unsigned gm = __ballot_sync(0xffffffffu, want_gather); gm; gm &= gm - 1u) {
+                    const int src = __ffs(gm) - 1;
+                    V3 qp(0, 0, 0), qn(0, 0, 0);
+                    if ((int)lane == src) { const Frame &fq = frames[L.sp - 1]; qp = fq.p; qn = fq.vN; }
+                    qp = V3(__shfl_sync(0xffffffffu, qp.x, src), __shfl_sync(0xffffffffu, qp.y, src), __shfl_sync(0xffffffffu, qp.z, src));
+                    qn = V3(__shfl_sync(0xffffffffu, qn.x, src), __shfl_sync(0xffffffffu, qn.y, src), __shfl_sync(0xffffffffu, qn.z, src));
+                    V3 irr, dirv;
+                    estimate_irradiance_warp(a.gather, qp, qn, irr, dirv, pm_scratch + (tid >> 5));
+                    if ((int)lane == src) { L.hit.p = irr; L.sw = dirv; want_gather = false; }
+                }
                 const int st = running ? (L.sp == 0 ? -1 : (int)L.stage[L.sp - 1]) : 127;
                 const int mn = __reduce_min_sync(0xffffffffu, st);
                 if (mn == 127) break;
@@ -235,6 +432,7 @@ wf_render(SceneView s, WaveArgs a)
                 V3 c;
                 const int r = sample_step(L, frames[L.sp > 0 ? L.sp - 1 : 0], frames[L.sp < BHRT_MAX_FRAMES ? L.sp : BHRT_MAX_FRAMES - 1],
                                           s, a.cfg, a.gather, L.bgu, L.bgv, rc, c);
+                if (r == STEP_GATHER) { want_gather = true; continue; }
                 if (r == STEP_RAY) { running = false; continue; }
                 if (r == STEP_DONE) {
                     a.samples[L.work] = make_float4(c.x, c.y, c.z, 1.f);
