@@ -57,10 +57,15 @@ inline bool build_accel(const bhrt_scene_desc &D, AccelBlob &out, std::string *e
         std::vector<int> pair_of(m.n_bvh_nodes + 2, -1);
         std::vector<uint32_t> order;           // internal node ids in pair order
         {
-            std::vector<uint32_t> st;
-            st.push_back(1);
+            std::vector<uint32_t> st, depth;
+            st.push_back(1); depth.push_back(0);
             while (!st.empty()) {
                 uint32_t n = st.back(); st.pop_back();
+                const uint32_t dn = depth.back(); depth.pop_back();
+                // the traversal defers one sibling per level on a fixed stack: a deeper tree cannot be
+                // traversed correctly, so it is refused here instead of dropping nodes silently
+                if (dn > BHRT_BVH_STACK) { if (err) *err = "mesh BVH deeper than BHRT_BVH_STACK levels"; return false; }
+                if (dn > A.max_depth) A.max_depth = dn;
                 if (n == 0 || n > (uint32_t)m.n_bvh_nodes) { if (err) *err = "mesh BVH child index out of range"; return false; }
                 uint32_t d = bvh[n].data;
                 if (BHRT_BVH_LEAF(d)) continue;
@@ -68,8 +73,8 @@ inline bool build_accel(const bhrt_scene_desc &D, AccelBlob &out, std::string *e
                 pair_of[n] = (int)order.size();
                 order.push_back(n);
                 uint32_t c1 = BHRT_BVH_CHILD(d);
-                st.push_back(c1 + 1);
-                st.push_back(c1);           // child 1 is numbered right after its parent
+                st.push_back(c1 + 1); depth.push_back(dn + 1);
+                st.push_back(c1); depth.push_back(dn + 1);          // child 1 is numbered right after its parent
             }
         }
         auto word = [&](uint32_t n) -> uint32_t {

@@ -163,7 +163,7 @@ struct alignas(16) TriRec { F4 a, b, c; };
 struct alignas(64) PairNode { float box1[6], box2[6]; uint32_t word1, word2, pad0, pad1; };
 struct MeshAccel {
     float root_box[6];
-    uint32_t root_word, pad;
+    uint32_t root_word, max_depth;          // max_depth: levels below the root (checked against BHRT_BVH_STACK at upload)
     int64_t pairs_off, tris_off;            // byte offsets into SceneView::accel_data
     int64_t vn_off, vt_off, fn_off, ft_off; // byte offsets into SceneView::mesh_data (attributes of the final hit)
 };

@@ -62,7 +62,7 @@ struct bhrt_ctx {
     DevBuf accels, accel_data;
     bool kernel_ready = false;
     int kernel_smem = 0, render_blocks = 1;
-    unsigned pool_lanes = 2048;                 // lanes (camera samples in flight) per CTA, 2.3 KB of state each
+    unsigned pool_lanes = 3072;                 // lanes (camera samples in flight) per CTA, 2.3 KB of state each
     int mesh_budget = WF_MESH_BUDGET;
     unsigned mesh_batch = WF_BLOCK;
     DevBuf lanes, frames, samples, wave_counters;
