@@ -303,18 +303,22 @@ BHRT_HD bool photon_key(const float *origin, float cell, const int *dim, V3 p, u
 
 // ------------------------------------------------------------------------------------------
 // Box::IntersectRay (reference Objects/Box/Box.cpp:3-46)
-BHRT_HD bool intersect_box(const float *b, const Ray &r, float t_max, float &t_min)
+BHRT_HD bool intersect_box6(float b0, float b1, float b2, float b3, float b4, float b5, const Ray &r, float t_max, float &t_min)
 {
-    float tz1 = (r.dir.z != 0) ? (b[2] - r.p.z) / r.dir.z : BHRT_BIGFLOAT;
-    float tz2 = (r.dir.z != 0) ? (b[5] - r.p.z) / r.dir.z : -BHRT_BIGFLOAT;
-    float ty1 = (r.dir.y != 0) ? (b[1] - r.p.y) / r.dir.y : BHRT_BIGFLOAT;
-    float ty2 = (r.dir.y != 0) ? (b[4] - r.p.y) / r.dir.y : -BHRT_BIGFLOAT;
-    float tx1 = (r.dir.x != 0) ? (b[0] - r.p.x) / r.dir.x : BHRT_BIGFLOAT;
-    float tx2 = (r.dir.x != 0) ? (b[3] - r.p.x) / r.dir.x : -BHRT_BIGFLOAT;
+    float tz1 = (r.dir.z != 0) ? (b2 - r.p.z) / r.dir.z : BHRT_BIGFLOAT;
+    float tz2 = (r.dir.z != 0) ? (b5 - r.p.z) / r.dir.z : -BHRT_BIGFLOAT;
+    float ty1 = (r.dir.y != 0) ? (b1 - r.p.y) / r.dir.y : BHRT_BIGFLOAT;
+    float ty2 = (r.dir.y != 0) ? (b4 - r.p.y) / r.dir.y : -BHRT_BIGFLOAT;
+    float tx1 = (r.dir.x != 0) ? (b0 - r.p.x) / r.dir.x : BHRT_BIGFLOAT;
+    float tx2 = (r.dir.x != 0) ? (b3 - r.p.x) / r.dir.x : -BHRT_BIGFLOAT;
     float tMin = fmaxr(fmaxr(fminr(tx1, tx2), fminr(ty1, ty2)), fminr(tz1, tz2));
     float tMax = fminr(fminr(fmaxr(tx1, tx2), fmaxr(ty1, ty2)), fmaxr(tz1, tz2));
     if (tMin <= tMax && tMin < t_max) { t_min = tMin; return true; }
     return false;
+}
+BHRT_HD bool intersect_box(const float *b, const Ray &r, float t_max, float &t_min)
+{
+    return intersect_box6(b[0], b[1], b[2], b[3], b[4], b[5], r, t_max, t_min);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -375,11 +379,9 @@ BHRT_HD void intersect_pair(const PairNode *pn, const Ray &r, float t_max, bool 
 {
     const F4 *q = reinterpret_cast<const F4 *>(pn);
     F4 q0 = ld4(q), q1 = ld4(q + 1), q2 = ld4(q + 2), q3 = ld4(q + 3);
-    float b1[6] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y };
-    float b2[6] = { q1.z, q1.w, q2.x, q2.y, q2.z, q2.w };
     t1 = BHRT_BIGFLOAT; t2 = BHRT_BIGFLOAT;
-    h1 = intersect_box(b1, r, t_max, t1);
-    h2 = intersect_box(b2, r, t_max, t2);
+    h1 = intersect_box6(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, t_max, t1);
+    h2 = intersect_box6(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, t_max, t2);
     w1 = f2u(q3.x); w2 = f2u(q3.y);
 }
 
@@ -546,17 +548,19 @@ struct alignas(16) Query {
 BHRT_HD bool scene_trace_graph(const SceneView &s, const Query &q, Hit &h, uint32_t &mesh_mask)
 {
     const bool shadow = (q.kind == Q_SHADOW);
+    // the rays in the space of the current ancestors: depths 1 and 2 (every repository scene) stay in
+    // registers, deeper graphs use the array
     Ray rs[BHRT_MAX_DEPTH + 1];
-    rs[0] = q.ray;
+    Ray r1 = q.ray, r2 = q.ray;
     h.init();
     mesh_mask = 0;
     int mesh_ordinal = 0;
     for (int k = 0; k < s.n_nodes; k++) {
         const bhrt_node &nd = s.nodes[k];
         const int d = nd.depth;
-        const Ray &pr = rs[d - 1];
+        const Ray pr = d == 1 ? q.ray : (d == 2 ? r1 : (d == 3 ? r2 : rs[d - 1]));
         Ray r = to_node(nd.xf, pr);
-        if (d < s.max_depth) rs[d] = r;
+        if (d == 1) r1 = r; else if (d == 2) r2 = r; else if (d < s.max_depth) rs[d] = r;
         bool hit = false;
         if (nd.kind == BHRT_OBJ_SPHERE) {
             // Sphere::IntersectRay (Sphere.cpp:8-49) / the inline quadratic of GenLight.cpp:24-43
