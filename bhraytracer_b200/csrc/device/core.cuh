@@ -1133,14 +1133,15 @@ BHRT_FN void estimate_irradiance(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad
         if (c[a] < 0 || c[a] >= pg.dim[a]) inside = false;
     }
     // starting level from the population of the query's coarse cell (surface density guess):
-    // expect ~ n_c * pi / 16^l qualifying photons within one level-l cell edge
+    // expect ~ n_c * pi / 4^l qualifying photons within one level-l cell edge
     int level = 0;
     if (inside) {
         uint32_t coarse = (uint32_t)c[0] + (uint32_t)pg.dim[0] * ((uint32_t)c[1] + (uint32_t)pg.dim[1] * (uint32_t)c[2]);
         float n_c = (float)(pg.coarse_start[coarse + 1] - pg.coarse_start[coarse]) * 3.14159265f;
-        float need = 2.f * pg.k * 16.f;
-        while (level < BHRT_PM_LEVELS - 1 && n_c > need) { level++; need *= 16.f; }
+        float need = 2.f * pg.k * 4.f;
+        while (level < BHRT_PM_LEVELS - 1 && n_c > need) { level++; need *= 4.f; }
     }
+    bool coarsened = false;         // a finer level held too few photons: do not try it again
     PmRange R;
     int hist[32];
     for (;;) {
@@ -1166,7 +1167,7 @@ BHRT_FN void estimate_irradiance(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad
                 if (level == 0) { sumP = sumP + pm_power(&pg.recs[i], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w; }
             }
         if (total <= pg.k) {
-            if (level > 0) { level--; continue; }           // the k nearest do not fit in this block: one level up
+            if (level > 0) { level--; coarsened = true; continue; }           // the k nearest do not fit in this block: one level up
             if (total == 0) return;
             // at most k photons qualified within the radius: area = pi * radius^2 (dist2[0] never shrank)
             float area = 3.14159265358979323846f * r2;
@@ -1174,6 +1175,8 @@ BHRT_FN void estimate_irradiance(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad
             direction = normalized(sumD);
             return;
         }
+        // far more than k: a finer level answers the same question from a quarter of the photons
+        if (!coarsened && level < BHRT_PM_LEVELS - 1 && total > 8 * pg.k) { level++; continue; }
         // ---- more than k qualify: find the k-th smallest squared distance by a radix-32 select on
         // u = (int)(d2 * scale * 2^15), a 20-bit key whose top digit is the bin of pass A (the
         // products are exact scalings by powers of two, so every pass sees the same digits)

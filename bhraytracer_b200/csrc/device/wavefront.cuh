@@ -199,9 +199,10 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
     if (inside) {
         uint32_t coarse = (uint32_t)c[0] + (uint32_t)pg.dim[0] * ((uint32_t)c[1] + (uint32_t)pg.dim[1] * (uint32_t)c[2]);
         float n_c = (float)(pg.coarse_start[coarse + 1] - pg.coarse_start[coarse]) * 3.14159265f;
-        float need = 2.f * pg.k * 16.f;
-        while (level < BHRT_PM_LEVELS - 1 && n_c > need) { level++; need *= 16.f; }
+        float need = 2.f * pg.k * 4.f;
+        while (level < BHRT_PM_LEVELS - 1 && n_c > need) { level++; need *= 4.f; }
     }
+    bool coarsened = false;         // a finer level held too few photons: do not try it again
     for (;;) {
         // lane n < 27 owns the key range of cell n of the 3x3x3 block (pm_ranges, one cell per lane)
         uint32_t my_b = 0, my_e = 0;
@@ -251,13 +252,14 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
         for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
         __syncwarp();
         if (total <= pg.k) {
-            if (level > 0) { level--; continue; }
+            if (level > 0) { level--; coarsened = true; continue; }
             if (total == 0) return;
             sumP = wf_sum3(sumP); sumD = wf_sum3(sumD);
             irrad = sumP * (1.0f / (3.14159265358979323846f * r2));
             direction = normalized(sumD);
             return;
         }
+        if (!coarsened && level < BHRT_PM_LEVELS - 1 && total > 8 * pg.k) { level++; continue; }
         // ---- radix-32 select of the k-th smallest squared distance
         uint32_t prefix = 0;
         int shift = 15, need = pg.k;
