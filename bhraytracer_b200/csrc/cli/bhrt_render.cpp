@@ -3,7 +3,10 @@
 // It stays C++ and reaches the GPU only through the C ABI of include/bhrt.h.
 //
 // usage: bhrt_render <scene.xml> <out_prefix> [--det] [--spp N] [--gi N] [--seed S] [--size W H]
-//                    [--device D] [--aov] [--photons N]
+//                    [--device D] [--aov] [--photons N] [--photons-out F.dat] [--photons-in F.dat]
+// --photons-out writes the caustic map like the reference does (Main.cpp:380-385: 24-byte records,
+// powers already scaled by 1/stored; PhotonMapViewer/PhotonMapViz.cpp reads this file); --photons-in
+// renders with such a file (e.g. one the reference wrote) instead of emitting photons.
 // writes <out_prefix>.png (RenderImage::SaveImage equivalent) and, with --aov, <out_prefix>.aov in
 // the layout of oracle/ref_build/driver.cpp; prints one JSON line.
 #include <cstdio>
@@ -21,6 +24,7 @@ int main(int argc, char **argv)
     memset(&p, 0, sizeof(p));
     p.mode = BHRT_MODE_PATH; p.spp = 32; p.gi_depth = 3; p.tir_budget = 16; p.seed = 1;
     int W = 0, H = 0, device = 0, aov = 0, photons = 0;
+    const char *photons_out = nullptr, *photons_in = nullptr;
     for (int a = 3; a < argc; a++) {
         if (!strcmp(argv[a], "--det")) p.mode = BHRT_MODE_DET;
         else if (!strcmp(argv[a], "--spp") && a + 1 < argc) p.spp = atoi(argv[++a]);
@@ -29,6 +33,8 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[a], "--size") && a + 2 < argc) { W = atoi(argv[++a]); H = atoi(argv[++a]); }
         else if (!strcmp(argv[a], "--device") && a + 1 < argc) device = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--photons") && a + 1 < argc) photons = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--photons-out") && a + 1 < argc) photons_out = argv[++a];
+        else if (!strcmp(argv[a], "--photons-in") && a + 1 < argc) photons_in = argv[++a];
         else if (!strcmp(argv[a], "--aov")) aov = 1;
         else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
     }
@@ -50,6 +56,32 @@ int main(int argc, char **argv)
             fprintf(stderr, "photon map: %s\n", bhrt_last_error()); return 4;
         }
         p.use_photon_map = 1; p.photon_k = 1000; p.photon_radius = 0.5f;
+    }
+    if (photons_in) {
+        FILE *fp = fopen(photons_in, "rb");
+        if (!fp) { fprintf(stderr, "cannot read %s\n", photons_in); return 3; }
+        std::vector<uint8_t> rec;
+        uint8_t buf[24 * 4096];
+        size_t got;
+        while ((got = fread(buf, 1, sizeof(buf), fp)) > 0) rec.insert(rec.end(), buf, buf + got);
+        fclose(fp);
+        stored = (int)(rec.size() / 24);
+        // the file holds scaled powers already: total_stored = 1 leaves them as they are
+        if (bhrt_photons_set(ctx, rec.data(), stored, 0) || bhrt_photons_build(ctx, 1)) { fprintf(stderr, "photon map: %s\n", bhrt_last_error()); return 4; }
+        p.use_photon_map = 1; p.photon_k = 1000; p.photon_radius = 0.5f;
+    }
+    if (photons_out && stored > 0 && !photons_in) {
+        std::vector<uint8_t> rec((size_t)stored * 24);
+        int32_t got = 0;
+        if (bhrt_photons_get(ctx, rec.data(), stored, &got)) { fprintf(stderr, "photon map: %s\n", bhrt_last_error()); return 4; }
+        for (int i = 0; i < got; i++) {                 // ScalePhotonPowers(1 / stored) (Main.cpp:380, cyPhotonMap.h:149-152)
+            float pw; memcpy(&pw, &rec[(size_t)i * 24 + 12], 4);
+            pw *= 1.0f / (float)got;
+            memcpy(&rec[(size_t)i * 24 + 12], &pw, 4);
+        }
+        FILE *fp = fopen(photons_out, "wb");
+        if (!fp || fwrite(rec.data(), 24, (size_t)got, fp) != (size_t)got) { fprintf(stderr, "cannot write %s\n", photons_out); return 3; }
+        fclose(fp);
     }
     size_t n = (size_t)W * H;
     std::vector<uint8_t> rgb8(n * 3);

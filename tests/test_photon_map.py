@@ -242,3 +242,23 @@ def test_gpu_emit_build_render_caustic(renderer):
     gain = with_pm["linear"].sum() - without["linear"].sum()
     ref_gain_8bit = (ref.sum() - without["rgb8"].astype(np.float64).sum())
     assert gain > 0 and ref_gain_8bit > 0
+
+
+@pytest.mark.gpu
+def test_cli_photon_dat_round_trip(built, tmp_path):
+    """bhrt_render --photons-out writes the reference's on-disk map (24-byte records, scaled powers,
+    Main.cpp:380-385); --photons-in renders with such a file -- here the REFERENCE's own dump from the
+    fixture, which must give the reference's image."""
+    cli = os.path.join(ROOT, "bhraytracer_b200", "lib", "bhrt_render")
+    ref_dat = tmp_path / "ref.dat"
+    GOLD["photons"].tofile(str(ref_dat))
+    subprocess.check_output([cli, SCENE, str(tmp_path / "in"), "--det", "--size", str(W), str(H), "--photons-in", str(ref_dat), "--aov"], cwd=ROOT)
+    a = read_aov(str(tmp_path / "in.aov"))
+    check_gather_image(a["rgb8"], a["hit_id"])
+    out_dat = tmp_path / "ours.dat"
+    info = json.loads(subprocess.check_output([cli, SCENE, str(tmp_path / "out"), "--det", "--size", str(W), str(H), "--photons", "20000",
+                                               "--photons-out", str(out_dat)], cwd=ROOT).decode().splitlines()[-1])
+    rec = as_records(np.fromfile(str(out_dat), dtype=np.uint8).reshape(-1, 24))
+    assert len(rec) == info["photons_stored"] == 20000
+    # scaled like the reference's file: mean power * N is the light's emitted power scale
+    assert abs(float(rec["power"].astype(np.float64).sum()) / float(GOLD["mean_power"]) - 1.0) < 0.05
