@@ -106,10 +106,13 @@ BHRT_HD V3 xf_vec_from(const bhrt_xform &t, V3 d) { return mat_tmul(t.itm, d); }
 struct Ray { V3 p, dir; };
 
 struct alignas(16) Hit {    // reference scene.h:62-75 (HitInfo)
+    // (the first 32 bytes are what a traversal leaves behind -- z, node, front and, for a mesh, the
+    // winning triangle in uvw / duvw0.x; scene_trace_finish recomputes everything else)
     float z;
-    V3 p, N, uvw, duvw0, duvw1;
     int node;               // index into nodes, -1 = none
     bool front;
+    V3 uvw, duvw0;
+    V3 p, N, duvw1;
     BHRT_HD void init()
     {
         z = BHRT_BIGFLOAT; node = -1; front = true;
@@ -1282,15 +1285,17 @@ struct ShadeCfg {
     int gi_depth, tir_budget;
 };
 
-struct alignas(16) Lane {
-    // camera sample this lane is evaluating (wavefront bookkeeping; unused by the estimator)
+// camera sample a lane is evaluating: written when the sample starts, read when it ends
+struct alignas(16) LaneCold {
     unsigned long long work;
     int pi, pj, sidx;
     float bgu, bgv;
-    int sp;                 // frames in use; 0 = waiting for the primary ray
+    int pad_;
+};
+struct alignas(16) Lane {
+    // ---- persistent part: the first BHRT_LANE_PERSIST bytes travel between the lane pool and the
+    // thread on every pass
     Query q;                // the pending ray query
-    Hit hit;                // its answer (closest) ...
-    bool hit_ok;            // ... and whether anything was hit / the shadow ray is blocked
     Rng rng;
     V3 ret;                 // value returned by the child frame that just completed
     // scratch of the top frame's wait states (a child frame runs to completion in between, so
@@ -1299,10 +1304,16 @@ struct alignas(16) Lane {
     V3 sw;                  // direct: the sampled light direction vL
     float sf;               // refraction: glossiness of the refraction lobe
     int si;                 // refraction: remaining internal-reflection budget      direct: light index
+    int sp;                 // frames in use; 0 = waiting for the primary ray
+    bool hit_ok;            // anything was hit / the shadow ray is blocked
+    uint32_t mesh_mask;     // wavefront: mesh nodes whose root box the pending ray entered
     int hit_id; float hit_z;    // primary AOVs of this sample
-    uint32_t mesh_mask;         // wavefront: mesh nodes whose root box the pending ray entered
     uint8_t stage[BHRT_MAX_FRAMES];     // stage of every live recursion level (the frames themselves live apart)
+    Hit hit;                // the query's answer; only its first 32 bytes are persistent
+    // ---- not copied
+    LaneCold cold;
 };
+#define BHRT_LANE_PERSIST 176
 // The recursion levels of one lane: the estimator only ever touches the top frame and, when it
 // recurses, the slot above it.
 struct LaneStack { Frame fr[BHRT_MAX_FRAMES]; };

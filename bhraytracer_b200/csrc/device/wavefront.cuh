@@ -35,6 +35,7 @@
 // count.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstddef>
 #include "core.cuh"
 
 namespace BHRT_NS {
@@ -141,6 +142,22 @@ __device__ __forceinline__ void wf_load(T &dst, const T *src)
     uint4 *d4 = reinterpret_cast<uint4 *>(&dst);
 #pragma unroll
     for (int i = 0; i < (int)(sizeof(T) / 16); i++) d4[i] = s4[i];
+}
+// the persistent part of a lane record only (core.cuh: BHRT_LANE_PERSIST)
+__device__ __forceinline__ void wf_load_lane(Lane &dst, const Lane *src)
+{
+    static_assert(offsetof(Lane, hit) + 32 == BHRT_LANE_PERSIST && BHRT_LANE_PERSIST % 16 == 0 && offsetof(Hit, p) >= 28, "Lane layout");
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(&dst);
+#pragma unroll
+    for (int i = 0; i < BHRT_LANE_PERSIST / 16; i++) d4[i] = s4[i];
+}
+__device__ __forceinline__ void wf_store_lane(Lane *dst, const Lane &src)
+{
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(&src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+    for (int i = 0; i < BHRT_LANE_PERSIST / 16; i++) d4[i] = s4[i];
 }
 template <typename T>
 __device__ __forceinline__ void wf_store(T *dst, const T &src)
@@ -406,7 +423,7 @@ wf_render(SceneView s, WaveArgs a)
             bool want_new = valid && first;
             bool running = valid && !first;
             if (running) {
-                wf_load(L, &lanes[id]);
+                wf_load_lane(L, &lanes[id]);
                 // the answer of the pending query: winner-only work of a closest hit
                 if (L.q.kind == Q_CLOSEST) L.hit_ok = scene_trace_finish(s, L.q, L.hit);
             }
@@ -433,12 +450,13 @@ wf_render(SceneView s, WaveArgs a)
                 if (st != mn) continue;
                 V3 c;
                 const int r = sample_step(L, frames[L.sp > 0 ? L.sp - 1 : 0], frames[L.sp < BHRT_MAX_FRAMES ? L.sp : BHRT_MAX_FRAMES - 1],
-                                          s, a.cfg, a.gather, L.bgu, L.bgv, rc, c);
+                                          s, a.cfg, a.gather, L.sp == 0 ? lanes[id].cold.bgu : 0.f, L.sp == 0 ? lanes[id].cold.bgv : 0.f, rc, c);
                 if (r == STEP_GATHER) { want_gather = true; continue; }
                 if (r == STEP_RAY) { running = false; continue; }
                 if (r == STEP_DONE) {
-                    a.samples[L.work] = make_float4(c.x, c.y, c.z, 1.f);
-                    if (L.sidx == 0) { const size_t p = (size_t)L.pj * s.width + L.pi; a.hit_id[p] = L.hit_id; a.zbuf[p] = L.hit_z; }
+                    const LaneCold &lc = lanes[id].cold;
+                    a.samples[lc.work] = make_float4(c.x, c.y, c.z, 1.f);
+                    if (lc.sidx == 0) { const size_t p = (size_t)lc.pj * s.width + lc.pi; a.hit_id[p] = L.hit_id; a.zbuf[p] = L.hit_z; }
                     want_new = true;
                     running = false;
                 }
@@ -458,8 +476,10 @@ wf_render(SceneView s, WaveArgs a)
                     else {
                         int pi, pj, sidx;
                         if (work_to_pixel(s, a, g, pi, pj, sidx)) {
-                            L.work = g; L.pi = pi; L.pj = pj; L.sidx = sidx;
-                            L.bgu = (float)pi / s.width; L.bgv = (float)pj / s.height;
+                            LaneCold lc;
+                            lc.work = g; lc.pi = pi; lc.pj = pj; lc.sidx = sidx;
+                            lc.bgu = (float)pi / s.width; lc.bgv = (float)pj / s.height; lc.pad_ = 0;
+                            lanes[id].cold = lc;
                             L.rng.seed(a.seed, (uint64_t)pj * s.width + pi, (uint64_t)sidx);
                             Ray pr = primary_ray(s, pi, pj, !det, L.rng);
                             sample_begin(L, pr, rc);
@@ -479,7 +499,7 @@ wf_render(SceneView s, WaveArgs a)
                 L.hit.z = h.z; L.hit.node = h.node; L.hit.front = h.front;
                 L.mesh_mask = 0;
                 if (!blocked && (mask || s.n_mesh_nodes > BHRT_MESH_MASK_BITS)) { L.mesh_mask = mask; to_mesh = true; }
-                wf_store(&lanes[id], L);
+                wf_store_lane(&lanes[id], L);
                 lkey[id] = (unsigned char)wf_key(s, L, frames[L.sp > 0 ? L.sp - 1 : 0]);
             } else if (valid) lkey[id] = WF_KEY_DEAD;
             // queue the rays that entered a mesh
