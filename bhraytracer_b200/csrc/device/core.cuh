@@ -821,7 +821,18 @@ BHRT_HD V3 tile_clamp(V3 uvw)
     if (u.z < 0) u.z += 1;
     return u;
 }
-BHRT_HD V3 texel(const uint8_t *p) { return V3(p[0] / 255.0f, p[1] / 255.0f, p[2] / 255.0f); }
+// Color24::ToColor (cyColor.h:236).  In the kernels the texel table is RGBX8 (expanded at upload:
+// one aligned 32-bit load per texel instead of three byte loads); the CPU harness reads the host's RGB8.
+BHRT_HD V3 texel(const uint8_t *d, int index)
+{
+#ifdef __CUDA_ARCH__
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(d) + index);
+    return V3((float)(v & 255u) / 255.0f, (float)((v >> 8) & 255u) / 255.0f, (float)((v >> 16) & 255u) / 255.0f);
+#else
+    const uint8_t *p = d + 3 * index;
+    return V3(p[0] / 255.0f, p[1] / 255.0f, p[2] / 255.0f);
+#endif
+}
 
 BHRT_FN V3 texture_sample(const SceneView &s, const bhrt_texture &t, V3 uvw)
 {
@@ -841,11 +852,15 @@ BHRT_FN V3 texture_sample(const SceneView &s, const bhrt_texture &t, V3 uvw)
     if (iy < 0) iy -= (iy / height - 1) * height;
     if (iy >= height) iy -= (iy / height) * height;
     int iyp = iy + 1; if (iyp >= height) iyp -= height;
+#ifdef __CUDA_ARCH__
+    const uint8_t *d = s.texels + (t.texel_offset / 3) * 4;        // RGBX8 on the device (texel_offset counts RGB8 bytes)
+#else
     const uint8_t *d = s.texels + t.texel_offset;
-    return texel(d + 3 * (iy * width + ix)) * ((1 - fx) * (1 - fy)) +
-           texel(d + 3 * (iy * width + ixp)) * (fx * (1 - fy)) +
-           texel(d + 3 * (iyp * width + ix)) * ((1 - fx) * fy) +
-           texel(d + 3 * (iyp * width + ixp)) * (fx * fy);
+#endif
+    return texel(d, iy * width + ix) * ((1 - fx) * (1 - fy)) +
+           texel(d, iy * width + ixp) * (fx * (1 - fy)) +
+           texel(d, iyp * width + ix) * ((1 - fx) * fy) +
+           texel(d, iyp * width + ixp) * (fx * fy);
 }
 
 // Texture::Sample(uvw, duvw) (scene.h:318-337): 32-tap elliptical Halton filter when duvw != 0

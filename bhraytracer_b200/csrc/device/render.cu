@@ -173,7 +173,13 @@ int bhrt_upload_scene(bhrt_ctx *c, const bhrt_scene_desc *d)
     c->photons.count = 0; c->photons.built = false;     // a photon map belongs to the scene it was traced in
     if ((r = upload(c, c->texmaps, d->texmaps, sizeof(bhrt_texmap) * d->n_texmaps))) return r;
     if ((r = upload(c, c->textures, d->textures, sizeof(bhrt_texture) * d->n_textures))) return r;
-    if ((r = upload(c, c->texels, d->texels, d->texel_bytes))) return r;
+    // texels: RGB8 -> RGBX8 (one aligned 32-bit load per texel in the kernels)
+    if (d->texel_bytes % 3) return set_err(BHRT_ERR_ARG, "bhrt_upload_scene: texel_bytes is not a multiple of 3");
+    for (int i = 0; i < d->n_textures; i++)
+        if (d->textures[i].kind == BHRT_TEX_FILE && d->textures[i].texel_offset % 3) return set_err(BHRT_ERR_ARG, "bhrt_upload_scene: texel_offset is not a multiple of 3");
+    std::vector<uint8_t> rgbx((d->texel_bytes / 3) * 4);
+    for (size_t i = 0, n = d->texel_bytes / 3; i < n; i++) { rgbx[4 * i] = d->texels[3 * i]; rgbx[4 * i + 1] = d->texels[3 * i + 1]; rgbx[4 * i + 2] = d->texels[3 * i + 2]; rgbx[4 * i + 3] = 0; }
+    if ((r = upload(c, c->texels, rgbx.data(), rgbx.size()))) return r;
     if ((r = upload(c, c->meshes, d->meshes, sizeof(bhrt_mesh) * d->n_meshes))) return r;
     if ((r = upload(c, c->mesh_data, d->mesh_data, d->mesh_bytes))) return r;
     if ((r = upload(c, c->tex_offsets, offs.data(), sizeof(float) * offs.size()))) return r;
