@@ -505,16 +505,6 @@ BHRT_HD void mesh_trav_step(MeshTrav &T)
     if (BHRT_BVH_LEAF(T.cur)) mesh_trav_leaf(T); else mesh_trav_internal(T);
 }
 
-BHRT_HD bool mesh_trace(const SceneView &s, const MeshAccel &A, const Ray &ray, bool any_hit, float t_max_shadow,
-                        float &z, bool &front, int hitSide, MeshHit &mh)
-{
-    MeshTrav T;
-    mesh_trav_begin(T, s, A, ray, any_hit, t_max_shadow, z, front, hitSide);
-    while (!T.done) mesh_trav_step(T);
-    if (!any_hit && T.result) { z = T.z; front = T.front; mh = T.mh; }
-    return T.result;
-}
-
 // ------------------------------------------------------------------------------------------
 // A ray query: the ONE place the estimator meets the geometry.  kind CLOSEST = recursive()
 // (reference Main.cpp:389-413, linear DFS over the scene graph); kind SHADOW = GenLight::Shadow /

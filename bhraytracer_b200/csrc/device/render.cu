@@ -1,10 +1,10 @@
 // render.cu -- libbhrt.so: the sm_100a render kernels and the C ABI of include/bhrt.h.
 //
-// Replaces BeginRender() (reference Main.cpp:178-242): the OpenMP loop over image columns
-// becomes a grid of warps, each owning an 8x4 pixel tile (coherent primary rays); every
-// thread evaluates its pixel's samples with the explicit-stack estimator of core.cuh and
-// adds them in sample order, so a pixel's value is independent of the launch geometry.
-// A second kernel resolves sum/spp -> gamma -> Color24.
+// Replaces BeginRender() (reference Main.cpp:178-242): the OpenMP loop over image columns becomes
+// ONE launch of the persistent kernel wf_render (wavefront.cuh: every CTA runs its own wavefront
+// over a pool of camera samples; exact build here, fast-math build in render_fast.cu), wf_reduce
+// adds the samples of a pixel in sample order, and resolve_kernel does sum/spp -> gamma -> Color24.
+// The photon kernels live in photon.cuh.
 //
 // There is NO CPU fallback in this library: every entry point needs a CUDA device.
 #include <cuda_runtime.h>

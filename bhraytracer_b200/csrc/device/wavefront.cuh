@@ -16,19 +16,22 @@
 // touched by this CTA only, so it lives in L1/L2) and loops over three phases separated by
 // __syncthreads() -- the only synchronisation there is:
 //
-//   P1 lanes   one pass over the CTA's live lanes, SORTED BY THE STAGE THEY RUN NEXT (a warp
-//              executes one case of the estimator; the whole CTA walks the cases in step, which
-//              keeps its instruction footprint small): complete the pending closest hit
-//              (winner-only transcendental work), run the estimator coroutine up to its next ray,
-//              write finished samples and start the next camera sample (warp-aggregated fetch
-//              from the global work counter), then answer the new ray against the scene graph
-//              (warp-uniform node loop, analytic objects, mesh root boxes).  Rays that entered a
-//              mesh are queued; everything else is already answered.
-//   P2 meshes  BVH traversal of the queued rays.  Each THREAD keeps its traversal (stack
-//              included) across iterations and may spend at most WF_MESH_BUDGET node steps per
-//              iteration, so a ray that needs thousands of steps occupies one thread for many
-//              iterations while its lane simply stays out of the live list -- nobody waits for it.
-//   P3 sort    counting sort of the live lanes by next stage (shared memory).
+//   P1 lanes   one pass over the CTA's live lanes, SORTED BY WHAT THEY WILL EXECUTE NEXT (stage x
+//              class of the pending ray's answer, wf_key): warps take 32-lane chunks of the sorted
+//              list from a shared cursor, so a warp executes one case of the estimator and the
+//              whole CTA walks the cases in step.  Per chunk: complete the pending closest hit
+//              (winner-only transcendental work), run the estimator coroutine up to its next ray
+//              (min-stage scheduling inside the warp), write finished samples and start the next
+//              camera sample (warp-aggregated fetch from the global work counter), then answer
+//              the new ray against the scene graph (warp-uniform node loop, analytic objects,
+//              mesh root boxes).  Rays that entered a mesh are queued; the rest is answered.
+//   P3 sort    counting sort of the live lanes by key (shared memory, no atomics).
+//   P2 meshes  BVH traversal of the queued rays, run only when enough are queued to keep every
+//              thread busy.  Each THREAD keeps its traversal (stack included) across iterations
+//              and gets a few more trips after the queue has drained, so a ray that needs
+//              thousands of steps occupies one thread for many iterations while its lane simply
+//              stays out of the live list -- nobody waits for it.  A second sort merges the lanes
+//              it completed.
 //
 // Sample colours go to a per-chunk buffer and are added to the accumulation buffer IN SAMPLE ORDER
 // by wf_reduce, so a pixel's sum is bit-identical whatever the pool size, launch geometry or GPU
@@ -159,15 +162,6 @@ __device__ __forceinline__ void wf_store_lane(Lane *dst, const Lane &src)
 #pragma unroll
     for (int i = 0; i < BHRT_LANE_PERSIST / 16; i++) d4[i] = s4[i];
 }
-template <typename T>
-__device__ __forceinline__ void wf_store(T *dst, const T &src)
-{
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(&src);
-    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d4[i] = s4[i];
-}
-
 // Work item g of the chunk -> (pixel, sample).  Sample-major: consecutive items are the pixels of
 // one 8x8 tile, so the lanes of a warp start on neighbouring primary rays.
 __device__ __forceinline__ bool work_to_pixel(const SceneView &s, const WaveArgs &a, unsigned long long g, int &pi, int &pj, int &sidx)
