@@ -60,7 +60,7 @@ def main():
     kernel = sys.argv[3] if len(sys.argv) > 3 else "wf_render"
     bucket = int(sys.argv[4]) if len(sys.argv) > 4 else 10
     table = line_table(so, kernel)
-    out = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "-k", "regex:" + kernel]).decode(errors="replace")
+    out = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"]).decode(errors="replace")
     rows = list(csv.reader(io.StringIO(out)))
     hdr = rows[1]
     ia, ie, it, ism = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
