@@ -1,0 +1,332 @@
+/* bhrt_oracle.c -- TEST INFRASTRUCTURE, never linked into the product.
+ *
+ * A plain-C restatement of the reference's deterministic hot path for BASELINE config 1 (the
+ * reference's own CPU-runnable case: spheres + planes, point / direct lights, Blinn-Phong with
+ * hard shadows, 1 spp at the pixel corner), written from the reference sources cited at every
+ * function (paths relative to /root/reference/BHRayTracer).  It is independent of csrc/device:
+ * the only thing it shares with the product is the POD scene description of include/bhrt.h.
+ *
+ * PINNED: tests/test_oracle_restatement.py checks it against the committed outputs of the
+ * reference itself (tests/golden/cfg1_spheres_plane_det.npz, made by oracle/_ref/bhrt_ref --det):
+ * primary hit ids and z bit-exact, RGB8 identical, ray counts identical.  The real reference
+ * (oracle/_ref, built by oracle/build_ref.py) remains the oracle for everything outside this
+ * file's scope -- refraction, GI, textures, meshes, photon map -- where a restatement would only
+ * repeat the reference with more room for error.
+ *
+ * Scope check: bhrt_oracle_render_det returns -2 for scenes with meshes, textures or refractive
+ * materials.  "D-mode" = the four switches of SURVEY.md 8(c): no jitter, GI off, every light with
+ * its exact direction, no glossy refraction.
+ *
+ * Build: gcc -O2 -ffp-contract=off -shared -fPIC (oracle/Makefile).  x86-64 without -mfma
+ * contracts nothing, like the reference's own build.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../include/bhrt.h"
+
+#define BIGFLOAT 1.0e30f          /* Scenes/scene.h:38 */
+#define SHADOW_BIAS 0.00001f      /* Lights/GenLight.cpp:5 */
+#define PI_D 3.14159265           /* "#define PI 3.14159265" (Main.cpp, a double literal) */
+enum { HIT_FRONT = 1, HIT_BACK = 2, HIT_FRONT_AND_BACK = 3 };      /* scene.h:57-60 */
+
+typedef struct { float x, y, z; } v3;
+static v3 V(float x, float y, float z) { v3 r = { x, y, z }; return r; }
+/* cyVector.h:273-386 -- component-wise, in this order */
+static v3 add(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+static v3 sub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+static v3 mulf(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
+static v3 mulv(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
+static v3 divf(v3 a, float s) { return V(a.x / s, a.y / s, a.z / s); }
+static v3 neg(v3 a) { return V(-a.x, -a.y, -a.z); }
+static float dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static v3 cross(v3 a, v3 b) { return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+static float len(v3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }     /* cy::Sqrt = sqrtss */
+static v3 norm(v3 a) { return divf(a, len(a)); }                                /* GetNormalized: *this / Length() */
+static v3 ld(const float *p) { return V(p[0], p[1], p[2]); }
+
+/* Matrix3f * Vec3f, column-major cells (cyMatrix.h:297-302) */
+static v3 mat_mul(const float *m, v3 p)
+{
+    return V(p.x * m[0] + p.y * m[3] + p.z * m[6], p.x * m[1] + p.y * m[4] + p.z * m[7], p.x * m[2] + p.y * m[5] + p.z * m[8]);
+}
+/* Transformation::TransposeMult (scene.h:238-245) */
+static v3 mat_tmul(const float *m, v3 d)
+{
+    return V(m[0] * d.x + m[1] * d.y + m[2] * d.z, m[3] * d.x + m[4] * d.y + m[5] * d.z, m[6] * d.x + m[7] * d.y + m[8] * d.z);
+}
+static v3 transform_to(const bhrt_xform *t, v3 p) { return mat_mul(t->itm, sub(p, ld(t->pos))); }      /* scene.h:220 */
+static v3 transform_from(const bhrt_xform *t, v3 p) { return add(mat_mul(t->tm, p), ld(t->pos)); }     /* scene.h:221 */
+static v3 vector_transform_from(const bhrt_xform *t, v3 d) { return mat_tmul(t->itm, d); }             /* scene.h:227 */
+
+typedef struct { v3 p, dir; } ray_t;
+/* Node::ToNodeCoords (scene.h:490-496): the direction is the difference of two transformed points */
+static ray_t to_node_coords(const bhrt_xform *t, ray_t r)
+{
+    ray_t o;
+    o.p = transform_to(t, r.p);
+    o.dir = sub(transform_to(t, add(r.p, r.dir)), o.p);
+    return o;
+}
+
+typedef struct { float z; v3 p, N; int node; int front; } hit_t;     /* scene.h:62-75, the fields config 1 reads */
+
+/* Sphere::IntersectRay (Objects/Sphere/Sphere.cpp:8-75), unit sphere at the origin */
+static int sphere_intersect(ray_t ray, hit_t *h, int hitSide)
+{
+    v3 dir = ray.dir, oc = ray.p;
+    float A = dot(dir, dir);
+    float B = 2 * dot(dir, oc);
+    float C = dot(oc, oc) - 1;
+    float DD = B * B - 4 * A * C;
+    if (DD > 0) {
+        float t1 = (-B + sqrtf(DD)) / (2 * A);
+        float t2 = (-B - sqrtf(DD)) / (2 * A);
+        float t = BIGFLOAT;
+        int front = 1;
+        if (t1 < 0 && t2 < 0) return 0;
+        else if (t1 * t2 <= 0) {
+            if (hitSide == HIT_FRONT) return 0;
+            t = t1; front = 0;
+        } else if (t1 > 0 && t2 > 0) {
+            if (hitSide == HIT_FRONT || hitSide == HIT_FRONT_AND_BACK) { t = t2; front = 1; }
+            else if (hitSide == HIT_BACK) { t = t1; front = 0; }
+        }
+        if (h->z < t || t <= 0) return 0;
+        h->z = t;
+        h->p = add(oc, mulf(dir, h->z));
+        h->N = h->p;
+        h->front = front;
+        return 1;       /* (uv: untextured scenes only, see the scope check) */
+    }
+    return 0;
+}
+
+/* Plane::IntersectRay (Objects/Plane/Plane.cpp:8-49), the z = 0 plane within [-1,1]^2 */
+static int plane_intersect(ray_t ray, hit_t *h, int hitSide)
+{
+    float rayPz = ray.p.z, rayDz = ray.dir.z;
+    if (rayDz == 0.0f) return 0;
+    float t = -rayPz / rayDz;
+    if (t <= 0 || t > h->z) return 0;
+    v3 x = add(ray.p, mulf(ray.dir, t));
+    if (x.x < -1 || x.x > 1 || x.y < -1 || x.y > 1) return 0;
+    int front = dot(neg(ray.dir), V(0, 0, 1)) > 0;
+    if (!front && hitSide == HIT_FRONT) return 0;
+    else if (front && hitSide == HIT_BACK) return 0;
+    h->p = x; h->N = V(0, 0, 1); h->z = t; h->front = front;
+    return 1;
+}
+
+/* Node::FromNodeCoords(HitInfo) (scene.h:497-501) */
+static void from_node_coords(const bhrt_xform *t, hit_t *h)
+{
+    h->p = transform_from(t, h->p);
+    h->N = norm(vector_transform_from(t, h->N));
+}
+
+typedef struct {
+    const bhrt_scene_desc *d;
+    int *first_child, *next_sibling;      /* the Node tree rebuilt from the DFS table */
+    uint64_t rays_closest, rays_shadow;
+} scene_t;
+static const bhrt_xform IDENTITY = { { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, { 0, 0, 0 } };
+
+/* recursive() (Main.cpp:389-413); `root` = -1 is rootNode (identity transform) */
+static void recursive(scene_t *s, int root, ray_t ray, hit_t *out, int *bHit, int hitSide)
+{
+    int first = root < 0 ? (s->d->n_nodes > 0 ? 0 : -1) : s->first_child[root];
+    if (first < 0) return;
+    for (int c = first; c >= 0; c = (root < 0 ? s->next_sibling[c] : s->next_sibling[c])) {
+        const bhrt_node *n = &s->d->nodes[c];
+        ray_t tr = to_node_coords(&n->xf, ray);
+        if (n->kind != BHRT_OBJ_NONE) {
+            int got = n->kind == BHRT_OBJ_SPHERE ? sphere_intersect(tr, out, hitSide) : plane_intersect(tr, out, hitSide);
+            if (got) { out->node = c; *bHit = 1; from_node_coords(&n->xf, out); }
+        }
+        recursive(s, c, tr, out, bHit, hitSide);
+    }
+    for (int c = first; c >= 0; c = s->next_sibling[c])
+        if (c == out->node) { from_node_coords(root < 0 ? &IDENTITY : &s->d->nodes[root].xf, out); break; }
+}
+
+/* ShadowRayRecursive (Lights/GenLight.cpp:15-69): children first, then the node's own object; the
+ * plane test bounds-checks with the PARENT-space ray (:54), the sphere test ignores origins inside (:36) */
+static int shadow_recursive(scene_t *s, int root, ray_t ray, float t_max)
+{
+    ray_t tr = to_node_coords(root < 0 ? &IDENTITY : &s->d->nodes[root].xf, ray);
+    int first = root < 0 ? (s->d->n_nodes > 0 ? 0 : -1) : s->first_child[root];
+    for (int c = first; c >= 0; c = s->next_sibling[c])
+        if (shadow_recursive(s, c, tr, t_max)) return 1;
+    if (root >= 0 && s->d->nodes[root].kind == BHRT_OBJ_SPHERE) {
+        v3 dir = tr.dir, oc = tr.p;
+        float A = dot(dir, dir), B = 2 * dot(dir, oc), C = dot(oc, oc) - 1;
+        float DD = B * B - 4 * A * C;
+        if (DD > 0) {
+            float t1 = (-B + sqrtf(DD)) / (2 * A), t2 = (-B - sqrtf(DD)) / (2 * A);
+            float t = t1 <= t2 ? t1 : t2;                       /* cy::Min */
+            if (t < 0) return 0;
+            if (t < t_max && t > SHADOW_BIAS) return 1;
+        }
+    } else if (root >= 0 && s->d->nodes[root].kind == BHRT_OBJ_PLANE) {
+        float t = -tr.p.z / tr.dir.z;
+        if (t < 0) return 0;
+        v3 x = add(ray.p, mulf(ray.dir, t));                    /* (sic) the untransformed ray */
+        if (x.x < -1 || x.x > 1 || x.y < -1 || x.y > 1) return 0;
+        if (t < t_max && t > SHADOW_BIAS) return 1;
+        return 0;
+    }
+    return 0;
+}
+/* GenLight::Shadow (GenLight.cpp:10-13) */
+static float shadow(scene_t *s, ray_t ray, float t_max)
+{
+    s->rays_shadow++;
+    return shadow_recursive(s, -1, ray, t_max) ? 0.f : 1.f;
+}
+
+/* Light::Illuminate / Direction (Lights/lights.h:29-87, PointLight.cpp:7-18); size 0 in D-mode scenes */
+static v3 illuminate(scene_t *s, const bhrt_light *L, v3 p)
+{
+    v3 I = ld(L->intensity);
+    if (L->kind == BHRT_LIGHT_AMBIENT) return I;
+    if (L->kind == BHRT_LIGHT_DIRECT) { ray_t r = { p, neg(ld(L->v)) }; return mulf(I, shadow(s, r, BIGFLOAT)); }
+    v3 centerDir = sub(ld(L->v), p);
+    float r = len(centerDir), rr = r * r;
+    if (rr == 0) return V(BIGFLOAT, BIGFLOAT, BIGFLOAT);
+    ray_t sr = { p, centerDir };
+    return divf(mulf(I, shadow(s, sr, 1)), rr);
+}
+static v3 light_direction(const bhrt_light *L, v3 p)
+{
+    if (L->kind == BHRT_LIGHT_AMBIENT) return V(0, 0, 0);
+    if (L->kind == BHRT_LIGHT_DIRECT) return ld(L->v);
+    return norm(sub(p, ld(L->v)));
+}
+static float gray(const bhrt_light *L) { return (L->intensity[0] + L->intensity[1] + L->intensity[2]) / 3.0f; }   /* cyColor.h:83 */
+static void clamp_white(v3 *c) { if (c->x > 1) c->x = 1.f; if (c->y > 1) c->y = 1.f; if (c->z > 1) c->z = 1.f; }   /* MtlBlinn.cpp:79-83 */
+
+/* MtlBlinn::Shade (Materials/Blinn/MtlBlinn.cpp:89-138) in D-mode for a non-refractive, untextured
+ * material: the refraction term is zero, GI is switched off, PathTracing_DiffuseNSpecular (:304-351)
+ * loops over every light with its exact direction */
+static v3 shade(scene_t *s, ray_t ray, const hit_t *h, const bhrt_light *lights, int n_lights)
+{
+    const bhrt_material *M = &s->d->materials[s->d->nodes[h->node].material];
+    v3 vN = norm(h->N);
+    v3 vV = norm(sub(ray.p, h->p));
+    float cosPhi1 = dot(vN, vV);
+    if (cosPhi1 > 1) cosPhi1 = 1;
+    if (cosPhi1 <= 0) cosPhi1 = 0;
+    float R0 = (float)pow((double)((1 - M->ior) / (1 + M->ior)), 2.0);
+    float F = (float)(R0 + (1 - R0) * pow((double)(1 - cosPhi1), 5.0));
+    v3 newSpecular = add(ld(M->specular.color), mulf(ld(M->refraction), F));
+    clamp_white(&newSpecular);
+    v3 out = V(0, 0, 0);        /* refraction term: zero colour, clamped, added (:115-118) */
+    v3 D = V(0, 0, 0);
+    for (int li = 0; li < n_lights; li++) {
+        v3 vL = neg(norm(light_direction(&lights[li], h->p)));
+        float cosTheta = dot(vL, vN);
+        if (cosTheta > 0) {
+            v3 vH = norm(add(vL, vV));
+            v3 irrad = illuminate(s, &lights[li], h->p);
+            v3 brdf = add(mulf(ld(M->diffuse.color), cosTheta), mulf(newSpecular, powf(dot(vH, vN), M->glossiness)));
+            D = add(D, mulv(irrad, brdf));
+        }
+    }
+    clamp_white(&D);                                            /* :343 */
+    if (D.x != D.x) D = V(0, 0, 0);                             /* :344-347 */
+    out = add(out, D);
+    return out;
+}
+
+/* Color24::FloatToByte (cyColor.h:271-272) */
+static uint8_t float_to_byte(float r)
+{
+    int v = (int)(r * 255 + 0.5f);
+    return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+int bhrt_oracle_in_scope(const bhrt_scene_desc *d)
+{
+    if (d->n_meshes > 0 || d->n_texmaps > 0 || d->background.texmap >= 0) return 0;
+    for (int i = 0; i < d->n_nodes; i++) if (d->nodes[i].kind == BHRT_OBJ_MESH) return 0;
+    for (int i = 0; i < d->n_materials; i++) {
+        const bhrt_material *m = &d->materials[i];
+        if (m->refraction[0] != 0 || m->refraction[1] != 0 || m->refraction[2] != 0) return 0;
+        if (m->diffuse.texmap >= 0 || m->specular.texmap >= 0) return 0;
+    }
+    for (int i = 0; i < d->n_lights; i++) if (d->lights[i].kind == BHRT_LIGHT_POINT && d->lights[i].size != 0) return 0;
+    return 1;
+}
+
+/* BeginRender() + PathTracing() (Main.cpp:178-242,143-172) in D-mode.  Outputs: hit_id[H*W] (node
+ * index in DFS order, -1 = miss), z[H*W], linear[H*W*3], rgb8[H*W*3], rays[2] = closest, shadow. */
+int bhrt_oracle_render_det(const bhrt_scene_desc *d, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays)
+{
+    if (!d || !bhrt_oracle_in_scope(d)) return -2;
+    scene_t s;
+    memset(&s, 0, sizeof(s));
+    s.d = d;
+    int n = d->n_nodes;
+    s.first_child = (int *)malloc(sizeof(int) * (n + 1));
+    s.next_sibling = (int *)malloc(sizeof(int) * (n + 1));
+    int *last_child = (int *)malloc(sizeof(int) * (n + 1));
+    int last_root = -1;
+    for (int i = 0; i < n; i++) { s.first_child[i] = -1; s.next_sibling[i] = -1; last_child[i] = -1; }
+    for (int i = 0; i < n; i++) {             /* children in document order = DFS pre-order of the table */
+        int p = d->nodes[i].parent;
+        if (p < 0) { if (last_root >= 0) s.next_sibling[last_root] = i; last_root = i; }
+        else { if (last_child[p] >= 0) s.next_sibling[last_child[p]] = i; else s.first_child[p] = i; last_child[p] = i; }
+    }
+    free(last_child);
+
+    /* camera frame (Main.cpp:179-192), float with a double tan() */
+    const bhrt_camera *c = &d->camera;
+    int W = c->width, H = c->height;
+    float aor = W / (float)H;
+    float tan_h_pov = (float)tan(c->fov / 2 * PI_D / 180.0);
+    float l = c->focaldist;
+    float h = 2 * l * tan_h_pov;
+    float w = aor * h;
+    v3 camZ = neg(ld(c->dir)), camY = ld(c->up), camX = cross(camY, camZ), pos = ld(c->pos);
+    v3 topLeft = sub(add(sub(pos, mulf(camZ, l)), divf(mulf(camY, h), 2)), divf(mulf(camX, w), 2));
+    v3 dd_x = divf(mulf(camX, w), (float)W), dd_y = divf(mulf(camY, h), (float)H);
+
+    /* CalculateLightsIntensity (Main.cpp:112-123): lights sorted ascending by Gray() (insertion sort = std::sort below 16 elements) */
+    bhrt_light lights[BHRT_MAX_LIGHTS];
+    int nl = d->n_lights;
+    for (int i = 0; i < nl; i++) {
+        bhrt_light v = d->lights[i];
+        int k = i;
+        if (i > 0 && gray(&v) < gray(&lights[0])) { for (k = i; k > 0; k--) lights[k] = lights[k - 1]; lights[0] = v; continue; }
+        while (k > 0 && gray(&v) < gray(&lights[k - 1])) { lights[k] = lights[k - 1]; k--; }
+        lights[k] = v;
+    }
+
+    for (int j = 0; j < H; j++)
+        for (int i = 0; i < W; i++) {
+            /* pixel corner: (i + 1/2) with integer 1/2 == 0 (Main.cpp:145); direction not normalised (:153) */
+            v3 pc = sub(add(topLeft, mulf(dd_x, (float)i)), mulf(dd_y, (float)j));
+            ray_t ray = { pos, sub(pc, pos) };
+            hit_t hit;
+            hit.z = BIGFLOAT; hit.node = -1; hit.front = 1; hit.p = V(0, 0, 0); hit.N = V(0, 0, 0);
+            int bHit = 0;
+            s.rays_closest++;
+            recursive(&s, -1, ray, &hit, &bHit, HIT_FRONT);
+            v3 col;
+            if (bHit) col = shade(&s, ray, &hit, lights, nl);
+            else col = ld(d->background.color);                 /* background.Sample without a texture (Main.cpp:166-167) */
+            size_t p = (size_t)j * W + i;
+            hit_id[p] = bHit ? hit.node : -1;
+            z[p] = hit.z;
+            linear[3 * p] = col.x; linear[3 * p + 1] = col.y; linear[3 * p + 2] = col.z;
+            const float ig = 1 / 2.2f;                          /* Main.cpp:128,220-227 */
+            rgb8[3 * p] = float_to_byte(powf(col.x, ig));
+            rgb8[3 * p + 1] = float_to_byte(powf(col.y, ig));
+            rgb8[3 * p + 2] = float_to_byte(powf(col.z, ig));
+        }
+    rays[0] = s.rays_closest; rays[1] = s.rays_shadow;
+    free(s.first_child); free(s.next_sibling);
+    return 0;
+}

@@ -1,0 +1,43 @@
+"""ctypes binding of oracle/_build/libbhrt_oracle.so (oracle/bhrt_oracle.c: the plain-C restatement of
+the reference's deterministic path for BASELINE config 1).  Test infrastructure only."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(ROOT, "oracle", "_build", "libbhrt_oracle.so")
+        if not os.path.exists(path):
+            import subprocess
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "all"])
+        _LIB = C.CDLL(path)
+        _LIB.bhrt_oracle_render_det.argtypes = [C.c_void_p] * 6
+        _LIB.bhrt_oracle_render_det.restype = C.c_int
+        _LIB.bhrt_oracle_in_scope.argtypes = [C.c_void_p]
+        _LIB.bhrt_oracle_in_scope.restype = C.c_int
+    return _LIB
+
+
+def in_scope(scene):
+    return bool(lib().bhrt_oracle_in_scope(C.cast(scene.desc, C.c_void_p)))
+
+
+def render_det(scene):
+    """scene: bhraytracer_b200.Scene (the host loader's flattened description)."""
+    w, h = scene.width, scene.height
+    n = w * h
+    hit, z = np.empty(n, np.int32), np.empty(n, np.float32)
+    lin, rgb = np.empty(n * 3, np.float32), np.empty(n * 3, np.uint8)
+    rays = (C.c_uint64 * 2)()
+    rc = lib().bhrt_oracle_render_det(C.cast(scene.desc, C.c_void_p), hit.ctypes.data, z.ctypes.data, lin.ctypes.data, rgb.ctypes.data,
+                                      C.cast(rays, C.c_void_p))
+    if rc != 0:
+        raise ValueError("scene outside the restatement's scope (rc %d)" % rc)
+    return dict(hit_id=hit.reshape(h, w), z=z.reshape(h, w), linear=lin.reshape(h, w, 3), rgb8=rgb.reshape(h, w, 3),
+                rays_closest=int(rays[0]), rays_shadow=int(rays[1]))

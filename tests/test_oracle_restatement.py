@@ -1,0 +1,92 @@
+"""oracle/bhrt_oracle.c -- the plain-C restatement of the reference's deterministic path for BASELINE
+config 1 (spheres + planes, point/direct lights, Blinn-Phong, hard shadows).
+
+ 1. PIN: against the reference's own output (tests/golden, made by oracle/_ref/bhrt_ref --det) and,
+    where /root/reference exists, against the reference run live on its own sphere scenes.
+ 2. USE: our device code (tests/emu on CPU, the kernels through the C ABI on the GPU) against the
+    restatement at sizes and cameras no fixture covers."""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import bhraytracer_b200 as b
+import oracle_c
+from aovio import read_aov
+from conftest import EMU_BIN, REF_BIN, ROOT
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF_ROOT = "/root/reference/BHRayTracer"
+
+
+def same(a, o):
+    assert (a["hit_id"] == o["hit_id"]).all(), "primary hit ids differ"
+    assert (a["z"].view(np.uint32) == o["z"].view(np.uint32)).all(), "primary hit distances differ in bits"
+    assert np.abs(a["rgb8"].astype(np.int32) - o["rgb8"].astype(np.int32)).max() <= 1
+
+
+def test_restatement_is_pinned_by_the_reference_golden(built):
+    g = np.load(os.path.join(GOLD, "cfg1_spheres_plane_det.npz"))
+    scene = b.LoadScene("scenes/cfg1_spheres_plane.xml", int(g["width"]), int(g["height"]))
+    assert oracle_c.in_scope(scene)
+    o = oracle_c.render_det(scene)
+    assert (o["hit_id"] == g["hit_id"]).all()
+    assert (o["z"].view(np.uint32) == g["z_bits"]).all()
+    assert (o["rgb8"] == g["rgb8"]).all()
+    assert (o["rays_closest"], o["rays_shadow"]) == (int(g["rays_closest"]), int(g["rays_shadow"]))
+
+
+@pytest.mark.skipif(not (os.path.isdir(REF_ROOT) and os.path.exists(REF_BIN)), reason="needs /root/reference and oracle/_ref")
+@pytest.mark.parametrize("name", ["proj2", "proj3", "proj3Test", "proj4"])
+def test_restatement_matches_the_reference_live_on_its_own_scenes(built, tmp_path, name):
+    src = open(os.path.join(REF_ROOT, "Resource", "Data", name + ".xml")).read()
+    small = re.sub(r'<width value="\d+"\s*/>', '<width value="160"/>', src)
+    small = re.sub(r'<height value="\d+"\s*/>', '<height value="120"/>', small)
+    path = str(tmp_path / (name + ".xml"))
+    open(path, "w").write(small)
+    info = json.loads(subprocess.check_output([REF_BIN, path, str(tmp_path / "ref"), "--det", "--threads", "2"], cwd=REF_ROOT,
+                                              stderr=subprocess.DEVNULL).decode().splitlines()[-1])
+    ref = read_aov(str(tmp_path / "ref.aov"))
+    scene = b.LoadScene(path)
+    if not oracle_c.in_scope(scene):
+        pytest.skip("outside the restatement's scope")
+    o = oracle_c.render_det(scene)
+    same(o, ref)
+    assert (o["rays_closest"], o["rays_shadow"]) == (info["rays_closest"], info["rays_shadow"])
+
+
+@pytest.mark.parametrize("w,h", [(97, 61), (33, 200)])
+def test_device_code_on_cpu_matches_the_restatement(built, tmp_path, w, h):
+    scene = b.LoadScene("scenes/cfg1_spheres_plane.xml", w, h)
+    o = oracle_c.render_det(scene)
+    out = subprocess.check_output([EMU_BIN, "scenes/cfg1_spheres_plane.xml", str(tmp_path / "e"), "--det", "--size", str(w), str(h)],
+                                  cwd=ROOT, stderr=subprocess.DEVNULL)
+    info = json.loads(out.decode().splitlines()[-1])
+    same(read_aov(str(tmp_path / "e.aov")), o)
+    assert (info["rays_closest"], info["rays_shadow"]) == (o["rays_closest"], o["rays_shadow"])
+
+
+def test_scope_check_refuses_what_the_restatement_does_not_cover(built):
+    for name in ("det_refract", "det_textured", "det_mesh"):
+        scene = b.LoadScene(os.path.join("scenes", name + ".xml"), 32, 24)
+        assert not oracle_c.in_scope(scene)
+        with pytest.raises(ValueError):
+            oracle_c.render_det(scene)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h", [(800, 600), (251, 97)])
+def test_kernels_match_the_restatement(built, w, h):
+    scene = b.LoadScene("scenes/cfg1_spheres_plane.xml", w, h)
+    o = oracle_c.render_det(scene)
+    r = b.Renderer(0)
+    try:
+        r.upload(scene)
+        out = r.render(mode=b.MODE_DET)
+    finally:
+        r.close()
+    same(out, o)
+    assert (out["rays_closest"], out["rays_shadow"]) == (o["rays_closest"], o["rays_shadow"])
