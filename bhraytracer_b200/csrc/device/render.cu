@@ -65,6 +65,7 @@ struct bhrt_ctx {
     unsigned pool_lanes = 3072;                 // lanes (camera samples in flight) per CTA, 2.3 KB of state each
     int mesh_budget = WF_MESH_BUDGET;
     unsigned mesh_batch = WF_BLOCK;
+    int trav_min = 3, trav_max = 12, trav_pct = 50;
     DevBuf lanes, frames, samples, wave_counters;
 };
 
@@ -109,6 +110,7 @@ int bhrt_create(int device, bhrt_ctx **out)
     // tuning knobs
     if (const char *e = getenv("BHRT_POOL_LANES")) { long v = atol(e); if (v >= 32 && v <= 32768) c->pool_lanes = (unsigned)v; }
     if (const char *e = getenv("BHRT_MESH_BUDGET")) { long v = atol(e); if (v >= 1) c->mesh_budget = (int)v; }
+    if (const char *e = getenv("BHRT_TRAV")) { int x, y, z; if (sscanf(e, "%d,%d,%d", &x, &y, &z) == 3 && x >= 0 && y >= 1) { c->trav_min = x; c->trav_max = y; c->trav_pct = z; } }
     if (const char *e = getenv("BHRT_MESH_BATCH")) { long v = atol(e); if (v >= 1) c->mesh_batch = (unsigned)v; }
     *out = c;
     return BHRT_OK;
@@ -267,6 +269,7 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     a.pool = (c->pool_lanes + 31u) & ~31u;
     a.mesh_budget = c->mesh_budget;
     a.mesh_batch = c->mesh_batch;
+    a.trav_min = c->trav_min; a.trav_max = c->trav_max; a.trav_pct = c->trav_pct;
     auto al16 = [](int v) { return (v + 15) & ~15; };
     a.smem_nodes = 0;
     a.smem_materials = al16(a.smem_nodes + c->view.n_nodes * (int)sizeof(bhrt_node));

@@ -108,6 +108,7 @@ struct WaveArgs {
     unsigned pool;              // lanes per CTA (<= 65535)
     int mesh_budget;            // traversal trips a thread may still run after the last warp left the lanes pass
     unsigned mesh_batch;        // queued rays that switch the traversal phase on
+    int trav_min, trav_max, trav_pct;   // internal-node steps per trip: at least / at most / until this % of the job lanes is still at an internal node
     int smem_nodes, smem_materials, smem_lights, smem_offsets, smem_wave, smem_gather;   // byte offsets into dynamic shared memory
 };
 
@@ -591,9 +592,12 @@ wf_render(SceneView s, WaveArgs a)
                 if (have && !J.in_trav) finished = !mesh_job_next(J, s);
                 // internal nodes: lanes that reach a leaf wait here for the others (a few trips),
                 // then all leaves are processed together -- the triangle tests run converged
-                for (int r = 0; r < 4; r++) {
-                    const bool go = have && !finished && !J.T.done && !BHRT_BVH_LEAF(J.T.cur);
-                    if (!__any_sync(0xffffffffu, go)) break;
+                for (int r = 0; r < a.trav_max; r++) {
+                    const bool in_job = have && !finished && !J.T.done;
+                    const bool go = in_job && !BHRT_BVH_LEAF(J.T.cur);
+                    const unsigned gm = __ballot_sync(0xffffffffu, go), jm = __ballot_sync(0xffffffffu, in_job);
+                    // stop when no lane is at an internal node, or (after a few steps) when most are waiting at a leaf
+                    if (!gm || (r >= a.trav_min && 100 * __popc(gm) <= a.trav_pct * __popc(jm))) break;
                     if (go) mesh_trav_internal(J.T);
                 }
                 if (have && !finished && !J.T.done && BHRT_BVH_LEAF(J.T.cur)) mesh_trav_leaf(J.T);
