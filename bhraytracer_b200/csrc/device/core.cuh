@@ -27,6 +27,7 @@
 // texture filter and the libm-grade transcendentals from dozens of sites; inlined everywhere the
 // render kernel was 935 KB of SASS and spent most issue slots waiting for instruction fetch.
 #define BHRT_FN BHRT_HD_NOINLINE
+#define BHRT_RESTRICT __restrict__
 
 // The whole device code lives in namespace BHRT_NS: `bhrt` in the exact build (render.cu, tests/emu)
 // and `bhrt_fast` in render_fast.cu, which compiles the same source with --use_fast_math for the
@@ -1386,7 +1387,7 @@ BHRT_FN void direct_finish(const SceneView &s, bool have_gather, V3 irr, V3 vL, 
 // irradiance in L.hit.p and the mean photon direction in L.sw, and calls again.
 enum { STEP_CONT = 0, STEP_RAY = 1, STEP_DONE = 2, STEP_GATHER = 3 };
 // `f` = the top frame (fr[sp-1]; unused while sp == 0), `child` = the slot above it (fr[sp]).
-BHRT_HD int sample_step(Lane &L, Frame &f, Frame &child, const SceneView &s, const ShadeCfg &cfg, const PhotonGather &pg, float bgu, float bgv,
+BHRT_HD int sample_step(Lane &BHRT_RESTRICT L, Frame &BHRT_RESTRICT f, Frame &BHRT_RESTRICT child, const SceneView &s, const ShadeCfg &cfg, const PhotonGather &pg, float bgu, float bgv,
                         RayCounters &rc, V3 &color)
 {
     const bool det = (cfg.mode == BHRT_MODE_DET);
