@@ -77,11 +77,17 @@ BHRT_HD float gray(V3 c) { return (c.x + c.y + c.z) / 3.0f; }     // cyColor.h:8
 BHRT_HD void clamp_white(V3 &c) { if (c.x > 1) c.x = 1.f; if (c.y > 1) c.y = 1.f; if (c.z > 1) c.z = 1.f; }  // MtlBlinn.cpp:79-83
 BHRT_HD bool saturated(V3 c) { return c.x >= 1 && c.y >= 1 && c.z >= 1; }
 BHRT_HD bool is_nan(float v) { return v != v; }
-// one out-of-line copy of each libm-grade transcendental (never --use_fast_math)
-BHRT_FN float m_pow(float a, float b) { return powf(a, b); }
-BHRT_FN float m_sin(float a) { return sinf(a); }
-BHRT_FN float m_cos(float a) { return cosf(a); }
-BHRT_FN float m_tan(float a) { return tanf(a); }
+// exact build: one out-of-line copy of each libm-grade transcendental; fast build (--use_fast_math):
+// powf / sinf / cosf / tanf become a few SFU instructions and are inlined
+#if BHRT_FAST
+#define BHRT_MATH_FN BHRT_HD
+#else
+#define BHRT_MATH_FN BHRT_FN
+#endif
+BHRT_MATH_FN float m_pow(float a, float b) { return powf(a, b); }
+BHRT_MATH_FN float m_sin(float a) { return sinf(a); }
+BHRT_MATH_FN float m_cos(float a) { return cosf(a); }
+BHRT_MATH_FN float m_tan(float a) { return tanf(a); }
 BHRT_FN float m_acos(float a) { return acosf(a); }
 BHRT_FN float m_asin(float a) { return asinf(a); }
 BHRT_FN float m_atan2(float a, float b) { return atan2f(a, b); }
