@@ -946,7 +946,7 @@ BHRT_HD V3 random_crossing_vector(V3 v, Rng &rng)
     return r;
 }
 // GetSampleAlongNormal (MtlBlinn.cpp:602-617): uniform disk of radius R at the tip of N
-BHRT_FN V3 sample_along_normal(V3 N, float R, Rng &rng)
+BHRT_MATH_FN V3 sample_along_normal(V3 N, float R, Rng &rng)
 {
     float r = rng.rnd01();
     r = sqrtf(r) * R;
@@ -957,7 +957,7 @@ BHRT_FN V3 sample_along_normal(V3 N, float R, Rng &rng)
     return N + normalized(a1) * x + normalized(a2) * y;
 }
 // GetSampleAlongLightDirection (MtlBlinn.cpp:619-635): Phong lobe about N, unnormalised result
-BHRT_FN V3 sample_along_direction(V3 N, float gloss, float &theta_out, Rng &rng)
+BHRT_MATH_FN V3 sample_along_direction(V3 N, float gloss, float &theta_out, Rng &rng)
 {
     float wt = acos_safe(m_pow(rng.rnd01(), 1.f / (gloss + 1.f)));
     theta_out = wt;
@@ -969,7 +969,7 @@ BHRT_FN V3 sample_along_direction(V3 N, float gloss, float &theta_out, Rng &rng)
     return N + normalized(a1) * x + normalized(a2) * y;
 }
 // GetSampleInSemiSphere (MtlBlinn.cpp:697-716): cosine-weighted hemisphere, retried while N.d <= 0
-BHRT_FN V3 sample_semisphere(V3 N, float &theta_out, Rng &rng)
+BHRT_MATH_FN V3 sample_semisphere(V3 N, float &theta_out, Rng &rng)
 {
     for (int guard = 0; guard < 64; guard++) {
         V3 axisY = normalized(cross(N, random_crossing_vector(N, rng)));
