@@ -882,7 +882,7 @@ BHRT_HD V3 texcolor_sample(const SceneView &s, const bhrt_texcolor &tc, V3 uvw)
     return color * texture_sample(s, s.textures[m.texture], xf_to(m.xf, uvw));
 }
 // TexturedColor::Sample(uvw,duvw) (scene.h:411) -> TextureMap::Sample(uvw,duvw) (:372-380)
-BHRT_FN V3 texcolor_sample_filtered(const SceneView &s, V3 color, int texmap, V3 uvw, V3 d0, V3 d1)
+BHRT_MATH_FN V3 texcolor_sample_filtered(const SceneView &s, V3 color, int texmap, V3 uvw, V3 d0, V3 d1)
 {
     if (texmap < 0) return color;
     const bhrt_texmap &m = s.texmaps[texmap];
@@ -893,7 +893,7 @@ BHRT_FN V3 texcolor_sample_filtered(const SceneView &s, V3 color, int texmap, V3
     return color * texture_sample_filtered(s, s.textures[m.texture], u, e0, e1);
 }
 // TexturedColor::SampleEnvironment (scene.h:414-420); dir is NOT normalised by the callers
-BHRT_FN V3 sample_environment(const SceneView &s, V3 dir)
+BHRT_MATH_FN V3 sample_environment(const SceneView &s, V3 dir)
 {
     float z = m_asin(-dir.z) / 3.14159265358979323846f + 0.5f;
     float x = dir.x / (fabsf(dir.x) + fabsf(dir.y));
@@ -1023,7 +1023,7 @@ BHRT_HD V3 light_direction(const bhrt_light &L, V3 p)
 }
 
 // GetSampleInLight (MtlBlinn.cpp:637-695)
-BHRT_FN V3 sample_in_light(const bhrt_light &L, V3 p, float kd, float ks, float gloss, Rng &rng)
+BHRT_MATH_FN V3 sample_in_light(const bhrt_light &L, V3 p, float kd, float ks, float gloss, Rng &rng)
 {
     if (L.kind != BHRT_LIGHT_POINT) return -normalized(light_direction(L, p));
     V3 vL = ld3(L.v) - p;
@@ -1048,7 +1048,7 @@ BHRT_FN V3 sample_in_light(const bhrt_light &L, V3 p, float kd, float ks, float 
 }
 
 // HandleRayWhenRefractionRayOut (MtlBlinn.cpp:543-589)
-BHRT_FN Ray handle_refraction_out(const Ray &inRay, const Hit &ih, float ior, bool &toOut, float rgloss, Rng *rng)
+BHRT_MATH_FN Ray handle_refraction_out(const Ray &inRay, const Hit &ih, float ior, bool &toOut, float rgloss, Rng *rng)
 {
     V3 vN = ih.N;
     V3 vV = -inRay.dir;
@@ -1354,7 +1354,7 @@ BHRT_HD void sample_begin(Lane &L, const Ray &primary, RayCounters &rc)
 }
 
 // Blinn BRDF * cos of the direct term (MtlBlinn.cpp:319-327) for light direction vL
-BHRT_FN V3 direct_brdf(const SceneView &s, const Frame &f, const bhrt_material &M, V3 vL)
+BHRT_MATH_FN V3 direct_brdf(const SceneView &s, const Frame &f, const bhrt_material &M, V3 vL)
 {
     float cosTheta = dot(vL, f.vN);
     V3 vH = normalized(vL + f.vV);
@@ -1365,7 +1365,7 @@ BHRT_FN V3 direct_brdf(const SceneView &s, const Frame &f, const bhrt_material &
 
 // End of PathTracing_DiffuseNSpecular: the caustic gather term (MtlBlinn.cpp:329-342, only when a
 // photon map is in use), then the clamp / NaN epilogue (MtlBlinn.cpp:343-350,131-136)
-BHRT_FN void direct_finish(const SceneView &s, bool have_gather, V3 irr, V3 vL, Frame &f, const bhrt_material &M, V3 D)
+BHRT_MATH_FN void direct_finish(const SceneView &s, bool have_gather, V3 irr, V3 vL, Frame &f, const bhrt_material &M, V3 D)
 {
     if (have_gather) {
         float cosTheta = -dot(vL, f.vN);
