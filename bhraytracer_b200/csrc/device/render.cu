@@ -277,11 +277,13 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     a.smem_offsets = al16(a.smem_lights + c->view.n_lights * (int)sizeof(bhrt_light));
     a.smem_wave = al16(a.smem_offsets + 2 * (BHRT_TEX_SAMPLES - 1) * (int)sizeof(float));
     a.smem_gather = al16(a.smem_wave + wf_wave_smem_bytes(a.pool));
-    const int smem_bytes = al16(a.smem_gather + (WF_BLOCK / 32) * (int)sizeof(PmWarpScratch));
+    // (the per-warp gather scratch only when a photon map is in use: without it the CTA stays under 32 KB)
+    const int smem_bytes = al16(a.smem_gather + (a.gather.use ? (WF_BLOCK / 32) * (int)sizeof(PmWarpScratch) : 0));
     // stochastic frames run the fast-math build of the kernel unless the caller asks for the exact one
     const bool fast = p->mode == BHRT_MODE_PATH && !(p->flags & BHRT_FLAG_EXACT_MATH);
     if (!c->kernel_ready || c->kernel_smem != smem_bytes) {
         CU(cudaFuncSetAttribute(wf_render, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        CU(cudaFuncSetAttribute(wf_render, cudaFuncAttributePreferredSharedMemoryCarveout, (smem_bytes + 2048) * 100 / (228 * 1024) + 1));
         int per_sm = 0, per_sm_fast = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_render, WF_BLOCK, smem_bytes));
         if (int e = bhrt_fast_prepare(smem_bytes, &per_sm_fast)) return set_err(BHRT_ERR_CUDA, std::string("bhrt_render: ") + cudaGetErrorString((cudaError_t)e));

@@ -22,6 +22,8 @@ int bhrt_fast_prepare(int smem_bytes, int *blocks_per_sm)
 {
     cudaError_t e = cudaFuncSetAttribute(bhrt_fast::wf_render, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return (int)e;
+    // one CTA per SM: leave L1 (where the thread-local lane copies live) all the rest
+    cudaFuncSetAttribute(bhrt_fast::wf_render, cudaFuncAttributePreferredSharedMemoryCarveout, (smem_bytes + 2048) * 100 / (228 * 1024) + 1);
     return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, bhrt_fast::wf_render, WF_BLOCK, smem_bytes);
 }
 

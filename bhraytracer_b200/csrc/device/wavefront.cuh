@@ -44,43 +44,52 @@
 namespace BHRT_NS {
 
 #define WF_BLOCK 1024
-#define WF_NKEYS 128
+#define WF_NKEYS 48
 #define WF_MESH_BUDGET 4
 // Sort keys.  A lane's key says what its next pass through the estimator will execute, as far as that
 // is known when the lanes are sorted:
-//   bits 6..4  the stage that consumes the pending ray's answer (5 in use)
-//   bits 3..1  class of the answer: closest-hit stages -> 0 = miss, else 1 + material of the hit node
-//              (capped); shadow stage -> material of the shading point
+//   bits 5..3  the stage that consumes the pending ray's answer (6 slots)
+//   bits 2..1  class of the answer: closest-hit stages -> 0 = miss, else the behaviour class of the
+//              hit node's material; shadow stage -> class of the shading point's material
+//              (1 diffuse only, 2 has a specular lobe, 3 refractive -- wf_material_class)
 //   bit  0     the GI budget of the frame is used up (the next level shades direct light only)
 // so a warp's 32 lanes not only run the same case of the state machine, they take the same branches
-// inside it (refractive / glossy / diffuse material, miss -> environment, ...).
-enum { WF_ST_PRIMARY = 0, WF_ST_REFR_IN = 1, WF_ST_REFR_OUT = 2, WF_ST_GI_TRACE = 3, WF_ST_SHADOW = 4, WF_ST_OTHER = 5, WF_KEY_DEAD = 127 };
+// inside it (refractive / glossy / diffuse material, miss -> environment, ...).  48 keys keep the
+// sort's tables -- and with them the CTA's shared memory -- under 32 KB, which leaves L1 (where the
+// thread-local lane copies live) the largest configuration.
+enum { WF_ST_PRIMARY = 0, WF_ST_REFR_IN = 1, WF_ST_REFR_OUT = 2, WF_ST_GI_TRACE = 3, WF_ST_SHADOW = 4, WF_ST_OTHER = 5, WF_KEY_DEAD = 63 };
 __device__ __forceinline__ unsigned wf_stage_slot(int stage)
 {
     // ST_REFR 0, ST_REFR_IN_WAIT 1, ST_REFR_OUT_WAIT 2, ST_REFR_WAIT 3, ST_GI 4, ST_GI_TRACE_WAIT 5, ST_GI_WAIT 6, ST_DIRECT 7, ST_SHADOW_WAIT 8
     const unsigned long long table = 0x5455355215ull;      // nibble i = slot of stage i (ST_GATHER_WAIT 9 never waits across a sort)
     return (unsigned)((table >> (4 * stage)) & 15ull);
 }
+__device__ __forceinline__ unsigned wf_material_class(const bhrt_material &m)
+{
+    if (m.refraction[0] != 0.f || m.refraction[1] != 0.f || m.refraction[2] != 0.f) return 3u;
+    if (m.specular.color[0] != 0.f || m.specular.color[1] != 0.f || m.specular.color[2] != 0.f) return 2u;
+    return 1u;
+}
 // key of a lane whose pending ray has been answered (hit_ok / hit node known)
 __device__ __forceinline__ unsigned wf_key(const SceneView &s, const Lane &L, const Frame &top)
 {
     if (L.sp == 0) {
-        const unsigned cls = (L.hit.node >= 0) ? 1u + min((unsigned)s.nodes[L.hit.node].material, 6u) : 0u;
-        return (WF_ST_PRIMARY << 4) | (cls << 1);
+        const unsigned cls = (L.hit.node >= 0) ? wf_material_class(s.materials[s.nodes[L.hit.node].material]) : 0u;
+        return (WF_ST_PRIMARY << 3) | (cls << 1);
     }
     const unsigned slot = wf_stage_slot(L.stage[L.sp - 1]);
     unsigned cls;
-    if (slot == WF_ST_SHADOW || slot == WF_ST_OTHER) cls = min((unsigned)top.mtl, 7u);
-    else cls = (L.q.kind == Q_CLOSEST && L.hit.node >= 0) ? 1u + min((unsigned)s.nodes[L.hit.node].material, 6u) : 0u;
-    return (slot << 4) | (cls << 1) | (top.gi <= 0 ? 1u : 0u);
+    if (slot == WF_ST_SHADOW || slot == WF_ST_OTHER) cls = wf_material_class(s.materials[top.mtl]);
+    else cls = (L.q.kind == Q_CLOSEST && L.hit.node >= 0) ? wf_material_class(s.materials[s.nodes[L.hit.node].material]) : 0u;
+    return (slot << 3) | (cls << 1) | (top.gi <= 0 ? 1u : 0u);
 }
 // the same after a BVH traversal changed the answer: only the class bits of a closest-hit stage move
 __device__ __forceinline__ unsigned wf_key_patch(const SceneView &s, unsigned key, int hit_node)
 {
-    const unsigned slot = key >> 4;
+    const unsigned slot = key >> 3;
     if (slot == WF_ST_SHADOW || slot == WF_ST_OTHER) return key;
-    const unsigned cls = hit_node >= 0 ? 1u + min((unsigned)s.nodes[hit_node].material, 6u) : 0u;
-    return (key & ~0xeu) | (cls << 1);
+    const unsigned cls = hit_node >= 0 ? wf_material_class(s.materials[s.nodes[hit_node].material]) : 0u;
+    return (key & ~0x6u) | (cls << 1);
 }
 
 struct WaveCounters {
@@ -528,7 +537,7 @@ wf_render(SceneView s, WaveArgs a)
                 for (unsigned j = lane; j < WF_NKEYS; j += 32u) row[j] = 0;
                 __syncwarp();
                 const unsigned peers = __match_any_sync(0xffffffffu, k);
-                if ((int)lane == __ffs(peers) - 1) row[k] = (unsigned short)__popc(peers);
+                if (k != WF_KEY_DEAD && (int)lane == __ffs(peers) - 1) row[k] = (unsigned short)__popc(peers);
             }
             __syncthreads();
             if (tid < WF_NKEYS) {
@@ -539,7 +548,7 @@ wf_render(SceneView s, WaveArgs a)
             __syncthreads();
             if (tid == 0) {
                 unsigned acc = 0;
-                for (int k = 0; k < WF_KEY_DEAD; k++) { key_base[k] = acc; acc += key_count[k]; }
+                for (int k = 0; k < WF_NKEYS; k++) { key_base[k] = acc; acc += key_count[k]; }
                 n_live_s = acc;
                 p1_cursor = 0;
                 // decisions every thread must agree on, taken while nobody changes their inputs
