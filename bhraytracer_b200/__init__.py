@@ -87,7 +87,8 @@ DEVICE_SYMBOLS = ["bhrt_abi_version", "bhrt_last_error", "bhrt_create", "bhrt_de
                   "bhrt_photons_emit", "bhrt_photons_buffer", "bhrt_photons_set", "bhrt_photons_get",
                   "bhrt_photons_build"]
 HOST_SYMBOLS = ["bhrt_host_load_scene", "bhrt_host_free_scene", "bhrt_host_last_error", "bhrt_host_scene_desc",
-                "bhrt_host_node_name", "bhrt_host_warnings", "bhrt_host_set_resolution", "bhrt_host_save_png"]
+                "bhrt_host_node_name", "bhrt_host_warnings", "bhrt_host_set_resolution", "bhrt_host_save_png",
+                "bhrt_host_zbuffer_image", "bhrt_host_sample_count_image"]
 
 _host = None
 _dev = None
@@ -112,6 +113,10 @@ def host_lib():
         L.bhrt_host_warnings.argtypes = [C.c_void_p]
         L.bhrt_host_set_resolution.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.bhrt_host_save_png.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+        L.bhrt_host_zbuffer_image.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.bhrt_host_zbuffer_image.restype = None
+        L.bhrt_host_sample_count_image.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.bhrt_host_sample_count_image.restype = C.c_int
         _host = L
     return _host
 
@@ -195,6 +200,22 @@ class Scene:
 def LoadScene(filename, width=None, height=None):
     """Reference-named entry point (xmlload.cpp:65)."""
     return Scene(filename, width, height)
+
+
+def zbuffer_image(z):
+    """RenderImage::ComputeZBufferImage (scene.h:579-600) of a float z buffer (bhrt_outputs.z)."""
+    z = np.ascontiguousarray(z, dtype=np.float32)
+    out = np.empty(z.shape, np.uint8)
+    host_lib().bhrt_host_zbuffer_image(z.ctypes.data, z.size, out.ctypes.data)
+    return out
+
+
+def sample_count_image(count):
+    """RenderImage::ComputeSampleCountImage (scene.h:602-626); returns (image, max count)."""
+    count = np.ascontiguousarray(count, dtype=np.uint8)
+    out = np.empty(count.shape, np.uint8)
+    smax = host_lib().bhrt_host_sample_count_image(count.ctypes.data, count.size, out.ctypes.data)
+    return out, smax
 
 
 def save_png(path, img):

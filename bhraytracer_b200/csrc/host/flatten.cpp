@@ -248,6 +248,40 @@ int bhrt_host_set_resolution(bhrt_host_scene *scene, int32_t width, int32_t heig
     scene->flat.desc.camera.width = width; scene->flat.desc.camera.height = height;
     return BHRT_OK;
 }
+// RenderImage::ComputeZBufferImage (reference Scenes/scene.h:579-600)
+void bhrt_host_zbuffer_image(const float *z, int32_t n, uint8_t *out)
+{
+    const float BIG = 1.0e30f;
+    float zmin = BIG, zmax = 0;
+    for (int i = 0; i < n; i++) {
+        if (z[i] == BIG) continue;
+        if (zmin > z[i]) zmin = z[i];
+        if (zmax < z[i]) zmax = z[i];
+    }
+    for (int i = 0; i < n; i++) {
+        if (z[i] == BIG) { out[i] = 0; continue; }
+        float f = (zmax - z[i]) / (zmax - zmin);
+        int c = int(f * 255);
+        out[i] = (uint8_t)(c < 0 ? 0 : (c > 255 ? 255 : c));
+    }
+}
+
+// RenderImage::ComputeSampleCountImage (reference Scenes/scene.h:602-626)
+int bhrt_host_sample_count_image(const uint8_t *count, int32_t n, uint8_t *out)
+{
+    uint8_t smin = 255, smax = 0;
+    for (int i = 0; i < n; i++) {
+        if (smin > count[i]) smin = count[i];
+        if (smax < count[i]) smax = count[i];
+    }
+    for (int i = 0; i < n; i++) {
+        if (smax == smin) { out[i] = 0; continue; }
+        int c = (255 * (count[i] - smin)) / (smax - smin);
+        out[i] = (uint8_t)(c < 0 ? 0 : (c > 255 ? 255 : c));
+    }
+    return smax;
+}
+
 int bhrt_host_save_png(const char *path, const uint8_t *data, int32_t width, int32_t height, int32_t comp)
 {
     if (!path || !data || width <= 0 || height <= 0) return BHRT_ERR_ARG;

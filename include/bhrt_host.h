@@ -38,6 +38,12 @@ int bhrt_host_set_resolution(bhrt_host_scene *scene, int32_t width, int32_t heig
 /* RenderImage::SaveImage (reference Scenes/scene.h:628,634-644): 8-bit RGB (comp=3) or grey (comp=1) PNG. */
 int bhrt_host_save_png(const char *path, const uint8_t *data, int32_t width, int32_t height, int32_t comp);
 
+/* RenderImage::ComputeZBufferImage (reference Scenes/scene.h:579-600): 8-bit depth image, nearest = 255,
+ * farthest = 0, misses (z == 1e30) = 0.  `z` is bhrt_outputs.z. */
+void bhrt_host_zbuffer_image(const float *z, int32_t n, uint8_t *out);
+/* RenderImage::ComputeSampleCountImage (scene.h:602-626): counts stretched to 0..255; returns the maximum count. */
+int bhrt_host_sample_count_image(const uint8_t *count, int32_t n, uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,3 +117,23 @@ def test_set_resolution_and_png_roundtrip(built, tmp_path):
     assert d.n_textures == 1 and d.texel_bytes == 64 * 48 * 3
     tex = np.ctypeslib.as_array((C.c_uint8 * d.texel_bytes).from_address(d.texels)).reshape(48, 64, 3)
     assert (tex == img).all()
+
+
+def test_render_image_side_buffers(built):
+    """RenderImage::ComputeZBufferImage / ComputeSampleCountImage (reference scene.h:579-626) restated in numpy."""
+    rng = np.random.default_rng(3)
+    z = rng.uniform(2.0, 90.0, (40, 50)).astype(np.float32)
+    z[rng.random(z.shape) < 0.2] = np.float32(1.0e30)
+    img = b.zbuffer_image(z)
+    hit = z != np.float32(1.0e30)
+    zmin, zmax = z[hit].min(), z[hit].max()
+    want = np.zeros(z.shape, np.uint8)
+    f = (zmax - z[hit]) / (zmax - zmin)
+    want[hit] = np.clip((f * np.float32(255)).astype(np.int32), 0, 255)
+    assert (img == want).all() and img[~hit].max() == 0 and img.max() == 255
+    cnt = rng.integers(3, 40, (40, 50)).astype(np.uint8)
+    simg, smax = b.sample_count_image(cnt)
+    assert smax == cnt.max()
+    assert (simg == (255 * (cnt.astype(np.int32) - cnt.min())) // (int(cnt.max()) - int(cnt.min()))).all()
+    flat, m = b.sample_count_image(np.full((4, 4), 7, np.uint8))
+    assert m == 7 and (flat == 0).all()
