@@ -1390,7 +1390,8 @@ BHRT_MATH_FN void direct_finish(const SceneView &s, bool have_gather, V3 irr, V3
 // The wavefront sorts lanes by the stage they are about to run, so a warp executes one case.
 // STEP_GATHER: the estimator needs the caustic irradiance estimate at the top frame's (p, vN): the
 // caller evaluates it (estimate_irradiance; a whole warp per query in the kernel), leaves the
-// irradiance in L.hit.p and the mean photon direction in L.sw, and calls again.
+// irradiance in L.ret and the mean photon direction in L.sw (neither is live in this stage), and
+// calls again.
 enum { STEP_CONT = 0, STEP_RAY = 1, STEP_DONE = 2, STEP_GATHER = 3 };
 // `f` = the top frame (fr[sp-1]; unused while sp == 0), `child` = the slot above it (fr[sp]).
 BHRT_HD int sample_step(Lane &BHRT_RESTRICT L, Frame &BHRT_RESTRICT f, Frame &BHRT_RESTRICT child, const SceneView &s, const ShadeCfg &cfg, const PhotonGather &pg, float bgu, float bgv,
@@ -1618,8 +1619,8 @@ BHRT_HD int sample_step(Lane &BHRT_RESTRICT L, Frame &BHRT_RESTRICT f, Frame &BH
             break;
         }
         case ST_GATHER_WAIT:
-            // the caustic term (MtlBlinn.cpp:329-342) with the estimate the caller left in L.hit.p / L.sw
-            direct_finish(s, true, L.hit.p, L.sw, f, M, L.sv);
+            // the caustic term (MtlBlinn.cpp:329-342) with the estimate the caller left in L.ret / L.sw
+            direct_finish(s, true, L.ret, L.sw, f, M, L.sv);
             done = true;
             break;
         }
@@ -1653,7 +1654,7 @@ BHRT_HD bool sample_advance(Lane &L, LaneStack &S, const SceneView &s, const Sha
     for (;;) {
         const int top = L.sp > 0 ? L.sp - 1 : 0, up = L.sp < BHRT_MAX_FRAMES ? L.sp : BHRT_MAX_FRAMES - 1;
         int r = sample_step(L, S.fr[top], S.fr[up], s, cfg, pg, bgu, bgv, rc, color);
-        if (r == STEP_GATHER) { estimate_irradiance(pg, S.fr[top].p, S.fr[top].vN, L.hit.p, L.sw); continue; }
+        if (r == STEP_GATHER) { estimate_irradiance(pg, S.fr[top].p, S.fr[top].vN, L.ret, L.sw); continue; }
         if (r == STEP_RAY) return false;
         if (r == STEP_DONE) return true;
     }

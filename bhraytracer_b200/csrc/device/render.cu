@@ -278,7 +278,7 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     a.smem_wave = al16(a.smem_offsets + 2 * (BHRT_TEX_SAMPLES - 1) * (int)sizeof(float));
     a.smem_gather = al16(a.smem_wave + wf_wave_smem_bytes(a.pool));
     // (the per-warp gather scratch only when a photon map is in use: without it the CTA stays under 32 KB)
-    const int smem_bytes = al16(a.smem_gather + (a.gather.use ? (WF_BLOCK / 32) * (int)sizeof(PmWarpScratch) : 0));
+    const int smem_bytes = al16(a.smem_gather + (a.gather.use ? (WF_BLOCK / 32) * (int)sizeof(PmWarpScratch) + (int)a.pool * 2 : 0));
     // stochastic frames run the fast-math build of the kernel unless the caller asks for the exact one
     const bool fast = p->mode == BHRT_MODE_PATH && !(p->flags & BHRT_FLAG_EXACT_MATH);
     if (!c->kernel_ready || c->kernel_smem != smem_bytes) {

@@ -194,7 +194,7 @@ __device__ __forceinline__ bool work_to_pixel(const SceneView &s, const WaveArgs
 // running the scalar version visits the same tens of thousands of photons alone, with its histogram
 // in thread-local memory; the reference spends 85 % of a photon-mapped render here.
 // All arguments are warp-uniform; every lane returns the same result.  `wsm` = this warp's scratch.
-struct PmWarpScratch { int hist[32]; float cd2[BHRT_PM_CAND]; uint32_t cidx[BHRT_PM_CAND]; int ncand; int pad[3]; };
+struct PmWarpScratch { int hist[256]; float cd2[BHRT_PM_CAND]; uint32_t cidx[BHRT_PM_CAND]; int ncand; int pad[3]; };
 
 __device__ __forceinline__ float wf_sum(float v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
 __device__ __forceinline__ float wf_max(float v) { for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
@@ -208,21 +208,15 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
     const float r2 = pg.radius * pg.radius;
     float f[3] = { (pos.x - pg.origin[0]) / pg.cell, (pos.y - pg.origin[1]) / pg.cell, (pos.z - pg.origin[2]) / pg.cell };
     int c[3], sub[3];
-    bool inside = true;
     for (int a = 0; a < 3; a++) {
         c[a] = (int)floorf(f[a]);
         if (c[a] < -1 || c[a] > pg.dim[a]) return;
         int s_ = (int)((f[a] - c[a]) * 16.f);
         sub[a] = s_ < 0 ? 0 : (s_ > 15 ? 15 : s_);
-        if (c[a] < 0 || c[a] >= pg.dim[a]) inside = false;
     }
+    // start at the coarse level; the loop below moves to finer levels, before reading any photon, while
+    // the 3x3x3 block holds far more photons than a query needs
     int level = 0;
-    if (inside) {
-        uint32_t coarse = (uint32_t)c[0] + (uint32_t)pg.dim[0] * ((uint32_t)c[1] + (uint32_t)pg.dim[1] * (uint32_t)c[2]);
-        float n_c = (float)(pg.coarse_start[coarse + 1] - pg.coarse_start[coarse]) * 3.14159265f;
-        float need = 2.f * pg.k * 4.f;
-        while (level < BHRT_PM_LEVELS - 1 && n_c > need) { level++; need *= 4.f; }
-    }
     bool coarsened = false;         // a finer level held too few photons: do not try it again
     for (;;) {
         // lane n < 27 owns the key range of cell n of the 3x3x3 block (pm_ranges, one cell per lane)
@@ -249,9 +243,31 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
         const float cell_l = pg.cell / (float)(1 << level);
         float bound2 = 0.998f * cell_l * cell_l;
         if (bound2 > r2) bound2 = r2;
+        // a cell farther from the query than the search bound holds nothing of interest (the corners of
+        // the block, mostly): skip it
+        if (lane < 27u && my_e > my_b) {
+            const int sh = 4 - level;
+            const int dz = (int)lane / 9 - 1, dy = ((int)lane / 3) % 3 - 1, dx = (int)lane % 3 - 1;
+            const int g3[3] = { ((c[0] << level) | (sub[0] >> sh)) + dx, ((c[1] << level) | (sub[1] >> sh)) + dy, ((c[2] << level) | (sub[2] >> sh)) + dz };
+            const float q3[3] = { pos.x, pos.y, pos.z };
+            float md2 = 0;
+            for (int ax = 0; ax < 3; ax++) {
+                const float lo = pg.origin[ax] + (float)g3[ax] * cell_l, hi = lo + cell_l;
+                const float d = q3[ax] < lo ? lo - q3[ax] : (q3[ax] > hi ? q3[ax] - hi : 0.f);
+                md2 += d * d;
+            }
+            if (md2 * 0.999f >= bound2) my_e = my_b;
+        }
+        // far more photons in the block than the k a query needs: the next finer level first
+        {
+            unsigned visit = my_e - my_b;
+            for (int o = 16; o > 0; o >>= 1) visit += __shfl_xor_sync(0xffffffffu, visit, o);
+            if (!coarsened && level < BHRT_PM_LEVELS - 1 && visit > 12u * (unsigned)pg.k) { level++; continue; }
+        }
         const float scale = 32.f / bound2;
-        // ---- pass A
-        wsm->hist[lane] = 0;
+        // ---- pass A (256-bin histogram of a 24-bit distance key: the crossing bin then usually holds
+        // few enough photons for the exact ranking, so a query is two passes over its photons)
+        for (int j = (int)lane; j < 256; j += 32) wsm->hist[j] = 0;
         __syncwarp();
         int total = 0;
         V3 sumP(0, 0, 0), sumD(0, 0, 0);
@@ -264,8 +280,8 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
                 if (!(d2 < bound2)) continue;
                 F4 B = ld4(&pg.recs[i].b);
                 if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;
-                uint32_t u = (uint32_t)((d2 * scale) * 32768.f); if (u > 0xfffffu) u = 0xfffffu;
-                atomicAdd(&wsm->hist[u >> 15], 1);
+                uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
+                atomicAdd(&wsm->hist[u >> 16], 1);
                 total++;
                 if (level == 0) { sumP = sumP + pm_power(&pg.recs[i], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w; }
             }
@@ -281,22 +297,32 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
             return;
         }
         if (!coarsened && level < BHRT_PM_LEVELS - 1 && total > 8 * pg.k) { level++; continue; }
-        // ---- radix-32 select of the k-th smallest squared distance
+        // ---- radix-256 select of the k-th smallest squared distance (u = 24-bit key, top digit = pass A's bin)
         uint32_t prefix = 0;
-        int shift = 15, need = pg.k;
+        int shift = 16, need = pg.k;
         for (;;) {
-            const int h = wsm->hist[lane];
-            int incl = h;
+            // each lane owns 8 consecutive bins
+            int hb8[8], mine = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { hb8[j] = wsm->hist[lane * 8 + j]; mine += hb8[j]; }
+            int incl = mine;
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
             const unsigned m = __ballot_sync(0xffffffffu, incl >= need);
-            const int b = m ? __ffs(m) - 1 : 31;
-            const int cum = __shfl_sync(0xffffffffu, incl - h, b), hb = __shfl_sync(0xffffffffu, h, b);
+            const int owner = m ? __ffs(m) - 1 : 31;
+            int b = 0, cum = 0, hb = 0;
+            if ((int)lane == owner) {
+                cum = incl - mine;
+                int j = 0;
+                for (; j < 7; j++) { if (cum + hb8[j] >= need) break; cum += hb8[j]; }
+                b = (int)lane * 8 + j; hb = hb8[j];
+            }
+            b = __shfl_sync(0xffffffffu, b, owner); cum = __shfl_sync(0xffffffffu, cum, owner); hb = __shfl_sync(0xffffffffu, hb, owner);
             need -= cum;
-            prefix = (prefix << 5) | (uint32_t)b;
+            prefix = (prefix << 8) | (uint32_t)b;
             if (hb <= BHRT_PM_CAND || shift == 0) break;
-            shift -= 5;
+            shift -= 8;
             __syncwarp();
-            wsm->hist[lane] = 0;
+            for (int j = (int)lane; j < 256; j += 32) wsm->hist[j] = 0;
             __syncwarp();
             for (int n = 0; n < 27; n++) {
                 const uint32_t bb = __shfl_sync(0xffffffffu, my_b, n), e = __shfl_sync(0xffffffffu, my_e, n);
@@ -305,11 +331,11 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
                     V3 dif(A.x - pos.x, A.y - pos.y, A.z - pos.z);
                     float d2 = length2(dif);
                     if (!(d2 < bound2)) continue;
-                    uint32_t u = (uint32_t)((d2 * scale) * 32768.f); if (u > 0xfffffu) u = 0xfffffu;
-                    if ((u >> (shift + 5)) != prefix) continue;
+                    uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
+                    if ((u >> (shift + 8)) != prefix) continue;
                     F4 B = ld4(&pg.recs[i].b);
                     if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;
-                    atomicAdd(&wsm->hist[(u >> shift) & 31u], 1);
+                    atomicAdd(&wsm->hist[(u >> shift) & 255u], 1);
                 }
             }
             __syncwarp();
@@ -327,7 +353,7 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
                 V3 dif(A.x - pos.x, A.y - pos.y, A.z - pos.z);
                 float d2 = length2(dif);
                 if (!(d2 < bound2)) continue;
-                uint32_t u = (uint32_t)((d2 * scale) * 32768.f); if (u > 0xfffffu) u = 0xfffffu;
+                uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
                 const uint32_t top = u >> shift;
                 if (top > prefix) continue;
                 F4 B = ld4(&pg.recs[i].b);
@@ -383,10 +409,11 @@ wf_render(SceneView s, WaveArgs a)
     unsigned short *mq = list + P;                                         // [P] mesh queue (ring)
     unsigned char *lkey = (unsigned char *)(mq + P);                       // [P] key of lane id
     unsigned char *pend = lkey + P;                                        // [P] lane id is queued / being traversed
-    PmWarpScratch *pm_scratch = (PmWarpScratch *)(smem + a.smem_gather);   // [WF_BLOCK / 32]
+    PmWarpScratch *pm_scratch = (PmWarpScratch *)(smem + a.smem_gather);   // [WF_BLOCK / 32]   (only with a photon map)
+    unsigned short *gq = (unsigned short *)(pm_scratch + WF_BLOCK / 32);   // [P] lanes waiting for a caustic gather
     unsigned short *gcount = (unsigned short *)(pend + P);                 // [P/32][WF_NKEYS] per-group key counts / offsets (P is a multiple of 32)
     __shared__ unsigned key_count[WF_NKEYS], key_base[WF_NKEYS];
-    __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor;
+    __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor, gq_count, gq_cursor;
 
     Lane *const lanes = a.lanes + (size_t)blockIdx.x * P;
     Frame *const frames_all = a.frames + (size_t)blockIdx.x * P * BHRT_MAX_FRAMES;
@@ -395,7 +422,7 @@ wf_render(SceneView s, WaveArgs a)
 
     for (unsigned i = tid; i < P; i += WF_BLOCK) { list[i] = (unsigned short)i; lkey[i] = WF_KEY_DEAD; pend[i] = 0; }
     if (tid < WF_NKEYS) key_count[tid] = 0;
-    if (tid == 0) { n_live_s = P; n_pending_s = 0; mq_head = 0; mq_tail = 0; p1_cursor = 0; run_mesh_s = 0; done_s = 0; }
+    if (tid == 0) { n_live_s = P; n_pending_s = 0; mq_head = 0; mq_tail = 0; p1_cursor = 0; run_mesh_s = 0; done_s = 0; gq_count = 0; gq_cursor = 0; }
     __syncthreads();
 
     RayCounters rc; rc.closest = 0; rc.shadow = 0;
@@ -435,19 +462,10 @@ wf_render(SceneView s, WaveArgs a)
             // stages (and reach a stage after different numbers of steps): each trip runs ONE
             // stage -- the earliest any lane is in -- for all lanes that are in it, so later
             // stages wait until the stragglers have caught up and then run together.
-            bool want_gather = false;
+            // (a caustic gather asked for by a step parks the lane: the queries of the whole CTA are
+            // evaluated after the pass, one per warp at a time -- see the gather phase below)
+            bool to_gather = false;
             for (;;) {
-                // caustic gathers asked for in the last trip: the whole warp evaluates them, one query at a time
-                for (unsigned gm = __ballot_sync(0xffffffffu, want_gather); gm; gm &= gm - 1u) {
-                    const int src = __ffs(gm) - 1;
-                    V3 qp(0, 0, 0), qn(0, 0, 0);
-                    if ((int)lane == src) { const Frame &fq = frames[L.sp - 1]; qp = fq.p; qn = fq.vN; }
-                    qp = V3(__shfl_sync(0xffffffffu, qp.x, src), __shfl_sync(0xffffffffu, qp.y, src), __shfl_sync(0xffffffffu, qp.z, src));
-                    qn = V3(__shfl_sync(0xffffffffu, qn.x, src), __shfl_sync(0xffffffffu, qn.y, src), __shfl_sync(0xffffffffu, qn.z, src));
-                    V3 irr, dirv;
-                    estimate_irradiance_warp(a.gather, qp, qn, irr, dirv, pm_scratch + (tid >> 5));
-                    if ((int)lane == src) { L.hit.p = irr; L.sw = dirv; want_gather = false; }
-                }
                 const int st = running ? (L.sp == 0 ? -1 : (int)L.stage[L.sp - 1]) : 127;
                 const int mn = __reduce_min_sync(0xffffffffu, st);
                 if (mn == 127) break;
@@ -455,7 +473,7 @@ wf_render(SceneView s, WaveArgs a)
                 V3 c;
                 const int r = sample_step(L, frames[L.sp > 0 ? L.sp - 1 : 0], frames[L.sp < BHRT_MAX_FRAMES ? L.sp : BHRT_MAX_FRAMES - 1],
                                           s, a.cfg, a.gather, L.sp == 0 ? lanes[id].cold.bgu : 0.f, L.sp == 0 ? lanes[id].cold.bgv : 0.f, rc, c);
-                if (r == STEP_GATHER) { want_gather = true; continue; }
+                if (r == STEP_GATHER) { to_gather = true; running = false; continue; }
                 if (r == STEP_RAY) { running = false; continue; }
                 if (r == STEP_DONE) {
                     const LaneCold &lc = lanes[id].cold;
@@ -495,7 +513,7 @@ wf_render(SceneView s, WaveArgs a)
             // ---- the new ray against the scene graph (every surviving lane has one)
             const bool alive = valid && !dead;
             bool to_mesh = false;
-            if (alive) {
+            if (alive && !to_gather) {
                 Hit h;
                 uint32_t mask;
                 const bool blocked = scene_trace_graph(s, L.q, h, mask);
@@ -503,9 +521,20 @@ wf_render(SceneView s, WaveArgs a)
                 L.hit.z = h.z; L.hit.node = h.node; L.hit.front = h.front;
                 L.mesh_mask = 0;
                 if (!blocked && (mask || s.n_mesh_nodes > BHRT_MESH_MASK_BITS)) { L.mesh_mask = mask; to_mesh = true; }
+            }
+            if (alive) {
                 wf_store_lane(&lanes[id], L);
                 lkey[id] = (unsigned char)wf_key(s, L, frames[L.sp > 0 ? L.sp - 1 : 0]);
             } else if (valid) lkey[id] = WF_KEY_DEAD;
+            // park the lanes that wait for a caustic gather
+            const unsigned gmask = __ballot_sync(0xffffffffu, to_gather);
+            if (gmask) {
+                const int leader = __ffs(gmask) - 1;
+                unsigned base = 0;
+                if ((int)lane == leader) base = atomicAdd(&gq_count, (unsigned)__popc(gmask));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (to_gather) { gq[base + __popc(gmask & ((1u << lane) - 1u))] = (unsigned short)id; pend[id] = 1; }
+            }
             // queue the rays that entered a mesh
             const unsigned mm = __ballot_sync(0xffffffffu, to_mesh);
             if (mm) {
@@ -518,6 +547,26 @@ wf_render(SceneView s, WaveArgs a)
         }
         first = false;
         __syncthreads();
+        // ================= caustic gathers of the parked lanes: one query per warp at a time =================
+        // (evaluated here rather than inside the pass: the queries of a pass sit in a few chunks, and the
+        // warps that own those chunks would keep all the others waiting at the barrier)
+        if (a.gather.use) {
+            const unsigned ng = gq_count;
+            for (;;) {
+                unsigned i = 0;
+                if (lane == 0) i = atomicAdd(&gq_cursor, 1u);
+                i = __shfl_sync(0xffffffffu, i, 0);
+                if (i >= ng) break;
+                const unsigned gid = gq[i];
+                Lane &Lg = lanes[gid];
+                const Frame &fq = frames_all[(size_t)gid * BHRT_MAX_FRAMES + (Lg.sp - 1)];
+                V3 irr, dirv;
+                estimate_irradiance_warp(a.gather, fq.p, fq.vN, irr, dirv, pm_scratch + (tid >> 5));
+                if (lane == 0) { Lg.ret = irr; Lg.sw = dirv; pend[gid] = 0; }
+            }
+            __syncthreads();
+            if (tid == 0) { gq_count = 0; gq_cursor = 0; }
+        }
         long long c_mark = clock64();
         t_p1 += c_mark - c_begin;
 
