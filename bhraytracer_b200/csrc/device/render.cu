@@ -65,6 +65,8 @@ struct bhrt_ctx {
     unsigned pool_lanes = 3072;                 // lanes (camera samples in flight) per CTA, 2.3 KB of state each
     int mesh_budget = WF_MESH_BUDGET;
     unsigned mesh_batch = WF_BLOCK;
+    unsigned gather_batch = 0;                  // 0 = 11/12 of the pool
+    bool pool_lanes_set = false;
     int trav_min = 3, trav_max = 12, trav_pct = 50;
     DevBuf lanes, frames, samples, wave_counters;
 };
@@ -108,9 +110,10 @@ int bhrt_create(int device, bhrt_ctx **out)
     CU(cudaEventCreate(&c->ev1));
     if (c->counters.ensure(8 * sizeof(unsigned long long))) { delete c; return set_err(BHRT_ERR_CUDA, "cudaMalloc(counters)"); }
     // tuning knobs
-    if (const char *e = getenv("BHRT_POOL_LANES")) { long v = atol(e); if (v >= 32 && v <= 32768) c->pool_lanes = (unsigned)v; }
+    if (const char *e = getenv("BHRT_POOL_LANES")) { long v = atol(e); if (v >= 32 && v <= 32768) { c->pool_lanes = (unsigned)v; c->pool_lanes_set = true; } }
     if (const char *e = getenv("BHRT_MESH_BUDGET")) { long v = atol(e); if (v >= 1) c->mesh_budget = (int)v; }
     if (const char *e = getenv("BHRT_TRAV")) { int x, y, z; if (sscanf(e, "%d,%d,%d", &x, &y, &z) == 3 && x >= 0 && y >= 1) { c->trav_min = x; c->trav_max = y; c->trav_pct = z; } }
+    if (const char *e = getenv("BHRT_GATHER_BATCH")) { long v = atol(e); if (v >= 1) c->gather_batch = (unsigned)v; }
     if (const char *e = getenv("BHRT_MESH_BATCH")) { long v = atol(e); if (v >= 1) c->mesh_batch = (unsigned)v; }
     *out = c;
     return BHRT_OK;
@@ -267,8 +270,12 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     if (chunk > 0 && n_pix_share * (size_t)chunk > max_samples) chunk = (int)(max_samples / n_pix_share);
     if (chunk < 1) chunk = 1;
     a.pool = (c->pool_lanes + 31u) & ~31u;
+    // photon-mapped frames are dominated by the caustic gathers, whose phase balances its 32 warps the
+    // better the more queries it has: four times the lanes, gathered when nearly all of them are parked
+    if (a.gather.use && !c->pool_lanes_set) a.pool = 12288;
     a.mesh_budget = c->mesh_budget;
     a.mesh_batch = c->mesh_batch;
+    a.gather_batch = c->gather_batch ? c->gather_batch : a.pool - a.pool / 12;
     a.trav_min = c->trav_min; a.trav_max = c->trav_max; a.trav_pct = c->trav_pct;
     auto al16 = [](int v) { return (v + 15) & ~15; };
     a.smem_nodes = 0;

@@ -117,6 +117,7 @@ struct WaveArgs {
     unsigned pool;              // lanes per CTA (<= 65535)
     int mesh_budget;            // traversal trips a thread may still run after the last warp left the lanes pass
     unsigned mesh_batch;        // queued rays that switch the traversal phase on
+    unsigned gather_batch;      // parked caustic queries that switch the gather phase on
     int trav_min, trav_max, trav_pct;   // internal-node steps per trip: at least / at most / until this % of the job lanes is still at an internal node
     int smem_nodes, smem_materials, smem_lights, smem_offsets, smem_wave, smem_gather;   // byte offsets into dynamic shared memory
 };
@@ -413,7 +414,7 @@ wf_render(SceneView s, WaveArgs a)
     unsigned short *gq = (unsigned short *)(pm_scratch + WF_BLOCK / 32);   // [P] lanes waiting for a caustic gather
     unsigned short *gcount = (unsigned short *)(pend + P);                 // [P/32][WF_NKEYS] per-group key counts / offsets (P is a multiple of 32)
     __shared__ unsigned key_count[WF_NKEYS], key_base[WF_NKEYS];
-    __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor, gq_count, gq_cursor;
+    __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor, gq_count, gq_cursor, run_gather_s;
 
     Lane *const lanes = a.lanes + (size_t)blockIdx.x * P;
     Frame *const frames_all = a.frames + (size_t)blockIdx.x * P * BHRT_MAX_FRAMES;
@@ -551,6 +552,11 @@ wf_render(SceneView s, WaveArgs a)
         // (evaluated here rather than inside the pass: the queries of a pass sit in a few chunks, and the
         // warps that own those chunks would keep all the others waiting at the barrier)
         if (a.gather.use) {
+            // (batched like the BVH traversal: a phase with few queries cannot keep 32 warps evenly busy)
+            if (tid == 0) run_gather_s = gq_count > 0 && (gq_count >= a.gather_batch || n_live <= P / 4);
+            __syncthreads();
+        }
+        if (a.gather.use && run_gather_s) {
             const unsigned ng = gq_count;
             for (;;) {
                 unsigned i = 0;
