@@ -414,7 +414,7 @@ wf_render(SceneView s, WaveArgs a)
     unsigned short *gq = (unsigned short *)(pm_scratch + WF_BLOCK / 32);   // [P] lanes waiting for a caustic gather
     unsigned short *gcount = (unsigned short *)(pend + P);                 // [P/32][WF_NKEYS] per-group key counts / offsets (P is a multiple of 32)
     __shared__ unsigned key_count[WF_NKEYS], key_base[WF_NKEYS];
-    __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor, gq_count, gq_cursor, run_gather_s;
+    __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor, gq_count, gq_cursor, run_gather_s, n_parked_s;
 
     Lane *const lanes = a.lanes + (size_t)blockIdx.x * P;
     Frame *const frames_all = a.frames + (size_t)blockIdx.x * P * BHRT_MAX_FRAMES;
@@ -423,7 +423,7 @@ wf_render(SceneView s, WaveArgs a)
 
     for (unsigned i = tid; i < P; i += WF_BLOCK) { list[i] = (unsigned short)i; lkey[i] = WF_KEY_DEAD; pend[i] = 0; }
     if (tid < WF_NKEYS) key_count[tid] = 0;
-    if (tid == 0) { n_live_s = P; n_pending_s = 0; mq_head = 0; mq_tail = 0; p1_cursor = 0; run_mesh_s = 0; done_s = 0; gq_count = 0; gq_cursor = 0; }
+    if (tid == 0) { n_live_s = P; n_pending_s = 0; mq_head = 0; mq_tail = 0; p1_cursor = 0; run_mesh_s = 0; done_s = 0; gq_count = 0; gq_cursor = 0; n_parked_s = 0; }
     __syncthreads();
 
     RayCounters rc; rc.closest = 0; rc.shadow = 0;
@@ -532,7 +532,7 @@ wf_render(SceneView s, WaveArgs a)
             if (gmask) {
                 const int leader = __ffs(gmask) - 1;
                 unsigned base = 0;
-                if ((int)lane == leader) base = atomicAdd(&gq_count, (unsigned)__popc(gmask));
+                if ((int)lane == leader) { base = atomicAdd(&gq_count, (unsigned)__popc(gmask)); atomicAdd(&n_parked_s, (unsigned)__popc(gmask)); }
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (to_gather) { gq[base + __popc(gmask & ((1u << lane) - 1u))] = (unsigned short)id; pend[id] = 1; }
             }
@@ -568,7 +568,7 @@ wf_render(SceneView s, WaveArgs a)
                 const Frame &fq = frames_all[(size_t)gid * BHRT_MAX_FRAMES + (Lg.sp - 1)];
                 V3 irr, dirv;
                 estimate_irradiance_warp(a.gather, fq.p, fq.vN, irr, dirv, pm_scratch + (tid >> 5));
-                if (lane == 0) { Lg.ret = irr; Lg.sw = dirv; pend[gid] = 0; }
+                if (lane == 0) { Lg.ret = irr; Lg.sw = dirv; pend[gid] = 0; atomicSub(&n_parked_s, 1u); }
             }
             __syncthreads();
             if (tid == 0) { gq_count = 0; gq_cursor = 0; }
@@ -608,7 +608,7 @@ wf_render(SceneView s, WaveArgs a)
                 p1_cursor = 0;
                 // decisions every thread must agree on, taken while nobody changes their inputs
                 run_mesh_s = round == 0 && n_pending_s > 0 && (mq_tail - mq_head >= a.mesh_batch || acc < WF_BLOCK);
-                done_s = acc == 0 && n_pending_s == 0;
+                done_s = acc == 0 && n_pending_s == 0 && n_parked_s == 0;
             }
             __syncthreads();
             for (unsigned g = tid >> 5; g < n_groups; g += WF_BLOCK / 32) {
