@@ -262,3 +262,23 @@ def test_cli_photon_dat_round_trip(built, tmp_path):
     assert len(rec) == info["photons_stored"] == 20000
     # scaled like the reference's file: mean power * N is the light's emitted power scale
     assert abs(float(rec["power"].astype(np.float64).sum()) / float(GOLD["mean_power"]) - 1.0) < 0.05
+
+
+@pytest.mark.gpu
+def test_gpu_photon_mapped_frame_loses_no_sample(renderer):
+    """Lanes parked for a caustic gather must all come back: every pixel's sample count equals spp (a
+    frame much smaller than the lane pools, so the pools drain with lanes still parked)."""
+    import torch
+    import bhraytracer_b200 as b
+    scene = b.LoadScene(SCENE, 53, 37)
+    renderer.upload(scene)
+    renderer.photons_set(GOLD["photons"])
+    renderer.photons_build(1)
+    renderer.render_device(renderer.params(mode=b.MODE_PATH, spp=3, seed=2, use_photon_map=True, photon_k=100))
+    ptr, nbytes = renderer.accum_buffer()
+
+    class _A:
+        __cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+    acc = torch.as_tensor(_A(), device="cuda").cpu().numpy().reshape(37, 53, 4)
+    assert (acc[:, :, 3] == 3).all()
+    assert np.isfinite(acc).all()
