@@ -831,7 +831,7 @@ BHRT_HD V3 texel(const uint8_t *d, int index)
 #endif
 }
 
-BHRT_FN V3 texture_sample(const SceneView &s, const bhrt_texture &t, V3 uvw)
+BHRT_MATH_FN V3 texture_sample(const SceneView &s, const bhrt_texture &t, V3 uvw)
 {
     V3 u = tile_clamp(uvw);
     if (t.kind == BHRT_TEX_CHECKER) {
@@ -861,7 +861,7 @@ BHRT_FN V3 texture_sample(const SceneView &s, const bhrt_texture &t, V3 uvw)
 }
 
 // Texture::Sample(uvw, duvw) (scene.h:318-337): 32-tap elliptical Halton filter when duvw != 0
-BHRT_FN V3 texture_sample_filtered(const SceneView &s, const bhrt_texture &t, V3 uvw, V3 d0, V3 d1)
+BHRT_MATH_FN V3 texture_sample_filtered(const SceneView &s, const bhrt_texture &t, V3 uvw, V3 d0, V3 d1)
 {
     V3 c = texture_sample(s, t, uvw);
     if (length2(d0) + length2(d1) == 0) return c;
