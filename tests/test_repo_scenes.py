@@ -56,3 +56,38 @@ def test_reference_scene_file_renders_like_the_reference(built, tmp_path, name):
         # one random number left (the light's disk sample): the images agree except in penumbrae
         d = np.abs(emu["rgb8"].astype(np.int32) - ref["rgb8"].astype(np.int32)).max(axis=2)
         assert (d > 1).mean() < 0.15
+
+
+def test_ppm_texture_and_backslash_paths_like_the_reference(built, tmp_path):
+    """binary PPM textures (Texture.cpp:18-54) and `\\`-separated asset paths as the repo's
+    scene files write them (xmlload.cpp:178,208-211; oracle patch O-6 maps them on Linux): a textured floor
+    and a checkerboard wall, our loader + device code against the reference run live on the same file."""
+    rng = np.random.default_rng(7)
+    tex = rng.integers(0, 256, (24, 32, 3), dtype=np.uint8)
+    os.makedirs(tmp_path / "tex")
+    with open(tmp_path / "tex" / "noise.ppm", "wb") as f:
+        f.write(b"P6\n# made by the test\n32 24\n255\n" + tex.tobytes())
+    scene = tmp_path / "ppm.xml"
+    scene.write_text(r'''<xml><scene>
+      <object type="plane" name="floor" material="floorMtl"><scale value="12"/></object>
+      <object type="plane" name="wall" material="wallMtl"><scale value="12"/><rotate angle="90" x="1"/><translate y="10" z="6"/></object>
+      <object type="sphere" name="ball" material="ballMtl"><scale value="2"/><translate x="1" y="-1" z="2"/></object>
+      <material type="blinn" name="floorMtl"><diffuse texture="tex\noise.ppm"><scale value="0.25"/></diffuse><specular value="0.1"/></material>
+      <material type="blinn" name="wallMtl"><diffuse texture="checkerboard"><color1 r="0.9" g="0.2" b="0.2"/><color2 r="0.1" g="0.1" b="0.9"/><scale value="0.2"/></diffuse><specular value="0"/></material>
+      <material type="blinn" name="ballMtl"><diffuse r="0.3" g="0.8" b="0.3"/><specular value="0.6"/><glossiness value="40"/></material>
+      <light type="point" name="key"><intensity value="300"/><position x="-4" y="-8" z="14"/></light>
+    </scene>
+    <camera><position x="0" y="-22" z="8"/><target x="0" y="0" z="3"/><up x="0" y="0" z="1"/><fov value="40"/><width value="160"/><height value="120"/></camera></xml>''')
+    ref_info = json.loads(subprocess.check_output([REF_BIN, str(scene), str(tmp_path / "ref"), "--det", "--threads", "2"], cwd=str(tmp_path),
+                                                  stderr=subprocess.DEVNULL).decode().splitlines()[-1])
+    ref = read_aov(str(tmp_path / "ref.aov"))
+    info = json.loads(subprocess.check_output([EMU_BIN, str(scene), str(tmp_path / "emu"), "--det"], cwd=str(tmp_path),
+                                              stderr=subprocess.DEVNULL).decode().splitlines()[-1])
+    emu = read_aov(str(tmp_path / "emu.aov"))
+    assert (emu["hit_id"] == ref["hit_id"]).all() and (emu["z"].view(np.uint32) == ref["z"].view(np.uint32)).all()
+    d = np.abs(emu["rgb8"].astype(np.int32) - ref["rgb8"].astype(np.int32))
+    assert d.max() <= 1, "8-bit error %d on %d pixels" % (d.max(), int((d.max(axis=2) > 1).sum()))
+    assert (info["rays_closest"], info["rays_shadow"]) == (ref_info["rays_closest"], ref_info["rays_shadow"])
+    # the texture really is in the picture: the floor is not one flat colour
+    floor = emu["rgb8"][emu["hit_id"] == 0]
+    assert floor.std() > 10
