@@ -456,8 +456,10 @@ wf_render(SceneView s, WaveArgs a)
             bool running = valid && !first;
             if (running) {
                 wf_load_lane(L, &lanes[id]);
-                // the answer of the pending query: winner-only work of a closest hit
-                if (L.q.kind == Q_CLOSEST) L.hit_ok = scene_trace_finish(s, L.q, L.hit);
+                // the answer of the pending query: winner-only work of a closest hit (a lane that comes
+                // back from a caustic gather has no new answer: its last query was consumed before)
+                const bool from_gather = L.sp > 0 && L.stage[L.sp - 1] == ST_GATHER_WAIT;
+                if (L.q.kind == Q_CLOSEST && !from_gather) L.hit_ok = scene_trace_finish(s, L.q, L.hit);
             }
             // The estimator coroutine up to its next ray.  Lanes of a warp may be in different
             // stages (and reach a stage after different numbers of steps): each trip runs ONE
