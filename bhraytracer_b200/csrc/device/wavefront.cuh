@@ -163,15 +163,17 @@ __device__ __forceinline__ void wf_load_lane(Lane &dst, const Lane *src)
     static_assert(offsetof(Lane, hit) + 32 == BHRT_LANE_PERSIST && BHRT_LANE_PERSIST % 16 == 0 && offsetof(Hit, p) >= 28, "Lane layout");
     const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
     uint4 *d4 = reinterpret_cast<uint4 *>(&dst);
+    // (streaming loads / stores: a record is read once and written once per pass; it should not push
+    // the thread-local copies out of L1)
 #pragma unroll
-    for (int i = 0; i < BHRT_LANE_PERSIST / 16; i++) d4[i] = s4[i];
+    for (int i = 0; i < BHRT_LANE_PERSIST / 16; i++) d4[i] = __ldcs(s4 + i);
 }
 __device__ __forceinline__ void wf_store_lane(Lane *dst, const Lane &src)
 {
     const uint4 *s4 = reinterpret_cast<const uint4 *>(&src);
     uint4 *d4 = reinterpret_cast<uint4 *>(dst);
 #pragma unroll
-    for (int i = 0; i < BHRT_LANE_PERSIST / 16; i++) d4[i] = s4[i];
+    for (int i = 0; i < BHRT_LANE_PERSIST / 16; i++) __stcs(d4 + i, s4[i]);
 }
 // Work item g of the chunk -> (pixel, sample).  Sample-major: consecutive items are the pixels of
 // one 8x8 tile, so the lanes of a warp start on neighbouring primary rays.
