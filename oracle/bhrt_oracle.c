@@ -1,21 +1,23 @@
 /* bhrt_oracle.c -- TEST INFRASTRUCTURE, never linked into the product.
  *
- * A plain-C restatement of the reference's deterministic hot path for BASELINE config 1 (the
- * reference's own CPU-runnable case: spheres + planes, point / direct lights, Blinn-Phong with
- * hard shadows, 1 spp at the pixel corner), written from the reference sources cited at every
- * function (paths relative to /root/reference/BHRayTracer).  It is independent of csrc/device:
- * the only thing it shares with the product is the POD scene description of include/bhrt.h.
+ * A plain-C restatement of the reference's deterministic hot path for analytic scenes (spheres +
+ * planes; point / direct / ambient lights; Blinn-Phong with hard shadows; Fresnel refraction with
+ * absorption and total internal reflection; checker and bitmap textures with the plane's ray
+ * differentials; textured background and environment; 1 spp at the pixel corner), written from the
+ * reference sources cited at every function (paths relative to /root/reference/BHRayTracer).  It is
+ * independent of csrc/device: the only thing it shares with the product is the POD scene
+ * description of include/bhrt.h.
  *
  * PINNED: tests/test_oracle_restatement.py checks it against the committed outputs of the
- * reference itself (tests/golden/cfg1_spheres_plane_det.npz, made by oracle/_ref/bhrt_ref --det):
- * primary hit ids and z bit-exact, RGB8 identical, ray counts identical.  The real reference
- * (oracle/_ref, built by oracle/build_ref.py) remains the oracle for everything outside this
- * file's scope -- refraction, GI, textures, meshes, photon map -- where a restatement would only
- * repeat the reference with more room for error.
+ * reference itself (tests/golden/{cfg1_spheres_plane,det_refract,det_textured}_det.npz, made by
+ * oracle/_ref/bhrt_ref --det): primary hit ids and z bit-exact, RGB8 identical, ray counts
+ * identical.  The real reference (oracle/_ref, built by oracle/build_ref.py) remains the oracle
+ * for everything outside this file's scope -- GI, triangle meshes, area lights, photon map --
+ * where a restatement would only repeat the reference with more room for error.
  *
- * Scope check: bhrt_oracle_render_det returns -2 for scenes with meshes, textures or refractive
- * materials.  "D-mode" = the four switches of SURVEY.md 8(c): no jitter, GI off, every light with
- * its exact direction, no glossy refraction.
+ * Scope check: bhrt_oracle_render_det returns -2 for scenes with meshes or area lights.
+ * "D-mode" = the four switches of SURVEY.md 8(c): no jitter, GI off, every light with its exact
+ * direction, no glossy refraction.
  *
  * Build: gcc -O2 -ffp-contract=off -shared -fPIC (oracle/Makefile).  x86-64 without -mfma
  * contracts nothing, like the reference's own build.
@@ -28,6 +30,10 @@
 
 #define BIGFLOAT 1.0e30f          /* Scenes/scene.h:38 */
 #define SHADOW_BIAS 0.00001f      /* Lights/GenLight.cpp:5 */
+#define BIAS 0.0001f              /* Materials/Blinn/MtlBlinn.cpp:10 */
+#define EULER_N 2.7182818f        /* MtlBlinn.cpp:11 */
+#define TEXTURE_SAMPLE_COUNT 32   /* Scenes/scene.h:18 */
+#define PI_F ((float)3.14159265358979323846)   /* (float)M_PI */
 #define PI_D 3.14159265           /* "#define PI 3.14159265" (Main.cpp, a double literal) */
 enum { HIT_FRONT = 1, HIT_BACK = 2, HIT_FRONT_AND_BACK = 3 };      /* scene.h:57-60 */
 
@@ -70,7 +76,9 @@ static ray_t to_node_coords(const bhrt_xform *t, ray_t r)
     return o;
 }
 
-typedef struct { float z; v3 p, N; int node; int front; } hit_t;     /* scene.h:62-75, the fields config 1 reads */
+typedef struct { float z; v3 p, N, uvw, duvw[2]; int node; int front; } hit_t;     /* scene.h:62-75 (mtlID: meshes only) */
+/* HitInfo::Init (scene.h:74) */
+static void hit_init(hit_t *h) { h->z = BIGFLOAT; h->node = -1; h->front = 1; h->p = V(0, 0, 0); h->N = V(0, 0, 0); h->uvw = V(0.5f, 0.5f, 0.5f); h->duvw[0] = V(0, 0, 0); h->duvw[1] = V(0, 0, 0); }
 
 /* Sphere::IntersectRay (Objects/Sphere/Sphere.cpp:8-75), unit sphere at the origin */
 static int sphere_intersect(ray_t ray, hit_t *h, int hitSide)
@@ -98,13 +106,20 @@ static int sphere_intersect(ray_t ray, hit_t *h, int hitSide)
         h->p = add(oc, mulf(dir, h->z));
         h->N = h->p;
         h->front = front;
-        return 1;       /* (uv: untextured scenes only, see the scope check) */
+        /* :57-70 -- float atan2/asin promoted to double by the double literal PI; uvw.z is never
+         * assigned in the reference (an uninitialised local), 2-D textures do not read it */
+        v3 d = norm(h->N);
+        h->uvw.x = (float)(0.5f + atan2f(d.y, d.x) / (2 * PI_D));
+        h->uvw.y = (float)(0.5f - asinf(d.z) / (PI_D));
+        h->uvw.z = 0;
+        h->duvw[0] = V(0, 0, 0); h->duvw[1] = V(0, 0, 0);
+        return 1;
     }
     return 0;
 }
 
 /* Plane::IntersectRay (Objects/Plane/Plane.cpp:8-49), the z = 0 plane within [-1,1]^2 */
-static int plane_intersect(ray_t ray, hit_t *h, int hitSide)
+static int plane_intersect(ray_t ray, hit_t *h, int hitSide, v3 dd_x, v3 dd_y)
 {
     float rayPz = ray.p.z, rayDz = ray.dir.z;
     if (rayDz == 0.0f) return 0;
@@ -116,6 +131,22 @@ static int plane_intersect(ray_t ray, hit_t *h, int hitSide)
     if (!front && hitSide == HIT_FRONT) return 0;
     else if (front && hitSide == HIT_BACK) return 0;
     h->p = x; h->N = V(0, 0, 1); h->z = t; h->front = front;
+    h->uvw = V((1 + h->p.x) / 2.f, (1 + h->p.y) / 2.f, 0);
+    /* RAY_DIFFERENTIAL block (:51-70): the globals dd_x, dd_y are the PRIMARY rays' pixel steps, used
+     * for every ray; "0 + vec" is a component-wise + 0.0f */
+    v3 nd = norm(ray.dir);
+    float scaled_t = len(mulf(ray.dir, t));
+    float ndnd = dot(nd, nd);
+    float den = powf(ndnd, 1.5f);
+    v3 dDX = divf(sub(mulf(dd_x, ndnd), mulf(nd, dot(nd, dd_x))), den);
+    v3 dDY = divf(sub(mulf(dd_y, ndnd), mulf(nd, dot(nd, dd_y))), den);
+    float d_t_x = -(0 + scaled_t * dot(dDX, h->N) / dot(nd, h->N));
+    float d_t_y = -(0 + scaled_t * dot(dDY, h->N) / dot(nd, h->N));
+    v3 zero = V(0, 0, 0);
+    v3 hx = add(add(mulf(dDX, scaled_t), zero), mulf(nd, d_t_x));
+    v3 hy = add(add(mulf(dDY, scaled_t), zero), mulf(nd, d_t_y));
+    h->duvw[0] = divf(hx, 2.f);
+    h->duvw[1] = divf(hy, 2.f);
     return 1;
 }
 
@@ -130,6 +161,9 @@ typedef struct {
     const bhrt_scene_desc *d;
     int *first_child, *next_sibling;      /* the Node tree rebuilt from the DFS table */
     uint64_t rays_closest, rays_shadow;
+    v3 dd_x, dd_y;                        /* Main.cpp:31 globals, read by Plane.cpp */
+    const bhrt_light *lights; int n_lights;       /* sorted (Main.cpp:112-123) */
+    float tex_x[TEXTURE_SAMPLE_COUNT], tex_y[TEXTURE_SAMPLE_COUNT];   /* scene.h:323-329 offsets */
 } scene_t;
 static const bhrt_xform IDENTITY = { { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, { 0, 0, 0 } };
 
@@ -142,7 +176,7 @@ static void recursive(scene_t *s, int root, ray_t ray, hit_t *out, int *bHit, in
         const bhrt_node *n = &s->d->nodes[c];
         ray_t tr = to_node_coords(&n->xf, ray);
         if (n->kind != BHRT_OBJ_NONE) {
-            int got = n->kind == BHRT_OBJ_SPHERE ? sphere_intersect(tr, out, hitSide) : plane_intersect(tr, out, hitSide);
+            int got = n->kind == BHRT_OBJ_SPHERE ? sphere_intersect(tr, out, hitSide) : plane_intersect(tr, out, hitSide, s->dd_x, s->dd_y);
             if (got) { out->node = c; *bHit = 1; from_node_coords(&n->xf, out); }
         }
         recursive(s, c, tr, out, bHit, hitSide);
@@ -207,10 +241,179 @@ static v3 light_direction(const bhrt_light *L, v3 p)
 static float gray(const bhrt_light *L) { return (L->intensity[0] + L->intensity[1] + L->intensity[2]) / 3.0f; }   /* cyColor.h:83 */
 static void clamp_white(v3 *c) { if (c->x > 1) c->x = 1.f; if (c->y > 1) c->y = 1.f; if (c->z > 1) c->z = 1.f; }   /* MtlBlinn.cpp:79-83 */
 
-/* MtlBlinn::Shade (Materials/Blinn/MtlBlinn.cpp:89-138) in D-mode for a non-refractive, untextured
- * material: the refraction term is zero, GI is switched off, PathTracing_DiffuseNSpecular (:304-351)
- * loops over every light with its exact direction */
-static v3 shade(scene_t *s, ray_t ray, const hit_t *h, const bhrt_light *lights, int n_lights)
+/* ---- textures ------------------------------------------------------------------------------ */
+/* Texture::TileClamp (scene.h:344-354) */
+static v3 tile_clamp(v3 uvw)
+{
+    v3 u = V(uvw.x - (int)uvw.x, uvw.y - (int)uvw.y, uvw.z - (int)uvw.z);
+    if (u.x < 0) u.x += 1;
+    if (u.y < 0) u.y += 1;
+    if (u.z < 0) u.z += 1;
+    return u;
+}
+static v3 texel(const scene_t *s, const bhrt_texture *T, int i)        /* Color24::ToColor (cyColor.h:236) */
+{
+    const uint8_t *t = s->d->texels + T->texel_offset + 3 * (size_t)i;
+    return V(t[0] / 255.0f, t[1] / 255.0f, t[2] / 255.0f);
+}
+/* TextureFile::Sample (Textures/Texture.cpp:100-123), TextureChecker::Sample (:127-136) */
+static v3 texture_sample(const scene_t *s, const bhrt_texture *T, v3 uvw)
+{
+    v3 u = tile_clamp(uvw);
+    if (T->kind == BHRT_TEX_CHECKER) {
+        if (u.x <= 0.5f) return u.y <= 0.5f ? ld(T->color1) : ld(T->color2);
+        return u.y <= 0.5f ? ld(T->color2) : ld(T->color1);
+    }
+    int width = T->width, height = T->height;
+    if (width + height == 0) return V(0, 0, 0);
+    float x = width * u.x, y = height * u.y;
+    int ix = (int)x, iy = (int)y;
+    float fx = x - ix, fy = y - iy;
+    if (ix < 0) ix -= (ix / width - 1) * width;
+    if (ix >= width) ix -= (ix / width) * width;
+    int ixp = ix + 1;
+    if (ixp >= width) ixp -= width;
+    if (iy < 0) iy -= (iy / height - 1) * height;
+    if (iy >= height) iy -= (iy / height) * height;
+    int iyp = iy + 1;
+    if (iyp >= height) iyp -= height;
+    return add(add(add(mulf(texel(s, T, iy * width + ix), (1 - fx) * (1 - fy)), mulf(texel(s, T, iy * width + ixp), fx * (1 - fy))),
+                   mulf(texel(s, T, iyp * width + ix), (1 - fx) * fy)), mulf(texel(s, T, iyp * width + ixp), fx * fy));
+}
+/* Halton (scene.h:137-146) */
+static float halton(int index, int base)
+{
+    float r = 0, f = 1.0f / (float)base;
+    for (int i = index; i > 0; i /= base) { r += f * (i % base); f /= (float)base; }
+    return r;
+}
+/* Texture::Sample(uvw, duvw, elliptic = true) (scene.h:318-337) */
+static v3 texture_sample_filtered(const scene_t *s, const bhrt_texture *T, v3 uvw, const v3 *duvw)
+{
+    v3 c = texture_sample(s, T, uvw);
+    if (dot(duvw[0], duvw[0]) + dot(duvw[1], duvw[1]) == 0) return c;
+    for (int i = 1; i < TEXTURE_SAMPLE_COUNT; i++)
+        c = add(c, texture_sample(s, T, add(add(uvw, mulf(duvw[0], s->tex_x[i])), mulf(duvw[1], s->tex_y[i]))));
+    return divf(c, (float)TEXTURE_SAMPLE_COUNT);
+}
+/* TexturedColor::Sample(uvw) / TextureMap::Sample(uvw) (scene.h:371,410) */
+static v3 texcolor_sample(const scene_t *s, const bhrt_texcolor *tc, v3 uvw)
+{
+    if (tc->texmap < 0) return ld(tc->color);
+    const bhrt_texmap *m = &s->d->texmaps[tc->texmap];
+    v3 t = m->texture >= 0 ? texture_sample(s, &s->d->textures[m->texture], transform_to(&m->xf, uvw)) : V(0, 0, 0);
+    return mulv(ld(tc->color), t);
+}
+/* TexturedColor::Sample(uvw, duvw) / TextureMap::Sample(uvw, duvw) (scene.h:372-380,411); `color` is
+ * passed separately because Shade() swaps in the Fresnel-boosted specular colour (MtlBlinn.cpp:111-113) */
+static v3 texcolor_sample_filtered(const scene_t *s, v3 color, int texmap, v3 uvw, const v3 *duvw)
+{
+    if (texmap < 0) return color;
+    const bhrt_texmap *m = &s->d->texmaps[texmap];
+    if (m->texture < 0) return mulv(color, V(0, 0, 0));
+    v3 u = transform_to(&m->xf, uvw);
+    v3 dd[2];
+    dd[0] = sub(transform_to(&m->xf, add(duvw[0], uvw)), u);
+    dd[1] = sub(transform_to(&m->xf, add(duvw[1], uvw)), u);
+    return mulv(color, texture_sample_filtered(s, &s->d->textures[m->texture], u, dd));
+}
+/* TexturedColor::SampleEnvironment (scene.h:414-420) */
+static v3 sample_environment(const scene_t *s, v3 dir)
+{
+    float z = asinf(-dir.z) / PI_F + 0.5f;
+    float x = dir.x / (fabsf(dir.x) + fabsf(dir.y));
+    float y = dir.y / (fabsf(dir.x) + fabsf(dir.y));
+    v3 uvw = add(V(0.5f, 0.5f, 0.0f), mulf(add(mulf(V(0.5f, 0.5f, 0), x), mulf(V(-0.5f, 0.5f, 0), y)), z));
+    return texcolor_sample(s, &s->d->environment, uvw);
+}
+
+/* ---- shading -------------------------------------------------------------------------------- */
+static int all_white(v3 c) { return c.x >= 1 && c.y >= 1 && c.z >= 1; }
+static const v3 NAN_PURPLE = { 1.0f, 0.0f, 1.0f };                  /* cyColor.h:130 */
+static v3 shade(scene_t *s, ray_t ray, const hit_t *h, int bounceCount);
+/* one top-level recursive() call (Main.cpp:389) */
+static int trace(scene_t *s, ray_t ray, hit_t *h, int hitSide)
+{
+    int bHit = 0;
+    hit_init(h);
+    s->rays_closest++;
+    recursive(s, -1, ray, h, &bHit, hitSide);
+    return bHit && h->node >= 0;
+}
+
+/* HandleRayWhenRefractionRayOut (MtlBlinn.cpp:544-596), refractionGlossiness = 0 (D-4) */
+static ray_t ray_leaving(ray_t inRay, const hit_t *in, float ior, int *toOut)
+{
+    v3 vN = in->N, vV = neg(inRay.dir);
+    float cosPhi1 = dot(vV, neg(vN));
+    float sinPhi1 = sqrtf(1 - cosPhi1 * cosPhi1);
+    float sinPhi2 = ior * sinPhi1;
+    ray_t o;
+    if (sinPhi2 <= 1) {
+        float cosPhi2 = sqrtf(1 - sinPhi2 * sinPhi2);
+        v3 vTn = mulf(vN, cosPhi2);
+        v3 vTp = mulf(norm(cross(vN, cross(vN, vV))), sinPhi2);
+        v3 vT = add(vTn, vTp);
+        o.dir = norm(norm(vT));
+        o.p = add(in->p, mulf(vN, BIAS));
+        *toOut = 1;
+    } else {
+        o.dir = sub(mulf(vN, -2 * cosPhi1), vV);
+        o.p = sub(in->p, mulf(vN, BIAS));
+        *toOut = 0;
+    }
+    return o;
+}
+/* RefractionOut (MtlBlinn.cpp:520-542) */
+static v3 refraction_out(scene_t *s, ray_t outRay, v3 absorption, v3 refraction, int bounceCount)
+{
+    v3 out;
+    hit_t h;
+    if (trace(s, outRay, &h, HIT_FRONT)) {
+        v3 af = V(powf(EULER_N, -absorption.x * h.z), powf(EULER_N, -absorption.y * h.z), powf(EULER_N, -absorption.z * h.z));
+        out = mulv(mulv(refraction, af), shade(s, outRay, &h, bounceCount));
+    } else out = mulv(refraction, sample_environment(s, outRay.dir));
+    clamp_white(&out);
+    return out;
+}
+/* RefractionRecusive (MtlBlinn.cpp:476-518) */
+static v3 refraction_recursive(scene_t *s, v3 refraction, float ior, v3 vT, v3 p, v3 vN, v3 absorption, int bounceCount)
+{
+    ray_t in = { sub(p, mulf(vN, BIAS)), vT };
+    hit_t h;
+    if (!trace(s, in, &h, HIT_FRONT_AND_BACK)) return NAN_PURPLE;
+    v3 c = V(0, 0, 0);
+    if (!h.front) {
+        int out;
+        ray_t next = ray_leaving(in, &h, ior, &out);
+        if (out) c = refraction_out(s, next, absorption, refraction, bounceCount);
+        else if (bounceCount <= 0) c = V(0, 0, 0);                  /* total internal reflection, budget spent */
+        else c = refraction_recursive(s, refraction, ior, next.dir, h.p, h.N, absorption, bounceCount - 1);
+    } else c = shade(s, in, &h, bounceCount);
+    clamp_white(&c);
+    return c;
+}
+/* PathTracing_Refraction (MtlBlinn.cpp:438-473), refractionGlossiness = 0 */
+static v3 refraction_term(scene_t *s, v3 refraction, v3 absorption, float ior, const hit_t *h, float cosPhi1, v3 vN, v3 vV, int bounceCount)
+{
+    v3 c = V(0, 0, 0);
+    if (bounceCount <= 0) return c;
+    if (!(refraction.x == 0.0f && refraction.y == 0.0f && refraction.z == 0.0f)) {
+        float sinPhi1 = sqrtf(1 - cosPhi1 * cosPhi1);
+        float sinPhi2 = sinPhi1 / ior;
+        float cosPhi2 = sqrtf(1 - sinPhi2 * sinPhi2);
+        v3 vTn = mulf(vN, -cosPhi2);
+        v3 vTp = mulf(norm(cross(vN, cross(vN, vV))), sinPhi2);
+        v3 vT = norm(add(vTn, vTp));
+        c = refraction_recursive(s, refraction, ior, norm(vT), h->p, vN, absorption, bounceCount);
+    }
+    clamp_white(&c);
+    return c;
+}
+
+/* MtlBlinn::Shade (Materials/Blinn/MtlBlinn.cpp:89-138) in D-mode: GI is switched off (D-2),
+ * PathTracing_DiffuseNSpecular (:304-351) loops over every light with its exact direction (D-3) */
+static v3 shade(scene_t *s, ray_t ray, const hit_t *h, int bounceCount)
 {
     const bhrt_material *M = &s->d->materials[s->d->nodes[h->node].material];
     v3 vN = norm(h->N);
@@ -222,21 +425,27 @@ static v3 shade(scene_t *s, ray_t ray, const hit_t *h, const bhrt_light *lights,
     float F = (float)(R0 + (1 - R0) * pow((double)(1 - cosPhi1), 5.0));
     v3 newSpecular = add(ld(M->specular.color), mulf(ld(M->refraction), F));
     clamp_white(&newSpecular);
-    v3 out = V(0, 0, 0);        /* refraction term: zero colour, clamped, added (:115-118) */
+    v3 out = V(0, 0, 0);
+    out = add(out, refraction_term(s, mulf(ld(M->refraction), 1 - F), ld(M->absorption), M->ior, h, cosPhi1, vN, vV, bounceCount));
+    if (all_white(out)) return out;
     v3 D = V(0, 0, 0);
-    for (int li = 0; li < n_lights; li++) {
-        v3 vL = neg(norm(light_direction(&lights[li], h->p)));
+    for (int li = 0; li < s->n_lights; li++) {
+        v3 vL = neg(norm(light_direction(&s->lights[li], h->p)));
         float cosTheta = dot(vL, vN);
         if (cosTheta > 0) {
             v3 vH = norm(add(vL, vV));
-            v3 irrad = illuminate(s, &lights[li], h->p);
-            v3 brdf = add(mulf(ld(M->diffuse.color), cosTheta), mulf(newSpecular, powf(dot(vH, vN), M->glossiness)));
+            v3 irrad = illuminate(s, &s->lights[li], h->p);
+            v3 kd = texcolor_sample_filtered(s, ld(M->diffuse.color), M->diffuse.texmap, h->uvw, h->duvw);
+            v3 ks = texcolor_sample_filtered(s, newSpecular, M->specular.texmap, h->uvw, h->duvw);
+            v3 brdf = add(mulf(kd, cosTheta), mulf(ks, powf(dot(vH, vN), M->glossiness)));
             D = add(D, mulv(irrad, brdf));
         }
     }
     clamp_white(&D);                                            /* :343 */
     if (D.x != D.x) D = V(0, 0, 0);                             /* :344-347 */
     out = add(out, D);
+    if (all_white(out)) return out;
+    if (out.x != out.x) out = NAN_PURPLE;                       /* :133-136 */
     return out;
 }
 
@@ -249,20 +458,16 @@ static uint8_t float_to_byte(float r)
 
 int bhrt_oracle_in_scope(const bhrt_scene_desc *d)
 {
-    if (d->n_meshes > 0 || d->n_texmaps > 0 || d->background.texmap >= 0) return 0;
+    if (d->n_meshes > 0) return 0;
     for (int i = 0; i < d->n_nodes; i++) if (d->nodes[i].kind == BHRT_OBJ_MESH) return 0;
-    for (int i = 0; i < d->n_materials; i++) {
-        const bhrt_material *m = &d->materials[i];
-        if (m->refraction[0] != 0 || m->refraction[1] != 0 || m->refraction[2] != 0) return 0;
-        if (m->diffuse.texmap >= 0 || m->specular.texmap >= 0) return 0;
-    }
     for (int i = 0; i < d->n_lights; i++) if (d->lights[i].kind == BHRT_LIGHT_POINT && d->lights[i].size != 0) return 0;
     return 1;
 }
 
 /* BeginRender() + PathTracing() (Main.cpp:178-242,143-172) in D-mode.  Outputs: hit_id[H*W] (node
- * index in DFS order, -1 = miss), z[H*W], linear[H*W*3], rgb8[H*W*3], rays[2] = closest, shadow. */
-int bhrt_oracle_render_det(const bhrt_scene_desc *d, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays)
+ * index in DFS order, -1 = miss), z[H*W], linear[H*W*3], rgb8[H*W*3], rays[2] = closest, shadow.
+ * tir_budget = INTERNAL_REFLECTION_BOUNCE (Main.cpp:41; 16 in the reference). */
+int bhrt_oracle_render_det2(const bhrt_scene_desc *d, int tir_budget, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays)
 {
     if (!d || !bhrt_oracle_in_scope(d)) return -2;
     scene_t s;
@@ -292,6 +497,15 @@ int bhrt_oracle_render_det(const bhrt_scene_desc *d, int32_t *hit_id, float *z, 
     v3 camZ = neg(ld(c->dir)), camY = ld(c->up), camX = cross(camY, camZ), pos = ld(c->pos);
     v3 topLeft = sub(add(sub(pos, mulf(camZ, l)), divf(mulf(camY, h), 2)), divf(mulf(camX, w), 2));
     v3 dd_x = divf(mulf(camX, w), (float)W), dd_y = divf(mulf(camY, h), (float)H);
+    s.dd_x = dd_x; s.dd_y = dd_y;
+
+    /* the elliptic filter offsets of Texture::Sample (scene.h:323-329) */
+    for (int i = 1; i < TEXTURE_SAMPLE_COUNT; i++) {
+        float x = halton(i, 2), y = halton(i, 3);
+        float r = sqrtf(x) * 0.5f;
+        s.tex_x[i] = r * sinf(y * PI_F * 2);
+        s.tex_y[i] = r * cosf(y * PI_F * 2);
+    }
 
     /* CalculateLightsIntensity (Main.cpp:112-123): lights sorted ascending by Gray() (insertion sort = std::sort below 16 elements) */
     bhrt_light lights[BHRT_MAX_LIGHTS];
@@ -303,6 +517,7 @@ int bhrt_oracle_render_det(const bhrt_scene_desc *d, int32_t *hit_id, float *z, 
         while (k > 0 && gray(&v) < gray(&lights[k - 1])) { lights[k] = lights[k - 1]; k--; }
         lights[k] = v;
     }
+    s.lights = lights; s.n_lights = nl;
 
     for (int j = 0; j < H; j++)
         for (int i = 0; i < W; i++) {
@@ -310,13 +525,10 @@ int bhrt_oracle_render_det(const bhrt_scene_desc *d, int32_t *hit_id, float *z, 
             v3 pc = sub(add(topLeft, mulf(dd_x, (float)i)), mulf(dd_y, (float)j));
             ray_t ray = { pos, sub(pc, pos) };
             hit_t hit;
-            hit.z = BIGFLOAT; hit.node = -1; hit.front = 1; hit.p = V(0, 0, 0); hit.N = V(0, 0, 0);
-            int bHit = 0;
-            s.rays_closest++;
-            recursive(&s, -1, ray, &hit, &bHit, HIT_FRONT);
+            int bHit = trace(&s, ray, &hit, HIT_FRONT);
             v3 col;
-            if (bHit) col = shade(&s, ray, &hit, lights, nl);
-            else col = ld(d->background.color);                 /* background.Sample without a texture (Main.cpp:166-167) */
+            if (bHit) col = shade(&s, ray, &hit, tir_budget);
+            else col = texcolor_sample(&s, &d->background, V((float)i / W, (float)j / H, 0.0f));      /* Main.cpp:165-167 */
             size_t p = (size_t)j * W + i;
             hit_id[p] = bHit ? hit.node : -1;
             z[p] = hit.z;
@@ -329,4 +541,9 @@ int bhrt_oracle_render_det(const bhrt_scene_desc *d, int32_t *hit_id, float *z, 
     rays[0] = s.rays_closest; rays[1] = s.rays_shadow;
     free(s.first_child); free(s.next_sibling);
     return 0;
+}
+
+int bhrt_oracle_render_det(const bhrt_scene_desc *d, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays)
+{
+    return bhrt_oracle_render_det2(d, 16, hit_id, z, linear, rgb8, rays);
 }

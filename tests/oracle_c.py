@@ -1,5 +1,5 @@
 """ctypes binding of oracle/_build/libbhrt_oracle.so (oracle/bhrt_oracle.c: the plain-C restatement of
-the reference's deterministic path for BASELINE config 1).  Test infrastructure only."""
+the reference's deterministic path for analytic scenes).  Test infrastructure only."""
 import ctypes as C
 import os
 

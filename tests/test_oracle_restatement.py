@@ -1,5 +1,6 @@
-"""oracle/bhrt_oracle.c -- the plain-C restatement of the reference's deterministic path for BASELINE
-config 1 (spheres + planes, point/direct lights, Blinn-Phong, hard shadows).
+"""oracle/bhrt_oracle.c -- the plain-C restatement of the reference's deterministic path for analytic
+scenes (spheres + planes, point/direct lights, Blinn-Phong, hard shadows, Fresnel refraction with
+absorption and total internal reflection, checker/bitmap textures, textured background/environment).
 
  1. PIN: against the reference's own output (tests/golden, made by oracle/_ref/bhrt_ref --det) and,
     where /root/reference exists, against the reference run live on its own sphere scenes.
@@ -28,9 +29,10 @@ def same(a, o):
     assert np.abs(a["rgb8"].astype(np.int32) - o["rgb8"].astype(np.int32)).max() <= 1
 
 
-def test_restatement_is_pinned_by_the_reference_golden(built):
-    g = np.load(os.path.join(GOLD, "cfg1_spheres_plane_det.npz"))
-    scene = b.LoadScene("scenes/cfg1_spheres_plane.xml", int(g["width"]), int(g["height"]))
+@pytest.mark.parametrize("name", ["cfg1_spheres_plane", "det_refract", "det_textured"])
+def test_restatement_is_pinned_by_the_reference_golden(built, name):
+    g = np.load(os.path.join(GOLD, name + "_det.npz"))
+    scene = b.LoadScene("scenes/%s.xml" % name, int(g["width"]), int(g["height"]))
     assert oracle_c.in_scope(scene)
     o = oracle_c.render_det(scene)
     assert (o["hit_id"] == g["hit_id"]).all()
@@ -40,8 +42,8 @@ def test_restatement_is_pinned_by_the_reference_golden(built):
 
 
 @pytest.mark.skipif(not (os.path.isdir(REF_ROOT) and os.path.exists(REF_BIN)), reason="needs /root/reference and oracle/_ref")
-@pytest.mark.parametrize("name", ["proj2", "proj3", "proj3Test", "proj4"])
-def test_restatement_matches_the_reference_live_on_its_own_scenes(built, tmp_path, name):
+@pytest.mark.parametrize("name", ["proj2", "proj3", "proj3Test", "proj4", "proj5", "proj7", "proj9", "proj10"])
+def test_restatement_matches_the_reference_live_on_its_own_scenes(built, tmp_path, monkeypatch, name):
     src = open(os.path.join(REF_ROOT, "Resource", "Data", name + ".xml")).read()
     small = re.sub(r'<width value="\d+"\s*/>', '<width value="160"/>', src)
     small = re.sub(r'<height value="\d+"\s*/>', '<height value="120"/>', small)
@@ -50,6 +52,7 @@ def test_restatement_matches_the_reference_live_on_its_own_scenes(built, tmp_pat
     info = json.loads(subprocess.check_output([REF_BIN, path, str(tmp_path / "ref"), "--det", "--threads", "2"], cwd=REF_ROOT,
                                               stderr=subprocess.DEVNULL).decode().splitlines()[-1])
     ref = read_aov(str(tmp_path / "ref.aov"))
+    monkeypatch.chdir(REF_ROOT)                 # texture paths in the reference's scenes are relative to its root
     scene = b.LoadScene(path)
     if not oracle_c.in_scope(scene):
         pytest.skip("outside the restatement's scope")
@@ -58,11 +61,12 @@ def test_restatement_matches_the_reference_live_on_its_own_scenes(built, tmp_pat
     assert (o["rays_closest"], o["rays_shadow"]) == (info["rays_closest"], info["rays_shadow"])
 
 
-@pytest.mark.parametrize("w,h", [(97, 61), (33, 200)])
-def test_device_code_on_cpu_matches_the_restatement(built, tmp_path, w, h):
-    scene = b.LoadScene("scenes/cfg1_spheres_plane.xml", w, h)
+@pytest.mark.parametrize("name,w,h", [("cfg1_spheres_plane", 97, 61), ("cfg1_spheres_plane", 33, 200), ("det_refract", 131, 77),
+                                      ("det_textured", 90, 141)])
+def test_device_code_on_cpu_matches_the_restatement(built, tmp_path, name, w, h):
+    scene = b.LoadScene("scenes/%s.xml" % name, w, h)
     o = oracle_c.render_det(scene)
-    out = subprocess.check_output([EMU_BIN, "scenes/cfg1_spheres_plane.xml", str(tmp_path / "e"), "--det", "--size", str(w), str(h)],
+    out = subprocess.check_output([EMU_BIN, "scenes/%s.xml" % name, str(tmp_path / "e"), "--det", "--size", str(w), str(h)],
                                   cwd=ROOT, stderr=subprocess.DEVNULL)
     info = json.loads(out.decode().splitlines()[-1])
     same(read_aov(str(tmp_path / "e.aov")), o)
@@ -70,7 +74,7 @@ def test_device_code_on_cpu_matches_the_restatement(built, tmp_path, w, h):
 
 
 def test_scope_check_refuses_what_the_restatement_does_not_cover(built):
-    for name in ("det_refract", "det_textured", "det_mesh"):
+    for name in ("det_mesh", "det_objmtl", "cfg3_textured_arealight"):
         scene = b.LoadScene(os.path.join("scenes", name + ".xml"), 32, 24)
         assert not oracle_c.in_scope(scene)
         with pytest.raises(ValueError):
@@ -78,9 +82,10 @@ def test_scope_check_refuses_what_the_restatement_does_not_cover(built):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("w,h", [(800, 600), (251, 97)])
-def test_kernels_match_the_restatement(built, w, h):
-    scene = b.LoadScene("scenes/cfg1_spheres_plane.xml", w, h)
+@pytest.mark.parametrize("name,w,h", [("cfg1_spheres_plane", 800, 600), ("cfg1_spheres_plane", 251, 97), ("det_refract", 403, 301),
+                                      ("det_textured", 333, 222)])
+def test_kernels_match_the_restatement(built, name, w, h):
+    scene = b.LoadScene("scenes/%s.xml" % name, w, h)
     o = oracle_c.render_det(scene)
     r = b.Renderer(0)
     try:
