@@ -1,21 +1,25 @@
 /* bhrt_oracle.c -- TEST INFRASTRUCTURE, never linked into the product.
  *
- * A plain-C restatement of the reference's deterministic hot path for analytic scenes (spheres +
- * planes; point / direct / ambient lights; Blinn-Phong with hard shadows; Fresnel refraction with
- * absorption and total internal reflection; checker and bitmap textures with the plane's ray
- * differentials; textured background and environment; 1 spp at the pixel corner), written from the
+ * A plain-C restatement of the reference's deterministic hot path (spheres, planes and triangle
+ * meshes traversed through the reference's own BVH topology; point / direct / ambient lights;
+ * Blinn-Phong with hard shadows; Fresnel refraction with absorption and total internal reflection;
+ * checker and bitmap textures with the plane's ray differentials; textured background and
+ * environment; 1 spp at the pixel corner), written from the
  * reference sources cited at every function (paths relative to /root/reference/BHRayTracer).  It is
  * independent of csrc/device: the only thing it shares with the product is the POD scene
  * description of include/bhrt.h.
  *
  * PINNED: tests/test_oracle_restatement.py checks it against the committed outputs of the
- * reference itself (tests/golden/{cfg1_spheres_plane,det_refract,det_textured}_det.npz, made by
- * oracle/_ref/bhrt_ref --det): primary hit ids and z bit-exact, RGB8 identical, ray counts
- * identical.  The real reference (oracle/_ref, built by oracle/build_ref.py) remains the oracle
- * for everything outside this file's scope -- GI, triangle meshes, area lights, photon map --
- * where a restatement would only repeat the reference with more room for error.
+ * reference itself (all five tests/golden/*_det.npz, made by oracle/_ref/bhrt_ref --det): primary
+ * hit ids and z bit-exact, RGB8 identical, ray counts identical; and, where /root/reference is
+ * present, against the reference run live on 16 of its own scenes and on this repository's five
+ * config scenes.  The real reference (oracle/_ref, built by oracle/build_ref.py) remains the
+ * oracle for what is outside this file's scope -- the stochastic estimator (GI, area lights,
+ * jitter) and the photon map -- where parity is statistical and a restatement would only repeat
+ * the reference with more room for error.
  *
- * Scope check: bhrt_oracle_render_det returns -2 for scenes with meshes or area lights.
+ * Scope check: bhrt_oracle_render_det returns -2 for scenes with area lights (the D-mode switches
+ * leave PointLight::Illuminate's random sample in place, PointLight.cpp:13-15).
  * "D-mode" = the four switches of SURVEY.md 8(c): no jitter, GI off, every light with its exact
  * direction, no glossy refraction.
  *
@@ -150,6 +154,149 @@ static int plane_intersect(ray_t ray, hit_t *h, int hitSide, v3 dd_x, v3 dd_y)
     return 1;
 }
 
+/* ---- triangle meshes ------------------------------------------------------------------------- */
+#define PERP_FACE_DET 0.001745f        /* Objects/TriObj/TriObj.cpp:12 */
+static float fmin_cy(float a, float b) { return a <= b ? a : b; }      /* cyCore.h:187-188 */
+static float fmax_cy(float a, float b) { return a >= b ? a : b; }
+typedef struct {
+    const float *v, *vn, *vt;
+    const uint32_t *f, *fn, *ft;
+    const bhrt_bvh_node *bvh;
+    const uint32_t *elems;
+} mesh_t;
+static mesh_t mesh_view(const bhrt_scene_desc *d, int i)
+{
+    const bhrt_mesh *m = &d->meshes[i];
+    const uint8_t *b = d->mesh_data;
+    mesh_t r = { (const float *)(b + m->v_off), (const float *)(b + m->vn_off), (const float *)(b + m->vt_off),
+                 (const uint32_t *)(b + m->f_off), (const uint32_t *)(b + m->fn_off), (const uint32_t *)(b + m->ft_off),
+                 (const bhrt_bvh_node *)(b + m->bvh_off), (const uint32_t *)(b + m->elems_off) };
+    return r;
+}
+/* Box::IntersectRay (Objects/Box/Box.cpp:3-46); Corner(0) = pmin, Corner(7) = pmax (scene.h:100-107) */
+static int box_intersect(const float *box, ray_t r, float t_max, float *t_min)
+{
+    v3 v0 = V(box[0], box[1], box[2]), v7 = V(box[3], box[4], box[5]);
+    v3 nz = V(0, 0, 1), ny = V(0, 1, 0), nx = V(1, 0, 0);
+    float nDotrr = dot(nz, r.dir), nDotrp = dot(nz, r.p);
+    float tz1 = (nDotrr != 0) ? (dot(nz, v0) - nDotrp) / nDotrr : BIGFLOAT;
+    float tz2 = (nDotrr != 0) ? (dot(nz, v7) - nDotrp) / nDotrr : -BIGFLOAT;
+    nDotrr = dot(ny, r.dir); nDotrp = dot(ny, r.p);
+    float ty1 = (nDotrr != 0) ? (dot(ny, v0) - nDotrp) / nDotrr : BIGFLOAT;
+    float ty2 = (nDotrr != 0) ? (dot(ny, v7) - nDotrp) / nDotrr : -BIGFLOAT;
+    nDotrr = dot(nx, r.dir); nDotrp = dot(nx, r.p);
+    float tx1 = (nDotrr != 0) ? (dot(nx, v0) - nDotrp) / nDotrr : BIGFLOAT;
+    float tx2 = (nDotrr != 0) ? (dot(nx, v7) - nDotrp) / nDotrr : -BIGFLOAT;
+    float tMin = fmax_cy(fmax_cy(fmin_cy(tx1, tx2), fmin_cy(ty1, ty2)), fmin_cy(tz1, tz2));
+    float tMax = fmin_cy(fmin_cy(fmax_cy(tx1, tx2), fmax_cy(ty1, ty2)), fmax_cy(tz1, tz2));
+    if (tMin <= tMax && tMin < t_max) { *t_min = tMin; return 1; }
+    return 0;
+}
+static float cross2(float ax, float ay, float bx, float by) { return (-ay) * bx + ax * by; }     /* cyVector.h:260 */
+/* TriMesh::Interpolate (cyTriMesh.h:191) */
+static v3 interpolate(const float *v, const uint32_t *f, uint32_t face, v3 bc)
+{
+    return add(add(mulf(ld(v + 3 * f[3 * face]), bc.x), mulf(ld(v + 3 * f[3 * face + 1]), bc.y)), mulf(ld(v + 3 * f[3 * face + 2]), bc.z));
+}
+/* TriObj::IntersectTriangle (TriObj.cpp:68-189) */
+static int triangle_intersect(const mesh_t *m, ray_t ray, hit_t *h, int hitSide, uint32_t face)
+{
+    v3 v0 = ld(m->v + 3 * m->f[3 * face]), v1 = ld(m->v + 3 * m->f[3 * face + 1]), v2 = ld(m->v + 3 * m->f[3 * face + 2]);
+    v3 vN = cross(sub(v1, v0), sub(v2, v0));
+    float t_divisor = dot(vN, ray.dir);
+    if (t_divisor == 0) return 0;
+    float perp = t_divisor / (len(vN) * len(ray.dir));
+    if (perp > -PERP_FACE_DET && perp < PERP_FACE_DET) return 0;
+    float t = (dot(vN, v0) - dot(vN, ray.p)) / t_divisor;
+    if (t <= 0 || t > h->z) return 0;
+    int front = t_divisor < 0;
+    if (!front && hitSide == HIT_FRONT) return 0;
+    else if (front && hitSide == HIT_BACK) return 0;
+    v3 vX = add(ray.p, mulf(ray.dir, t));
+    v3 a = V(fabsf(vN.x), fabsf(vN.y), fabsf(vN.z));
+    float p0x = 0, p0y = 0, p1x = 0, p1y = 0, p2x = 0, p2y = 0, px = 0, py = 0;
+    if (a.x >= a.y && a.x >= a.z) { p0x = v0.y; p0y = v0.z; p1x = v1.y; p1y = v1.z; p2x = v2.y; p2y = v2.z; px = vX.y; py = vX.z; }
+    else if (a.y >= a.x && a.y >= a.z) { p0x = v0.x; p0y = v0.z; p1x = v1.x; p1y = v1.z; p2x = v2.x; p2y = v2.z; px = vX.x; py = vX.z; }
+    else if (a.z >= a.y && a.z >= a.x) { p0x = v0.x; p0y = v0.y; p1x = v1.x; p1y = v1.y; p2x = v2.x; p2y = v2.y; px = vX.x; py = vX.y; }
+    float a0 = cross2(p1x - px, p1y - py, p2x - px, p2y - py) / 2.f;
+    float a1 = cross2(p2x - px, p2y - py, p0x - px, p0y - py) / 2.f;
+    float a2 = cross2(p0x - px, p0y - py, p1x - px, p1y - py) / 2.f;
+    if ((a2 < 0 || a1 < 0 || a0 < 0) && !(a0 < 0 && a1 < 0 && a2 < 0)) return 0;
+    float area = a0 + a1 + a2;
+    v3 bc = V(a0 / area, a1 / area, a2 / area);
+    h->z = t;
+    h->N = interpolate(m->vn, m->fn, face, bc);            /* GetNormal: not normalised */
+    h->p = vX;
+    h->front = front;
+    h->uvw = interpolate(m->vt, m->ft, face, bc);
+    h->duvw[0] = V(0, 0, 0); h->duvw[1] = V(0, 0, 0);
+    return 1;
+}
+#define BVH_LEAF(d) ((d) >> 31)                            /* cyBVH.h:187-203 */
+#define BVH_COUNT(d) ((((d) >> 28) & 7u) + 1u)
+#define BVH_OFFSET(d) ((d) & 0x0fffffffu)
+#define BVH_CHILD(d) ((d) & 0x7fffffffu)
+/* TriObj::TraceBVHNode (TriObj.cpp:192-270) */
+static int trace_bvh_node(const mesh_t *m, ray_t ray, hit_t *h, int hitSide, uint32_t node)
+{
+    uint32_t data = m->bvh[node].data;
+    if (BVH_LEAF(data)) {
+        int bHit = 0;
+        for (uint32_t i = 0; i < BVH_COUNT(data); i++)
+            if (triangle_intersect(m, ray, h, hitSide, m->elems[BVH_OFFSET(data) + i])) bHit = 1;
+        return bHit;
+    }
+    uint32_t c1 = BVH_CHILD(data), c2 = c1 + 1;
+    float tmin1 = BIGFLOAT, tmin2 = BIGFLOAT;
+    int hit1 = box_intersect(m->bvh[c1].box, ray, h->z, &tmin1);
+    int hit2 = box_intersect(m->bvh[c2].box, ray, h->z, &tmin2);
+    if (!hit1 && !hit2) return 0;
+    uint32_t nearc = tmin1 < tmin2 ? c1 : c2, farc = tmin1 < tmin2 ? c2 : c1;
+    float tmin_far = tmin1 < tmin2 ? tmin2 : tmin1;
+    if (trace_bvh_node(m, ray, h, hitSide, nearc)) {
+        hit_t tmp = *h;
+        if (tmp.z > tmin_far && trace_bvh_node(m, ray, &tmp, hitSide, farc)) *h = tmp;
+        return 1;
+    }
+    return trace_bvh_node(m, ray, h, hitSide, farc);
+}
+/* TriObj::IntersectRay (TriObj.cpp:17-39) */
+static int mesh_intersect(const mesh_t *m, ray_t ray, hit_t *h, int hitSide)
+{
+    float tmin = -1;
+    if (box_intersect(m->bvh[1].box, ray, h->z, &tmin)) return trace_bvh_node(m, ray, h, hitSide, 1);
+    return 0;
+}
+/* TriObj::TraceBVHShadow (TriObj.cpp:272-307); `a | b` with both operands evaluated, left first (gcc) */
+static int trace_bvh_shadow(const mesh_t *m, ray_t ray, float *t_min, int *hitOnce, uint32_t node)
+{
+    if (*hitOnce) return *hitOnce;
+    uint32_t data = m->bvh[node].data;
+    if (BVH_LEAF(data)) {
+        hit_t h;
+        hit_init(&h);
+        for (uint32_t i = 0; i < BVH_COUNT(data); i++)
+            if (triangle_intersect(m, ray, &h, HIT_FRONT, m->elems[BVH_OFFSET(data) + i])) { *hitOnce = 1; *t_min = h.z; }
+        return *hitOnce;
+    }
+    uint32_t c1 = BVH_CHILD(data), c2 = c1 + 1;
+    float tmin1 = BIGFLOAT, tmin2 = BIGFLOAT;
+    int hit1 = box_intersect(m->bvh[c1].box, ray, BIGFLOAT, &tmin1);
+    int hit2 = box_intersect(m->bvh[c2].box, ray, BIGFLOAT, &tmin2);
+    if (!hit1 && !hit2) return 0;
+    int r1 = trace_bvh_shadow(m, ray, t_min, hitOnce, c1);
+    int r2 = trace_bvh_shadow(m, ray, t_min, hitOnce, c2);
+    return r1 | r2;
+}
+/* TriObj::ShadowRecursive (TriObj.cpp:41-66) */
+static int mesh_shadow(const mesh_t *m, ray_t ray, float t_max)
+{
+    float tmin = -1, t_min = BIGFLOAT;
+    int bHit = 0;
+    if (box_intersect(m->bvh[1].box, ray, BIGFLOAT, &tmin)) trace_bvh_shadow(m, ray, &t_min, &bHit, 1);
+    return bHit && t_min > BIAS && t_min < t_max;
+}
+
 /* Node::FromNodeCoords(HitInfo) (scene.h:497-501) */
 static void from_node_coords(const bhrt_xform *t, hit_t *h)
 {
@@ -176,7 +323,10 @@ static void recursive(scene_t *s, int root, ray_t ray, hit_t *out, int *bHit, in
         const bhrt_node *n = &s->d->nodes[c];
         ray_t tr = to_node_coords(&n->xf, ray);
         if (n->kind != BHRT_OBJ_NONE) {
-            int got = n->kind == BHRT_OBJ_SPHERE ? sphere_intersect(tr, out, hitSide) : plane_intersect(tr, out, hitSide, s->dd_x, s->dd_y);
+            int got;
+            if (n->kind == BHRT_OBJ_SPHERE) got = sphere_intersect(tr, out, hitSide);
+            else if (n->kind == BHRT_OBJ_PLANE) got = plane_intersect(tr, out, hitSide, s->dd_x, s->dd_y);
+            else { mesh_t m = mesh_view(s->d, n->mesh); got = mesh_intersect(&m, tr, out, hitSide); }
             if (got) { out->node = c; *bHit = 1; from_node_coords(&n->xf, out); }
         }
         recursive(s, c, tr, out, bHit, hitSide);
@@ -210,6 +360,9 @@ static int shadow_recursive(scene_t *s, int root, ray_t ray, float t_max)
         if (x.x < -1 || x.x > 1 || x.y < -1 || x.y > 1) return 0;
         if (t < t_max && t > SHADOW_BIAS) return 1;
         return 0;
+    } else if (root >= 0 && s->d->nodes[root].kind == BHRT_OBJ_MESH) {
+        mesh_t m = mesh_view(s->d, s->d->nodes[root].mesh);
+        return mesh_shadow(&m, tr, t_max);
     }
     return 0;
 }
@@ -458,8 +611,6 @@ static uint8_t float_to_byte(float r)
 
 int bhrt_oracle_in_scope(const bhrt_scene_desc *d)
 {
-    if (d->n_meshes > 0) return 0;
-    for (int i = 0; i < d->n_nodes; i++) if (d->nodes[i].kind == BHRT_OBJ_MESH) return 0;
     for (int i = 0; i < d->n_lights; i++) if (d->lights[i].kind == BHRT_LIGHT_POINT && d->lights[i].size != 0) return 0;
     return 1;
 }
