@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(_HERE, "lib")
+LIB_DIR = os.environ.get("BHRT_LIB_DIR") or os.path.join(_HERE, "lib")
 
 MODE_PATH = 0   # "H-mode": HEAD's stochastic estimator
 MODE_DET = 1    # "D-mode": the deterministic switches of SURVEY.md 8(c)
