@@ -302,7 +302,7 @@ def bench_ours(args):
                             "frac": round(achieved / peak, 4), "traffic": traffic, "peak_kind": peak_kind,
                             "algorithmic_bytes_per_ray": round(bytes_per_ray, 1), "bytes_source": src,
                             "kernel_ms_per_launch": round(kernel_ms, 3), "rays_per_launch": int(rays_per_launch),
-                            "note": "algorithmic bytes are defined on the reference's data structures (SURVEY.md 8d); the scene (<= 20 MB) is L2-resident, the measured DRAM traffic is the kernel's own lane state (profiles/r1t_wf_render_ncu_summary.json)"}
+                            "note": "algorithmic bytes are defined on the reference's data structures (SURVEY.md 8d); the scene (<= 20 MB) is L2-resident, the measured DRAM traffic is the kernel's own lane state (profiles/r1u_wf_render_ncu_summary.json)"}
         # ---- CPU baseline: the reference itself on this box's host cores, bounded sample
         if world == 1 and os.path.exists(REF_BIN) and not args.no_cpu:
             info = run_reference(REF_BIN, CPU_W, CPU_H, SPP)
