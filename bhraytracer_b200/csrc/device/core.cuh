@@ -223,8 +223,9 @@ struct PhotonRecord {
 // slip, cyPhotonMap.h:196 -- and the 8-bit colour ratio in the bits of b.w).
 struct alignas(16) GatherRec { F4 a, b; };
 
-#define BHRT_PM_LEVELS 5            // grid levels: cell, cell/2, ... cell/16
-#define BHRT_PM_FINE_BITS 12        // 4 octree levels below a coarse cell -> 12 Morton bits
+#define BHRT_PM_SUB_BITS 4                          // octree levels below a coarse cell (6 -> cell/64 was measured: 3x SLOWER on config 5)
+#define BHRT_PM_LEVELS (BHRT_PM_SUB_BITS + 1)       // grid levels: cell, cell/2, ... cell/16
+#define BHRT_PM_FINE_BITS (3 * BHRT_PM_SUB_BITS)    // Morton bits of the finest sub-cell
 // Read-only view of the gather structure (photon_build.hpp / photon.cuh build it): photons sorted
 // by key = coarse cell << 12 | Morton code of the 1/16 sub-cell.  Every cell of every level is a
 // contiguous key range, so ONE sorted array serves all five resolutions; a query picks the level
@@ -295,11 +296,11 @@ BHRT_HD GatherRec photon_gather_rec(const PhotonRecord &r, float power_scale)
     memcpy(&g.b.w, &rgb, 4);
     return g;
 }
-// Morton code (x,y,z interleaved, most significant level first) of a 4-bit sub-cell coordinate
-BHRT_HD uint32_t photon_morton12(uint32_t x, uint32_t y, uint32_t z)
+// Morton code (x,y,z interleaved, most significant level first) of a BHRT_PM_SUB_BITS-bit sub-cell coordinate
+BHRT_HD uint32_t photon_morton(uint32_t x, uint32_t y, uint32_t z)
 {
     uint32_t m = 0;
-    for (int j = 3; j >= 0; j--) m = (m << 3) | (((x >> j) & 1u) << 2) | (((y >> j) & 1u) << 1) | ((z >> j) & 1u);
+    for (int j = BHRT_PM_SUB_BITS - 1; j >= 0; j--) m = (m << 3) | (((x >> j) & 1u) << 2) | (((y >> j) & 1u) << 1) | ((z >> j) & 1u);
     return m;
 }
 // Sort key of a position (shared by the host and the device builder); false = outside the grid
@@ -308,10 +309,12 @@ BHRT_HD bool photon_key(const float *origin, float cell, const int *dim, V3 p, u
     float fx = (p.x - origin[0]) / cell, fy = (p.y - origin[1]) / cell, fz = (p.z - origin[2]) / cell;
     int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
     if (cx < 0 || cy < 0 || cz < 0 || cx >= dim[0] || cy >= dim[1] || cz >= dim[2]) return false;
-    int sx = (int)((fx - cx) * 16.f), sy = (int)((fy - cy) * 16.f), sz = (int)((fz - cz) * 16.f);
-    sx = sx < 0 ? 0 : (sx > 15 ? 15 : sx); sy = sy < 0 ? 0 : (sy > 15 ? 15 : sy); sz = sz < 0 ? 0 : (sz > 15 ? 15 : sz);
+    const float sc = (float)(1 << BHRT_PM_SUB_BITS);
+    const int smax = (1 << BHRT_PM_SUB_BITS) - 1;
+    int sx = (int)((fx - cx) * sc), sy = (int)((fy - cy) * sc), sz = (int)((fz - cz) * sc);
+    sx = sx < 0 ? 0 : (sx > smax ? smax : sx); sy = sy < 0 ? 0 : (sy > smax ? smax : sy); sz = sz < 0 ? 0 : (sz > smax ? smax : sz);
     uint32_t coarse = (uint32_t)cx + (uint32_t)dim[0] * ((uint32_t)cy + (uint32_t)dim[1] * (uint32_t)cz);
-    key = (coarse << BHRT_PM_FINE_BITS) | photon_morton12((uint32_t)sx, (uint32_t)sy, (uint32_t)sz);
+    key = (coarse << BHRT_PM_FINE_BITS) | photon_morton((uint32_t)sx, (uint32_t)sy, (uint32_t)sz);
     return true;
 }
 
@@ -1104,7 +1107,7 @@ BHRT_HD uint32_t pm_lower_bound(const uint32_t *keys, uint32_t lo, uint32_t hi, 
 // key ranges of the 27 level-`level` cells around (coarse cell c, sub-cell s)
 BHRT_HD void pm_ranges(const PhotonGather &pg, int level, const int *c, const int *sub, PmRange &R)
 {
-    const int sh = 4 - level;                         // sub-cell bits dropped at this level
+    const int sh = BHRT_PM_SUB_BITS - level;          // sub-cell bits dropped at this level
     const int span = 1 << level;                      // level cells per coarse cell edge
     int g[3] = { (c[0] << level) | (sub[0] >> sh), (c[1] << level) | (sub[1] >> sh), (c[2] << level) | (sub[2] >> sh) };
     int n = 0;
@@ -1119,7 +1122,7 @@ BHRT_HD void pm_ranges(const PhotonGather &pg, int level, const int *c, const in
                 uint32_t lo = pg.coarse_start[coarse], hi = pg.coarse_start[coarse + 1];
                 if (lo == hi) continue;
                 if (level == 0) { R.b[n] = lo; R.e[n] = hi; continue; }
-                uint32_t m = photon_morton12((uint32_t)(x & (span - 1)) << sh, (uint32_t)(y & (span - 1)) << sh, (uint32_t)(z & (span - 1)) << sh);
+                uint32_t m = photon_morton((uint32_t)(x & (span - 1)) << sh, (uint32_t)(y & (span - 1)) << sh, (uint32_t)(z & (span - 1)) << sh);
                 uint32_t k0 = (coarse << BHRT_PM_FINE_BITS) | m;
                 uint32_t k1 = k0 + (1u << (3 * sh));
                 R.b[n] = pm_lower_bound(pg.keys, lo, hi, k0);
@@ -1140,15 +1143,15 @@ BHRT_FN void estimate_irradiance(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad
     irrad = V3(0, 0, 0); direction = V3(0, 0, 0);
     if (pg.n_photons <= 0) return;
     const float r2 = pg.radius * pg.radius;
-    // the query's coarse cell and 1/16 sub-cell, computed like photon_key does
+    // the query's coarse cell and finest sub-cell, computed like photon_key does
     float f[3] = { (pos.x - pg.origin[0]) / pg.cell, (pos.y - pg.origin[1]) / pg.cell, (pos.z - pg.origin[2]) / pg.cell };
     int c[3], sub[3];
     bool inside = true;
     for (int a = 0; a < 3; a++) {
         c[a] = (int)floorf(f[a]);
         if (c[a] < -1 || c[a] > pg.dim[a]) return;          // farther than one cell from the grid: nothing in range
-        int s_ = (int)((f[a] - c[a]) * 16.f);
-        sub[a] = s_ < 0 ? 0 : (s_ > 15 ? 15 : s_);
+        int s_ = (int)((f[a] - c[a]) * (float)(1 << BHRT_PM_SUB_BITS));
+        sub[a] = s_ < 0 ? 0 : (s_ > (1 << BHRT_PM_SUB_BITS) - 1 ? (1 << BHRT_PM_SUB_BITS) - 1 : s_);
         if (c[a] < 0 || c[a] >= pg.dim[a]) inside = false;
     }
     // starting level from the population of the query's coarse cell (surface density guess):

@@ -24,7 +24,7 @@ struct PhotonGrid {
 
 // Grid over the bounding box [lo,hi] of the photons.  The coarse cell is slightly larger than the
 // gather radius (so the radius itself is a safe block bound at level 0) and grows if the box would
-// need more than 2^20 coarse cells (key layout: 20 bits coarse | 12 bits Morton).
+// need more coarse cells than the key has room for (key layout: 32 - BHRT_PM_FINE_BITS bits coarse | BHRT_PM_FINE_BITS bits Morton).
 inline PhotonGrid photon_grid(const float lo[3], const float hi[3], float radius)
 {
     PhotonGrid g;
@@ -37,7 +37,7 @@ inline PhotonGrid photon_grid(const float lo[3], const float hi[3], float radius
             if (g.dim[a] < 1) g.dim[a] = 1;
             n *= g.dim[a];
         }
-        if (n < (double)(1u << 20)) break;
+        if (n < (double)(1u << (32 - BHRT_PM_FINE_BITS))) break;
         cell *= 1.26f;
     }
     g.cell = cell;

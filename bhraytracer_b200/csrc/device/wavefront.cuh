@@ -214,8 +214,8 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
     for (int a = 0; a < 3; a++) {
         c[a] = (int)floorf(f[a]);
         if (c[a] < -1 || c[a] > pg.dim[a]) return;
-        int s_ = (int)((f[a] - c[a]) * 16.f);
-        sub[a] = s_ < 0 ? 0 : (s_ > 15 ? 15 : s_);
+        int s_ = (int)((f[a] - c[a]) * (float)(1 << BHRT_PM_SUB_BITS));
+        sub[a] = s_ < 0 ? 0 : (s_ > (1 << BHRT_PM_SUB_BITS) - 1 ? (1 << BHRT_PM_SUB_BITS) - 1 : s_);
     }
     // start at the coarse level; the loop below moves to finer levels, before reading any photon, while
     // the 3x3x3 block holds far more photons than a query needs
@@ -225,7 +225,7 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
         // lane n < 27 owns the key range of cell n of the 3x3x3 block (pm_ranges, one cell per lane)
         uint32_t my_b = 0, my_e = 0;
         if (lane < 27u) {
-            const int sh = 4 - level, span = 1 << level;
+            const int sh = BHRT_PM_SUB_BITS - level, span = 1 << level;
             const int dz = (int)lane / 9 - 1, dy = ((int)lane / 3) % 3 - 1, dx = (int)lane % 3 - 1;
             const int x = ((c[0] << level) | (sub[0] >> sh)) + dx, y = ((c[1] << level) | (sub[1] >> sh)) + dy, z = ((c[2] << level) | (sub[2] >> sh)) + dz;
             if (!(x < 0 || y < 0 || z < 0 || x >= pg.dim[0] * span || y >= pg.dim[1] * span || z >= pg.dim[2] * span)) {
@@ -235,7 +235,7 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
                 if (lo != hi) {
                     if (level == 0) { my_b = lo; my_e = hi; }
                     else {
-                        const uint32_t m = photon_morton12((uint32_t)(x & (span - 1)) << sh, (uint32_t)(y & (span - 1)) << sh, (uint32_t)(z & (span - 1)) << sh);
+                        const uint32_t m = photon_morton((uint32_t)(x & (span - 1)) << sh, (uint32_t)(y & (span - 1)) << sh, (uint32_t)(z & (span - 1)) << sh);
                         const uint32_t k0 = (coarse << BHRT_PM_FINE_BITS) | m, k1 = k0 + (1u << (3 * sh));
                         my_b = pm_lower_bound(pg.keys, lo, hi, k0);
                         my_e = pm_lower_bound(pg.keys, my_b, hi, k1);
@@ -249,7 +249,7 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
         // a cell farther from the query than the search bound holds nothing of interest (the corners of
         // the block, mostly): skip it
         if (lane < 27u && my_e > my_b) {
-            const int sh = 4 - level;
+            const int sh = BHRT_PM_SUB_BITS - level;
             const int dz = (int)lane / 9 - 1, dy = ((int)lane / 3) % 3 - 1, dx = (int)lane % 3 - 1;
             const int g3[3] = { ((c[0] << level) | (sub[0] >> sh)) + dx, ((c[1] << level) | (sub[1] >> sh)) + dy, ((c[2] << level) | (sub[2] >> sh)) + dz };
             const float q3[3] = { pos.x, pos.y, pos.z };
