@@ -1297,7 +1297,7 @@ struct alignas(128) Frame {              // one 128-byte line per recursion leve
 };
 enum { ST_REFR = 0, ST_REFR_IN_WAIT = 1, ST_REFR_OUT_WAIT = 2, ST_REFR_WAIT = 3, ST_GI = 4, ST_GI_TRACE_WAIT = 5, ST_GI_WAIT = 6,
        ST_DIRECT = 7, ST_SHADOW_WAIT = 8, ST_GATHER_WAIT = 9 };
-#define BHRT_MAX_FRAMES 16
+#define BHRT_MAX_FRAMES 64
 
 struct ShadeCfg {
     int mode;           // BHRT_MODE_*
@@ -1327,7 +1327,10 @@ struct alignas(16) Lane {
     bool hit_ok;            // anything was hit / the shadow ray is blocked
     uint32_t mesh_mask;     // wavefront: mesh nodes whose root box the pending ray entered
     int hit_id; float hit_z;    // primary AOVs of this sample
-    uint8_t stage[BHRT_MAX_FRAMES];     // stage of every live recursion level (the frames themselves live apart)
+    // stage of the top recursion level; a level below the top waits for the child above it, either in
+    // ST_REFR_WAIT or in ST_GI_WAIT: one bit each (the frames themselves live apart)
+    uint8_t top_stage;
+    uint8_t gi_wait[15];    // bit i: level i is in ST_GI_WAIT (else ST_REFR_WAIT)
     Hit hit;                // the query's answer; only its first 32 bytes are persistent
     // ---- not copied
     LaneCold cold;
@@ -1336,6 +1339,23 @@ struct alignas(16) Lane {
 // The recursion levels of one lane: the estimator only ever touches the top frame and, when it
 // recurses, the slot above it.
 struct LaneStack { Frame fr[BHRT_MAX_FRAMES]; };
+// the stage of the top recursion level, and the push / pop of a level
+BHRT_HD int lane_stage(const Lane &L) { return L.top_stage; }
+BHRT_HD void lane_push(Lane &L, int child_stage)
+{
+    const int i = L.sp - 1;         // the level that now waits for the child
+    if (i >= 0) {
+        const uint8_t bit = (uint8_t)(1u << (i & 7));
+        if (L.top_stage == ST_GI_WAIT) L.gi_wait[i >> 3] |= bit; else L.gi_wait[i >> 3] &= (uint8_t)~bit;
+    }
+    L.top_stage = (uint8_t)child_stage;
+    L.sp++;
+}
+BHRT_HD void lane_pop(Lane &L)
+{
+    L.sp--;
+    if (L.sp > 0) { const int i = L.sp - 1; L.top_stage = ((L.gi_wait[i >> 3] >> (i & 7)) & 1) ? ST_GI_WAIT : ST_REFR_WAIT; }
+}
 
 BHRT_HD void frame_begin(Frame &f, const SceneView &s, V3 ray_p, const Hit &h, int bounce, int gi)
 {
@@ -1411,12 +1431,11 @@ BHRT_HD int sample_step(Lane &BHRT_RESTRICT L, Frame &BHRT_RESTRICT f, Frame &BH
         L.hit_z = L.hit.z;
         if (!L.hit_ok) { color = texcolor_sample(s, s.background, V3(bgu, bgv, 0.0f)); return STEP_DONE; }   // Main.cpp:166-167
         frame_begin(child, s, L.q.ray.p, L.hit, cfg.tir_budget, cfg.gi_depth);
-        L.stage[0] = ST_REFR;
-        L.sp = 1;
+        lane_push(L, ST_REFR);
         return STEP_CONT;
     }
     {
-        uint8_t &stage = L.stage[L.sp - 1];
+        uint8_t &stage = L.top_stage;
         const bhrt_material &M = s.materials[f.mtl];
         bool push_child = false;    // a child frame was pushed at fr[sp]
         bool done = false;          // this frame finished, value in f.out
@@ -1644,10 +1663,10 @@ BHRT_HD int sample_step(Lane &BHRT_RESTRICT L, Frame &BHRT_RESTRICT f, Frame &BH
             if (saturated(f.out)) done = true;
             else { stage = ST_DIRECT; L.si = 0; L.sv = V3(0, 0, 0); }
         }
-        if (push_child) { L.stage[L.sp] = ST_REFR; L.sp++; return STEP_CONT; }
+        if (push_child) { lane_push(L, ST_REFR); return STEP_CONT; }
         if (done) {
             L.ret = f.out;
-            L.sp--;
+            lane_pop(L);
             if (L.sp == 0) { color = L.ret; return STEP_DONE; }
         }
     }

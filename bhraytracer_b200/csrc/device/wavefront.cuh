@@ -77,7 +77,7 @@ __device__ __forceinline__ unsigned wf_key(const SceneView &s, const Lane &L, co
         const unsigned cls = (L.hit.node >= 0) ? wf_material_class(s.materials[s.nodes[L.hit.node].material]) : 0u;
         return (WF_ST_PRIMARY << 3) | (cls << 1);
     }
-    const unsigned slot = wf_stage_slot(L.stage[L.sp - 1]);
+    const unsigned slot = wf_stage_slot(lane_stage(L));
     unsigned cls;
     if (slot == WF_ST_SHADOW || slot == WF_ST_OTHER) cls = wf_material_class(s.materials[top.mtl]);
     else cls = (L.q.kind == Q_CLOSEST && L.hit.node >= 0) ? wf_material_class(s.materials[s.nodes[L.hit.node].material]) : 0u;
@@ -110,7 +110,7 @@ struct WaveArgs {
     unsigned long long n_work;  // n_pix_work * chunk_spp
     PhotonGather gather;
     Lane *lanes;                // [gridDim.x][pool] lane headers
-    Frame *frames;              // [gridDim.x][pool][BHRT_MAX_FRAMES] recursion levels
+    Frame *frames;              // [gridDim.x][BHRT_MAX_FRAMES][pool] recursion levels (level-major: only the low levels are ever touched)
     float4 *samples;            // [chunk_spp][n_pix_work]
     int *hit_id; float *zbuf;
     WaveCounters *cnt;
@@ -453,14 +453,14 @@ wf_render(SceneView s, WaveArgs a)
             Lane L;
             // the recursion levels are used in place (global memory, cached in L1 while this lane is
             // being stepped): a step touches the top frame and, when it recurses, the slot above it
-            Frame *const frames = frames_all + (size_t)id * BHRT_MAX_FRAMES;
+            Frame *const frames = frames_all + id;      // level l of this lane: frames[l * P]
             bool want_new = valid && first;
             bool running = valid && !first;
             if (running) {
                 wf_load_lane(L, &lanes[id]);
                 // the answer of the pending query: winner-only work of a closest hit (a lane that comes
                 // back from a caustic gather has no new answer: its last query was consumed before)
-                const bool from_gather = L.sp > 0 && L.stage[L.sp - 1] == ST_GATHER_WAIT;
+                const bool from_gather = L.sp > 0 && lane_stage(L) == ST_GATHER_WAIT;
                 if (L.q.kind == Q_CLOSEST && !from_gather) L.hit_ok = scene_trace_finish(s, L.q, L.hit);
             }
             // The estimator coroutine up to its next ray.  Lanes of a warp may be in different
@@ -471,12 +471,12 @@ wf_render(SceneView s, WaveArgs a)
             // evaluated after the pass, one per warp at a time -- see the gather phase below)
             bool to_gather = false;
             for (;;) {
-                const int st = running ? (L.sp == 0 ? -1 : (int)L.stage[L.sp - 1]) : 127;
+                const int st = running ? (L.sp == 0 ? -1 : lane_stage(L)) : 127;
                 const int mn = __reduce_min_sync(0xffffffffu, st);
                 if (mn == 127) break;
                 if (st != mn) continue;
                 V3 c;
-                const int r = sample_step(L, frames[L.sp > 0 ? L.sp - 1 : 0], frames[L.sp < BHRT_MAX_FRAMES ? L.sp : BHRT_MAX_FRAMES - 1],
+                const int r = sample_step(L, frames[(size_t)(L.sp > 0 ? L.sp - 1 : 0) * P], frames[(size_t)(L.sp < BHRT_MAX_FRAMES ? L.sp : BHRT_MAX_FRAMES - 1) * P],
                                           s, a.cfg, a.gather, L.sp == 0 ? lanes[id].cold.bgu : 0.f, L.sp == 0 ? lanes[id].cold.bgv : 0.f, rc, c);
                 if (r == STEP_GATHER) { to_gather = true; running = false; continue; }
                 if (r == STEP_RAY) { running = false; continue; }
@@ -529,7 +529,7 @@ wf_render(SceneView s, WaveArgs a)
             }
             if (alive) {
                 wf_store_lane(&lanes[id], L);
-                lkey[id] = (unsigned char)wf_key(s, L, frames[L.sp > 0 ? L.sp - 1 : 0]);
+                lkey[id] = (unsigned char)wf_key(s, L, frames[(size_t)(L.sp > 0 ? L.sp - 1 : 0) * P]);
             } else if (valid) lkey[id] = WF_KEY_DEAD;
             // park the lanes that wait for a caustic gather
             const unsigned gmask = __ballot_sync(0xffffffffu, to_gather);
@@ -569,7 +569,7 @@ wf_render(SceneView s, WaveArgs a)
                 if (i >= ng) break;
                 const unsigned gid = gq[i];
                 Lane &Lg = lanes[gid];
-                const Frame &fq = frames_all[(size_t)gid * BHRT_MAX_FRAMES + (Lg.sp - 1)];
+                const Frame &fq = frames_all[(size_t)(Lg.sp - 1) * P + gid];
                 V3 irr, dirv;
                 estimate_irradiance_warp(a.gather, fq.p, fq.vN, irr, dirv, pm_scratch + (tid >> 5));
                 if (lane == 0) { Lg.ret = irr; Lg.sw = dirv; pend[gid] = 0; atomicSub(&n_parked_s, 1u); }

@@ -618,7 +618,7 @@ int bhrt_oracle_in_scope(const bhrt_scene_desc *d)
 /* BeginRender() + PathTracing() (Main.cpp:178-242,143-172) in D-mode.  Outputs: hit_id[H*W] (node
  * index in DFS order, -1 = miss), z[H*W], linear[H*W*3], rgb8[H*W*3], rays[2] = closest, shadow.
  * tir_budget = INTERNAL_REFLECTION_BOUNCE (Main.cpp:41; 16 in the reference). */
-int bhrt_oracle_render_det2(const bhrt_scene_desc *d, int tir_budget, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays)
+static int render_det(const bhrt_scene_desc *d, int tir_budget, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays, uint32_t *pixel_rays)
 {
     if (!d || !bhrt_oracle_in_scope(d)) return -2;
     scene_t s;
@@ -676,6 +676,7 @@ int bhrt_oracle_render_det2(const bhrt_scene_desc *d, int tir_budget, int32_t *h
             v3 pc = sub(add(topLeft, mulf(dd_x, (float)i)), mulf(dd_y, (float)j));
             ray_t ray = { pos, sub(pc, pos) };
             hit_t hit;
+            const uint64_t c0 = s.rays_closest, s0 = s.rays_shadow;
             int bHit = trace(&s, ray, &hit, HIT_FRONT);
             v3 col;
             if (bHit) col = shade(&s, ray, &hit, tir_budget);
@@ -688,10 +689,22 @@ int bhrt_oracle_render_det2(const bhrt_scene_desc *d, int tir_budget, int32_t *h
             rgb8[3 * p] = float_to_byte(powf(col.x, ig));
             rgb8[3 * p + 1] = float_to_byte(powf(col.y, ig));
             rgb8[3 * p + 2] = float_to_byte(powf(col.z, ig));
+            if (pixel_rays) { pixel_rays[2 * p] = (uint32_t)(s.rays_closest - c0); pixel_rays[2 * p + 1] = (uint32_t)(s.rays_shadow - s0); }
         }
     rays[0] = s.rays_closest; rays[1] = s.rays_shadow;
     free(s.first_child); free(s.next_sibling);
     return 0;
+}
+
+int bhrt_oracle_render_det2(const bhrt_scene_desc *d, int tir_budget, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays)
+{
+    return render_det(d, tir_budget, hit_id, z, linear, rgb8, rays, NULL);
+}
+/* the same, plus the (closest, shadow) ray counts of every pixel: pixel_rays[H*W*2] */
+int bhrt_oracle_render_det3(const bhrt_scene_desc *d, int tir_budget, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays,
+                            uint32_t *pixel_rays)
+{
+    return render_det(d, tir_budget, hit_id, z, linear, rgb8, rays, pixel_rays);
 }
 
 int bhrt_oracle_render_det(const bhrt_scene_desc *d, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays)

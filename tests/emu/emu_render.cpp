@@ -59,6 +59,7 @@ int main(int argc, char **argv)
     int emit_n = 0; const char *emit_file = nullptr;
     const char *photon_file = nullptr; int photon_total = 1, photon_k = 1000; float photon_radius = 0.5f;
     const char *query_in = nullptr, *query_out = nullptr;
+    const char *pixel_rays = nullptr;
     unsigned long long seed = 1;
     for (int a = 3; a < argc; a++) {
         if (!strcmp(argv[a], "--det")) det = 1;
@@ -70,6 +71,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[a], "--samples") && a + 2 < argc) { smp_b = atoi(argv[++a]); smp_e = atoi(argv[++a]); }
         else if (!strcmp(argv[a], "--emit") && a + 2 < argc) { emit_n = atoi(argv[++a]); emit_file = argv[++a]; }
         else if (!strcmp(argv[a], "--photons") && a + 4 < argc) { photon_file = argv[++a]; photon_total = atoi(argv[++a]); photon_k = atoi(argv[++a]); photon_radius = (float)atof(argv[++a]); }
+        else if (!strcmp(argv[a], "--pixel-rays") && a + 1 < argc) pixel_rays = argv[++a];
         else if (!strcmp(argv[a], "--queries") && a + 2 < argc) { query_in = argv[++a]; query_out = argv[++a]; }
         else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
     }
@@ -192,6 +194,7 @@ int main(int argc, char **argv)
     std::vector<float> linear((size_t)W * H * 3, 0.f), z((size_t)W * H, 0.f), acc((size_t)W * H * 4, 0.f);
     std::vector<uint8_t> rgb8((size_t)W * H * 3, 0);
     std::vector<int32_t> hitid((size_t)W * H, 0);
+    std::vector<uint32_t> pixrays((size_t)W * H * 2, 0);     // per-pixel (closest, shadow) ray counts, written with --pixel-rays
     unsigned long long closest = 0, shadow = 0;
     double t0 = omp_get_wtime();
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : closest, shadow)
@@ -217,6 +220,7 @@ int main(int argc, char **argv)
             rgb8[3 * p] = float_to_byte(g.x); rgb8[3 * p + 1] = float_to_byte(g.y); rgb8[3 * p + 2] = float_to_byte(g.z);
             hitid[p] = id0; z[p] = z0;
             closest += rc.closest; shadow += rc.shadow;
+            pixrays[2 * p] = (uint32_t)rc.closest; pixrays[2 * p + 1] = (uint32_t)rc.shadow;
         }
     }
     double ms = (omp_get_wtime() - t0) * 1e3;
@@ -238,6 +242,12 @@ int main(int argc, char **argv)
     fwrite(hitid.data(), 4, hitid.size(), fp);
     fwrite(z.data(), 4, z.size(), fp);
     fclose(fp);
+    if (pixel_rays) {
+        fp = fopen(pixel_rays, "wb");
+        if (!fp) return 4;
+        fwrite(pixrays.data(), 4, pixrays.size(), fp);
+        fclose(fp);
+    }
     fp = fopen((std::string(argv[2]) + ".acc").c_str(), "wb");
     if (!fp) return 4;
     fwrite(acc.data(), 4, acc.size(), fp);

@@ -1,0 +1,225 @@
+#!/usr/bin/env python3
+"""Random-scene parity fuzzer (CPU only, test infrastructure).
+
+Generates random scenes in the reference's XML dialect -- nested transformed groups, spheres, planes,
+OBJ meshes, Blinn materials with refraction / absorption / checker and bitmap textures, point /
+direct / ambient lights -- and renders each in deterministic mode with
+
+  * the C restatement of the reference  (oracle/bhrt_oracle.c),
+  * our device code compiled for the CPU (build/emu_render, the source nvcc builds into the kernels),
+  * the reference itself                (oracle/_ref/bhrt_ref, when it has been built),
+
+then compares primary hit ids, z bits, 8-bit pixels and the ray counters.
+
+usage: fuzz_parity.py [--seeds A:B] [--size WxH] [--keep DIR] [--no-ref]
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bhrt_ref")
+EMU_BIN = os.path.join(ROOT, "build", "emu_render")
+MESHES = ["scenes/assets/torus_small.obj", "scenes/assets/blob_small.obj", "scenes/assets/cube_mtl.obj"]
+BITMAPS = ["scenes/assets/bricks.png", "scenes/assets/clouds.png"]
+
+
+def f(x):
+    return "%.4g" % x
+
+
+def transform(rng, indent, scale=(0.5, 4.0), spread=8.0, lift=True):
+    out = []
+    if rng.random() < 0.7:
+        if rng.random() < 0.6:
+            out.append('<scale value="%s"/>' % f(rng.uniform(*scale)))
+        else:
+            out.append('<scale x="%s" y="%s" z="%s"/>' % tuple(f(rng.uniform(*scale)) for _ in range(3)))
+    for _ in range(rng.choice([0, 0, 1, 2])):
+        axis = rng.choice(["x", "y", "z"])
+        out.append('<rotate angle="%s" %s="1"/>' % (f(rng.uniform(-180, 180)), axis))
+    if rng.random() < 0.9:
+        out.append('<translate x="%s" y="%s" z="%s"/>' % (f(rng.uniform(-spread, spread)), f(rng.uniform(-spread, spread)),
+                                                          f(rng.uniform(0, spread) if lift else rng.uniform(-spread, spread))))
+    return "".join(indent + t + "\n" for t in out)
+
+
+def texture(rng, indent):
+    kind = rng.choice(["checkerboard"] + BITMAPS)
+    s = ' texture="%s">\n' % kind
+    if kind == "checkerboard":
+        s += indent + '  <color1 r="%s" g="%s" b="%s"/>\n' % tuple(f(rng.random()) for _ in range(3))
+        s += indent + '  <color2 r="%s" g="%s" b="%s"/>\n' % tuple(f(rng.random()) for _ in range(3))
+    if rng.random() < 0.8:
+        s += indent + '  <scale value="%s"/>\n' % f(rng.choice([0.05, 0.1, 0.25, 0.5, 1.0, 2.0]))
+    if rng.random() < 0.3:
+        s += indent + '  <rotate angle="%s" z="1"/>\n' % f(rng.uniform(-90, 90))
+    if rng.random() < 0.3:
+        s += indent + '  <translate x="%s" y="%s"/>\n' % (f(rng.uniform(-1, 1)), f(rng.uniform(-1, 1)))
+    return s
+
+
+def material(rng, name):
+    s = '    <material type="blinn" name="%s">\n' % name
+    col = 'r="%s" g="%s" b="%s"' % tuple(f(rng.random()) for _ in range(3))
+    if rng.random() < 0.35:
+        s += "      <diffuse " + col + texture(rng, "      ") + "      </diffuse>\n"
+    else:
+        s += "      <diffuse " + col + "/>\n"
+    s += '      <specular value="%s"/>\n' % f(rng.choice([0, 0.2, 0.5, 0.8, 1.0]))
+    s += '      <glossiness value="%s"/>\n' % f(rng.choice([5, 20, 60, 200]))
+    if rng.random() < 0.3:
+        s += '      <refraction value="%s" index="%s"/>\n' % (f(rng.uniform(0.5, 1.0)), f(rng.choice([1.1, 1.33, 1.52, 2.0])))
+        if rng.random() < 0.5:
+            s += '      <absorption r="%s" g="%s" b="%s"/>\n' % tuple(f(rng.uniform(0, 0.3)) for _ in range(3))
+    s += "    </material>\n"
+    return s
+
+
+def obj(rng, depth, mats, counter, meshes):
+    ind = "    " + "  " * depth
+    kinds = ["sphere", "sphere", "plane"] + (["obj"] if meshes else [])
+    kind = rng.choice(kinds + ([None] if depth < 2 else []))
+    counter[0] += 1
+    name = "n%d" % counter[0]
+    if kind is None:
+        s = ind + '<object name="%s">\n' % name
+    elif kind == "obj":
+        s = ind + '<object type="obj" name="%s" material="%s">\n' % (rng.choice(MESHES), rng.choice(mats))
+    else:
+        s = ind + '<object type="%s" name="%s" material="%s">\n' % (kind, name, rng.choice(mats))
+    s += transform(rng, ind + "  ", scale=(3, 12) if kind == "plane" else (0.5, 4.0))
+    if depth < 3:
+        for _ in range(rng.choice([0, 0, 0, 1, 2] if kind else [1, 2, 3])):
+            s += obj(rng, depth + 1, mats, counter, meshes)
+    s += ind + "</object>\n"
+    return s
+
+
+def scene_xml(seed, w, h, meshes=True):
+    rng = random.Random(seed)
+    mats = ["m%d" % i for i in range(rng.randint(2, 5))]
+    s = "<xml>\n  <scene>\n"
+    if rng.random() < 0.5:
+        s += '    <background r="1" g="1" b="1" texture="%s"/>\n' % rng.choice(BITMAPS)
+    else:
+        s += '    <background r="%s" g="%s" b="%s"/>\n' % tuple(f(rng.random()) for _ in range(3))
+    if rng.random() < 0.5:
+        s += '    <environment value="%s" texture="%s"/>\n' % (f(rng.uniform(0.2, 1)), rng.choice(BITMAPS))
+    else:
+        s += '    <environment value="%s"/>\n' % f(rng.uniform(0, 1))
+    # a ground plane most of the time, then random objects
+    counter = [0]
+    if rng.random() < 0.8:
+        s += '    <object type="plane" name="ground" material="%s">\n      <scale value="30"/>\n    </object>\n' % mats[0]
+    for _ in range(rng.randint(2, 6)):
+        s += obj(rng, 0, mats, counter, meshes)
+    for m in mats:
+        s += material(rng, m)
+    for i in range(rng.randint(1, 3)):
+        kind = rng.choice(["point", "point", "direct", "ambient"])
+        s += '    <light type="%s" name="l%d">\n' % (kind, i)
+        if kind == "point":
+            s += '      <intensity value="%s"/>\n      <position x="%s" y="%s" z="%s"/>\n' % (
+                f(rng.uniform(50, 400)), f(rng.uniform(-12, 12)), f(rng.uniform(-12, 12)), f(rng.uniform(8, 25)))
+        elif kind == "direct":
+            s += '      <intensity value="%s"/>\n      <direction x="%s" y="%s" z="%s"/>\n' % (
+                f(rng.uniform(0.2, 0.9)), f(rng.uniform(-1, 1)), f(rng.uniform(-1, 1)), f(rng.uniform(-1, -0.2)))
+        else:
+            s += '      <intensity value="%s"/>\n' % f(rng.uniform(0.05, 0.3))
+        s += "    </light>\n"
+    s += "  </scene>\n  <camera>\n"
+    s += '    <position x="%s" y="%s" z="%s"/>\n' % (f(rng.uniform(-10, 10)), f(rng.uniform(-45, -25)), f(rng.uniform(3, 20)))
+    s += '    <target x="%s" y="%s" z="%s"/>\n    <up x="0" y="0" z="1"/>\n' % (f(rng.uniform(-3, 3)), f(rng.uniform(-3, 3)), f(rng.uniform(0, 6)))
+    s += '    <fov value="%s"/>\n    <width value="%d"/>\n    <height value="%d"/>\n  </camera>\n</xml>\n' % (f(rng.uniform(25, 60)), w, h)
+    return s
+
+
+def compare(a, b, what):
+    """-> list of human-readable differences between two AOV dicts"""
+    diffs = []
+    n = int((a["hit_id"] != b["hit_id"]).sum())
+    if n:
+        diffs.append("%s: %d primary hit ids differ" % (what, n))
+    n = int((a["z"].view(np.uint32) != b["z"].view(np.uint32)).sum())
+    if n:
+        diffs.append("%s: %d z values differ in bits" % (what, n))
+    d = np.abs(a["rgb8"].astype(np.int32) - b["rgb8"].astype(np.int32))
+    if d.max() > 0:
+        diffs.append("%s: %d 8-bit channels differ (max %d)" % (what, int((d > 0).sum()), int(d.max())))
+    if (a["rays_closest"], a["rays_shadow"]) != (b["rays_closest"], b["rays_shadow"]):
+        diffs.append("%s: ray counts %s vs %s" % (what, (a["rays_closest"], a["rays_shadow"]), (b["rays_closest"], b["rays_shadow"])))
+    return diffs
+
+
+def run_binary(binary, path, out_prefix):
+    from aovio import read_aov
+    out = subprocess.check_output([binary, path, out_prefix, "--det"] + (["--threads", "2"] if binary == REF_BIN else []),
+                                  cwd=ROOT, stderr=subprocess.DEVNULL)
+    info = json.loads(out.decode().splitlines()[-1])
+    r = read_aov(out_prefix + ".aov")
+    r["rays_closest"], r["rays_shadow"] = info["rays_closest"], info["rays_shadow"]
+    return r
+
+
+def check_seed(seed, w, h, workdir, use_ref=True, meshes=True):
+    """-> (list of differences, scene path)"""
+    import bhraytracer_b200 as b
+    import oracle_c
+    path = os.path.join(workdir, "fuzz_%d.xml" % seed)
+    open(path, "w").write(scene_xml(seed, w, h, meshes))
+    cwd = os.getcwd()
+    os.chdir(ROOT)                      # asset paths in the scenes are relative to the repository root
+    try:
+        scene = b.LoadScene(path)
+        o = oracle_c.render_det(scene)
+    finally:
+        os.chdir(cwd)
+    e = run_binary(EMU_BIN, path, os.path.join(workdir, "emu_%d" % seed))
+    diffs = compare(e, o, "device code vs restatement")
+    if use_ref and os.path.exists(REF_BIN):
+        r = run_binary(REF_BIN, path, os.path.join(workdir, "ref_%d" % seed))
+        diffs += compare(o, r, "restatement vs reference")
+        diffs += compare(e, r, "device code vs reference")
+    return diffs, path
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", default="0:20")
+    ap.add_argument("--size", default="96x64")
+    ap.add_argument("--keep", default=None)
+    ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--no-meshes", action="store_true")
+    a = ap.parse_args()
+    lo, hi = (int(x) for x in a.seeds.split(":"))
+    w, h = (int(x) for x in a.size.split("x"))
+    workdir = a.keep or tempfile.mkdtemp(prefix="bhrt_fuzz_")
+    os.makedirs(workdir, exist_ok=True)
+    bad = 0
+    for seed in range(lo, hi):
+        try:
+            diffs, path = check_seed(seed, w, h, workdir, not a.no_ref, not a.no_meshes)
+        except subprocess.CalledProcessError as ex:
+            print("seed %d: %s exited with %s" % (seed, os.path.basename(ex.cmd[0]), ex.returncode))
+            bad += 1
+            continue
+        if diffs:
+            bad += 1
+            print("seed %d (%s):\n  " % (seed, path) + "\n  ".join(diffs))
+        else:
+            print("seed %d ok" % seed)
+    print("%d of %d seeds differ" % (bad, hi - lo))
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
