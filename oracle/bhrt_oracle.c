@@ -308,6 +308,7 @@ typedef struct {
     const bhrt_scene_desc *d;
     int *first_child, *next_sibling;      /* the Node tree rebuilt from the DFS table */
     uint64_t rays_closest, rays_shadow;
+    int depth, max_depth;                 /* Shade() recursion: current / deepest level of the frame */
     v3 dd_x, dd_y;                        /* Main.cpp:31 globals, read by Plane.cpp */
     const bhrt_light *lights; int n_lights;       /* sorted (Main.cpp:112-123) */
     float tex_x[TEXTURE_SAMPLE_COUNT], tex_y[TEXTURE_SAMPLE_COUNT];   /* scene.h:323-329 offsets */
@@ -566,7 +567,15 @@ static v3 refraction_term(scene_t *s, v3 refraction, v3 absorption, float ior, c
 
 /* MtlBlinn::Shade (Materials/Blinn/MtlBlinn.cpp:89-138) in D-mode: GI is switched off (D-2),
  * PathTracing_DiffuseNSpecular (:304-351) loops over every light with its exact direction (D-3) */
+static v3 shade_body(scene_t *s, ray_t ray, const hit_t *h, int bounceCount);
 static v3 shade(scene_t *s, ray_t ray, const hit_t *h, int bounceCount)
+{
+    if (++s->depth > s->max_depth) s->max_depth = s->depth;
+    v3 c = shade_body(s, ray, h, bounceCount);
+    s->depth--;
+    return c;
+}
+static v3 shade_body(scene_t *s, ray_t ray, const hit_t *h, int bounceCount)
 {
     const bhrt_material *M = &s->d->materials[s->d->nodes[h->node].material];
     v3 vN = norm(h->N);
@@ -618,6 +627,10 @@ int bhrt_oracle_in_scope(const bhrt_scene_desc *d)
 /* BeginRender() + PathTracing() (Main.cpp:178-242,143-172) in D-mode.  Outputs: hit_id[H*W] (node
  * index in DFS order, -1 = miss), z[H*W], linear[H*W*3], rgb8[H*W*3], rays[2] = closest, shadow.
  * tir_budget = INTERNAL_REFLECTION_BOUNCE (Main.cpp:41; 16 in the reference). */
+static int g_last_max_depth;
+/* deepest Shade() recursion of the last frame rendered (not thread-safe; the reference has no bound on it) */
+int bhrt_oracle_last_max_depth(void) { return g_last_max_depth; }
+
 static int render_det(const bhrt_scene_desc *d, int tir_budget, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays, uint32_t *pixel_rays)
 {
     if (!d || !bhrt_oracle_in_scope(d)) return -2;
@@ -692,6 +705,7 @@ static int render_det(const bhrt_scene_desc *d, int tir_budget, int32_t *hit_id,
             if (pixel_rays) { pixel_rays[2 * p] = (uint32_t)(s.rays_closest - c0); pixel_rays[2 * p + 1] = (uint32_t)(s.rays_shadow - s0); }
         }
     rays[0] = s.rays_closest; rays[1] = s.rays_shadow;
+    g_last_max_depth = s.max_depth;
     free(s.first_child); free(s.next_sibling);
     return 0;
 }

@@ -45,4 +45,4 @@ def render_det(scene, tir_budget=16):
     if rc != 0:
         raise ValueError("scene outside the restatement's scope (rc %d)" % rc)
     return dict(hit_id=hit.reshape(h, w), z=z.reshape(h, w), linear=lin.reshape(h, w, 3), rgb8=rgb.reshape(h, w, 3),
-                rays_closest=int(rays[0]), rays_shadow=int(rays[1]), pixel_rays=pix.reshape(h, w, 2))
+                rays_closest=int(rays[0]), rays_shadow=int(rays[1]), pixel_rays=pix.reshape(h, w, 2), max_depth=int(L.bhrt_oracle_last_max_depth()))

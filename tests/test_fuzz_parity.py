@@ -19,8 +19,8 @@ from conftest import REF_BIN, ROOT
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import fuzz_parity  # noqa: E402
 
-SEEDS = [0, 1, 2, 3, 4, 5, 11, 17, 56, 173, 319]
-SEEDS_GPU = SEEDS + list(range(600, 630))
+SEEDS = [0, 1, 2, 3, 4, 5, 11, 17, 56, 173, 319, 2000, 2001, 2002, 2003]      # >= 2000: the generator's second dialect
+SEEDS_GPU = SEEDS + list(range(600, 630)) + list(range(2010, 2020))
 
 
 @pytest.mark.parametrize("seed", SEEDS)
