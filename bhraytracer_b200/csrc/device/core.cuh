@@ -206,7 +206,7 @@ struct SceneView {
     int width, height;
 };
 
-struct RayCounters { unsigned long long closest, shadow; };
+struct RayCounters { unsigned long long closest, shadow; unsigned overflow = 0; };   // overflow: Shade() levels refused for lack of frames
 
 // The reference's 24-byte photon (cyPhotonMap.h:72-80): position, max-channel power, 8-bit
 // colour ratio, kd-tree plane bits + sign of dir.z, 16-bit fixed-point dir.x / dir.y.
@@ -1297,11 +1297,13 @@ struct alignas(128) Frame {              // one 128-byte line per recursion leve
 };
 enum { ST_REFR = 0, ST_REFR_IN_WAIT = 1, ST_REFR_OUT_WAIT = 2, ST_REFR_WAIT = 3, ST_GI = 4, ST_GI_TRACE_WAIT = 5, ST_GI_WAIT = 6,
        ST_DIRECT = 7, ST_SHADOW_WAIT = 8, ST_GATHER_WAIT = 9 };
-#define BHRT_MAX_FRAMES 64
+#define BHRT_MAX_FRAMES 64          // default depth of the estimator's stack (levels of MtlBlinn::Shade recursion)
+#define BHRT_MAX_FRAMES_LIMIT 4096  // the host doubles the depth up to here when a frame overflows it (render.cu)
 
 struct ShadeCfg {
     int mode;           // BHRT_MODE_*
     int gi_depth, tir_budget;
+    int max_frames;     // frames available per lane: a Shade() level beyond it is refused (black) and counted
 };
 
 // camera sample a lane is evaluating: written when the sample starts, read when it ends
@@ -1338,13 +1340,13 @@ struct alignas(16) Lane {
 #define BHRT_LANE_PERSIST 176
 // The recursion levels of one lane: the estimator only ever touches the top frame and, when it
 // recurses, the slot above it.
-struct LaneStack { Frame fr[BHRT_MAX_FRAMES]; };
+struct LaneStack { Frame *fr; };     // cfg.max_frames frames, owned by the caller (CPU harness)
 // the stage of the top recursion level, and the push / pop of a level
 BHRT_HD int lane_stage(const Lane &L) { return L.top_stage; }
 BHRT_HD void lane_push(Lane &L, int child_stage)
 {
     const int i = L.sp - 1;         // the level that now waits for the child
-    if (i >= 0) {
+    if (i >= 0 && i < 120) {        // (a GI child exists only while f.gi >= 0, i.e. on the first gi_depth + 1 levels)
         const uint8_t bit = (uint8_t)(1u << (i & 7));
         if (L.top_stage == ST_GI_WAIT) L.gi_wait[i >> 3] |= bit; else L.gi_wait[i >> 3] &= (uint8_t)~bit;
     }
@@ -1354,7 +1356,7 @@ BHRT_HD void lane_push(Lane &L, int child_stage)
 BHRT_HD void lane_pop(Lane &L)
 {
     L.sp--;
-    if (L.sp > 0) { const int i = L.sp - 1; L.top_stage = ((L.gi_wait[i >> 3] >> (i & 7)) & 1) ? ST_GI_WAIT : ST_REFR_WAIT; }
+    if (L.sp > 0) { const int i = L.sp - 1; L.top_stage = (i < 120 && ((L.gi_wait[i >> 3] >> (i & 7)) & 1)) ? ST_GI_WAIT : ST_REFR_WAIT; }
 }
 
 BHRT_HD void frame_begin(Frame &f, const SceneView &s, V3 ray_p, const Hit &h, int bounce, int gi)
@@ -1508,11 +1510,11 @@ BHRT_HD int sample_step(Lane &BHRT_RESTRICT L, Frame &BHRT_RESTRICT f, Frame &BH
                 return STEP_RAY;
             }
             f.mult = V3(1, 1, 1);
-            if (L.sp < BHRT_MAX_FRAMES) {
+            if (L.sp < cfg.max_frames) {
                 frame_begin(child, s, rin.p, L.hit, L.si, f.gi - 1);
                 push_child = true;
                 stage = ST_REFR_WAIT;
-            } else refr_resolved = true;
+            } else { rc.overflow++; refr_resolved = true; }
             break;
         }
         case ST_REFR_OUT_WAIT: {
@@ -1522,11 +1524,11 @@ BHRT_HD int sample_step(Lane &BHRT_RESTRICT L, Frame &BHRT_RESTRICT f, Frame &BH
                 float hz = L.hit.z;
                 V3 af(m_pow(BHRT_EULER, -ab.x * hz), m_pow(BHRT_EULER, -ab.y * hz), m_pow(BHRT_EULER, -ab.z * hz));
                 f.mult = L.sv * af;
-                if (L.sp < BHRT_MAX_FRAMES) {
+                if (L.sp < cfg.max_frames) {
                     frame_begin(child, s, nx.p, L.hit, L.si, f.gi - 1);
                     push_child = true;
                     stage = ST_REFR_WAIT;
-                } else refr_resolved = true;
+                } else { rc.overflow++; refr_resolved = true; }
             } else {
                 R = L.sv * sample_environment(s, nx.dir);
                 clamp_white(R);
@@ -1566,11 +1568,14 @@ BHRT_HD int sample_step(Lane &BHRT_RESTRICT L, Frame &BHRT_RESTRICT f, Frame &BH
         case ST_GI_TRACE_WAIT: {
             const Ray g = L.q.ray;
             if (L.hit_ok) {
-                if (fabsf(L.hit.z) > BHRT_BIAS && L.sp < BHRT_MAX_FRAMES) {
+                if (fabsf(L.hit.z) > BHRT_BIAS && L.sp < cfg.max_frames) {
                     frame_begin(child, s, g.p, L.hit, f.bounce, f.gi - 1);
                     push_child = true;
                     stage = ST_GI_WAIT;
-                } else gi_resolved = true;      // indirect = black, black * albedo = black
+                } else {                         // indirect = black, black * albedo = black
+                    if (fabsf(L.hit.z) > BHRT_BIAS) rc.overflow++;
+                    gi_resolved = true;
+                }
             } else {
                 if (g.dir.x == g.dir.y && g.dir.x == 0) G = V3(1.0f, 0.0f, 1.0f);
                 else {
@@ -1678,7 +1683,7 @@ BHRT_HD bool sample_advance(Lane &L, LaneStack &S, const SceneView &s, const Sha
                             RayCounters &rc, V3 &color)
 {
     for (;;) {
-        const int top = L.sp > 0 ? L.sp - 1 : 0, up = L.sp < BHRT_MAX_FRAMES ? L.sp : BHRT_MAX_FRAMES - 1;
+        const int top = L.sp > 0 ? L.sp - 1 : 0, up = L.sp < cfg.max_frames ? L.sp : cfg.max_frames - 1;
         int r = sample_step(L, S.fr[top], S.fr[up], s, cfg, pg, bgu, bgv, rc, color);
         if (r == STEP_GATHER) { estimate_irradiance(pg, S.fr[top].p, S.fr[top].vN, L.ret, L.sw); continue; }
         if (r == STEP_RAY) return false;

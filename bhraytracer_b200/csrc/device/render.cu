@@ -63,6 +63,8 @@ struct bhrt_ctx {
     bool kernel_ready = false;
     int kernel_smem = 0, render_blocks = 1;
     unsigned pool_lanes = 3072;                 // lanes (camera samples in flight) per CTA, 2.3 KB of state each
+    size_t last_lanes_total = 0;
+    int max_frames = BHRT_MAX_FRAMES;   // depth of the estimator's stack; doubled when a frame overflowed it (launch_render)
     int mesh_budget = WF_MESH_BUDGET;
     unsigned mesh_batch = WF_BLOCK;
     unsigned gather_batch = 0;                  // 0 = 11/12 of the pool
@@ -225,8 +227,9 @@ int bhrt_upload_scene(bhrt_ctx *c, const bhrt_scene_desc *d)
     return BHRT_OK;
 }
 
-// One frame (or one rank's share of it) through the wavefront kernels of wavefront.cuh.
-static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
+// One frame (or one rank's share of it) through the wavefront kernels of wavefront.cuh, with c->max_frames
+// levels of Shade() recursion per lane; *overflow = levels that were refused for lack of frames.
+static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out, unsigned long long *overflow)
 {
     if (!c || !p) return set_err(BHRT_ERR_ARG, "bhrt_render: null argument");
     if (!c->have_scene) return set_err(BHRT_ERR_STATE, "bhrt_render: no scene uploaded");
@@ -237,6 +240,7 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     a.cfg.mode = p->mode;
     a.cfg.gi_depth = p->gi_depth;
     a.cfg.tir_budget = p->tir_budget > 0 ? p->tir_budget : 16;
+    a.cfg.max_frames = c->max_frames;
     a.seed = p->seed;
     int spp = p->mode == BHRT_MODE_DET ? 1 : p->spp;
     if (spp <= 0) return set_err(BHRT_ERR_ARG, "bhrt_render: spp must be > 0");
@@ -308,7 +312,7 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
         if (need < grid) grid = need < 1 ? 1u : (unsigned)need;
     }
     const size_t lanes_total = (size_t)grid * a.pool;
-    if (c->lanes.ensure(lanes_total * sizeof(Lane)) || c->frames.ensure(lanes_total * sizeof(Frame) * BHRT_MAX_FRAMES) ||
+    if (c->lanes.ensure(lanes_total * sizeof(Lane)) || c->frames.ensure(lanes_total * sizeof(Frame) * (size_t)c->max_frames) ||
         c->samples.ensure(n_pix_share * (size_t)chunk * sizeof(float4)) || c->wave_counters.ensure(sizeof(WaveCounters)))
         return set_err(BHRT_ERR_CUDA, "cudaMalloc(wavefront buffers) failed");
     a.lanes = (Lane *)c->lanes.p; a.frames = (Frame *)c->frames.p; a.samples = (float4 *)c->samples.p;
@@ -337,12 +341,14 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
         wf_reduce<<<(a.n_pix_work + 255) / 256, 256, 0, c->stream>>>(c->view, a, (float4 *)c->accum.p, s0 == sample_begin ? 1 : 0);
         c->launches += 2;
     }
-    unsigned long long rays[2] = { 0, 0 };
+    unsigned long long rays[4] = { 0, 0, 0, 0 };      // rays_closest, rays_shadow, next_work, depth_overflow
     CU(cudaMemcpyAsync(rays, &((WaveCounters *)c->wave_counters.p)->rays_closest, sizeof(rays), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev1, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->rendered_spp = n_spp_share;
+    *overflow = rays[3];
+    c->last_lanes_total = lanes_total;
     if (getenv("BHRT_DEBUG")) {
         WaveCounters h;
         CU(cudaMemcpy(&h, c->wave_counters.p, sizeof(h), cudaMemcpyDeviceToHost));
@@ -356,6 +362,25 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
         out->rays_closest = rays[0]; out->rays_shadow = rays[1]; out->kernel_ms = ms;
     }
     return BHRT_OK;
+}
+
+// The reference's Shade() recursion has no bound of its own (a plain refraction consumes nothing of the
+// internal-reflection budget, MtlBlinn.cpp:476-519).  Ours is bounded by the frames a lane owns: when a
+// frame ran into that bound, render it again with twice the depth (same seed, same samples), as long as
+// the frame stacks fit in half of the free device memory.
+static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
+{
+    for (;;) {
+        unsigned long long overflow = 0;
+        const int r = launch_render_once(c, p, out, &overflow);
+        if (r != BHRT_OK || overflow == 0 || c->max_frames * 2 > BHRT_MAX_FRAMES_LIMIT) return r;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return r;
+        const size_t need = c->last_lanes_total * sizeof(Frame) * (size_t)c->max_frames * 2;
+        if (need > (free_b + c->frames.bytes) / 2) return r;
+        c->max_frames *= 2;
+        if (getenv("BHRT_DEBUG")) fprintf(stderr, "[bhrt] %llu Shade() levels did not fit: rendering again with %d levels per lane\n", overflow, c->max_frames);
+    }
 }
 
 int bhrt_render_device(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out) { return launch_render(c, p, out); }

@@ -95,7 +95,7 @@ __device__ __forceinline__ unsigned wf_key_patch(const SceneView &s, unsigned ke
 struct WaveCounters {
     unsigned long long rays_closest, rays_shadow;
     unsigned long long next_work;           // next camera-sample work item of the chunk
-    unsigned long long pad;
+    unsigned long long depth_overflow;      // Shade() levels refused because the lanes' frame stacks were full (the host retries deeper)
     // clock64() cycles summed over the CTAs (warp 0): lanes pass, sort, BVH traversal; iterations, traversal phases
     unsigned long long prof[6];
 };
@@ -110,7 +110,7 @@ struct WaveArgs {
     unsigned long long n_work;  // n_pix_work * chunk_spp
     PhotonGather gather;
     Lane *lanes;                // [gridDim.x][pool] lane headers
-    Frame *frames;              // [gridDim.x][BHRT_MAX_FRAMES][pool] recursion levels (level-major: only the low levels are ever touched)
+    Frame *frames;              // [gridDim.x][cfg.max_frames][pool] recursion levels (level-major: only the low levels are ever touched)
     float4 *samples;            // [chunk_spp][n_pix_work]
     int *hit_id; float *zbuf;
     WaveCounters *cnt;
@@ -419,7 +419,7 @@ wf_render(SceneView s, WaveArgs a)
     __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor, gq_count, gq_cursor, run_gather_s, n_parked_s;
 
     Lane *const lanes = a.lanes + (size_t)blockIdx.x * P;
-    Frame *const frames_all = a.frames + (size_t)blockIdx.x * P * BHRT_MAX_FRAMES;
+    Frame *const frames_all = a.frames + (size_t)blockIdx.x * P * (size_t)a.cfg.max_frames;
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     const bool det = a.cfg.mode == BHRT_MODE_DET;
 
@@ -476,7 +476,7 @@ wf_render(SceneView s, WaveArgs a)
                 if (mn == 127) break;
                 if (st != mn) continue;
                 V3 c;
-                const int r = sample_step(L, frames[(size_t)(L.sp > 0 ? L.sp - 1 : 0) * P], frames[(size_t)(L.sp < BHRT_MAX_FRAMES ? L.sp : BHRT_MAX_FRAMES - 1) * P],
+                const int r = sample_step(L, frames[(size_t)(L.sp > 0 ? L.sp - 1 : 0) * P], frames[(size_t)(L.sp < a.cfg.max_frames ? L.sp : a.cfg.max_frames - 1) * P],
                                           s, a.cfg, a.gather, L.sp == 0 ? lanes[id].cold.bgu : 0.f, L.sp == 0 ? lanes[id].cold.bgv : 0.f, rc, c);
                 if (r == STEP_GATHER) { to_gather = true; running = false; continue; }
                 if (r == STEP_RAY) { running = false; continue; }
@@ -696,6 +696,7 @@ wf_render(SceneView s, WaveArgs a)
         c1 += __shfl_down_sync(0xffffffffu, c1, o);
     }
     if (lane == 0 && (c0 | c1)) { atomicAdd(&a.cnt->rays_closest, c0); atomicAdd(&a.cnt->rays_shadow, c1); }
+    if (rc.overflow) atomicAdd(&a.cnt->depth_overflow, (unsigned long long)rc.overflow);
     if (tid == 0) {
         atomicAdd(&a.cnt->prof[0], (unsigned long long)t_p1); atomicAdd(&a.cnt->prof[1], (unsigned long long)t_sort);
         atomicAdd(&a.cnt->prof[2], (unsigned long long)t_mesh); atomicAdd(&a.cnt->prof[3], (unsigned long long)n_iter);

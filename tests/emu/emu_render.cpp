@@ -60,6 +60,7 @@ int main(int argc, char **argv)
     const char *photon_file = nullptr; int photon_total = 1, photon_k = 1000; float photon_radius = 0.5f;
     const char *query_in = nullptr, *query_out = nullptr;
     const char *pixel_rays = nullptr;
+    int max_frames = 0;
     unsigned long long seed = 1;
     for (int a = 3; a < argc; a++) {
         if (!strcmp(argv[a], "--det")) det = 1;
@@ -72,6 +73,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[a], "--emit") && a + 2 < argc) { emit_n = atoi(argv[++a]); emit_file = argv[++a]; }
         else if (!strcmp(argv[a], "--photons") && a + 4 < argc) { photon_file = argv[++a]; photon_total = atoi(argv[++a]); photon_k = atoi(argv[++a]); photon_radius = (float)atof(argv[++a]); }
         else if (!strcmp(argv[a], "--pixel-rays") && a + 1 < argc) pixel_rays = argv[++a];
+        else if (!strcmp(argv[a], "--max-frames") && a + 1 < argc) max_frames = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--queries") && a + 2 < argc) { query_in = argv[++a]; query_out = argv[++a]; }
         else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
     }
@@ -188,6 +190,9 @@ int main(int argc, char **argv)
         }
     }
     ShadeCfg cfg; cfg.mode = det ? BHRT_MODE_DET : BHRT_MODE_PATH; cfg.gi_depth = gi; cfg.tir_budget = 16;
+    // the depth the library's host side converges to by doubling (render.cu: launch_render) when memory allows;
+    // --max-frames N pins it (the estimator then cuts deeper chains off, counted in "depth_overflow")
+    cfg.max_frames = max_frames > 0 ? max_frames : BHRT_MAX_FRAMES_LIMIT;
     if (row_e == 0) row_e = H;
     if (row_s < 1) row_s = 1;
     if (smp_e == 0) smp_e = spp;
@@ -195,15 +200,16 @@ int main(int argc, char **argv)
     std::vector<uint8_t> rgb8((size_t)W * H * 3, 0);
     std::vector<int32_t> hitid((size_t)W * H, 0);
     std::vector<uint32_t> pixrays((size_t)W * H * 2, 0);     // per-pixel (closest, shadow) ray counts, written with --pixel-rays
-    unsigned long long closest = 0, shadow = 0;
+    unsigned long long closest = 0, shadow = 0, overflowed = 0;
+    std::vector<std::vector<Frame>> stacks(omp_get_max_threads(), std::vector<Frame>(cfg.max_frames));
     double t0 = omp_get_wtime();
-#pragma omp parallel for schedule(dynamic, 4) reduction(+ : closest, shadow)
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : closest, shadow, overflowed)
     for (int j = row_b; j < row_e; j += row_s) {
         for (int i = 0; i < W; i++) {
             RayCounters rc; rc.closest = 0; rc.shadow = 0;
             V3 sum(0, 0, 0);
             int id0 = -1; float z0 = BHRT_BIGFLOAT;
-            Lane L; LaneStack S;
+            Lane L; LaneStack S; S.fr = stacks[omp_get_thread_num()].data();
             for (int sidx = smp_b; sidx < smp_e; sidx++) {
                 L.rng.seed(seed, (uint64_t)j * W + i, sidx);
                 Ray pr = primary_ray(s, i, j, !det, L.rng);
@@ -219,7 +225,7 @@ int main(int argc, char **argv)
             V3 g = gamma_correct(out);
             rgb8[3 * p] = float_to_byte(g.x); rgb8[3 * p + 1] = float_to_byte(g.y); rgb8[3 * p + 2] = float_to_byte(g.z);
             hitid[p] = id0; z[p] = z0;
-            closest += rc.closest; shadow += rc.shadow;
+            closest += rc.closest; shadow += rc.shadow; overflowed += rc.overflow;
             pixrays[2 * p] = (uint32_t)rc.closest; pixrays[2 * p + 1] = (uint32_t)rc.shadow;
         }
     }
@@ -252,7 +258,7 @@ int main(int argc, char **argv)
     if (!fp) return 4;
     fwrite(acc.data(), 4, acc.size(), fp);
     fclose(fp);
-    printf("{\"emu\": true, \"width\": %d, \"height\": %d, \"spp\": %d, \"ms\": %.3f, \"rays_closest\": %llu, \"rays_shadow\": %llu, \"nodes\": %d}\n",
-           W, H, spp, ms, closest, shadow, D.n_nodes);
+    printf("{\"emu\": true, \"width\": %d, \"height\": %d, \"spp\": %d, \"ms\": %.3f, \"rays_closest\": %llu, \"rays_shadow\": %llu, \"depth_overflow\": %llu, \"nodes\": %d}\n",
+           W, H, spp, ms, closest, shadow, overflowed, D.n_nodes);
     return 0;
 }

@@ -30,7 +30,7 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bhrt_ref")
 EMU_BIN = os.path.join(ROOT, "build", "emu_render")
 MESHES = ["scenes/assets/torus_small.obj", "scenes/assets/blob_small.obj", "scenes/assets/cube_mtl.obj"]
 BITMAPS = ["scenes/assets/bricks.png", "scenes/assets/clouds.png"]
-MAX_LEVELS = 64         # BHRT_MAX_FRAMES (csrc/device/core.cuh)
+MAX_LEVELS = 4096       # BHRT_MAX_FRAMES_LIMIT (csrc/device/core.cuh)
 
 
 def f(x):
@@ -203,8 +203,8 @@ def check_seed(seed, w, h, workdir, use_ref=True, meshes=True):
         os.chdir(cwd)
     e = run_binary(EMU_BIN, path, os.path.join(workdir, "emu_%d" % seed))
     if o["max_depth"] > MAX_LEVELS:
-        # the reference's Shade() recursion has no bound; the estimator's stack has: beyond it the frames
-        # are comparable only up to the rays of the cut-off tail
+        # the reference's Shade() recursion has no bound; the estimator's stack grows to MAX_LEVELS at most
+        # (render.cu: launch_render): beyond it the frames are comparable only up to the cut-off tail
         return ["DEEP: the reference recurses %d levels (estimator stack: %d)" % (o["max_depth"], MAX_LEVELS)], path
     diffs = compare(e, o, "device code vs restatement")
     if use_ref and os.path.exists(REF_BIN):
