@@ -214,7 +214,11 @@ int bhrt_destroy(bhrt_ctx *ctx);
 int bhrt_upload_scene(bhrt_ctx *ctx, const bhrt_scene_desc *scene);
 
 /* BeginRender() (Main.cpp:178-242) with host outputs: renders, resolves (divide by spp,
- * gamma, 8-bit) and copies the requested outputs to the caller's HOST buffers. */
+ * gamma, 8-bit) and copies the requested outputs to the caller's HOST buffers.
+ * MtlBlinn::Shade recursion is as deep as the scene makes it (the reference has no bound,
+ * MtlBlinn.cpp:476-519): a ctx starts with 64 levels per camera sample in flight and renders a
+ * frame again with twice as many while any level was refused (up to 4096, device memory
+ * permitting); kernel_ms is the time of the last pass. */
 int bhrt_render(bhrt_ctx *ctx, const bhrt_params *params, bhrt_outputs *out);
 
 /* The same frame, outputs left in device memory (accumulation buffer = sum over the
