@@ -4,7 +4,8 @@
  * meshes traversed through the reference's own BVH topology; point / direct / ambient lights;
  * Blinn-Phong with hard shadows; Fresnel refraction with absorption and total internal reflection;
  * checker and bitmap textures with the plane's ray differentials; textured background and
- * environment; 1 spp at the pixel corner), written from the
+ * environment; the caustic gather EstimateIrradiance / LocatePhotons over the reference's own
+ * balanced photon array; 1 spp at the pixel corner), written from the
  * reference sources cited at every function (paths relative to /root/reference/BHRayTracer).  It is
  * independent of csrc/device: the only thing it shares with the product is the POD scene
  * description of include/bhrt.h.
@@ -15,8 +16,10 @@
  * present, against the reference run live on 16 of its own scenes and on this repository's five
  * config scenes.  The real reference (oracle/_ref, built by oracle/build_ref.py) remains the
  * oracle for what is outside this file's scope -- the stochastic estimator (GI, area lights,
- * jitter) and the photon map -- where parity is statistical and a restatement would only repeat
- * the reference with more room for error.
+ * jitter) and the photon emission / kd-tree balancing -- where parity is statistical and a
+ * restatement would only repeat the reference with more room for error.  The gather itself is
+ * restated (bhrt_oracle_render_det_pm) and pinned by tests/golden/det_caustics_pm.npz: the
+ * reference's gather-lit frame from its own photon dump, identical in every 8-bit channel.
  *
  * Scope check: bhrt_oracle_render_det returns -2 for scenes with area lights (the D-mode switches
  * leave PointLight::Illuminate's random sample in place, PointLight.cpp:13-15).
@@ -309,6 +312,7 @@ typedef struct {
     int *first_child, *next_sibling;      /* the Node tree rebuilt from the DFS table */
     uint64_t rays_closest, rays_shadow;
     int depth, max_depth;                 /* Shade() recursion: current / deepest level of the frame */
+    const uint8_t *photons; int n_photons, half_photons;    /* the caustic map: balanced kd-tree in heap order (the reference's .dat dump), or NULL */
     v3 dd_x, dd_y;                        /* Main.cpp:31 globals, read by Plane.cpp */
     const bhrt_light *lights; int n_lights;       /* sorted (Main.cpp:112-123) */
     float tex_x[TEXTURE_SAMPLE_COUNT], tex_y[TEXTURE_SAMPLE_COUNT];   /* scene.h:323-329 offsets */
@@ -481,6 +485,116 @@ static v3 sample_environment(const scene_t *s, v3 dir)
     return texcolor_sample(s, &s->d->environment, uvw);
 }
 
+/* ---- caustic photon map: gather (cyPhotonMap.h) ---------------------------------------------- */
+#define MAX_PHOTONS_IN_AREA 1000      /* MtlBlinn.cpp:28 */
+#define MAX_AREA 0.5f                 /* MtlBlinn.cpp:29 (a double literal, passed as float radius) */
+/* PhotonMap::Photon (cyPhotonMap.h:72-90), 24 bytes; photon i (1-based, photons[i]) = record i - 1 of the dump */
+typedef struct { float pos[3]; float power; uint8_t rgb[3]; uint8_t planeAndDirZ; int16_t dirX, dirY; } photon_t;
+static const photon_t *photon_at(const scene_t *s, int index) { return (const photon_t *)(s->photons + 24 * (size_t)(index - 1)); }
+/* Photon::GetDirection (cyPhotonMap.h:192-214), with its dirX*dirX + dirY - dirY slip (:196) */
+static v3 photon_direction(const photon_t *p)
+{
+    v3 dir;
+    dir.x = (float)p->dirX / (float)0x7FFF;
+    dir.y = (float)p->dirY / (float)0x7FFF;
+    int dirXY2 = p->dirX * p->dirX + p->dirY - p->dirY;
+    if (dirXY2 > 0x3FFF0001) dirXY2 = 0x3FFF0001;
+    int dirZ2 = 0x3FFF0001 - dirXY2;
+    int dirZ = 0, place = 0x40000000, remainder = dirZ2;
+    while (place > remainder) place = place >> 2;
+    while (place) {
+        if (remainder >= dirZ + place) { remainder = remainder - dirZ - place; dirZ = dirZ + (place << 1); }
+        dirZ = dirZ >> 1;
+        place = place >> 2;
+    }
+    dir.z = (float)dirZ / (float)0x7FFF;
+    if (p->planeAndDirZ & 0x8) dir.z = -dir.z;
+    return dir;
+}
+typedef struct { v3 pos, normal; int maxPhotons, found; float *dist2; const photon_t **photon; } nearest_t;
+static float comp(v3 a, int axis) { return axis == 0 ? a.x : (axis == 1 ? a.y : a.z); }
+/* PhotonMap::LocatePhotons (cyPhotonMap.h:421-498), ellipticity 1 (normScale 0) */
+static void locate_photons(const scene_t *s, nearest_t *np, int index)
+{
+    const photon_t *p = photon_at(s, index);
+    int axis = p->planeAndDirZ & 0x3;
+    if (index < s->half_photons) {
+        float dist = comp(np->pos, axis) - p->pos[axis];
+        if (dist > 0) {
+            locate_photons(s, np, 2 * index + 1);
+            if (dist * dist < np->dist2[0]) locate_photons(s, np, 2 * index);
+        } else {
+            locate_photons(s, np, 2 * index);
+            if (dist * dist < np->dist2[0]) locate_photons(s, np, 2 * index + 1);
+        }
+    }
+    v3 dif = sub(ld(p->pos), np->pos);
+    float dist2 = dot(dif, dif);
+    if (dist2 < np->dist2[0]) {
+        if (dot(photon_direction(p), np->normal) >= 0) return;
+        if (np->found < np->maxPhotons) {
+            np->found++;
+            np->dist2[np->found] = dist2;
+            np->photon[np->found] = p;
+            if (np->found == np->maxPhotons) {          /* build a heap; dist2[0] is NOT updated here (:462-478) */
+                int half_found = np->found >> 1;
+                for (int k = half_found; k >= 1; k--) {
+                    int parent = k;
+                    const photon_t *tp = np->photon[k];
+                    float td2 = np->dist2[k];
+                    while (parent <= half_found) {
+                        int j = parent + parent;
+                        if (j < np->found && np->dist2[j] < np->dist2[j + 1]) j++;
+                        if (td2 >= np->dist2[j]) break;
+                        np->dist2[parent] = np->dist2[j];
+                        np->photon[parent] = np->photon[j];
+                        parent = j;
+                    }
+                    np->photon[parent] = tp;
+                    np->dist2[parent] = td2;
+                }
+            }
+        } else {
+            int parent = 1, j = 2;
+            while (j <= np->found) {
+                if (j < np->found && np->dist2[j] < np->dist2[j + 1]) j++;
+                if (dist2 > np->dist2[j]) break;
+                np->dist2[parent] = np->dist2[j];
+                np->photon[parent] = np->photon[j];
+                parent = j;
+                j <<= 1;
+            }
+            np->photon[parent] = p;
+            np->dist2[parent] = dist2;
+            np->dist2[0] = np->dist2[1];
+        }
+    }
+}
+/* PhotonMap::EstimateIrradiance<1000> (cyPhotonMap.h:332-382), constant filter */
+static void estimate_irradiance(const scene_t *s, v3 pos, v3 normal, float radius, v3 *irrad, v3 *direction)
+{
+    *irrad = V(0, 0, 0); *direction = V(0, 0, 0);
+    float found_dist2[MAX_PHOTONS_IN_AREA + 1];
+    const photon_t *found_photon[MAX_PHOTONS_IN_AREA + 1];
+    nearest_t np;
+    np.pos = pos; np.normal = normal; np.maxPhotons = MAX_PHOTONS_IN_AREA; np.found = 0;
+    np.dist2 = found_dist2; np.photon = found_photon;
+    np.dist2[0] = radius * radius;
+    locate_photons(s, &np, 1);
+    for (int i = 1; i <= np.found; i++) {
+        const photon_t *p = np.photon[i];
+        v3 power = mulf(V(p->rgb[0] / 255.0f, p->rgb[1] / 255.0f, p->rgb[2] / 255.0f), p->power);     /* GetPower (:83) */
+        float filter = 1;
+        *irrad = add(*irrad, mulf(power, filter));
+        *direction = add(*direction, mulf(photon_direction(p), filter * p->power));
+    }
+    if (np.found > 0) {
+        float area = PI_F * np.dist2[0];
+        if (area > 0) { float one_over_area = 1.0f / area; *irrad = mulf(*irrad, one_over_area); }
+        *direction = divf(*direction, len(*direction));
+    }
+}
+
 /* ---- shading -------------------------------------------------------------------------------- */
 static int all_white(v3 c) { return c.x >= 1 && c.y >= 1 && c.z >= 1; }
 static const v3 NAN_PURPLE = { 1.0f, 0.0f, 1.0f };                  /* cyColor.h:130 */
@@ -603,6 +717,19 @@ static v3 shade_body(scene_t *s, ray_t ray, const hit_t *h, int bounceCount)
             D = add(D, mulv(irrad, brdf));
         }
     }
+    if (s->photons && s->n_photons > 0) {
+        /* "Adding caustics for direct color" (:329-342) */
+        v3 vL, irr;
+        estimate_irradiance(s, h->p, h->N, MAX_AREA, &irr, &vL);
+        float cosTheta = -dot(vL, vN);
+        if (cosTheta > 0) {
+            v3 vH = norm(add(vL, vV));
+            v3 kd = texcolor_sample_filtered(s, ld(M->diffuse.color), M->diffuse.texmap, h->uvw, h->duvw);
+            v3 ks = texcolor_sample_filtered(s, newSpecular, M->specular.texmap, h->uvw, h->duvw);
+            v3 brdf = add(kd, divf(mulf(ks, powf(dot(vH, vN), M->glossiness)), cosTheta));
+            D = add(D, mulv(brdf, irr));
+        }
+    }
     clamp_white(&D);                                            /* :343 */
     if (D.x != D.x) D = V(0, 0, 0);                             /* :344-347 */
     out = add(out, D);
@@ -631,12 +758,14 @@ static int g_last_max_depth;
 /* deepest Shade() recursion of the last frame rendered (not thread-safe; the reference has no bound on it) */
 int bhrt_oracle_last_max_depth(void) { return g_last_max_depth; }
 
-static int render_det(const bhrt_scene_desc *d, int tir_budget, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays, uint32_t *pixel_rays)
+static int render_det(const bhrt_scene_desc *d, int tir_budget, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays, uint32_t *pixel_rays,
+                      const uint8_t *photons, int n_photons)
 {
     if (!d || !bhrt_oracle_in_scope(d)) return -2;
     scene_t s;
     memset(&s, 0, sizeof(s));
     s.d = d;
+    s.photons = photons; s.n_photons = n_photons; s.half_photons = n_photons / 2 - 1;       /* cyPhotonMap.h:257 */
     int n = d->n_nodes;
     s.first_child = (int *)malloc(sizeof(int) * (n + 1));
     s.next_sibling = (int *)malloc(sizeof(int) * (n + 1));
@@ -712,13 +841,22 @@ static int render_det(const bhrt_scene_desc *d, int tir_budget, int32_t *hit_id,
 
 int bhrt_oracle_render_det2(const bhrt_scene_desc *d, int tir_budget, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays)
 {
-    return render_det(d, tir_budget, hit_id, z, linear, rgb8, rays, NULL);
+    return render_det(d, tir_budget, hit_id, z, linear, rgb8, rays, NULL, NULL, 0);
 }
 /* the same, plus the (closest, shadow) ray counts of every pixel: pixel_rays[H*W*2] */
 int bhrt_oracle_render_det3(const bhrt_scene_desc *d, int tir_budget, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays,
                             uint32_t *pixel_rays)
 {
-    return render_det(d, tir_budget, hit_id, z, linear, rgb8, rays, pixel_rays);
+    return render_det(d, tir_budget, hit_id, z, linear, rgb8, rays, pixel_rays, NULL, 0);
+}
+
+/* the deterministic frame WITH the caustic gather (-DUSE_PhotonMap build of the reference): `photons` =
+ * n_photons 24-byte records exactly as the reference dumps them (Main.cpp:380-385: powers scaled, balanced
+ * kd-tree in heap order with the split planes in planeAndDirZ) */
+int bhrt_oracle_render_det_pm(const bhrt_scene_desc *d, int tir_budget, const uint8_t *photons, int n_photons, int32_t *hit_id, float *z,
+                              float *linear, uint8_t *rgb8, uint64_t *rays)
+{
+    return render_det(d, tir_budget, hit_id, z, linear, rgb8, rays, NULL, photons, n_photons);
 }
 
 int bhrt_oracle_render_det(const bhrt_scene_desc *d, int32_t *hit_id, float *z, float *linear, uint8_t *rgb8, uint64_t *rays)

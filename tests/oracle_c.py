@@ -46,3 +46,22 @@ def render_det(scene, tir_budget=16):
         raise ValueError("scene outside the restatement's scope (rc %d)" % rc)
     return dict(hit_id=hit.reshape(h, w), z=z.reshape(h, w), linear=lin.reshape(h, w, 3), rgb8=rgb.reshape(h, w, 3),
                 rays_closest=int(rays[0]), rays_shadow=int(rays[1]), pixel_rays=pix.reshape(h, w, 2), max_depth=int(L.bhrt_oracle_last_max_depth()))
+
+
+def render_det_pm(scene, photons, tir_budget=16):
+    """The gather-lit deterministic frame; photons: uint8[n, 24], the reference's own .dat dump."""
+    w, h = scene.width, scene.height
+    n = w * h
+    hit, z = np.empty(n, np.int32), np.empty(n, np.float32)
+    lin, rgb = np.empty(n * 3, np.float32), np.empty(n * 3, np.uint8)
+    rays = (C.c_uint64 * 2)()
+    ph = np.ascontiguousarray(photons, dtype=np.uint8).reshape(-1, 24)
+    L = lib()
+    L.bhrt_oracle_render_det_pm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    L.bhrt_oracle_render_det_pm.restype = C.c_int
+    rc = L.bhrt_oracle_render_det_pm(C.cast(scene.desc, C.c_void_p), tir_budget, ph.ctypes.data, len(ph), hit.ctypes.data, z.ctypes.data,
+                                     lin.ctypes.data, rgb.ctypes.data, C.cast(rays, C.c_void_p))
+    if rc != 0:
+        raise ValueError("scene outside the restatement's scope (rc %d)" % rc)
+    return dict(hit_id=hit.reshape(h, w), z=z.reshape(h, w), linear=lin.reshape(h, w, 3), rgb8=rgb.reshape(h, w, 3),
+                rays_closest=int(rays[0]), rays_shadow=int(rays[1]))

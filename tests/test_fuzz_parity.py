@@ -69,3 +69,15 @@ def test_a_stack_that_is_too_shallow_is_reported(built, tmp_path):
     shallow, deep = run(["--max-frames", "64"]), run([])
     assert shallow["depth_overflow"] > 0 and deep["depth_overflow"] == 0
     assert shallow["rays_closest"] < deep["rays_closest"]
+
+
+REF_PM = os.path.join(ROOT, "oracle", "_ref", "bhrt_ref_pm")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PM), reason="needs oracle/_ref (the reference emits the photons)")
+@pytest.mark.parametrize("seed", [64, 68, 111])
+def test_photon_gather_on_random_scenes(built, tmp_path, seed):
+    """Gather-lit frames from 5000 photons of the reference: restatement identical, device code <= 1/255.
+    (Seeds 68 and 111 are lit visibly by photons the reference's kd-tree cannot reach, see the tool.)"""
+    diffs, _ = fuzz_parity.check_seed_photon_map(seed, 96, 64, str(tmp_path), 5000)
+    assert not diffs, "\n".join(diffs)

@@ -150,3 +150,13 @@ def test_kernels_match_the_restatement_on_config_scenes(built, tmp_path, name, w
         r.close()
     same(out, o)
     assert (out["rays_closest"], out["rays_shadow"]) == (o["rays_closest"], o["rays_shadow"])
+
+
+def test_photon_gather_restatement_is_pinned_by_the_reference_golden(built):
+    """EstimateIrradiance / LocatePhotons (cyPhotonMap.h:332-498) over the reference's own photon dump: the
+    gather-lit deterministic frame of the reference, identical in every 8-bit channel."""
+    g = np.load(os.path.join(GOLD, "det_caustics_pm.npz"))
+    scene = b.LoadScene("scenes/det_caustics.xml", int(g["width"]), int(g["height"]))
+    o = oracle_c.render_det_pm(scene, g["photons"])
+    assert (o["hit_id"] == g["hit_id"]).all()
+    assert (o["rgb8"] == g["rgb8"]).all()
