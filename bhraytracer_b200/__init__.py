@@ -62,6 +62,7 @@ class SceneDesc(C.Structure):
 
 
 FLAG_EXACT_MATH = 1      # BHRT_FLAG_EXACT_MATH
+FLAG_BINARY_BVH = 2      # BHRT_FLAG_BINARY_BVH
 
 
 class Params(C.Structure):
@@ -85,7 +86,7 @@ DEVICE_SYMBOLS = ["bhrt_abi_version", "bhrt_last_error", "bhrt_create", "bhrt_de
                   "bhrt_render", "bhrt_render_device", "bhrt_accum_buffer", "bhrt_aov_buffers", "bhrt_resolve",
                   "bhrt_set_stream", "bhrt_launch_count",
                   "bhrt_photons_emit", "bhrt_photons_buffer", "bhrt_photons_set", "bhrt_photons_get",
-                  "bhrt_photons_build"]
+                  "bhrt_photons_build", "bhrt_debug_trace_mesh"]
 HOST_SYMBOLS = ["bhrt_host_load_scene", "bhrt_host_free_scene", "bhrt_host_last_error", "bhrt_host_scene_desc",
                 "bhrt_host_node_name", "bhrt_host_warnings", "bhrt_host_set_resolution", "bhrt_host_save_png",
                 "bhrt_host_zbuffer_image", "bhrt_host_sample_count_image"]
@@ -145,6 +146,7 @@ def device_lib():
         L.bhrt_photons_set.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int]
         L.bhrt_photons_get.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         L.bhrt_photons_build.argtypes = [C.c_void_p, C.c_int32]
+        L.bhrt_debug_trace_mesh.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         _dev = L
     return _dev
 
@@ -247,7 +249,7 @@ class Renderer:
 
     @staticmethod
     def params(mode=MODE_PATH, spp=32, gi_depth=3, tir_budget=16, seed=1, sample_range=None, rows=None,
-               row_stride=1, use_photon_map=False, photon_k=1000, photon_radius=0.5, exact_math=False):
+               row_stride=1, use_photon_map=False, photon_k=1000, photon_radius=0.5, exact_math=False, binary_bvh=False):
         p = Params()
         p.mode, p.spp, p.gi_depth, p.tir_budget, p.seed = mode, spp, gi_depth, tir_budget, seed
         if sample_range:
@@ -256,7 +258,7 @@ class Renderer:
             p.row_begin, p.row_end = rows
         p.row_stride = row_stride
         p.use_photon_map, p.photon_k, p.photon_radius = int(use_photon_map), photon_k, photon_radius
-        p.flags = FLAG_EXACT_MATH if exact_math else 0
+        p.flags = (FLAG_EXACT_MATH if exact_math else 0) | (FLAG_BINARY_BVH if binary_bvh else 0)
         return p
 
     def _alloc_outputs(self, want):
@@ -328,6 +330,14 @@ class Renderer:
         n = C.c_uint64()
         self._check(self._L.bhrt_launch_count(self._ctx, C.byref(n)))
         return n.value
+
+    def debug_trace_mesh(self, mesh, rays):
+        """bhrt_debug_trace_mesh: rays float32[n, 8] -> (binary, wide), float32[n, 4] each (result, z, face, front)."""
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        n = rays.shape[0]
+        a, w = np.empty((n, 4), np.float32), np.empty((n, 4), np.float32)
+        self._check(self._L.bhrt_debug_trace_mesh(self._ctx, int(mesh), n, rays.ctypes.data, a.ctypes.data, w.ctypes.data))
+        return a, w
 
     # ---- caustic photon map -------------------------------------------------------------------
     def photons_emit(self, target_stored, seed=1):

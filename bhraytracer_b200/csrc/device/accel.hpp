@@ -39,6 +39,117 @@ inline size_t accel_align(std::vector<uint8_t> &d)
     return o;
 }
 
+// Collapse the reference's binary cyBVH into the 8-wide tree of core.cuh (WideNode):
+//  * a subtree that holds at most 8 triangles becomes ONE leaf group -- its records are contiguous because
+//    cy::BVH partitions its element array in place (cyBVH.h:122-142), which is checked here, not assumed;
+//    `aux` marks where each of the reference's own leaves starts inside the group;
+//  * every other internal node starts with its two children and keeps replacing the child with the largest
+//    box surface -- in place, so the left-to-right (= the reference's DFS) order survives -- by that child's
+//    two children until it has 8 or nothing is left to open.
+// The topology of the reference tree is only regrouped, never rebuilt: every box is one of cyBVH's boxes.
+// A.wide_stack = the exact worst case of deferred entries of one traversal; 0 = no wide tree (too deep for
+// BHRT_WIDE_STACK, or element ranges that are not contiguous): the kernels then keep the binary traversal.
+inline bool build_wide(const bhrt_mesh &m, const bhrt_bvh_node *bvh, MeshAccel &A, std::vector<uint8_t> &data, std::string *err)
+{
+    (void)err;
+    const int nn = m.n_bvh_nodes;
+    // triangle range of every binary node (post-order over an explicit stack)
+    std::vector<uint32_t> first(nn + 2, 0), count(nn + 2, 0);
+    std::vector<uint8_t> contiguous(nn + 2, 1);
+    {
+        std::vector<std::pair<uint32_t, int>> st;
+        st.push_back(std::make_pair(1u, 0));
+        while (!st.empty()) {
+            const uint32_t n = st.back().first; const int phase = st.back().second;
+            const uint32_t d = bvh[n].data;
+            if (BHRT_BVH_LEAF(d)) { first[n] = BHRT_BVH_OFFSET(d); count[n] = BHRT_BVH_COUNT(d); st.pop_back(); continue; }
+            const uint32_t c1 = BHRT_BVH_CHILD(d), c2 = c1 + 1;
+            if (phase == 0) { st.back().second = 1; st.push_back(std::make_pair(c2, 0)); st.push_back(std::make_pair(c1, 0)); continue; }
+            first[n] = first[c1]; count[n] = count[c1] + count[c2];
+            contiguous[n] = contiguous[c1] && contiguous[c2] && first[c1] + count[c1] == first[c2];
+            st.pop_back();
+        }
+    }
+    A.wide_stack = 0; A.wide_nodes = 0; A.wide_root = BHRT_WIDE_EMPTY; A.wide_root_aux = 0;
+    A.wide_off = (int64_t)accel_align(data);
+    auto is_group = [&](uint32_t n) { return BHRT_BVH_LEAF(bvh[n].data) || (count[n] <= 8 && contiguous[n]); };
+    auto group_word = [&](uint32_t n, uint32_t &aux) -> uint32_t {
+        aux = 0;
+        std::vector<uint32_t> st(1, n);
+        while (!st.empty()) {
+            const uint32_t k = st.back(); st.pop_back();
+            const uint32_t d = bvh[k].data;
+            if (BHRT_BVH_LEAF(d)) { aux |= 1u << (BHRT_BVH_OFFSET(d) - first[n]); continue; }
+            st.push_back(BHRT_BVH_CHILD(d) + 1); st.push_back(BHRT_BVH_CHILD(d));
+        }
+        return 0x80000000u | ((count[n] - 1u) << 28) | first[n];
+    };
+    auto area = [&](uint32_t n) {
+        const float *b = bvh[n].box;
+        const float dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
+        return dx * dy + dy * dz + dz * dx;
+    };
+    if (is_group(1)) {                       // the whole mesh is one leaf group
+        A.wide_root = group_word(1, A.wide_root_aux);
+        A.wide_stack = 1;
+        data.resize(data.size() + sizeof(WideNode));     // (never read)
+        return true;
+    }
+    std::vector<WideNode> nodes;
+    std::vector<uint32_t> need;              // worst-case deferred entries of the subtree of each wide node
+    bool ok = true;
+    // recursive descent with an explicit stack of (binary node, wide index) pairs
+    struct Item { uint32_t bin, idx; };
+    std::vector<Item> work;
+    nodes.emplace_back(); need.push_back(0);
+    work.push_back(Item{ 1u, 0u });
+    std::vector<std::vector<uint32_t>> kids;         // internal wide children of each wide node (for `need`)
+    kids.emplace_back();
+    std::vector<uint32_t> fan(1, 0);
+    while (!work.empty()) {
+        const Item it = work.back(); work.pop_back();
+        std::vector<uint32_t> ch;
+        ch.push_back(BHRT_BVH_CHILD(bvh[it.bin].data)); ch.push_back(BHRT_BVH_CHILD(bvh[it.bin].data) + 1);
+        while (ch.size() < 8) {
+            int best = -1; float best_a = -1.f;
+            for (size_t i = 0; i < ch.size(); i++) if (!is_group(ch[i]) && area(ch[i]) > best_a) { best_a = area(ch[i]); best = (int)i; }
+            if (best < 0) break;
+            const uint32_t c1 = BHRT_BVH_CHILD(bvh[ch[best]].data);
+            ch[best] = c1; ch.insert(ch.begin() + best + 1, c1 + 1);
+        }
+        WideNode wn;
+        memset(&wn, 0, sizeof(wn));
+        for (int j = 0; j < 8; j++) wn.c[j].word = BHRT_WIDE_EMPTY;
+        fan[it.idx] = (uint32_t)ch.size();
+        for (size_t j = 0; j < ch.size(); j++) {
+            for (int k = 0; k < 6; k++) wn.c[j].box[k] = bvh[ch[j]].box[k];
+            if (is_group(ch[j])) wn.c[j].word = group_word(ch[j], wn.c[j].aux);
+            else {
+                const uint32_t idx = (uint32_t)nodes.size();
+                nodes.emplace_back(); need.push_back(0); kids.emplace_back(); fan.push_back(0);
+                wn.c[j].word = idx;
+                kids[it.idx].push_back(idx);
+                work.push_back(Item{ ch[j], idx });
+            }
+        }
+        nodes[it.idx] = wn;
+    }
+    // need(node) = (children - 1) + max over internal children; children were created after their parents
+    for (size_t i = nodes.size(); i-- > 0;) {
+        uint32_t mx = 0;
+        for (uint32_t k : kids[i]) if (need[k] > mx) mx = need[k];
+        need[i] = fan[i] - 1 + mx;
+    }
+    if (need[0] + 1 > BHRT_WIDE_STACK || nodes.size() >= 0x7fffffffu) ok = false;
+    if (!ok) { data.resize(data.size() + sizeof(WideNode)); return true; }
+    A.wide_root = 0; A.wide_root_aux = 0;
+    A.wide_stack = need[0] + 1; A.wide_nodes = (uint32_t)nodes.size();
+    const size_t o = data.size();
+    data.resize(o + nodes.size() * sizeof(WideNode));
+    memcpy(data.data() + o, nodes.data(), nodes.size() * sizeof(WideNode));
+    return true;
+}
+
 inline bool build_accel(const bhrt_scene_desc &D, AccelBlob &out, std::string *err)
 {
     out.meshes.clear();
@@ -120,6 +231,8 @@ inline bool build_accel(const bhrt_scene_desc &D, AccelBlob &out, std::string *e
             uint32_t tag = face | (axis << 30);
             memcpy(&t.c.w, &tag, 4);
         }
+        // ---- the wide tree: the same cyBVH collapsed to <= 8 children per node (fast build of the kernels)
+        if (!build_wide(m, bvh, A, out.data, err)) return false;
         out.meshes.push_back(A);
     }
     accel_align(out.data);

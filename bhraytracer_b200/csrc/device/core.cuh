@@ -175,11 +175,25 @@ struct alignas(16) TriRec { F4 a, b, c; };
 // both child boxes of one internal cyBVH node + the two child words (leaf: bit31 | (count-1) << 28 |
 // first TriRec; internal: PairNode index)
 struct alignas(64) PairNode { float box1[6], box2[6]; uint32_t word1, word2, pad0, pad1; };
+// ---- the WIDE tree (fast build, wavefront.cuh / wide.cuh): the same cyBVH collapsed to up to 8 children per
+// node (accel.hpp: build_wide).  One child = 32 bytes = two 128-bit loads: its box, its word (leaf group:
+// bit31 | (count-1) << 28 | first TriRec; internal: WideNode index; BHRT_WIDE_EMPTY: unused slot) and, for a
+// leaf group -- up to 8 triangles, the contiguous records of a whole cyBVH subtree -- `aux` = bit i set when
+// record i starts one of the reference's own leaves (the mesh shadow rule needs them, TriObj.cpp:272-291).
+// Children keep the DFS order of the binary tree, so visiting slots in order visits the reference's leaves in
+// the reference's order.
+struct alignas(32) WideChild { float box[6]; uint32_t word, aux; };
+struct alignas(256) WideNode { WideChild c[8]; };
+#define BHRT_WIDE_EMPTY 0xffffffffu
+#define BHRT_WIDE_STACK 64              // entries per traversal; a tree whose worst case needs more is not built (wide_stack = 0)
 struct MeshAccel {
     float root_box[6];
     uint32_t root_word, max_depth;          // max_depth: levels below the root (checked against BHRT_BVH_STACK at upload)
     int64_t pairs_off, tris_off;            // byte offsets into SceneView::accel_data
     int64_t vn_off, vt_off, fn_off, ft_off; // byte offsets into SceneView::mesh_data (attributes of the final hit)
+    int64_t wide_off;                       // WideNode array (accel_data)
+    uint32_t wide_root, wide_root_aux;      // word / aux of the root (a leaf group when the mesh has <= 8 triangles)
+    uint32_t wide_stack, wide_nodes;        // worst-case deferred entries of a traversal (0: no wide tree), node count
 };
 
 // ------------------------------------------------------------------------------------------
@@ -198,6 +212,7 @@ struct SceneView {
     const MeshAccel *accels;            // one per mesh
     const uint8_t *accel_data;
     int mesh_nodes[BHRT_MESH_MASK_BITS]; // node indices of the first 32 mesh nodes in DFS order
+    int use_wide;                       // every mesh has a wide tree (accel.hpp); CPU harness: traverse it (--wide)
     int n_mesh_nodes;                   // all mesh nodes of the scene graph
     const float *tex_offsets;           // 31 (x,y) pairs of the elliptical Halton filter (scene.h:322-329)
     bhrt_texcolor background, environment;
@@ -406,7 +421,9 @@ BHRT_HD void intersect_pair(const PairNode *pn, const Ray &r, float t_max, bool 
 #define BHRT_BVH_COUNT(d) ((((d) >> 28) & 0x7u) + 1)
 #define BHRT_BVH_OFFSET(d) ((d) & 0x0fffffffu)
 #define BHRT_BVH_CHILD(d) ((d) & 0x7fffffffu)
+#ifndef BHRT_BVH_STACK
 #define BHRT_BVH_STACK 64
+#endif
 
 // One traversal for both query kinds (the two heavy parts -- pair slab tests and triangle tests --
 // are shared, so a warp whose lanes mix closest-hit and shadow queries stays converged), written
@@ -435,9 +452,14 @@ struct MeshTrav {
     int hitSide;
     bool any_hit;
     bool done, result;
+#ifndef __CUDACC__
+    const WideNode *wide; uint32_t wide_root, wide_root_aux;    // CPU harness only (wide_trav_run)
+#endif
     uint32_t st_word[BHRT_BVH_STACK];
     float st_tmin[BHRT_BVH_STACK];
-    int st_hits[BHRT_BVH_STACK];
+#if !BHRT_FAST
+    int st_hits[BHRT_BVH_STACK];        // (fast build: only box-hit children are deferred, see mesh_trav_pop)
+#endif
 };
 
 BHRT_HD void mesh_trav_begin(MeshTrav &T, const SceneView &s, const MeshAccel &A, const Ray &ray, bool any_hit, float t_max_shadow,
@@ -450,6 +472,9 @@ BHRT_HD void mesh_trav_begin(MeshTrav &T, const SceneView &s, const MeshAccel &A
     if (!intersect_box(A.root_box, ray, any_hit ? BHRT_BIGFLOAT : z, tmin)) { T.done = true; return; }
     T.pairs = (const PairNode *)(s.accel_data + A.pairs_off);
     T.tris = (const TriRec *)(s.accel_data + A.tris_off);
+#ifndef __CUDACC__
+    T.wide = (const WideNode *)(s.accel_data + A.wide_off); T.wide_root = A.wide_root; T.wide_root_aux = A.wide_root_aux;
+#endif
     T.len_dir = length(ray.dir);
     T.cur = A.root_word;
     T.done = false;
@@ -464,8 +489,15 @@ BHRT_HD void mesh_trav_pop(MeshTrav &T)
     while (T.sp > 0) {
         T.sp--;
         if (!T.any_hit) {
+#if BHRT_FAST
+            // only children whose box was hit (tmin < z at that time) are deferred in this build, and z can only
+            // have shrunk through a hit in the near child since: the reference's "near child produced a hit and
+            // z <= tmin_far" is then the plain distance cull, and no hit count needs to be remembered
+            if (!(T.z > T.st_tmin[T.sp])) continue;
+#else
             bool nearHit = (T.hits != T.st_hits[T.sp]);
             if (nearHit && !(T.z > T.st_tmin[T.sp])) continue;
+#endif
         }
         T.cur = T.st_word[T.sp];
         return;
@@ -490,7 +522,13 @@ BHRT_HD void mesh_trav_internal(MeshTrav &T)
         // fewer node steps on BASELINE config 2, same image statistics.
         if (!(h1 && h2)) { T.cur = h1 ? w1 : w2; return; }
 #endif
-        if (T.sp < BHRT_BVH_STACK) { T.st_word[T.sp] = second; T.st_tmin[T.sp] = tsecond; T.st_hits[T.sp] = T.hits; T.sp++; }
+        if (T.sp < BHRT_BVH_STACK) {
+            T.st_word[T.sp] = second; T.st_tmin[T.sp] = tsecond;
+#if !BHRT_FAST
+            T.st_hits[T.sp] = T.hits;
+#endif
+            T.sp++;
+        }
         T.cur = first;
         return;
     }
@@ -518,6 +556,76 @@ BHRT_HD void mesh_trav_step(MeshTrav &T)
 {
     if (BHRT_BVH_LEAF(T.cur)) mesh_trav_leaf(T); else mesh_trav_internal(T);
 }
+
+#ifndef __CUDACC__
+// The traversal of the WIDE tree, stated for one thread (CPU harness, `emu_render --wide`): this is the
+// definition the kernels' 8-lanes-per-ray version (wide.cuh) evaluates in parallel -- lane j does the j-th
+// iteration of each `for (j ...)` loop below and ballots / shuffles replace the scalar bookkeeping.
+//   closest: children whose box is hit (tmin < z) are visited nearest first (ties: lower slot), deferred ones
+//            are dropped when tmin >= z at the time they are popped; a leaf group's records are all tested
+//            against the z the group was entered with and the nearest accepted one wins (ties: the later
+//            record, like TriObj::IntersectTriangle's `t > z` rejection met them in order);
+//   shadow:  children whose box is hit are visited in SLOT order, i.e. the reference's leaves in the
+//            reference's order; the first of the reference's leaves that holds a front-face hit decides
+//            (TraceBVHShadow, TriObj.cpp:272-291).  Like the fast build of the binary traversal, a child whose
+//            box the ray misses is not visited.
+inline void wide_trav_run(MeshTrav &T)
+{
+    uint32_t st_w[BHRT_WIDE_STACK]; float st_t[BHRT_WIDE_STACK]; uint32_t st_a[BHRT_WIDE_STACK];
+    int sp = 0;
+    uint32_t cur = T.wide_root, aux = T.wide_root_aux;
+    for (;;) {
+        if (BHRT_BVH_LEAF(cur)) {
+            const uint32_t cnt = BHRT_BVH_COUNT(cur), off = BHRT_BVH_OFFSET(cur);
+            bool hit[8]; float t[8]; bool fr[8]; MeshHit mh[8];
+            for (uint32_t j = 0; j < cnt; j++) {
+                t[j] = T.any_hit ? BHRT_BIGFLOAT : T.z;
+                hit[j] = intersect_trirec(T.tris + off + j, T.ray, T.len_dir, t[j], fr[j], T.any_hit ? (int)HIT_FRONT : T.hitSide, mh[j]);
+            }
+            if (T.any_hit) {
+                int f = -1;
+                for (uint32_t j = 0; j < cnt && f < 0; j++) if (hit[j]) f = (int)j;
+                if (f >= 0) {
+                    int b = f; while (b > 0 && !((aux >> b) & 1u)) b--;
+                    uint32_t e = (uint32_t)f + 1; while (e < cnt && !((aux >> e) & 1u)) e++;
+                    float lz = BHRT_BIGFLOAT;
+                    for (uint32_t j = (uint32_t)b; j < e; j++) if (hit[j] && t[j] < lz) lz = t[j];
+                    T.result = lz > BHRT_BIAS && lz < T.t_max_shadow; T.done = true; return;
+                }
+            } else {
+                int w = -1;
+                for (uint32_t j = 0; j < cnt; j++) if (hit[j] && (w < 0 || t[j] <= t[w])) w = (int)j;
+                if (w >= 0) { T.z = t[w]; T.front = fr[w]; T.mh = mh[w]; T.hits++; }
+            }
+        } else {
+            const WideNode &nd = T.wide[cur];
+            int order[8], n = 0; float tm[8];
+            for (int j = 0; j < 8; j++) {
+                if (nd.c[j].word == BHRT_WIDE_EMPTY) continue;
+                float tmin = -1;
+                if (!intersect_box(nd.c[j].box, T.ray, T.any_hit ? BHRT_BIGFLOAT : T.z, tmin)) continue;
+                tm[j] = tmin;
+                int k = n++;
+                if (!T.any_hit) while (k > 0 && tm[order[k - 1]] > tmin) { order[k] = order[k - 1]; k--; }
+                order[k] = j;
+            }
+            if (n > 0) {
+                for (int k = n - 1; k >= 1; k--) { st_w[sp] = nd.c[order[k]].word; st_t[sp] = tm[order[k]]; st_a[sp] = nd.c[order[k]].aux; sp++; }
+                cur = nd.c[order[0]].word; aux = nd.c[order[0]].aux;
+                continue;
+            }
+        }
+        bool found = false;
+        while (sp > 0) {
+            sp--;
+            if (!T.any_hit && !(st_t[sp] < T.z)) continue;
+            cur = st_w[sp]; aux = st_a[sp]; found = true;
+            break;
+        }
+        if (!found) { T.result = T.hits > 0; T.done = true; return; }
+    }
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // A ray query: the ONE place the estimator meets the geometry.  kind CLOSEST = recursive()
@@ -714,7 +822,12 @@ BHRT_HD bool mesh_job_harvest(MeshJob &J)
 // one action per call; returns true when the job is finished
 BHRT_HD bool mesh_job_step(MeshJob &J, const SceneView &s)
 {
-    if (!J.in_trav) { if (!mesh_job_next(J, s)) return true; }
+    if (!J.in_trav) {
+        if (!mesh_job_next(J, s)) return true;
+#ifndef __CUDACC__
+        if (s.use_wide && !J.T.done) wide_trav_run(J.T);
+#endif
+    }
     else mesh_trav_step(J.T);
     if (J.T.done) return mesh_job_harvest(J);
     return false;
@@ -1169,7 +1282,9 @@ BHRT_FN void estimate_irradiance(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad
     for (;;) {
         pm_ranges(pg, level, c, sub, R);
         const float cell_l = pg.cell / (float)(1 << level);
-        float bound2 = 0.998f * cell_l * cell_l;            // every photon this close lies in the 3x3x3 block
+        // every photon this close lies in the 3x3x3 block; at level 0 the cell edge exceeds the gather radius
+        // (photon_grid: cell >= 1.001 r), so the radius itself is the bound there
+        float bound2 = level == 0 ? r2 : 0.998f * cell_l * cell_l;
         if (bound2 > r2) bound2 = r2;
         const float scale = 32.f / bound2;
         // ---- pass A: 32-bin histogram of squared distances (and, at level 0, the plain sums)

@@ -33,7 +33,7 @@ struct PmEmitCounters {
 };
 
 __global__ void __launch_bounds__(128)
-pm_emit(SceneView s, PhotonEmitCfg cfg, unsigned long long seed, unsigned target, PhotonRecord *__restrict__ records, PmEmitCounters *cnt)
+pm_emit(SceneView s, PhotonEmitCfg cfg, unsigned long long seed, unsigned target, unsigned long long max_paths, PhotonRecord *__restrict__ records, PmEmitCounters *cnt)
 {
     const unsigned lane = threadIdx.x & 31u;
     PhotonLane P;
@@ -54,7 +54,9 @@ pm_emit(SceneView s, PhotonEmitCfg cfg, unsigned long long seed, unsigned target
             stored_now = __shfl_sync(0xffffffffu, stored_now, leader);
             base = __shfl_sync(0xffffffffu, base, leader);
             if (need) {
-                if (stored_now >= target) exhausted = true;
+                // (the reference's while-loop, Main.cpp:363, never ends when the scene cannot store a caustic photon;
+                // here the number of paths is bounded: the map then simply holds fewer photons than asked for)
+                if (stored_now >= target || base >= max_paths) exhausted = true;
                 else {
                     P.rng.seed(seed, base + __popc(nm & ((1u << lane) - 1u)), 0x50484f54u);
                     photon_begin(P, s, cfg, rays);
@@ -183,7 +185,11 @@ struct PhotonState {
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm_emit, 128, 0);
         if (per_sm < 1) per_sm = 1;
-        pm_emit<<<sm_count * per_sm, 128, 0, stream>>>(view, cfg, seed, (unsigned)target, records, counters);
+        // path budget: 4096 paths per photon asked for, at least 2^26 (config 5 needs ~30 paths per stored photon)
+        unsigned long long max_paths = 4096ull * (unsigned long long)target;
+        if (max_paths < (1ull << 26)) max_paths = 1ull << 26;
+        if (const char *e = getenv("BHRT_PHOTON_MAX_PATHS")) { const long long v = atoll(e); if (v > 0) max_paths = (unsigned long long)v; }
+        pm_emit<<<sm_count * per_sm, 128, 0, stream>>>(view, cfg, seed, (unsigned)target, max_paths, records, counters);
         launches++;
         PmEmitCounters h;
         if (cudaMemcpyAsync(&h, counters, sizeof(h), cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) {

@@ -18,12 +18,16 @@
 #include "accel.hpp"
 #include "photon.cuh"
 #include "wavefront.cuh"
+#include "wide.cuh"
 
 using namespace bhrt;
 
 // render_fast.cu: the same render kernel built with --use_fast_math (stochastic mode)
 extern "C" int bhrt_fast_prepare(int smem_bytes, int *blocks_per_sm);
 extern "C" int bhrt_fast_launch(const void *view, size_t view_bytes, const void *args, size_t args_bytes, unsigned grid, int smem_bytes, cudaStream_t stream);
+// the same with the round-1 traversal phase (one ray per thread, binary tree)
+extern "C" int bhrt_fastb_prepare(int smem_bytes, int *blocks_per_sm);
+extern "C" int bhrt_fastb_launch(const void *view, size_t view_bytes, const void *args, size_t args_bytes, unsigned grid, int smem_bytes, cudaStream_t stream);
 
 static thread_local std::string g_err;
 static int set_err(int code, const std::string &m) { g_err = m; return code; }
@@ -60,8 +64,9 @@ struct bhrt_ctx {
     int rendered_spp = 0;
     int n_materials = 0;
     DevBuf accels, accel_data;
-    bool kernel_ready = false;
-    int kernel_smem = 0, render_blocks = 1;
+    // per kernel variant (0 exact, 1 fast + wide traversal, 2 fast + binary traversal): prepared for this much shared memory
+    int kernel_smem[3] = { -1, -1, -1 }, render_blocks[3] = { 1, 1, 1 };
+    bool binary_bvh = false;                    // env BHRT_TRAVERSAL=binary
     unsigned pool_lanes = 3072;                 // lanes (camera samples in flight) per CTA, 2.3 KB of state each
     size_t last_lanes_total = 0;
     int max_frames = BHRT_MAX_FRAMES;   // depth of the estimator's stack; doubled when a frame overflowed it (launch_render)
@@ -83,6 +88,44 @@ __global__ void resolve_kernel(const float4 *__restrict__ accum, int n, float in
     linear[3 * p] = out.x; linear[3 * p + 1] = out.y; linear[3 * p + 2] = out.z;
     V3 g = gamma_correct(out);
     rgb8[3 * p] = float_to_byte(g.x); rgb8[3 * p + 1] = float_to_byte(g.y); rgb8[3 * p + 2] = float_to_byte(g.z);
+}
+
+// ---- test hook: the two mesh traversals side by side on caller-supplied rays (bhrt_debug_trace_mesh) ----
+// rays: 8 floats each -- p.xyz, dir.xyz (mesh-local), bound (closest: incoming z; shadow: t_max), kind (1 closest,
+// 2 shadow).  out: 4 floats per ray -- result (0/1), z, face id, front.
+__global__ void dbg_trace_binary(SceneView s, int mesh, int n, const float *__restrict__ rays, float *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *q = rays + 8 * (size_t)i;
+    Ray r; r.p = V3(q[0], q[1], q[2]); r.dir = V3(q[3], q[4], q[5]);
+    const bool shadow = q[7] == 2.f;
+    MeshTrav T;
+    mesh_trav_begin(T, s, s.accels[mesh], r, shadow, q[6], shadow ? BHRT_BIGFLOAT : q[6], true, shadow ? (int)HIT_FRONT : (int)HIT_FRONT_AND_BACK);
+    while (!T.done) mesh_trav_step(T);
+    float *o = out + 4 * (size_t)i;
+    o[0] = T.result ? 1.f : 0.f; o[1] = T.z; o[2] = (float)T.mh.face; o[3] = T.front ? 1.f : 0.f;
+}
+__global__ void __launch_bounds__(256)
+dbg_trace_wide(SceneView s, int mesh, int n, const float *__restrict__ rays, float *__restrict__ out)
+{
+    __shared__ OctShared shared[256 / 8];
+    const unsigned lane = threadIdx.x & 31u, sub = lane & 7u, oshift = lane & 24u;
+    const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+    const bool valid = i < n;
+    OctShared *S = shared + (threadIdx.x >> 3);
+    OctTrav T; T.done = true; T.cur = 0; T.sp = 0; T.result = false; T.z = 0; T.face = 0; T.front = true;
+    if (valid) {
+        const float *q = rays + 8 * (size_t)i;
+        Ray r; r.p = V3(q[0], q[1], q[2]); r.dir = V3(q[3], q[4], q[5]);
+        const bool shadow = q[7] == 2.f;
+        oct_begin(T, s, s.accels[mesh], r, shadow, q[6], shadow ? BHRT_BIGFLOAT : q[6], true, shadow ? (int)HIT_FRONT : (int)HIT_FRONT_AND_BACK);
+    }
+    oct_trace_mesh(T, S, valid, sub, oshift);
+    if (valid && sub == 0u) {
+        float *o = out + 4 * (size_t)i;
+        o[0] = T.result ? 1.f : 0.f; o[1] = T.z; o[2] = (float)T.face; o[3] = T.front ? 1.f : 0.f;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -117,6 +160,7 @@ int bhrt_create(int device, bhrt_ctx **out)
     if (const char *e = getenv("BHRT_TRAV")) { int x, y, z; if (sscanf(e, "%d,%d,%d", &x, &y, &z) == 3 && x >= 0 && y >= 1) { c->trav_min = x; c->trav_max = y; c->trav_pct = z; } }
     if (const char *e = getenv("BHRT_GATHER_BATCH")) { long v = atol(e); if (v >= 1) c->gather_batch = (unsigned)v; }
     if (const char *e = getenv("BHRT_MESH_BATCH")) { long v = atol(e); if (v >= 1) c->mesh_batch = (unsigned)v; }
+    if (const char *e = getenv("BHRT_TRAVERSAL")) c->binary_bvh = !strcmp(e, "binary");
     *out = c;
     return BHRT_OK;
 }
@@ -179,13 +223,24 @@ int bhrt_upload_scene(bhrt_ctx *c, const bhrt_scene_desc *d)
     c->sorted_lights = lights;
     c->photons.count = 0; c->photons.built = false;     // a photon map belongs to the scene it was traced in
     if ((r = upload(c, c->texmaps, d->texmaps, sizeof(bhrt_texmap) * d->n_texmaps))) return r;
-    if ((r = upload(c, c->textures, d->textures, sizeof(bhrt_texture) * d->n_textures))) return r;
-    // texels: RGB8 -> RGBX8 (one aligned 32-bit load per texel in the kernels)
-    if (d->texel_bytes % 3) return set_err(BHRT_ERR_ARG, "bhrt_upload_scene: texel_bytes is not a multiple of 3");
-    for (int i = 0; i < d->n_textures; i++)
-        if (d->textures[i].kind == BHRT_TEX_FILE && d->textures[i].texel_offset % 3) return set_err(BHRT_ERR_ARG, "bhrt_upload_scene: texel_offset is not a multiple of 3");
-    std::vector<uint8_t> rgbx((d->texel_bytes / 3) * 4);
-    for (size_t i = 0, n = d->texel_bytes / 3; i < n; i++) { rgbx[4 * i] = d->texels[3 * i]; rgbx[4 * i + 1] = d->texels[3 * i + 1]; rgbx[4 * i + 2] = d->texels[3 * i + 2]; rgbx[4 * i + 3] = 0; }
+    // texels: RGB8 -> RGBX8 (one aligned 32-bit load per texel in the kernels).  Every file texture is expanded
+    // from its OWN offset (any byte offset / padding between textures is fine in the descriptor); the device copy
+    // of the texture table gets texel_offset = 3 * (first RGBX8 texel), which is what texture_sample() divides by 3.
+    std::vector<bhrt_texture> dev_textures(d->textures, d->textures + d->n_textures);
+    std::vector<uint8_t> rgbx;
+    for (int i = 0; i < d->n_textures; i++) {
+        bhrt_texture &t = dev_textures[i];
+        if (t.kind != BHRT_TEX_FILE) continue;
+        const size_t n = (size_t)(t.width > 0 ? t.width : 0) * (size_t)(t.height > 0 ? t.height : 0);
+        if (t.texel_offset < 0 || (size_t)t.texel_offset + 3 * n > d->texel_bytes) return set_err(BHRT_ERR_ARG, "bhrt_upload_scene: texture texels outside the texel blob");
+        const uint8_t *src = d->texels + t.texel_offset;
+        const size_t first = rgbx.size() / 4;
+        rgbx.resize(rgbx.size() + 4 * n);
+        uint8_t *dst = rgbx.data() + 4 * first;
+        for (size_t k = 0; k < n; k++) { dst[4 * k] = src[3 * k]; dst[4 * k + 1] = src[3 * k + 1]; dst[4 * k + 2] = src[3 * k + 2]; dst[4 * k + 3] = 0; }
+        t.texel_offset = (int64_t)(3 * first);
+    }
+    if ((r = upload(c, c->textures, dev_textures.data(), sizeof(bhrt_texture) * dev_textures.size()))) return r;
     if ((r = upload(c, c->texels, rgbx.data(), rgbx.size()))) return r;
     if ((r = upload(c, c->meshes, d->meshes, sizeof(bhrt_mesh) * d->n_meshes))) return r;
     if ((r = upload(c, c->mesh_data, d->mesh_data, d->mesh_bytes))) return r;
@@ -214,6 +269,8 @@ int bhrt_upload_scene(bhrt_ctx *c, const bhrt_scene_desc *d)
     s.accel_data = (const uint8_t *)c->accel_data.p;
     c->n_materials = d->n_materials;
     fill_mesh_nodes(s, d->nodes, d->n_nodes);
+    s.use_wide = 1;
+    for (const MeshAccel &A : accel.meshes) if (!A.wide_stack) s.use_wide = 0;
     s.background = d->background; s.environment = d->environment;
     s.all_light_intensity = allI;
     s.cam_pos = fc.cam_pos; s.top_left = fc.top_left; s.dd_x = fc.dd_x; s.dd_y = fc.dd_y;
@@ -289,23 +346,27 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     a.smem_wave = al16(a.smem_offsets + 2 * (BHRT_TEX_SAMPLES - 1) * (int)sizeof(float));
     a.smem_gather = al16(a.smem_wave + wf_wave_smem_bytes(a.pool));
     // (the per-warp gather scratch only when a photon map is in use: without it the CTA stays under 32 KB)
-    const int smem_bytes = al16(a.smem_gather + (a.gather.use ? (WF_BLOCK / 32) * (int)sizeof(PmWarpScratch) + (int)a.pool * 2 : 0));
-    // stochastic frames run the fast-math build of the kernel unless the caller asks for the exact one
+    a.smem_oct = al16(a.smem_gather + (a.gather.use ? (WF_BLOCK / 32) * (int)sizeof(PmWarpScratch) + (int)a.pool * 2 : 0));
+    // stochastic frames run the fast-math build of the kernel unless the caller asks for the exact one; its
+    // traversal phase is the 8-lanes-per-ray one over the wide tree (per-octet stacks in shared memory) unless the
+    // binary one is asked for or a mesh has no wide tree
     const bool fast = p->mode == BHRT_MODE_PATH && !(p->flags & BHRT_FLAG_EXACT_MATH);
-    if (!c->kernel_ready || c->kernel_smem != smem_bytes) {
-        CU(cudaFuncSetAttribute(wf_render, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        CU(cudaFuncSetAttribute(wf_render, cudaFuncAttributePreferredSharedMemoryCarveout, (smem_bytes + 2048) * 100 / (228 * 1024) + 1));
-        int per_sm = 0, per_sm_fast = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_render, WF_BLOCK, smem_bytes));
-        if (int e = bhrt_fast_prepare(smem_bytes, &per_sm_fast)) return set_err(BHRT_ERR_CUDA, std::string("bhrt_render: ") + cudaGetErrorString((cudaError_t)e));
-        if (per_sm_fast < per_sm) per_sm = per_sm_fast;
+    const int variant = !fast ? 0 : ((c->binary_bvh || (p->flags & BHRT_FLAG_BINARY_BVH) || !c->view.use_wide) ? 2 : 1);
+    const int smem_bytes = variant == 1 ? al16(a.smem_oct + (WF_BLOCK / 8) * (int)sizeof(OctShared)) : a.smem_oct;
+    if (c->kernel_smem[variant] != smem_bytes) {
+        int per_sm = 0;
+        if (variant == 0) {
+            CU(cudaFuncSetAttribute(wf_render, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            CU(cudaFuncSetAttribute(wf_render, cudaFuncAttributePreferredSharedMemoryCarveout, (smem_bytes + 2048) * 100 / (228 * 1024) + 1));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_render, WF_BLOCK, smem_bytes));
+        } else if (int e = (variant == 1 ? bhrt_fast_prepare : bhrt_fastb_prepare)(smem_bytes, &per_sm))
+            return set_err(BHRT_ERR_CUDA, std::string("bhrt_render: ") + cudaGetErrorString((cudaError_t)e));
         if (per_sm < 1) return set_err(BHRT_ERR_LIMIT, "bhrt_render: scene tables do not fit in shared memory");
-        c->render_blocks = per_sm;
-        c->kernel_smem = smem_bytes;
-        c->kernel_ready = true;
+        c->render_blocks[variant] = per_sm;
+        c->kernel_smem[variant] = smem_bytes;
     }
     // grid: one resident CTA per slot, but no more CTAs than there is work for their pools
-    unsigned grid = (unsigned)(c->sm_count * c->render_blocks);
+    unsigned grid = (unsigned)(c->sm_count * c->render_blocks[variant]);
     {
         const unsigned long long work = (unsigned long long)n_pix_share * (unsigned long long)chunk;
         const unsigned long long need = (work + a.pool - 1) / a.pool;
@@ -334,8 +395,8 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
         a.chunk_spp = (sample_end - s0 < chunk) ? (sample_end - s0) : chunk;
         a.n_work = (unsigned long long)a.n_pix_work * (unsigned long long)a.chunk_spp;
         CU(cudaMemsetAsync(&((WaveCounters *)c->wave_counters.p)->next_work, 0, sizeof(unsigned long long), c->stream));
-        if (fast) {
-            if (int e = bhrt_fast_launch(&c->view, sizeof(c->view), &a, sizeof(a), grid, smem_bytes, c->stream))
+        if (variant) {
+            if (int e = (variant == 1 ? bhrt_fast_launch : bhrt_fastb_launch)(&c->view, sizeof(c->view), &a, sizeof(a), grid, smem_bytes, c->stream))
                 return set_err(BHRT_ERR_CUDA, std::string("wf_render (fast-math build): ") + cudaGetErrorString((cudaError_t)e));
         } else wf_render<<<grid, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a);
         wf_reduce<<<(a.n_pix_work + 255) / 256, 256, 0, c->stream>>>(c->view, a, (float4 *)c->accum.p, s0 == sample_begin ? 1 : 0);
@@ -442,6 +503,26 @@ int bhrt_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     if (r) return r;
     int spp = p->mode == BHRT_MODE_DET ? 1 : p->spp;
     return bhrt_resolve(c, spp, out);
+}
+
+int bhrt_debug_trace_mesh(bhrt_ctx *c, int32_t mesh, int32_t n, const float *rays, float *out_binary, float *out_wide)
+{
+    if (!c || !c->have_scene || !rays || n <= 0) return set_err(BHRT_ERR_ARG, "bhrt_debug_trace_mesh: bad argument");
+    if (mesh < 0 || (size_t)mesh * sizeof(MeshAccel) >= c->accels.bytes) return set_err(BHRT_ERR_ARG, "bhrt_debug_trace_mesh: bad mesh index");
+    if (!c->view.use_wide) return set_err(BHRT_ERR_STATE, "bhrt_debug_trace_mesh: the scene has a mesh without a wide tree");
+    CU(cudaSetDevice(c->device));
+    DevBuf dr, d0, d1;
+    if (dr.ensure((size_t)n * 32) || d0.ensure((size_t)n * 16) || d1.ensure((size_t)n * 16)) { dr.release(); d0.release(); d1.release(); return set_err(BHRT_ERR_CUDA, "cudaMalloc failed"); }
+    cudaMemcpyAsync(dr.p, rays, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream);
+    dbg_trace_binary<<<(n + 127) / 128, 128, 0, c->stream>>>(c->view, mesh, n, (const float *)dr.p, (float *)d0.p);
+    dbg_trace_wide<<<(unsigned)(((size_t)n * 8 + 255) / 256), 256, 0, c->stream>>>(c->view, mesh, n, (const float *)dr.p, (float *)d1.p);
+    c->launches += 2;
+    if (out_binary) cudaMemcpyAsync(out_binary, d0.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream);
+    if (out_wide) cudaMemcpyAsync(out_wide, d1.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    dr.release(); d0.release(); d1.release();
+    if (e != cudaSuccess) return set_err(BHRT_ERR_CUDA, std::string("bhrt_debug_trace_mesh: ") + cudaGetErrorString(e));
+    return BHRT_OK;
 }
 
 // ---- photon map ------------------------------------------------------------------------------

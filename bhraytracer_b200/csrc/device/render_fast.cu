@@ -9,7 +9,26 @@
 //
 // Same source, same data layout: the launcher in render.cu hands over its SceneView / WaveArgs as
 // plain bytes.
+//
+// This file is compiled TWICE (csrc/Makefile):
+//   render_fast.o      -DBHRT_FAST_WIDE=1  namespace bhrt_fast   traversal phase = 8 lanes per ray over the
+//                      8-wide collapse of the BVH with the stack in shared memory (wide.cuh) -- the default;
+//   render_fast_bin.o  -DBHRT_FAST_WIDE=0  namespace bhrt_fastb  traversal phase = one ray per thread over
+//                      the binary tree (round 1's kernel): the baseline the wide traversal is measured against
+//                      (BHRT_FLAG_BINARY_BVH / env BHRT_TRAVERSAL=binary), and the fallback for a mesh whose
+//                      BVH is too deep for the wide stack.
+#ifndef BHRT_FAST_WIDE
+#define BHRT_FAST_WIDE 1
+#endif
+#if BHRT_FAST_WIDE
 #define BHRT_NS bhrt_fast
+#define BHRT_FAST_ENTRY(name) bhrt_fast_##name
+#define BHRT_WIDE_P2 1
+#else
+#define BHRT_NS bhrt_fastb
+#define BHRT_FAST_ENTRY(name) bhrt_fastb_##name
+#define BHRT_WIDE_P2 0
+#endif
 #define BHRT_FAST 1
 #include <cuda_runtime.h>
 #include <cstring>
@@ -18,24 +37,24 @@
 extern "C" {
 
 __attribute__((visibility("hidden")))
-int bhrt_fast_prepare(int smem_bytes, int *blocks_per_sm)
+int BHRT_FAST_ENTRY(prepare)(int smem_bytes, int *blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute(bhrt_fast::wf_render, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(BHRT_NS::wf_render, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return (int)e;
     // one CTA per SM: leave L1 (where the thread-local lane copies live) all the rest
-    cudaFuncSetAttribute(bhrt_fast::wf_render, cudaFuncAttributePreferredSharedMemoryCarveout, (smem_bytes + 2048) * 100 / (228 * 1024) + 1);
-    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, bhrt_fast::wf_render, WF_BLOCK, smem_bytes);
+    cudaFuncSetAttribute(BHRT_NS::wf_render, cudaFuncAttributePreferredSharedMemoryCarveout, (smem_bytes + 2048) * 100 / (228 * 1024) + 1);
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, BHRT_NS::wf_render, WF_BLOCK, smem_bytes);
 }
 
 __attribute__((visibility("hidden")))
-int bhrt_fast_launch(const void *view, size_t view_bytes, const void *args, size_t args_bytes, unsigned grid, int smem_bytes, cudaStream_t stream)
+int BHRT_FAST_ENTRY(launch)(const void *view, size_t view_bytes, const void *args, size_t args_bytes, unsigned grid, int smem_bytes, cudaStream_t stream)
 {
-    if (view_bytes != sizeof(bhrt_fast::SceneView) || args_bytes != sizeof(bhrt_fast::WaveArgs)) return (int)cudaErrorInvalidValue;
-    bhrt_fast::SceneView v;
-    bhrt_fast::WaveArgs a;
+    if (view_bytes != sizeof(BHRT_NS::SceneView) || args_bytes != sizeof(BHRT_NS::WaveArgs)) return (int)cudaErrorInvalidValue;
+    BHRT_NS::SceneView v;
+    BHRT_NS::WaveArgs a;
     memcpy(&v, view, sizeof(v));
     memcpy(&a, args, sizeof(a));
-    bhrt_fast::wf_render<<<grid, WF_BLOCK, smem_bytes, stream>>>(v, a);
+    BHRT_NS::wf_render<<<grid, WF_BLOCK, smem_bytes, stream>>>(v, a);
     return (int)cudaGetLastError();
 }
 

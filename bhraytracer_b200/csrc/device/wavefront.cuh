@@ -34,12 +34,22 @@
 //              it completed.
 //
 // Sample colours go to a per-chunk buffer and are added to the accumulation buffer IN SAMPLE ORDER
-// by wf_reduce, so a pixel's sum is bit-identical whatever the pool size, launch geometry or GPU
-// count.
+// by wf_reduce, so on ONE GPU a pixel's sum is bit-identical whatever the pool size or launch geometry.
+// (Across GPUs the deterministic mode stays bit-identical -- each pixel is written by one rank -- while the
+// stochastic mode adds per-rank partial sums through NCCL: same samples, fp32 addition order differs.)
 #pragma once
 #include <cuda_runtime.h>
 #include <cstddef>
 #include "core.cuh"
+// BHRT_WIDE_P2: the traversal phase runs the 8-lanes-per-ray traversal of the wide BVH (wide.cuh) instead of one
+// ray per thread over the binary tree.  Set by render_fast.cu; the exact build keeps the binary tree, whose
+// visiting order is part of the deterministic mode's bit-exactness.
+#ifndef BHRT_WIDE_P2
+#define BHRT_WIDE_P2 0
+#endif
+#if BHRT_WIDE_P2
+#include "wide.cuh"
+#endif
 
 namespace BHRT_NS {
 
@@ -119,7 +129,7 @@ struct WaveArgs {
     unsigned mesh_batch;        // queued rays that switch the traversal phase on
     unsigned gather_batch;      // parked caustic queries that switch the gather phase on
     int trav_min, trav_max, trav_pct;   // internal-node steps per trip: at least / at most / until this % of the job lanes is still at an internal node
-    int smem_nodes, smem_materials, smem_lights, smem_offsets, smem_wave, smem_gather;   // byte offsets into dynamic shared memory
+    int smem_nodes, smem_materials, smem_lights, smem_offsets, smem_wave, smem_gather, smem_oct;   // byte offsets into dynamic shared memory
 };
 
 // dynamic shared memory needed by the CTA-local wavefront for `pool` lanes
@@ -244,7 +254,9 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
             }
         }
         const float cell_l = pg.cell / (float)(1 << level);
-        float bound2 = 0.998f * cell_l * cell_l;
+        // every photon this close lies in the 3x3x3 block; at level 0 the cell edge exceeds the gather radius
+        // (photon_grid: cell >= 1.001 r), so the radius itself is the bound there
+        float bound2 = level == 0 ? r2 : 0.998f * cell_l * cell_l;
         if (bound2 > r2) bound2 = r2;
         // a cell farther from the query than the search bound holds nothing of interest (the corners of
         // the block, mostly): skip it
@@ -429,7 +441,16 @@ wf_render(SceneView s, WaveArgs a)
     __syncthreads();
 
     RayCounters rc; rc.closest = 0; rc.shadow = 0;
+#if BHRT_WIDE_P2
+    // this OCTET's BVH traversal, kept across iterations (identical in its 8 lanes)
+    OctTrav OT; OT.done = true; OT.cur = 0; OT.sp = 0;
+    OctShared *const OS = (OctShared *)(smem + a.smem_oct) + (tid >> 3);
+    const unsigned sub = lane & 7u, oshift = lane & 24u;
+    uint32_t jmask = 0; int jextra = 0, jk = -1, jkind = Q_NONE;
+    bool in_trav = false, jblocked = false;
+#else
     MeshJob J;                      // this thread's BVH traversal, kept across iterations
+#endif
     bool have = false;
     unsigned jid = 0;
     bool first = true;
@@ -630,6 +651,99 @@ wf_render(SceneView s, WaveArgs a)
             // is still running after that stays in its thread until the next traversal phase
             const unsigned tail = mq_tail;
             int budget = n_live_s == 0 ? 64 : a.mesh_budget;    // nothing else to do: stay in the traversal
+#if BHRT_WIDE_P2
+            // ---- eight lanes per ray over the wide tree (wide.cuh).  A job is owned by an OCTET: everything below
+            // is octet-uniform except the per-child / per-triangle work inside oct_internal / oct_leaf.
+            for (;;) {
+                const bool need = !have;
+                const unsigned nm = __ballot_sync(0xffffffffu, need && sub == 0u);
+                unsigned head = 0;
+                if (lane == 0) head = *(volatile unsigned *)&mq_head;
+                head = __shfl_sync(0xffffffffu, head, 0);
+                const bool drained = head >= tail;
+                if (nm && !drained) {
+                    const int leader = __ffs(nm) - 1;
+                    unsigned base = 0;
+                    if ((int)lane == leader) base = atomicAdd(&mq_head, (unsigned)__popc(nm));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (need) {
+                        const unsigned i = base + __popc(nm & ((1u << oshift) - 1u));
+                        if (i < tail) {
+                            jid = mq[i % P];
+                            const Lane &Lg = lanes[jid];
+                            // mesh_job_begin (core.cuh)
+                            OS->hz = Lg.hit.z; OS->hnode = Lg.hit.node; OS->hfront = Lg.hit.front ? 1 : 0;
+                            OS->hface = 0; OS->ha0 = OS->ha1 = OS->ha2 = 0.f;
+                            jmask = Lg.mesh_mask;
+                            jextra = s.n_mesh_nodes > BHRT_MESH_MASK_BITS ? s.mesh_nodes[BHRT_MESH_MASK_BITS - 1] + 1 : s.n_nodes;
+                            have = true; in_trav = false; jblocked = false;
+                        }
+                    }
+                }
+                if (!__any_sync(0xffffffffu, have)) break;
+                // job control: the next mesh node of the ray (mesh_job_next), or none left: finished
+                bool finished = false;
+                if (have && !in_trav) {
+                    int k = -1;
+                    if (jmask) { k = s.mesh_nodes[__ffs(jmask) - 1]; jmask &= jmask - 1u; }
+                    else {
+                        while (jextra < s.n_nodes && s.nodes[jextra].kind != BHRT_OBJ_MESH) jextra++;
+                        if (jextra < s.n_nodes) k = jextra++;
+                    }
+                    if (k < 0) finished = true;
+                    else {
+                        Query q;
+                        wf_load(q, &lanes[jid].q);
+                        jk = k; jkind = q.kind;
+                        const Ray r = node_local_ray(s, k, q.ray);
+                        const MeshAccel &A = s.accels[s.nodes[k].mesh];
+                        if (q.kind == Q_SHADOW) oct_begin(OT, s, A, r, true, q.t_max, BHRT_BIGFLOAT, true, q.hitSide);
+                        else {
+                            // an equal-t candidate of an EARLIER node loses against the current winner
+                            const float hz = OS->hz;
+                            oct_begin(OT, s, A, r, false, 0.f, OS->hnode > k ? prev_float(hz) : hz, OS->hfront != 0, q.hitSide);
+                        }
+                        in_trav = true;
+                    }
+                }
+                // internal nodes while most octets are at one, then the leaf groups of all octets that reached one
+                for (int r = 0; r < a.trav_max; r++) {
+                    const bool in_job = have && in_trav && !OT.done;
+                    const bool go = in_job && !BHRT_BVH_LEAF(OT.cur);
+                    const unsigned gm = __ballot_sync(0xffffffffu, go), jm = __ballot_sync(0xffffffffu, in_job);
+                    if (!gm || (r >= a.trav_min && 100 * __popc(gm) <= a.trav_pct * __popc(jm))) break;
+                    oct_internal(OT, OS, go, sub, oshift);
+                }
+                {
+                    const bool at_leaf = have && in_trav && !OT.done && BHRT_BVH_LEAF(OT.cur);
+                    if (__any_sync(0xffffffffu, at_leaf)) oct_leaf(OT, OS, at_leaf, sub, oshift);
+                }
+                // mesh_job_harvest
+                if (have && in_trav && OT.done) {
+                    in_trav = false;
+                    if (OT.result) {
+                        if (jkind == Q_SHADOW) { jblocked = true; finished = true; }
+                        else { OS->hz = OT.z; OS->hfront = OT.front ? 1 : 0; OS->hnode = jk; OS->hface = OT.face; OS->ha0 = OT.a0; OS->ha1 = OT.a1; OS->ha2 = OT.a2; }
+                    }
+                }
+                if (finished) {
+                    if (sub == 0u) {
+                        Lane &Lg = lanes[jid];
+                        if (jblocked) Lg.hit_ok = true;
+                        else if (jkind == Q_CLOSEST) {
+                            const int hn = OS->hnode;
+                            Lg.hit.z = OS->hz; Lg.hit.node = hn; Lg.hit.front = OS->hfront != 0;
+                            Lg.hit.uvw = V3(OS->ha0, OS->ha1, OS->ha2); Lg.hit.duvw0.x = u2f(OS->hface);
+                            lkey[jid] = (unsigned char)wf_key_patch(s, lkey[jid], hn);
+                        }
+                        pend[jid] = 0;
+                        atomicSub(&n_pending_s, 1u);
+                    }
+                    have = false;
+                }
+                if (drained && --budget <= 0) break;
+            }
+#else
             for (;;) {
                 const bool need = !have;
                 const unsigned nm = __ballot_sync(0xffffffffu, need);
@@ -684,6 +798,7 @@ wf_render(SceneView s, WaveArgs a)
                 }
                 if (drained && --budget <= 0) break;
             }
+#endif
             __syncthreads();
             if (tid == 0 && mq_head > mq_tail) mq_head = mq_tail;       // over-claimed pops of an empty queue
             { const long long c = clock64(); t_mesh += c - c_mark; c_mark = c; }

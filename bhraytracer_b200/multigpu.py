@@ -78,7 +78,10 @@ class GpuEngine:
         return self.r.render_device(self.r.params(**kw))
 
     def reduce_buffers(self, det):
-        return [self.accum, self.hit_id, self.z] if det else [self.accum]
+        # hit_id / z are the AOVs of sample 0: in the stochastic mode only the rank that owns sample 0 writes
+        # them (zeros elsewhere, render.cu), in the deterministic mode every rank writes its own rows -- a sum
+        # all-reduce assembles them on every rank either way (x + 0 is exact)
+        return [self.accum, self.hit_id, self.z]
 
     def resolve(self, total_spp, want):
         return self.r.resolve(total_spp, want=want)
@@ -107,8 +110,11 @@ class GpuEngine:
 
 class DistributedRenderer:
     """BeginRender() across the ranks of a process group.  Every rank calls `render` with the same
-    arguments; every rank ends up with the full frame in its device buffers, rank `dst` gets host
-    copies of the requested outputs (other ranks get `{}` plus the counters)."""
+    arguments; every rank ends up with the full frame (accumulation buffer and the sample-0 AOVs hit_id / z)
+    in its device buffers, rank `dst` gets host copies of the requested outputs (other ranks get `{}` plus
+    the counters).  Deterministic frames are bit-identical whatever the world size; stochastic frames hold
+    the same SAMPLES whatever the world size, but the per-rank partial sums and NCCL's reduction change the
+    fp32 addition order, so the pixel sums agree to rounding (a few 1e-7), not in bits."""
 
     def __init__(self, engine, group=None):
         import torch.distributed as dist
@@ -175,18 +181,26 @@ class DistributedRenderer:
         if self.world == 1:
             eng.photons_build(stored)
             return stored, rays
-        rec = eng.photon_records()                     # uint8 tensor [stored * 24] on the engine's device
-        cnt = torch.tensor([stored, rays], dtype=torch.int64, device=rec.device)
-        cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
-        self.dist.all_gather(cnts, cnt, group=self.group)
-        counts = [int(c[0]) for c in cnts]
-        mx = max(counts)
-        pad = torch.zeros(mx * 24, dtype=torch.uint8, device=rec.device)
-        pad[:stored * 24] = rec[:stored * 24]
-        parts = [torch.empty_like(pad) for _ in range(self.world)]
-        self.dist.all_gather(parts, pad, group=self.group)
-        allrec = torch.cat([p[:c * 24] for p, c in zip(parts, counts)])
-        total = sum(counts)
-        eng.photons_set(allrec, total)
+        # Everything between the emission and photons_set runs ON THE ENGINE'S STREAM: photons_set copies
+        # out of `allrec` with a cudaMemcpyAsync on that stream, so the pad / all_gather / cat that produce
+        # it must be ordered before it (on torch's default stream nothing would order them).
+        import contextlib
+        stream = getattr(eng, "stream", None)
+        ctx = eng.torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+        with ctx:
+            rec = eng.photon_records()                     # uint8 tensor [stored * 24] on the engine's device
+            cnt = torch.tensor([stored, rays], dtype=torch.int64, device=rec.device)
+            cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
+            self.dist.all_gather(cnts, cnt, group=self.group)
+            counts = [int(c[0]) for c in cnts]
+            mx = max(counts)
+            pad = torch.zeros(mx * 24, dtype=torch.uint8, device=rec.device)
+            pad[:stored * 24] = rec[:stored * 24]
+            parts = [torch.empty_like(pad) for _ in range(self.world)]
+            self.dist.all_gather(parts, pad, group=self.group)
+            allrec = torch.cat([p[:c * 24] for p, c in zip(parts, counts)])
+            total = sum(counts)
+            eng.photons_set(allrec, total)                 # synchronises the stream before it returns
         eng.photons_build(total)
+        del allrec, parts, pad
         return total, int(sum(int(c[1]) for c in cnts))

@@ -189,6 +189,12 @@ typedef struct bhrt_params {
  * root and transcendentals and with FMA contraction.  This flag selects the exact build (IEEE
  * operations in the reference's order) for it as well.  The deterministic mode is always exact. */
 #define BHRT_FLAG_EXACT_MATH 1u
+/* The fast build traverses triangle meshes eight lanes per ray over an 8-wide regrouping of the reference's
+ * BVH (same boxes, same leaf order).  This flag selects the round-1 traversal instead -- one ray per thread
+ * over the binary tree -- for A/B measurements; it is also what runs when a mesh's BVH is too deep for the
+ * wide traversal's stack.  No effect on the exact build, which always walks the binary tree in the
+ * reference's visiting order.  Environment override: BHRT_TRAVERSAL=binary. */
+#define BHRT_FLAG_BINARY_BVH 2u
 
 /* Any pointer may be NULL to skip that output.  Layouts follow the reference's
  * colorArray / RenderImage (Main.cpp:202,229-230): row-major, j*W+i, row 0 at the top. */
@@ -247,9 +253,20 @@ int bhrt_set_stream(bhrt_ctx *ctx, void *cuda_stream);
 /* Number of kernels this ctx has launched since bhrt_create (bench.py's gpu_launches). */
 int bhrt_launch_count(bhrt_ctx *ctx, uint64_t *launches);
 
+/* TEST HOOK (tests/test_gpu_wide_bvh.py): trace n caller-supplied rays against triangle mesh `mesh` of the
+ * uploaded scene with BOTH mesh traversals of the library, in exact arithmetic -- one ray per thread over the
+ * binary tree (TriObj::TraceBVHNode / TraceBVHShadow made iterative, reference TriObj.cpp:192-307) and eight
+ * lanes per ray over its 8-wide regrouping -- so that a test can compare them ray by ray.
+ * rays: float[n*8] = origin xyz, direction xyz (mesh-local space), bound (closest: the incoming hit distance,
+ * shadow: t_max), kind (1 closest, 2 shadow).  out_*: float[n*4] = result (0/1), z, face id, front. */
+int bhrt_debug_trace_mesh(bhrt_ctx *ctx, int32_t mesh, int32_t n, const float *rays, float *out_binary, float *out_wide);
+
 /* Caustic photon map (reference Main.cpp:342-386, cyPhotonMap.h).
  * emit: traces photons until `target_stored` are stored on this GPU; records are the
- * reference's 24-byte Photon (cyPhotonMap.h:72-80) with UNSCALED power.
+ * reference's 24-byte Photon (cyPhotonMap.h:72-80) with UNSCALED power.  The reference's loop
+ * (Main.cpp:363) never ends when the scene cannot store a caustic photon; here the number of photon
+ * paths is bounded (4096 per photon asked for, at least 2^26; env BHRT_PHOTON_MAX_PATHS), and *stored
+ * then comes back smaller than target_stored (possibly 0) with status BHRT_OK.
  * photons_get/set: device<->host copies of the raw records (for an NCCL all-gather done by
  * the host).  build: scales powers by 1/total_stored (Main.cpp:380) and builds the gather
  * structure over the photons currently set. */

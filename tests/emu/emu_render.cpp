@@ -60,7 +60,7 @@ int main(int argc, char **argv)
     const char *photon_file = nullptr; int photon_total = 1, photon_k = 1000; float photon_radius = 0.5f;
     const char *query_in = nullptr, *query_out = nullptr;
     const char *pixel_rays = nullptr;
-    int max_frames = 0;
+    int max_frames = 0, wide = 0;
     unsigned long long seed = 1;
     for (int a = 3; a < argc; a++) {
         if (!strcmp(argv[a], "--det")) det = 1;
@@ -74,6 +74,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[a], "--photons") && a + 4 < argc) { photon_file = argv[++a]; photon_total = atoi(argv[++a]); photon_k = atoi(argv[++a]); photon_radius = (float)atof(argv[++a]); }
         else if (!strcmp(argv[a], "--pixel-rays") && a + 1 < argc) pixel_rays = argv[++a];
         else if (!strcmp(argv[a], "--max-frames") && a + 1 < argc) max_frames = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--wide")) wide = 1;
         else if (!strcmp(argv[a], "--queries") && a + 2 < argc) { query_in = argv[++a]; query_out = argv[++a]; }
         else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
     }
@@ -105,6 +106,14 @@ int main(int argc, char **argv)
     AccelBlob accel;
     if (!build_accel(D, accel, &err)) { fprintf(stderr, "accel: %s\n", err.c_str()); return 3; }
     s.accels = accel.meshes.data(); s.accel_data = accel.data.data();
+    if (wide) {
+        // traverse the 8-wide collapse of the BVH (the structure the kernels' fast build uses) instead of the binary tree
+        s.use_wide = 1;
+        for (auto &A : accel.meshes) {
+            if (!A.wide_stack) { fprintf(stderr, "--wide: a mesh has no wide tree\n"); return 3; }
+            fprintf(stderr, "wide tree: %u nodes, worst-case stack %u\n", A.wide_nodes, A.wide_stack);
+        }
+    }
     s.background = D.background; s.environment = D.environment;
     s.all_light_intensity = allI;
     s.cam_pos = fc.cam_pos; s.top_left = fc.top_left; s.dd_x = fc.dd_x; s.dd_y = fc.dd_y;
@@ -224,7 +233,8 @@ int main(int argc, char **argv)
             linear[3 * p] = out.x; linear[3 * p + 1] = out.y; linear[3 * p + 2] = out.z;
             V3 g = gamma_correct(out);
             rgb8[3 * p] = float_to_byte(g.x); rgb8[3 * p + 1] = float_to_byte(g.y); rgb8[3 * p + 2] = float_to_byte(g.z);
-            hitid[p] = id0; z[p] = z0;
+            // like render.cu: the AOVs of sample 0 are written by the share that owns sample 0, zeros elsewhere
+            if (smp_b == 0) { hitid[p] = id0; z[p] = z0; }
             closest += rc.closest; shadow += rc.shadow; overflowed += rc.overflow;
             pixrays[2 * p] = (uint32_t)rc.closest; pixrays[2 * p + 1] = (uint32_t)rc.shadow;
         }

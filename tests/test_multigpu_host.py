@@ -56,7 +56,7 @@ class EmuEngine:
         return dict(rays_closest=info["rays_closest"], rays_shadow=info["rays_shadow"], kernel_ms=info["ms"])
 
     def reduce_buffers(self, det):
-        return [self.accum, self.hit_id, self.z] if det else [self.accum]
+        return [self.accum, self.hit_id, self.z]
 
     def resolve(self, total_spp, want):
         acc = self.accum.numpy().reshape(H, W, 4)
@@ -104,6 +104,10 @@ def _worker(rank, world, port, tmp, q):
         res["path_rays"] = (pth["rays_closest"], pth["rays_shadow"])
         if rank == 0:
             res["path_accum"] = pth["accum"]
+        # the sample-0 AOVs reach a destination rank that does not own sample 0 (they were all zero there)
+        pth1 = dr.render(mode=0, spp=5, seed=9, want=("linear",), dst=1)
+        if rank == 1:
+            res["path_hit_dst1"], res["path_z_dst1"] = pth1["hit_id"], pth1["z"]
         # photons: sharded emission, all-gather, same full map on every rank
         eng2 = EmuEngine(os.path.join("scenes", "det_caustics.xml"), tmp, "p%d" % rank)
         dr2 = mg.DistributedRenderer(eng2)
@@ -180,6 +184,8 @@ def test_two_ranks_sample_ranges_sum_to_the_single_process_frame(two_ranks):
     assert (a[:, :, 3] == 5).all()                       # every pixel got all 5 samples, once
     assert np.allclose(a[:, :, :3], acc[:, :, :3], rtol=0, atol=4e-6)           # (s0+s1+s2) + (s3+s4) vs s0+..+s4
     assert out[0]["path_rays"] == out[1]["path_rays"] == (info["rays_closest"], info["rays_shadow"])
+    assert (out[1]["path_hit_dst1"] == aov["hit_id"]).all()
+    assert (out[1]["path_z_dst1"].view(np.uint32) == aov["z"].view(np.uint32)).all()
 
 
 def test_two_ranks_photon_all_gather(two_ranks):
