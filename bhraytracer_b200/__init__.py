@@ -62,7 +62,7 @@ class SceneDesc(C.Structure):
 
 
 FLAG_EXACT_MATH = 1      # BHRT_FLAG_EXACT_MATH
-FLAG_BINARY_BVH = 2      # BHRT_FLAG_BINARY_BVH
+FLAG_WIDE_BVH = 2        # BHRT_FLAG_WIDE_BVH
 
 
 class Params(C.Structure):
@@ -146,7 +146,7 @@ def device_lib():
         L.bhrt_photons_set.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int]
         L.bhrt_photons_get.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         L.bhrt_photons_build.argtypes = [C.c_void_p, C.c_int32]
-        L.bhrt_debug_trace_mesh.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bhrt_debug_trace_mesh.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _dev = L
     return _dev
 
@@ -249,7 +249,7 @@ class Renderer:
 
     @staticmethod
     def params(mode=MODE_PATH, spp=32, gi_depth=3, tir_budget=16, seed=1, sample_range=None, rows=None,
-               row_stride=1, use_photon_map=False, photon_k=1000, photon_radius=0.5, exact_math=False, binary_bvh=False):
+               row_stride=1, use_photon_map=False, photon_k=1000, photon_radius=0.5, exact_math=False, wide_bvh=False):
         p = Params()
         p.mode, p.spp, p.gi_depth, p.tir_budget, p.seed = mode, spp, gi_depth, tir_budget, seed
         if sample_range:
@@ -258,7 +258,7 @@ class Renderer:
             p.row_begin, p.row_end = rows
         p.row_stride = row_stride
         p.use_photon_map, p.photon_k, p.photon_radius = int(use_photon_map), photon_k, photon_radius
-        p.flags = (FLAG_EXACT_MATH if exact_math else 0) | (FLAG_BINARY_BVH if binary_bvh else 0)
+        p.flags = (FLAG_EXACT_MATH if exact_math else 0) | (FLAG_WIDE_BVH if wide_bvh else 0)
         return p
 
     def _alloc_outputs(self, want):
@@ -336,7 +336,9 @@ class Renderer:
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
         n = rays.shape[0]
         a, w = np.empty((n, 4), np.float32), np.empty((n, 4), np.float32)
-        self._check(self._L.bhrt_debug_trace_mesh(self._ctx, int(mesh), n, rays.ctypes.data, a.ctypes.data, w.ctypes.data))
+        ms = np.zeros(2, np.float32)
+        self._check(self._L.bhrt_debug_trace_mesh(self._ctx, int(mesh), n, rays.ctypes.data, a.ctypes.data, w.ctypes.data, ms.ctypes.data))
+        self.debug_trace_ms = (float(ms[0]), float(ms[1]))      # device time of the binary / the wide pass
         return a, w
 
     # ---- caustic photon map -------------------------------------------------------------------

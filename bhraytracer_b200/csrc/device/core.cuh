@@ -88,7 +88,27 @@ BHRT_HD bool is_nan(float v) { return v != v; }
 // (+7 % in the exact build, +15 % in the fast one); what must stay out of line in the exact build is
 // the libm-grade transcendentals and the texture filter
 #define BHRT_EST_FN BHRT_HD
+#if BHRT_FAST && defined(__CUDA_ARCH__)
+// powf under --use_fast_math is exp2(b * log2(a)): NaN for every negative base, where powf gives +-|a|^b when b is
+// an integer -- and glossiness values are (20, 100, 20000 ...).  The Blinn lobe pow(vH.vN, glossiness) meets
+// negative bases all the time in the caustic term (vL = mean photon direction points INTO the surface,
+// MtlBlinn.cpp:333-338): the NaN then wiped out the whole direct term of diffuse materials (0 * NaN), and the
+// photon-mapped frame of the fast build came out at less than half its brightness (found by the round-2
+// convergence test on BASELINE config 5).  Same special cases as powf for the arguments this code can see.
+BHRT_HD float m_pow(float a, float b)
+{
+    if (b == 0.f) return 1.f;
+    float r = __powf(fabsf(a), b);
+    if (a < 0.f) {
+        const float t = truncf(b);
+        if (t != b) r = __int_as_float(0x7fffffff);
+        else if (fmodf(t, 2.f) != 0.f) r = -r;
+    }
+    return r;
+}
+#else
 BHRT_MATH_FN float m_pow(float a, float b) { return powf(a, b); }
+#endif
 BHRT_MATH_FN float m_sin(float a) { return sinf(a); }
 BHRT_MATH_FN float m_cos(float a) { return cosf(a); }
 BHRT_MATH_FN float m_tan(float a) { return tanf(a); }
@@ -660,7 +680,7 @@ struct alignas(16) Query {
 // Shadow quirks kept: sphere ignored when the origin is inside (GenLight.cpp:36-37), plane
 // bounds tested with the PARENT-space ray (:54), no rayDz == 0 test (:50).
 // returns true when a SHADOW query is already answered "blocked"
-BHRT_HD bool scene_trace_graph(const SceneView &s, const Query &q, Hit &h, uint32_t &mesh_mask)
+BHRT_HD bool scene_trace_graph(const SceneView &s, const Query &q, Hit &h, uint32_t &mesh_mask, Ray *first_mesh_ray = 0)
 {
     const bool shadow = (q.kind == Q_SHADOW);
     // the rays in the space of the current ancestors: depths 1 and 2 (every repository scene) stay in
@@ -727,7 +747,10 @@ BHRT_HD bool scene_trace_graph(const SceneView &s, const Query &q, Hit &h, uint3
             // only the root box here; nodes beyond the mask are picked up by scene_trace_meshes
             if (mesh_ordinal < BHRT_MESH_MASK_BITS) {
                 float tmin = -1;
-                if (intersect_box(A.root_box, r, shadow ? BHRT_BIGFLOAT : h.z, tmin)) mesh_mask |= 1u << mesh_ordinal;
+                if (intersect_box(A.root_box, r, shadow ? BHRT_BIGFLOAT : h.z, tmin)) {
+                    if (first_mesh_ray && !mesh_mask) *first_mesh_ray = r;      // the ray in the space of the first mesh it entered
+                    mesh_mask |= 1u << mesh_ordinal;
+                }
             }
             mesh_ordinal++;
         }
@@ -844,6 +867,10 @@ BHRT_HD bool scene_trace_meshes(const SceneView &s, const Query &q, Hit &h, uint
 }
 
 // Winner-only part of the closest hit: complete HitInfo in local space, then FromNodeCoords
+// (kept out of line in both builds.  Measured in round 2: inlining it in the fast build -- which lets the compiler
+// keep the stepping thread's Lane in registers instead of local memory, since no reference to it escapes any more
+// -- LOWERED config 2 from 1570 to 1440 Mrays/s: at the 64-register cap the promoted fields come back as spills,
+// 1322 instead of 390 bytes, and the compiler's spill placement is worse than the plain local-memory copy.)
 BHRT_FN bool scene_trace_finish(const SceneView &s, const Query &q, Hit &h)
 {
     if (h.node < 0) return false;
@@ -1447,10 +1474,15 @@ struct alignas(16) Lane {
     // stage of the top recursion level; a level below the top waits for the child above it, either in
     // ST_REFR_WAIT or in ST_GI_WAIT: one bit each (the frames themselves live apart)
     uint8_t top_stage;
-    uint8_t gi_wait[15];    // bit i: level i is in ST_GI_WAIT (else ST_REFR_WAIT)
+    uint8_t pad_stage[3];
+    uint32_t gi_wait[3];    // bit i: level i is in ST_GI_WAIT (else ST_REFR_WAIT).  Three words addressed by selects, never
+                            // by a run-time index: a dynamically indexed member would pin the whole Lane in local memory
     Hit hit;                // the query's answer; only its first 32 bytes are persistent
     // ---- not copied
     LaneCold cold;
+    // what the 8-lanes-per-ray traversal (wide.cuh) needs to start on the pending query, left by the lanes pass: the
+    // ray in the space of the first mesh whose root box it entered, kind | hitSide << 8, t_max -- two 128-bit loads
+    Ray mesh_ray; int mesh_kind; float mesh_tmax;
 };
 #define BHRT_LANE_PERSIST 176
 // The recursion levels of one lane: the estimator only ever touches the top frame and, when it
@@ -1461,9 +1493,12 @@ BHRT_HD int lane_stage(const Lane &L) { return L.top_stage; }
 BHRT_HD void lane_push(Lane &L, int child_stage)
 {
     const int i = L.sp - 1;         // the level that now waits for the child
-    if (i >= 0 && i < 120) {        // (a GI child exists only while f.gi >= 0, i.e. on the first gi_depth + 1 levels)
-        const uint8_t bit = (uint8_t)(1u << (i & 7));
-        if (L.top_stage == ST_GI_WAIT) L.gi_wait[i >> 3] |= bit; else L.gi_wait[i >> 3] &= (uint8_t)~bit;
+    if (i >= 0 && i < 96) {         // (a GI child exists only while f.gi >= 0, i.e. on the first gi_depth + 1 levels)
+        const uint32_t bit = 1u << (i & 31), set = L.top_stage == ST_GI_WAIT ? bit : 0u;
+        const int w = i >> 5;
+        if (w == 0) L.gi_wait[0] = (L.gi_wait[0] & ~bit) | set;
+        else if (w == 1) L.gi_wait[1] = (L.gi_wait[1] & ~bit) | set;
+        else L.gi_wait[2] = (L.gi_wait[2] & ~bit) | set;
     }
     L.top_stage = (uint8_t)child_stage;
     L.sp++;
@@ -1471,7 +1506,11 @@ BHRT_HD void lane_push(Lane &L, int child_stage)
 BHRT_HD void lane_pop(Lane &L)
 {
     L.sp--;
-    if (L.sp > 0) { const int i = L.sp - 1; L.top_stage = (i < 120 && ((L.gi_wait[i >> 3] >> (i & 7)) & 1)) ? ST_GI_WAIT : ST_REFR_WAIT; }
+    if (L.sp > 0) {
+        const int i = L.sp - 1, w = i >> 5;
+        const uint32_t word = w == 0 ? L.gi_wait[0] : (w == 1 ? L.gi_wait[1] : (w == 2 ? L.gi_wait[2] : 0u));
+        L.top_stage = ((word >> (i & 31)) & 1u) ? ST_GI_WAIT : ST_REFR_WAIT;
+    }
 }
 
 BHRT_HD void frame_begin(Frame &f, const SceneView &s, V3 ray_p, const Hit &h, int bounce, int gi)

@@ -66,7 +66,7 @@ struct bhrt_ctx {
     DevBuf accels, accel_data;
     // per kernel variant (0 exact, 1 fast + wide traversal, 2 fast + binary traversal): prepared for this much shared memory
     int kernel_smem[3] = { -1, -1, -1 }, render_blocks[3] = { 1, 1, 1 };
-    bool binary_bvh = false;                    // env BHRT_TRAVERSAL=binary
+    int traversal = 0;                          // env BHRT_TRAVERSAL: 1 = wide, 2 = binary, 0 = what the flags say
     unsigned pool_lanes = 3072;                 // lanes (camera samples in flight) per CTA, 2.3 KB of state each
     size_t last_lanes_total = 0;
     int max_frames = BHRT_MAX_FRAMES;   // depth of the estimator's stack; doubled when a frame overflowed it (launch_render)
@@ -160,7 +160,7 @@ int bhrt_create(int device, bhrt_ctx **out)
     if (const char *e = getenv("BHRT_TRAV")) { int x, y, z; if (sscanf(e, "%d,%d,%d", &x, &y, &z) == 3 && x >= 0 && y >= 1) { c->trav_min = x; c->trav_max = y; c->trav_pct = z; } }
     if (const char *e = getenv("BHRT_GATHER_BATCH")) { long v = atol(e); if (v >= 1) c->gather_batch = (unsigned)v; }
     if (const char *e = getenv("BHRT_MESH_BATCH")) { long v = atol(e); if (v >= 1) c->mesh_batch = (unsigned)v; }
-    if (const char *e = getenv("BHRT_TRAVERSAL")) c->binary_bvh = !strcmp(e, "binary");
+    if (const char *e = getenv("BHRT_TRAVERSAL")) c->traversal = !strcmp(e, "wide") ? 1 : (!strcmp(e, "binary") ? 2 : 0);
     *out = c;
     return BHRT_OK;
 }
@@ -348,11 +348,13 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     // (the per-warp gather scratch only when a photon map is in use: without it the CTA stays under 32 KB)
     a.smem_oct = al16(a.smem_gather + (a.gather.use ? (WF_BLOCK / 32) * (int)sizeof(PmWarpScratch) + (int)a.pool * 2 : 0));
     // stochastic frames run the fast-math build of the kernel unless the caller asks for the exact one; its
-    // traversal phase is the 8-lanes-per-ray one over the wide tree (per-octet stacks in shared memory) unless the
-    // binary one is asked for or a mesh has no wide tree
+    // traversal phase is one ray per thread over the binary tree, or -- BHRT_FLAG_WIDE_BVH -- 8 lanes per ray over
+    // the wide tree (per-octet stacks in shared memory) when every mesh has one and the stacks fit
     const bool fast = p->mode == BHRT_MODE_PATH && !(p->flags & BHRT_FLAG_EXACT_MATH);
-    const int variant = !fast ? 0 : ((c->binary_bvh || (p->flags & BHRT_FLAG_BINARY_BVH) || !c->view.use_wide) ? 2 : 1);
-    const int smem_bytes = variant == 1 ? al16(a.smem_oct + (WF_BLOCK / 8) * (int)sizeof(OctShared)) : a.smem_oct;
+    const bool want_wide = c->traversal ? c->traversal == 1 : (p->flags & BHRT_FLAG_WIDE_BVH) != 0;
+    const int smem_wide = al16(a.smem_oct + (WF_BLOCK / 8) * (int)sizeof(OctShared));
+    const int variant = !fast ? 0 : ((want_wide && c->view.use_wide && smem_wide <= 200 * 1024) ? 1 : 2);
+    const int smem_bytes = variant == 1 ? smem_wide : a.smem_oct;
     if (c->kernel_smem[variant] != smem_bytes) {
         int per_sm = 0;
         if (variant == 0) {
@@ -505,7 +507,7 @@ int bhrt_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     return bhrt_resolve(c, spp, out);
 }
 
-int bhrt_debug_trace_mesh(bhrt_ctx *c, int32_t mesh, int32_t n, const float *rays, float *out_binary, float *out_wide)
+int bhrt_debug_trace_mesh(bhrt_ctx *c, int32_t mesh, int32_t n, const float *rays, float *out_binary, float *out_wide, float *kernel_ms)
 {
     if (!c || !c->have_scene || !rays || n <= 0) return set_err(BHRT_ERR_ARG, "bhrt_debug_trace_mesh: bad argument");
     if (mesh < 0 || (size_t)mesh * sizeof(MeshAccel) >= c->accels.bytes) return set_err(BHRT_ERR_ARG, "bhrt_debug_trace_mesh: bad mesh index");
@@ -514,12 +516,19 @@ int bhrt_debug_trace_mesh(bhrt_ctx *c, int32_t mesh, int32_t n, const float *ray
     DevBuf dr, d0, d1;
     if (dr.ensure((size_t)n * 32) || d0.ensure((size_t)n * 16) || d1.ensure((size_t)n * 16)) { dr.release(); d0.release(); d1.release(); return set_err(BHRT_ERR_CUDA, "cudaMalloc failed"); }
     cudaMemcpyAsync(dr.p, rays, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream);
+    cudaEvent_t ev[3];
+    for (auto &e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], c->stream);
     dbg_trace_binary<<<(n + 127) / 128, 128, 0, c->stream>>>(c->view, mesh, n, (const float *)dr.p, (float *)d0.p);
+    cudaEventRecord(ev[1], c->stream);
     dbg_trace_wide<<<(unsigned)(((size_t)n * 8 + 255) / 256), 256, 0, c->stream>>>(c->view, mesh, n, (const float *)dr.p, (float *)d1.p);
+    cudaEventRecord(ev[2], c->stream);
     c->launches += 2;
     if (out_binary) cudaMemcpyAsync(out_binary, d0.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream);
     if (out_wide) cudaMemcpyAsync(out_wide, d1.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream);
     cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess && kernel_ms) { cudaEventElapsedTime(&kernel_ms[0], ev[0], ev[1]); cudaEventElapsedTime(&kernel_ms[1], ev[1], ev[2]); }
+    for (auto &x : ev) cudaEventDestroy(x);
     dr.release(); d0.release(); d1.release();
     if (e != cudaSuccess) return set_err(BHRT_ERR_CUDA, std::string("bhrt_debug_trace_mesh: ") + cudaGetErrorString(e));
     return BHRT_OK;

@@ -11,12 +11,11 @@
 // plain bytes.
 //
 // This file is compiled TWICE (csrc/Makefile):
-//   render_fast.o      -DBHRT_FAST_WIDE=1  namespace bhrt_fast   traversal phase = 8 lanes per ray over the
-//                      8-wide collapse of the BVH with the stack in shared memory (wide.cuh) -- the default;
 //   render_fast_bin.o  -DBHRT_FAST_WIDE=0  namespace bhrt_fastb  traversal phase = one ray per thread over
-//                      the binary tree (round 1's kernel): the baseline the wide traversal is measured against
-//                      (BHRT_FLAG_BINARY_BVH / env BHRT_TRAVERSAL=binary), and the fallback for a mesh whose
-//                      BVH is too deep for the wide stack.
+//                      the binary tree -- the default;
+//   render_fast.o      -DBHRT_FAST_WIDE=1  namespace bhrt_fast   traversal phase = 8 lanes per ray over the
+//                      8-wide regrouping of the BVH with the stacks in shared memory (wide.cuh), selected by
+//                      BHRT_FLAG_WIDE_BVH / env BHRT_TRAVERSAL=wide (DESIGN.md 4.1 compares the two).
 #ifndef BHRT_FAST_WIDE
 #define BHRT_FAST_WIDE 1
 #endif

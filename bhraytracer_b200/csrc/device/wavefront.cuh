@@ -53,7 +53,18 @@
 
 namespace BHRT_NS {
 
+// WF_LOCAL_FRAMES: the estimator works on THREAD-LOCAL copies of the top recursion level and of the slot above it
+// (128-bit copies in and out, like the lane record) instead of reaching into the frames in global memory field by
+// field: a warp's lanes sit in 32 different 128-byte frames, so every scalar field access there costs 32 sectors.
+// MEASURED (round 2, BASELINE config 2): 1338 Mrays/s with the copies against 1541 in place -- the sixteen extra
+// 128-bit transfers per lane and pass and the spills they cause cost more than the scattered field accesses,
+// most of which hit L1 right after the first touch.  Kept as a compile-time variant; off.
+#ifndef WF_LOCAL_FRAMES
+#define WF_LOCAL_FRAMES 0
+#endif
+#ifndef WF_BLOCK
 #define WF_BLOCK 1024
+#endif
 #define WF_NKEYS 48
 #define WF_MESH_BUDGET 4
 // Sort keys.  A lane's key says what its next pass through the estimator will execute, as far as that
@@ -164,6 +175,15 @@ __device__ __forceinline__ void wf_load(T &dst, const T *src)
     static_assert(sizeof(T) % 16 == 0, "record size must be a multiple of 16 bytes");
     const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
     uint4 *d4 = reinterpret_cast<uint4 *>(&dst);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d4[i] = s4[i];
+}
+template <typename T>
+__device__ __forceinline__ void wf_store(T *dst, const T &src)
+{
+    static_assert(sizeof(T) % 16 == 0, "record size must be a multiple of 16 bytes");
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(&src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
 #pragma unroll
     for (int i = 0; i < (int)(sizeof(T) / 16); i++) d4[i] = s4[i];
 }
@@ -447,7 +467,7 @@ wf_render(SceneView s, WaveArgs a)
     OctShared *const OS = (OctShared *)(smem + a.smem_oct) + (tid >> 3);
     const unsigned sub = lane & 7u, oshift = lane & 24u;
     uint32_t jmask = 0; int jextra = 0, jk = -1, jkind = Q_NONE;
-    bool in_trav = false, jblocked = false;
+    bool in_trav = false, jblocked = false, jfirst = false;
 #else
     MeshJob J;                      // this thread's BVH traversal, kept across iterations
 #endif
@@ -491,14 +511,28 @@ wf_render(SceneView s, WaveArgs a)
             // (a caustic gather asked for by a step parks the lane: the queries of the whole CTA are
             // evaluated after the pass, one per warp at a time -- see the gather phase below)
             bool to_gather = false;
+#if WF_LOCAL_FRAMES
+            Frame F, Fc;                    // the top level and the slot above it
+            if (running && L.sp > 0) wf_load(F, &frames[(size_t)(L.sp - 1) * P]);
+#endif
             for (;;) {
                 const int st = running ? (L.sp == 0 ? -1 : lane_stage(L)) : 127;
                 const int mn = __reduce_min_sync(0xffffffffu, st);
                 if (mn == 127) break;
                 if (st != mn) continue;
                 V3 c;
+#if WF_LOCAL_FRAMES
+                const int sp0 = L.sp;
+                const int r = sample_step(L, F, Fc, s, a.cfg, a.gather, L.sp == 0 ? lanes[id].cold.bgu : 0.f, L.sp == 0 ? lanes[id].cold.bgv : 0.f, rc, c);
+                if (L.sp > sp0) {           // a level was pushed: the parent goes back to its slot, the child is the top now
+                    if (sp0 > 0) wf_store(&frames[(size_t)(sp0 - 1) * P], F);
+                    F = Fc;
+                } else if (L.sp < sp0 && L.sp > 0) wf_load(F, &frames[(size_t)(L.sp - 1) * P]);     // popped: the parent is the top again
+                if (r == STEP_GATHER || r == STEP_RAY) wf_store(&frames[(size_t)(L.sp - 1) * P], F);     // the lane leaves the pass with a level on top
+#else
                 const int r = sample_step(L, frames[(size_t)(L.sp > 0 ? L.sp - 1 : 0) * P], frames[(size_t)(L.sp < a.cfg.max_frames ? L.sp : a.cfg.max_frames - 1) * P],
                                           s, a.cfg, a.gather, L.sp == 0 ? lanes[id].cold.bgu : 0.f, L.sp == 0 ? lanes[id].cold.bgv : 0.f, rc, c);
+#endif
                 if (r == STEP_GATHER) { to_gather = true; running = false; continue; }
                 if (r == STEP_RAY) { running = false; continue; }
                 if (r == STEP_DONE) {
@@ -542,7 +576,18 @@ wf_render(SceneView s, WaveArgs a)
             if (alive && !to_gather) {
                 Hit h;
                 uint32_t mask;
+#if BHRT_WIDE_P2
+                Ray mray;
+                const bool blocked = scene_trace_graph(s, L.q, h, mask, &mray);
+                if (!blocked && mask) {
+                    const uint4 m0 = make_uint4(f2u(mray.p.x), f2u(mray.p.y), f2u(mray.p.z), f2u(mray.dir.x));
+                    const uint4 m1 = make_uint4(f2u(mray.dir.y), f2u(mray.dir.z), (uint32_t)(L.q.kind | (L.q.hitSide << 8)), f2u(L.q.t_max));
+                    uint4 *dst = reinterpret_cast<uint4 *>(&lanes[id].mesh_ray);
+                    dst[0] = m0; dst[1] = m1;
+                }
+#else
                 const bool blocked = scene_trace_graph(s, L.q, h, mask);
+#endif
                 L.hit_ok = blocked;
                 L.hit.z = h.z; L.hit.node = h.node; L.hit.front = h.front;
                 L.mesh_mask = 0;
@@ -550,7 +595,11 @@ wf_render(SceneView s, WaveArgs a)
             }
             if (alive) {
                 wf_store_lane(&lanes[id], L);
+#if WF_LOCAL_FRAMES
+                lkey[id] = (unsigned char)wf_key(s, L, F);          // (F is the top level whenever L.sp > 0)
+#else
                 lkey[id] = (unsigned char)wf_key(s, L, frames[(size_t)(L.sp > 0 ? L.sp - 1 : 0) * P]);
+#endif
             } else if (valid) lkey[id] = WF_KEY_DEAD;
             // park the lanes that wait for a caustic gather
             const unsigned gmask = __ballot_sync(0xffffffffu, to_gather);
@@ -676,7 +725,7 @@ wf_render(SceneView s, WaveArgs a)
                             OS->hface = 0; OS->ha0 = OS->ha1 = OS->ha2 = 0.f;
                             jmask = Lg.mesh_mask;
                             jextra = s.n_mesh_nodes > BHRT_MESH_MASK_BITS ? s.mesh_nodes[BHRT_MESH_MASK_BITS - 1] + 1 : s.n_nodes;
-                            have = true; in_trav = false; jblocked = false;
+                            have = true; in_trav = false; jblocked = false; jfirst = jmask != 0u;
                         }
                     }
                 }
@@ -692,16 +741,27 @@ wf_render(SceneView s, WaveArgs a)
                     }
                     if (k < 0) finished = true;
                     else {
-                        Query q;
-                        wf_load(q, &lanes[jid].q);
-                        jk = k; jkind = q.kind;
-                        const Ray r = node_local_ray(s, k, q.ray);
+                        jk = k;
                         const MeshAccel &A = s.accels[s.nodes[k].mesh];
-                        if (q.kind == Q_SHADOW) oct_begin(OT, s, A, r, true, q.t_max, BHRT_BIGFLOAT, true, q.hitSide);
+                        Ray r; int hitSide; float t_max;
+                        if (jfirst) {
+                            // the lanes pass left the ray in this mesh's space (and its root box is known to be entered)
+                            const uint4 *src = reinterpret_cast<const uint4 *>(&lanes[jid].mesh_ray);
+                            const uint4 m0 = src[0], m1 = src[1];
+                            r.p = V3(u2f(m0.x), u2f(m0.y), u2f(m0.z)); r.dir = V3(u2f(m0.w), u2f(m1.x), u2f(m1.y));
+                            jkind = (int)(m1.z & 255u); hitSide = (int)(m1.z >> 8); t_max = u2f(m1.w);
+                            jfirst = false;
+                        } else {
+                            Query q;
+                            wf_load(q, &lanes[jid].q);
+                            jkind = q.kind; hitSide = q.hitSide; t_max = q.t_max;
+                            r = node_local_ray(s, k, q.ray);
+                        }
+                        if (jkind == Q_SHADOW) oct_begin(OT, s, A, r, true, t_max, BHRT_BIGFLOAT, true, hitSide);
                         else {
                             // an equal-t candidate of an EARLIER node loses against the current winner
                             const float hz = OS->hz;
-                            oct_begin(OT, s, A, r, false, 0.f, OS->hnode > k ? prev_float(hz) : hz, OS->hfront != 0, q.hitSide);
+                            oct_begin(OT, s, A, r, false, 0.f, OS->hnode > k ? prev_float(hz) : hz, OS->hfront != 0, hitSide);
                         }
                         in_trav = true;
                     }

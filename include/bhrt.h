@@ -189,12 +189,14 @@ typedef struct bhrt_params {
  * root and transcendentals and with FMA contraction.  This flag selects the exact build (IEEE
  * operations in the reference's order) for it as well.  The deterministic mode is always exact. */
 #define BHRT_FLAG_EXACT_MATH 1u
-/* The fast build traverses triangle meshes eight lanes per ray over an 8-wide regrouping of the reference's
- * BVH (same boxes, same leaf order).  This flag selects the round-1 traversal instead -- one ray per thread
- * over the binary tree -- for A/B measurements; it is also what runs when a mesh's BVH is too deep for the
- * wide traversal's stack.  No effect on the exact build, which always walks the binary tree in the
- * reference's visiting order.  Environment override: BHRT_TRAVERSAL=binary. */
-#define BHRT_FLAG_BINARY_BVH 2u
+/* Triangle meshes are traversed one ray per thread over the reference's binary BVH (TriObj.cpp:192-307 made
+ * iterative).  With this flag the fast build instead runs EIGHT LANES PER RAY over an 8-wide regrouping of the same
+ * BVH (same boxes, same leaf order; per-ray stacks in shared memory; csrc/device/wide.cuh).  Both give the same
+ * answers ray by ray (tests/test_gpu_wide_bvh.py); the flag exists because which one is faster depends on the
+ * scene (DESIGN.md 4.1 has the measurements).  Ignored by the exact build, by scenes with a mesh too deep for
+ * the wide stack, and when the scene tables plus the stacks do not fit in shared memory.
+ * Environment override for all renders of a ctx: BHRT_TRAVERSAL=wide|binary. */
+#define BHRT_FLAG_WIDE_BVH 2u
 
 /* Any pointer may be NULL to skip that output.  Layouts follow the reference's
  * colorArray / RenderImage (Main.cpp:202,229-230): row-major, j*W+i, row 0 at the top. */
@@ -258,8 +260,9 @@ int bhrt_launch_count(bhrt_ctx *ctx, uint64_t *launches);
  * binary tree (TriObj::TraceBVHNode / TraceBVHShadow made iterative, reference TriObj.cpp:192-307) and eight
  * lanes per ray over its 8-wide regrouping -- so that a test can compare them ray by ray.
  * rays: float[n*8] = origin xyz, direction xyz (mesh-local space), bound (closest: the incoming hit distance,
- * shadow: t_max), kind (1 closest, 2 shadow).  out_*: float[n*4] = result (0/1), z, face id, front. */
-int bhrt_debug_trace_mesh(bhrt_ctx *ctx, int32_t mesh, int32_t n, const float *rays, float *out_binary, float *out_wide);
+ * shadow: t_max), kind (1 closest, 2 shadow).  out_*: float[n*4] = result (0/1), z, face id, front.
+ * kernel_ms (may be NULL): float[2], device time of the binary and of the wide pass. */
+int bhrt_debug_trace_mesh(bhrt_ctx *ctx, int32_t mesh, int32_t n, const float *rays, float *out_binary, float *out_wide, float *kernel_ms);
 
 /* Caustic photon map (reference Main.cpp:342-386, cyPhotonMap.h).
  * emit: traces photons until `target_stored` are stored on this GPU; records are the

@@ -7,12 +7,12 @@ Three bars, on BOTH builds of the kernel (fast-math = the one bench.py times, an
   (i)   16 spp: RMSE against the reference's high-spp mean <= 1.25 x the reference's own 16-spp RMSE;
   (ii)  convergence: the GPU at the reference's high spp against the mean M of the reference pair (A, B).
         var(G - M) = 1.5 s^2 and var(A - B) = 2 s^2 for the same estimator, so rmse(G, M) * sqrt(2 / 1.5) must
-        be <= 1.15 x rmse(A, B): a bias of more than ~0.5 x the 1024-spp noise (about 1/255 on these scenes,
-        1/16 of what the 16-spp bar can see) fails;
+        be <= 1.05 x rmse(A, B): a bias of more than ~0.3 x the 1024-spp noise (about 0.4/255 on these scenes,
+        1/30 of what the 16-spp bar can see) fails.  Measured: 0.993 ... 1.001 on all four configs, both builds;
   (iii) no low-frequency bias: image split into 8 x 6 tiles, every tile mean within 4 sigma (sigma from the
-        reference pair's per-pixel differences inside the tile) + 0.5/255 of the reference's tile mean, and
-        the whole-image mean within 0.5/255 (photon-mapped frame: 1/255 -- the photon map's own noise is shared
-        by all pixels of a run and is not captured by the per-pixel estimate).
+        reference pair's per-pixel differences inside the tile) + 0.1/255 of the reference's tile mean, and
+        the whole-image mean within 0.1/255 (photon-mapped frame: 0.5/255 -- the photon map's own noise is shared
+        by all pixels of a run and is not captured by the per-pixel estimate).  Measured: <= 3.2e-5 = 0.008/255.
 Reference behaviour pinned here: PointLight.cpp:13-14 (area-light shadow sample), MtlBlinn.cpp:602-617,
 637-695 (GetSampleAlongNormal / GetSampleInLight with int(size) >= 1), MtlBlinn.cpp:329-342 (caustic gather
 inside a stochastic frame)."""
@@ -78,6 +78,19 @@ def setup(renderer, name, g):
     return w, h, photons > 0
 
 
+def check_ray_counts(out, g, n_samples, pm, tol):
+    """Rays per camera sample against the reference's counters (same ray definition).  With the
+    photon map the reference's closest-hit counter also holds the photon paths it traced while emitting (its
+    recursive() is shared), so only the shadow rays are comparable there."""
+    ref_closest = float(g["closest_per_sample"])
+    ref_shadow = float(g["rays_per_sample"]) - ref_closest
+    shadow = out["rays_shadow"] / float(n_samples)
+    assert abs(shadow - ref_shadow) / ref_shadow < tol, "shadow rays per camera sample differ: %.4f vs %.4f" % (shadow, ref_shadow)
+    if not pm:
+        closest = out["rays_closest"] / float(n_samples)
+        assert abs(closest - ref_closest) / ref_closest < tol, "closest-hit rays per camera sample differ: %.4f vs %.4f" % (closest, ref_closest)
+
+
 @pytest.mark.parametrize("exact", [False, True], ids=["fast", "exact"])
 @pytest.mark.parametrize("name", CONV)
 def test_16spp_rmse_bar_on_the_benchmarked_configs(renderer, name, exact):
@@ -89,8 +102,7 @@ def test_16spp_rmse_bar_on_the_benchmarked_configs(renderer, name, exact):
     rmse = float(np.sqrt(np.mean((np.clip(out["linear"], 0, 1) - M) ** 2)))
     bound = 1.25 * max(float(g["rmse_ref_a"]), float(g["rmse_ref_b"]))
     assert rmse <= bound, "RMSE %.5f > %.5f" % (rmse, bound)
-    rps = (out["rays_closest"] + out["rays_shadow"]) / float(w * h * spp)
-    assert abs(rps - float(g["rays_per_sample"])) / float(g["rays_per_sample"]) < 0.02, "rays per camera sample differ"
+    check_ray_counts(out, g, w * h * spp, pm, 0.02)
 
 
 @pytest.mark.parametrize("exact", [False, True], ids=["fast", "exact"])
@@ -105,8 +117,7 @@ def test_convergence_to_the_reference_mean(renderer, name, exact):
     msg = "%s %s: %r" % (name, "exact" if exact else "fast", st)
     print(msg)
     assert abs(st["pair"] - float(g["rmse_pair"])) < 1e-4
-    assert st["ours"] <= 1.15 * st["pair"], msg
-    assert st["tile_excess"] <= (1.0 if pm else 0.5) / 255, msg
-    assert abs(st["mean_diff"]) <= (1.0 if pm else 0.5) / 255, msg
-    cps = out["rays_closest"] / float(w * h * spp)
-    assert abs(cps - float(g["closest_per_sample"])) / float(g["closest_per_sample"]) < 0.01, "closest-hit rays per camera sample differ"
+    assert st["ours"] <= 1.05 * st["pair"], msg
+    assert st["tile_excess"] <= (0.5 if pm else 0.1) / 255, msg
+    assert abs(st["mean_diff"]) <= (0.5 if pm else 0.1) / 255, msg
+    check_ray_counts(out, g, w * h * spp, pm, 0.01)
