@@ -311,7 +311,10 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     a.row_stride = p->row_stride > 1 ? p->row_stride : 1;
     a.n_rows = (row_end - row_begin + a.row_stride - 1) / a.row_stride;
     a.tiles_x = (c->width + 7) / 8;
-    a.n_pix_work = (unsigned)a.tiles_x * (unsigned)((a.n_rows + 7) / 8) * 64u;
+    // work items walk super-tiles of WF_ST x WF_ST tiles (wavefront.cuh: work_to_pixel); the padding tiles of the last
+    // row / column of super-tiles are items without a pixel (skipped)
+    a.stiles_x = (a.tiles_x + WF_ST - 1) / WF_ST;
+    a.n_pix_work = (unsigned)a.stiles_x * (unsigned)(((a.n_rows + 7) / 8 + WF_ST - 1) / WF_ST) * (unsigned)(WF_ST * WF_ST * 64);
     a.gather.use = 0;
     if (p->use_photon_map) {
         if (!c->photons.built) return set_err(BHRT_ERR_STATE, "bhrt_render: use_photon_map set but no photon map built");
@@ -334,6 +337,13 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     // photon-mapped frames are dominated by the caustic gathers, whose phase balances its 32 warps the
     // better the more queries it has: four times the lanes, gathered when nearly all of them are parked
     if (a.gather.use && !c->pool_lanes_set) a.pool = 12288;
+    // a CTA claims its work in batches of whole super-tiles: one (4096 items) normally, two for photon-mapped frames
+    // (measured on BASELINE config 5: 8192 items 7.6 s, 16384 items 8.1 s -- larger batches put whole caustic regions
+    // on a few CTAs and the others wait for them)
+    a.batch = (unsigned)(WF_ST * WF_ST * 64);
+    if (a.gather.use) a.batch *= 2;
+    while ((unsigned long long)(WF_RING - 1) * a.batch < (unsigned long long)a.pool + 32ull) a.batch *= 2;     // a pass must never run dry (wf_claim_topup)
+    if (const char *e = getenv("BHRT_WORK_BATCH")) { const long v = atol(e); if (v >= 1) a.batch = (unsigned)v * (unsigned)(WF_ST * WF_ST * 64); }
     a.mesh_budget = c->mesh_budget;
     a.mesh_batch = c->mesh_batch;
     a.gather_batch = c->gather_batch ? c->gather_batch : a.pool - a.pool / 12;
@@ -344,9 +354,9 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     a.smem_lights = al16(a.smem_materials + c->view.n_materials * (int)sizeof(bhrt_material));
     a.smem_offsets = al16(a.smem_lights + c->view.n_lights * (int)sizeof(bhrt_light));
     a.smem_wave = al16(a.smem_offsets + 2 * (BHRT_TEX_SAMPLES - 1) * (int)sizeof(float));
-    a.smem_gather = al16(a.smem_wave + wf_wave_smem_bytes(a.pool));
+    a.smem_gather = al16(a.smem_wave + wf_wave_smem_bytes(a.pool, a.gather.use != 0));
     // (the per-warp gather scratch only when a photon map is in use: without it the CTA stays under 32 KB)
-    a.smem_oct = al16(a.smem_gather + (a.gather.use ? (WF_BLOCK / 32) * (int)sizeof(PmWarpScratch) + (int)a.pool * 2 : 0));
+    a.smem_oct = al16(a.smem_gather + (a.gather.use ? (WF_BLOCK / 32) * (int)sizeof(PmWarpScratch) + (int)a.pool * 4 : 0));
     // stochastic frames run the fast-math build of the kernel unless the caller asks for the exact one; its
     // traversal phase is one ray per thread over the binary tree, or -- BHRT_FLAG_WIDE_BVH -- 8 lanes per ray over
     // the wide tree (per-octet stacks in shared memory) when every mesh has one and the stacks fit
@@ -418,6 +428,13 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
         const double tot = (double)(h.prof[0] + h.prof[1] + h.prof[2]);
         fprintf(stderr, "[bhrt] grid %u pool %u: lanes pass %.1f%%  sort %.1f%%  traversal %.1f%%  | %.0f iterations, %.0f kcycles per CTA\n", grid, a.pool,
                 100.0 * h.prof[0] / tot, 100.0 * h.prof[1] / tot, 100.0 * h.prof[2] / tot, (double)h.prof[3] / grid, tot / grid / 1e3);
+        if (h.pmprof[0]) {
+            const double q = (double)h.pmprof[0];
+            fprintf(stderr, "[bhrt] gather: %.0f queries; per query: %.2f level iterations, %.0f records in the block at the level used, %.0f qualifying when selected; "
+                            "warp cycles: setup %.0f  pass A %.0f  radix passes %.0f  final %.0f; <=k exits %.3f, refined after pass A %.3f, extra radix passes %.3f, selections %.3f\n",
+                    q, h.pmprof[6] / q, h.pmprof[5] / q, h.pmprof[11] / (h.pmprof[8] ? (double)h.pmprof[8] : 1.0), h.pmprof[1] / q, h.pmprof[2] / q, h.pmprof[3] / q, h.pmprof[4] / q,
+                    h.pmprof[7] / q, h.pmprof[10] / q, h.pmprof[9] / q, h.pmprof[8] / q);
+        }
     }
     if (out) {
         float ms = 0;

@@ -65,7 +65,7 @@ namespace BHRT_NS {
 #ifndef WF_BLOCK
 #define WF_BLOCK 1024
 #endif
-#define WF_NKEYS 48
+#define WF_NKEYS 49
 #define WF_MESH_BUDGET 4
 // Sort keys.  A lane's key says what its next pass through the estimator will execute, as far as that
 // is known when the lanes are sorted:
@@ -79,6 +79,8 @@ namespace BHRT_NS {
 // sort's tables -- and with them the CTA's shared memory -- under 32 KB, which leaves L1 (where the
 // thread-local lane copies live) the largest configuration.
 enum { WF_ST_PRIMARY = 0, WF_ST_REFR_IN = 1, WF_ST_REFR_OUT = 2, WF_ST_GI_TRACE = 3, WF_ST_SHADOW = 4, WF_ST_OTHER = 5, WF_KEY_DEAD = 63 };
+// a lane without a camera sample that found the CTA's claimed work used up in this pass: it asks again in the next one
+#define WF_KEY_IDLE 48
 __device__ __forceinline__ unsigned wf_stage_slot(int stage)
 {
     // ST_REFR 0, ST_REFR_IN_WAIT 1, ST_REFR_OUT_WAIT 2, ST_REFR_WAIT 3, ST_GI 4, ST_GI_TRACE_WAIT 5, ST_GI_WAIT 6, ST_DIRECT 7, ST_SHADOW_WAIT 8
@@ -119,6 +121,7 @@ struct WaveCounters {
     unsigned long long depth_overflow;      // Shade() levels refused because the lanes' frame stacks were full (the host retries deeper)
     // clock64() cycles summed over the CTAs (warp 0): lanes pass, sort, BVH traversal; iterations, traversal phases
     unsigned long long prof[6];
+    unsigned long long pmprof[16];          // -DBHRT_PM_PROF: per-phase clocks / counts of the caustic gather (see estimate_irradiance_warp)
 };
 
 struct WaveArgs {
@@ -127,6 +130,8 @@ struct WaveArgs {
     int sample_first;           // global index of the chunk's first sample
     int chunk_spp;              // samples per pixel in this chunk
     int row_begin, row_stride, n_rows, tiles_x;
+    int stiles_x;               // super-tiles (WF_ST x WF_ST tiles of 8x8 pixels) per row of super-tiles
+    unsigned batch;             // work items a CTA claims from the global counter at a time (a multiple of one super-tile)
     unsigned n_pix_work;        // tiles * 64 (work items outside the image are skipped)
     unsigned long long n_work;  // n_pix_work * chunk_spp
     PhotonGather gather;
@@ -144,7 +149,12 @@ struct WaveArgs {
 };
 
 // dynamic shared memory needed by the CTA-local wavefront for `pool` lanes
-static inline int wf_wave_smem_bytes(unsigned pool) { return (int)(pool * 2 /*list*/ + pool * 2 /*mesh queue*/ + pool /*key*/ + pool /*pending*/ + (pool / 32 + 1) * WF_NKEYS * 2 /*group counts*/ + 16); }
+static inline int wf_wave_smem_bytes(unsigned pool, bool gather)
+{
+    unsigned counts = (pool / 32 + 1) * WF_NKEYS * 2;       // group counts of the sort; with a photon map also the 4096 cell counters of the gather's query sort
+    if (gather && counts < 4096u * 4u) counts = 4096u * 4u;
+    return (int)(pool * 2 /*list*/ + pool * 2 /*mesh queue*/ + pool /*key*/ + pool /*pending*/ + counts + 16);
+}
 
 // Stage the small, uniformly-read scene tables in shared memory (node table, materials, lights,
 // texture-filter taps) and redirect the view to them.
@@ -205,18 +215,49 @@ __device__ __forceinline__ void wf_store_lane(Lane *dst, const Lane &src)
 #pragma unroll
     for (int i = 0; i < BHRT_LANE_PERSIST / 16; i++) __stcs(d4 + i, s4[i]);
 }
-// Work item g of the chunk -> (pixel, sample).  Sample-major: consecutive items are the pixels of
-// one 8x8 tile, so the lanes of a warp start on neighbouring primary rays.
+// Work item g of the chunk -> (pixel, sample).  Sample-major; within a sample the items walk SUPER-TILES of
+// WF_ST x WF_ST tiles of 8x8 pixels (64 x 64 pixels, 4096 items), tile by tile: consecutive items are the pixels of
+// one tile, so the lanes of a warp start on neighbouring primary rays, and a CTA -- which claims whole batches of
+// consecutive items, see wf_claim -- works on a compact patch of the image: its lanes meet the same textures, BVH
+// subtrees and (above all) photon cells, which is what makes the caustic gather cacheable.
+#define WF_ST 8
 __device__ __forceinline__ bool work_to_pixel(const SceneView &s, const WaveArgs &a, unsigned long long g, int &pi, int &pj, int &sidx)
 {
     const unsigned w = (unsigned)(g % a.n_pix_work);
     sidx = a.sample_first + (int)(g / a.n_pix_work);
     const unsigned tile = w >> 6, in = w & 63u;
-    const int tx = (int)(tile % (unsigned)a.tiles_x), ty = (int)(tile / (unsigned)a.tiles_x);
+    const unsigned st = tile / (WF_ST * WF_ST), lt = tile % (WF_ST * WF_ST);
+    const int tx = (int)(st % (unsigned)a.stiles_x) * WF_ST + (int)(lt % WF_ST), ty = (int)(st / (unsigned)a.stiles_x) * WF_ST + (int)(lt / WF_ST);
     const int i = tx * 8 + (int)(in & 7u), trow = ty * 8 + (int)(in >> 3);
     if (i >= s.width || trow >= a.n_rows) return false;
     pi = i; pj = a.row_begin + trow * a.row_stride;
     return true;
+}
+
+// A CTA takes its work from the global counter in batches of a.batch consecutive items and hands them to its warps
+// from shared memory.  WF_RING batches can be claimed ahead; thread 0 tops the ring up between passes so that a
+// pass never runs dry while the frame still has work (at most `pool` lanes ask for an item in one pass).
+#define WF_RING 8
+struct WfClaim {
+    unsigned long long base[WF_RING];   // first global item of the batch in ring slot k
+    unsigned long long taken;           // virtual items handed to warps so far (monotonic)
+    unsigned long long claimed;         // virtual items claimed from the global counter so far (multiple of a.batch)
+};
+__device__ __forceinline__ void wf_claim_topup(WfClaim &c, const WaveArgs &a)
+{
+    // (thread 0 only, between passes)
+    while (c.claimed - c.taken < (unsigned long long)a.pool + 32ull && c.claimed - c.taken + a.batch <= (unsigned long long)WF_RING * a.batch) {
+        const unsigned long long g = atomicAdd(&a.cnt->next_work, (unsigned long long)a.batch);
+        c.base[(c.claimed / a.batch) % WF_RING] = g;
+        c.claimed += a.batch;
+        if (g >= a.n_work) break;       // the frame has no work left: everything claimed from here on is past the end
+    }
+}
+// virtual item v of this CTA -> global item (>= a.n_work: no work)
+__device__ __forceinline__ unsigned long long wf_claim_item(const WfClaim &c, const WaveArgs &a, unsigned long long v)
+{
+    if (v >= c.claimed) return ~0ull;
+    return c.base[(v / a.batch) % WF_RING] + v % a.batch;
 }
 
 // ---- caustic irradiance estimate, one query per WARP ------------------------------------------------
@@ -227,14 +268,75 @@ __device__ __forceinline__ bool work_to_pixel(const SceneView &s, const WaveArgs
 // running the scalar version visits the same tens of thousands of photons alone, with its histogram
 // in thread-local memory; the reference spends 85 % of a photon-mapped render here.
 // All arguments are warp-uniform; every lane returns the same result.  `wsm` = this warp's scratch.
-struct PmWarpScratch { int hist[256]; float cd2[BHRT_PM_CAND]; uint32_t cidx[BHRT_PM_CAND]; int ncand; int pad[3]; };
+struct PmWarpScratch {
+    int hist[256]; float cd2[BHRT_PM_CAND]; uint32_t cidx[BHRT_PM_CAND]; int ncand; int pad[3];
+    uint32_t qidx[64]; float qd2[64];       // ring of photons that passed the distance test (pm_scan)
+};
+
+// One pass over the photons of the query's 3x3x3 block with WARP-LEVEL COMPACTION.  Only about a third of the block's
+// photons lie within the search bound; testing that costs a load and seven instructions, everything after it (the
+// direction test, the power unpacking, sums, histogram) five times as much.  So the lanes stride over the records doing
+// only the distance test, the survivors' indices go into a 64-entry ring in shared memory, and whenever the ring holds
+// 32 of them `body(index, d2, true)` runs for a FULL warp (and once more, partially filled, at the end).
+// my_b / my_e: lane n < 27 holds the record range of cell n.  Warp-convergent.
+template <typename Body>
+__device__ __forceinline__ void pm_scan(const PhotonGather &pg, uint32_t my_b, uint32_t my_e, int n_step, V3 pos, float bound2, PmWarpScratch *wsm, unsigned lane, Body body)
+{
+    unsigned head = 0, fill = 0;        // ring state (warp-uniform)
+    for (int n = 0; n < 27; n += n_step) {
+        const uint32_t b = __shfl_sync(0xffffffffu, my_b, n), e = __shfl_sync(0xffffffffu, my_e, n);
+        // four records per lane and trip: the loads are issued back to back (the pass is bound by their latency)
+        for (uint32_t base = b; base < e; base += 128u) {
+            F4 A[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t i = base + 32u * k + lane;
+                if (i < e) A[k] = ld4(&pg.recs[i].a); else { A[k].x = A[k].y = A[k].z = 3.0e18f; A[k].w = 0.f; }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (base + 32u * k >= e) break;         // (warp-uniform)
+                const uint32_t i = base + 32u * k + lane;
+                const float d2 = length2(V3(A[k].x - pos.x, A[k].y - pos.y, A[k].z - pos.z));
+                const bool ok = d2 < bound2;            // (records past the end sit at 3e18: never inside)
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) { const unsigned slot = (head + fill + __popc(m & ((1u << lane) - 1u))) & 63u; wsm->qidx[slot] = i; wsm->qd2[slot] = d2; }
+                fill += __popc(m);
+                if (fill >= 32u) {
+                    __syncwarp();
+                    const unsigned slot = (head + lane) & 63u;
+                    body(wsm->qidx[slot], wsm->qd2[slot], true);
+                    __syncwarp();
+                    head += 32u; fill -= 32u;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (fill) {     // (warp-uniform)
+        const unsigned slot = (head + lane) & 63u;
+        const bool act = lane < fill;
+        body(act ? wsm->qidx[slot] : 0u, act ? wsm->qd2[slot] : 0.f, act);
+    }
+    __syncwarp();
+}
 
 __device__ __forceinline__ float wf_sum(float v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
 __device__ __forceinline__ float wf_max(float v) { for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
 __device__ __forceinline__ V3 wf_sum3(V3 v) { return V3(wf_sum(v.x), wf_sum(v.y), wf_sum(v.z)); }
 
-__device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction, PmWarpScratch *wsm)
+#ifdef BHRT_PM_PROF
+#define PM_PROF_ADD(i, v) do { if (lane == 0) atomicAdd(&prof[i], (unsigned long long)(v)); } while (0)
+#define PM_PROF_MARK(i) do { const long long c_ = clock64(); PM_PROF_ADD(i, c_ - pm_t); pm_t = c_; } while (0)
+#else
+#define PM_PROF_ADD(i, v)
+#define PM_PROF_MARK(i)
+#endif
+__device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction, PmWarpScratch *wsm, unsigned long long *prof)
 {
+#ifdef BHRT_PM_PROF
+    long long pm_t = clock64();
+#endif
     const unsigned lane = threadIdx.x & 31u;
     irrad = V3(0, 0, 0); direction = V3(0, 0, 0);
     if (pg.n_photons <= 0) return;
@@ -251,7 +353,9 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
     // the 3x3x3 block holds far more photons than a query needs
     int level = 0;
     bool coarsened = false;         // a finer level held too few photons: do not try it again
+    PM_PROF_ADD(0, 1);
     for (;;) {
+        PM_PROF_ADD(6, 1);
         // lane n < 27 owns the key range of cell n of the 3x3x3 block (pm_ranges, one cell per lane)
         uint32_t my_b = 0, my_e = 0;
         if (lane < 27u) {
@@ -293,12 +397,29 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
             }
             if (md2 * 0.999f >= bound2) my_e = my_b;
         }
+        // At level 0 the three cells of a row of the block (dx = -1, 0, 1: lanes 3m, 3m+1, 3m+2) are consecutive coarse
+        // cells, i.e. ONE contiguous range of records: lane 3m takes the whole row (an empty or skipped cell in it only
+        // adds records that fail the distance test), so the scan below walks 9 long runs instead of 27 short ones.
+        const int n_step = level == 0 ? 3 : 1;
+        if (level == 0) {
+            const uint32_t b1 = __shfl_down_sync(0xffffffffu, my_b, 1), e1 = __shfl_down_sync(0xffffffffu, my_e, 1);
+            const uint32_t b2 = __shfl_down_sync(0xffffffffu, my_b, 2), e2 = __shfl_down_sync(0xffffffffu, my_e, 2);
+            if (lane < 27u && lane % 3u == 0u) {
+                uint32_t rb = 0xffffffffu, re = 0u;
+                if (my_e > my_b) { rb = my_b; re = my_e; }
+                if (e1 > b1) { rb = rb < b1 ? rb : b1; re = re > e1 ? re : e1; }
+                if (e2 > b2) { rb = rb < b2 ? rb : b2; re = re > e2 ? re : e2; }
+                if (re > rb) { my_b = rb; my_e = re; } else { my_b = 0u; my_e = 0u; }
+            } else { my_b = 0u; my_e = 0u; }
+        }
         // far more photons in the block than the k a query needs: the next finer level first
         {
             unsigned visit = my_e - my_b;
             for (int o = 16; o > 0; o >>= 1) visit += __shfl_xor_sync(0xffffffffu, visit, o);
-            if (!coarsened && level < BHRT_PM_LEVELS - 1 && visit > 12u * (unsigned)pg.k) { level++; continue; }
+            if (!coarsened && level < BHRT_PM_LEVELS - 1 && visit > 12u * (unsigned)pg.k) { PM_PROF_MARK(1); level++; continue; }
+            PM_PROF_ADD(5, visit);
         }
+        PM_PROF_MARK(1);
         const float scale = 32.f / bound2;
         // ---- pass A (256-bin histogram of a 24-bit distance key: the crossing bin then usually holds
         // few enough photons for the exact ranking, so a query is two passes over its photons)
@@ -306,24 +427,20 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
         __syncwarp();
         int total = 0;
         V3 sumP(0, 0, 0), sumD(0, 0, 0);
-        for (int n = 0; n < 27; n++) {
-            const uint32_t b = __shfl_sync(0xffffffffu, my_b, n), e = __shfl_sync(0xffffffffu, my_e, n);
-            for (uint32_t i = b + lane; i < e; i += 32u) {
-                F4 A = ld4(&pg.recs[i].a);
-                V3 dif(A.x - pos.x, A.y - pos.y, A.z - pos.z);
-                float d2 = length2(dif);
-                if (!(d2 < bound2)) continue;
-                F4 B = ld4(&pg.recs[i].b);
-                if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;
-                uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
-                atomicAdd(&wsm->hist[u >> 16], 1);
-                total++;
-                if (level == 0) { sumP = sumP + pm_power(&pg.recs[i], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w; }
-            }
-        }
+        pm_scan(pg, my_b, my_e, n_step, pos, bound2, wsm, lane, [&](uint32_t i, float d2, bool act) {
+            if (!act) return;
+            const F4 B = ld4(&pg.recs[i].b);
+            if (dot(V3(B.x, B.y, B.z), N) >= 0) return;
+            uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
+            atomicAdd(&wsm->hist[u >> 16], 1);
+            total++;
+            if (level == 0) { const float pw = ld4(&pg.recs[i].a).w; sumP = sumP + pm_power(&pg.recs[i], pw); sumD = sumD + V3(B.x, B.y, B.z) * pw; }
+        });
         for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
         __syncwarp();
+        PM_PROF_MARK(2);
         if (total <= pg.k) {
+            PM_PROF_ADD(7, 1);
             if (level > 0) { level--; coarsened = true; continue; }
             if (total == 0) return;
             sumP = wf_sum3(sumP); sumD = wf_sum3(sumD);
@@ -331,7 +448,8 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
             direction = normalized(sumD);
             return;
         }
-        if (!coarsened && level < BHRT_PM_LEVELS - 1 && total > 8 * pg.k) { level++; continue; }
+        if (!coarsened && level < BHRT_PM_LEVELS - 1 && total > 8 * pg.k) { PM_PROF_ADD(10, 1); level++; continue; }
+        PM_PROF_ADD(11, total);
         // ---- radix-256 select of the k-th smallest squared distance (u = 24-bit key, top digit = pass A's bin)
         uint32_t prefix = 0;
         int shift = 16, need = pg.k;
@@ -355,55 +473,46 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
             need -= cum;
             prefix = (prefix << 8) | (uint32_t)b;
             if (hb <= BHRT_PM_CAND || shift == 0) break;
+            PM_PROF_ADD(9, 1);
             shift -= 8;
             __syncwarp();
             for (int j = (int)lane; j < 256; j += 32) wsm->hist[j] = 0;
             __syncwarp();
-            for (int n = 0; n < 27; n++) {
-                const uint32_t bb = __shfl_sync(0xffffffffu, my_b, n), e = __shfl_sync(0xffffffffu, my_e, n);
-                for (uint32_t i = bb + lane; i < e; i += 32u) {
-                    F4 A = ld4(&pg.recs[i].a);
-                    V3 dif(A.x - pos.x, A.y - pos.y, A.z - pos.z);
-                    float d2 = length2(dif);
-                    if (!(d2 < bound2)) continue;
-                    uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
-                    if ((u >> (shift + 8)) != prefix) continue;
-                    F4 B = ld4(&pg.recs[i].b);
-                    if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;
-                    atomicAdd(&wsm->hist[(u >> shift) & 255u], 1);
-                }
-            }
+            pm_scan(pg, my_b, my_e, n_step, pos, bound2, wsm, lane, [&](uint32_t i, float d2, bool act) {
+                if (!act) return;
+                uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
+                if ((u >> (shift + 8)) != prefix) return;
+                const F4 B = ld4(&pg.recs[i].b);
+                if (dot(V3(B.x, B.y, B.z), N) >= 0) return;
+                atomicAdd(&wsm->hist[(u >> shift) & 255u], 1);
+            });
             __syncwarp();
         }
         // ---- last pass: everything below the crossing bin is in; the crossing bin's photons are candidates
+        PM_PROF_MARK(3);
         if (lane == 0) wsm->ncand = 0;
         __syncwarp();
         sumP = V3(0, 0, 0); sumD = V3(0, 0, 0);
         V3 subP(0, 0, 0), subD(0, 0, 0);
         float kth2 = 0, sub_max = 0;
-        for (int n = 0; n < 27; n++) {
-            const uint32_t bb = __shfl_sync(0xffffffffu, my_b, n), e = __shfl_sync(0xffffffffu, my_e, n);
-            for (uint32_t i = bb + lane; i < e; i += 32u) {
-                F4 A = ld4(&pg.recs[i].a);
-                V3 dif(A.x - pos.x, A.y - pos.y, A.z - pos.z);
-                float d2 = length2(dif);
-                if (!(d2 < bound2)) continue;
-                uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
-                const uint32_t top = u >> shift;
-                if (top > prefix) continue;
-                F4 B = ld4(&pg.recs[i].b);
-                if (dot(V3(B.x, B.y, B.z), N) >= 0) continue;
-                if (top < prefix) {
-                    sumP = sumP + pm_power(&pg.recs[i], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w;
-                    kth2 = fmaxf(kth2, d2);
-                } else {
-                    subP = subP + pm_power(&pg.recs[i], A.w); subD = subD + V3(B.x, B.y, B.z) * A.w;
-                    sub_max = fmaxf(sub_max, d2);
-                    const int slot = atomicAdd(&wsm->ncand, 1);
-                    if (slot < BHRT_PM_CAND) { wsm->cd2[slot] = d2; wsm->cidx[slot] = i; }
-                }
+        pm_scan(pg, my_b, my_e, n_step, pos, bound2, wsm, lane, [&](uint32_t i, float d2, bool act) {
+            if (!act) return;
+            uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
+            const uint32_t top = u >> shift;
+            if (top > prefix) return;
+            const F4 B = ld4(&pg.recs[i].b);
+            if (dot(V3(B.x, B.y, B.z), N) >= 0) return;
+            const float pw = ld4(&pg.recs[i].a).w;
+            if (top < prefix) {
+                sumP = sumP + pm_power(&pg.recs[i], pw); sumD = sumD + V3(B.x, B.y, B.z) * pw;
+                kth2 = fmaxf(kth2, d2);
+            } else {
+                subP = subP + pm_power(&pg.recs[i], pw); subD = subD + V3(B.x, B.y, B.z) * pw;
+                sub_max = fmaxf(sub_max, d2);
+                const int slot = atomicAdd(&wsm->ncand, 1);
+                if (slot < BHRT_PM_CAND) { wsm->cd2[slot] = d2; wsm->cidx[slot] = i; }
             }
-        }
+        });
         __syncwarp();
         const int ncand = wsm->ncand;
         if (ncand > BHRT_PM_CAND) {
@@ -429,6 +538,8 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
         const float area = 3.14159265358979323846f * kth2;
         irrad = area > 0 ? sumP * (1.0f / area) : sumP;
         direction = normalized(sumD);
+        PM_PROF_MARK(4);
+        PM_PROF_ADD(8, 1);
         return;
     }
 }
@@ -449,6 +560,8 @@ wf_render(SceneView s, WaveArgs a)
     unsigned short *gcount = (unsigned short *)(pend + P);                 // [P/32][WF_NKEYS] per-group key counts / offsets (P is a multiple of 32)
     __shared__ unsigned key_count[WF_NKEYS], key_base[WF_NKEYS];
     __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor, gq_count, gq_cursor, run_gather_s, n_parked_s;
+    __shared__ WfClaim claim;
+    __shared__ unsigned scan_part[32];
 
     Lane *const lanes = a.lanes + (size_t)blockIdx.x * P;
     Frame *const frames_all = a.frames + (size_t)blockIdx.x * P * (size_t)a.cfg.max_frames;
@@ -457,7 +570,11 @@ wf_render(SceneView s, WaveArgs a)
 
     for (unsigned i = tid; i < P; i += WF_BLOCK) { list[i] = (unsigned short)i; lkey[i] = WF_KEY_DEAD; pend[i] = 0; }
     if (tid < WF_NKEYS) key_count[tid] = 0;
-    if (tid == 0) { n_live_s = P; n_pending_s = 0; mq_head = 0; mq_tail = 0; p1_cursor = 0; run_mesh_s = 0; done_s = 0; gq_count = 0; gq_cursor = 0; n_parked_s = 0; }
+    if (tid == 0) {
+        n_live_s = P; n_pending_s = 0; mq_head = 0; mq_tail = 0; p1_cursor = 0; run_mesh_s = 0; done_s = 0; gq_count = 0; gq_cursor = 0; n_parked_s = 0;
+        claim.taken = 0; claim.claimed = 0;
+        wf_claim_topup(claim, a);
+    }
     __syncthreads();
 
     RayCounters rc; rc.closest = 0; rc.shadow = 0;
@@ -495,8 +612,10 @@ wf_render(SceneView s, WaveArgs a)
             // the recursion levels are used in place (global memory, cached in L1 while this lane is
             // being stepped): a step touches the top frame and, when it recurses, the slot above it
             Frame *const frames = frames_all + id;      // level l of this lane: frames[l * P]
-            bool want_new = valid && first;
-            bool running = valid && !first;
+            const bool was_idle = valid && !first && lkey[id] == WF_KEY_IDLE;
+            bool want_new = valid && (first || was_idle);
+            bool running = valid && !first && !was_idle;
+            bool idle = false;
             if (running) {
                 wf_load_lane(L, &lanes[id]);
                 // the answer of the pending query: winner-only work of a closest hit (a lane that comes
@@ -550,11 +669,26 @@ wf_render(SceneView s, WaveArgs a)
                 if (!m) break;
                 const int leader = __ffs(m) - 1;
                 unsigned long long base = 0;
-                if ((int)lane == leader) base = atomicAdd(&a.cnt->next_work, (unsigned long long)__popc(m));
+                // the CTA's claimed items are handed out without ever running past what is claimed (an item index
+                // beyond it could not be given back); a lane that gets none stays idle until the next pass
+                unsigned got = 0;
+                if ((int)lane == leader) {
+                    const unsigned want = (unsigned)__popc(m);
+                    for (;;) {
+                        const unsigned long long old = *(volatile unsigned long long *)&claim.taken;
+                        const unsigned long long avail = claim.claimed - old;
+                        got = avail < (unsigned long long)want ? (unsigned)avail : want;
+                        if (got == 0u) break;
+                        if (atomicCAS(&claim.taken, old, old + got) == old) { base = old; break; }
+                    }
+                }
                 base = __shfl_sync(0xffffffffu, base, leader);
+                got = __shfl_sync(0xffffffffu, got, leader);
                 if (want_new) {
-                    const unsigned long long g = base + __popc(m & ((1u << lane) - 1u));
-                    if (g >= a.n_work) { dead = true; want_new = false; }
+                    const unsigned rnk = (unsigned)__popc(m & ((1u << lane) - 1u));
+                    const unsigned long long g = rnk < got ? wf_claim_item(claim, a, base + rnk) : 0ull;
+                    if (rnk >= got) { idle = true; want_new = false; }
+                    else if (g >= a.n_work) { dead = true; want_new = false; }
                     else {
                         int pi, pj, sidx;
                         if (work_to_pixel(s, a, g, pi, pj, sidx)) {
@@ -571,7 +705,7 @@ wf_render(SceneView s, WaveArgs a)
                 }
             }
             // ---- the new ray against the scene graph (every surviving lane has one)
-            const bool alive = valid && !dead;
+            const bool alive = valid && !dead && !idle;
             bool to_mesh = false;
             if (alive && !to_gather) {
                 Hit h;
@@ -600,7 +734,7 @@ wf_render(SceneView s, WaveArgs a)
 #else
                 lkey[id] = (unsigned char)wf_key(s, L, frames[(size_t)(L.sp > 0 ? L.sp - 1 : 0) * P]);
 #endif
-            } else if (valid) lkey[id] = WF_KEY_DEAD;
+            } else if (valid) lkey[id] = idle ? (unsigned char)WF_KEY_IDLE : (unsigned char)WF_KEY_DEAD;
             // park the lanes that wait for a caustic gather
             const unsigned gmask = __ballot_sync(0xffffffffu, to_gather);
             if (gmask) {
@@ -632,16 +766,58 @@ wf_render(SceneView s, WaveArgs a)
         }
         if (a.gather.use && run_gather_s) {
             const unsigned ng = gq_count;
+            // ---- order the parked queries by photon cell (counting sort on a 12-bit key: the low 4 bits of each coarse
+            // cell coordinate; putting the queries of the most populated cells first was measured too: no gain).  The gather is bound by the L2 -> SM bandwidth of the records it streams (77 KB per
+            // query on BASELINE config 5, 32 warps at once); with the queries of one cell next to each other the 32
+            // warps stream the SAME block at the same time and all but the first find it in L1.  (`list` and the
+            // sort's group counters are free between the lanes pass and the next sort.)
+            unsigned short *const gq2 = gq + P;
+            {
+                unsigned *const cnt = (unsigned *)gcount;               // [4096]
+                unsigned short *const k16 = list;                       // key of entry i
+                for (unsigned i = tid; i < 4096u; i += WF_BLOCK) cnt[i] = 0u;
+                __syncthreads();
+                for (unsigned i = tid; i < ng; i += WF_BLOCK) {
+                    const unsigned gid = gq[i];
+                    const V3 qp = frames_all[(size_t)(lanes[gid].sp - 1) * P + gid].p;
+                    const int cx = (int)floorf((qp.x - a.gather.origin[0]) / a.gather.cell), cy = (int)floorf((qp.y - a.gather.origin[1]) / a.gather.cell),
+                              cz = (int)floorf((qp.z - a.gather.origin[2]) / a.gather.cell);
+                    const unsigned key = ((unsigned)cx & 15u) | (((unsigned)cy & 15u) << 4) | (((unsigned)cz & 15u) << 8);
+                    k16[i] = (unsigned short)key;
+                    atomicAdd(&cnt[key], 1u);
+                }
+                __syncthreads();
+                // exclusive scan of the 4096 counters: each thread owns WF_SCAN_PER consecutive ones
+                const unsigned per = (4096u + WF_BLOCK - 1u) / WF_BLOCK, c0 = tid * per;
+                unsigned mine = 0;
+                for (unsigned j = 0; j < per; j++) if (c0 + j < 4096u) mine += cnt[c0 + j];
+                unsigned incl = mine;
+                for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+                if (lane == 31u) scan_part[tid >> 5] = incl;
+                __syncthreads();
+                if (tid < 32u) {
+                    const unsigned v = tid < WF_BLOCK / 32 ? scan_part[tid] : 0u;
+                    unsigned inc2 = v;
+                    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc2, o); if ((int)lane >= o) inc2 += t; }
+                    scan_part[tid] = inc2 - v;
+                }
+                __syncthreads();
+                unsigned run = scan_part[tid >> 5] + incl - mine;
+                for (unsigned j = 0; j < per; j++) if (c0 + j < 4096u) { const unsigned t = cnt[c0 + j]; cnt[c0 + j] = run; run += t; }
+                __syncthreads();
+                for (unsigned i = tid; i < ng; i += WF_BLOCK) gq2[atomicAdd(&cnt[k16[i]], 1u)] = gq[i];
+                __syncthreads();
+            }
             for (;;) {
                 unsigned i = 0;
                 if (lane == 0) i = atomicAdd(&gq_cursor, 1u);
                 i = __shfl_sync(0xffffffffu, i, 0);
                 if (i >= ng) break;
-                const unsigned gid = gq[i];
+                const unsigned gid = gq2[i];
                 Lane &Lg = lanes[gid];
                 const Frame &fq = frames_all[(size_t)(Lg.sp - 1) * P + gid];
                 V3 irr, dirv;
-                estimate_irradiance_warp(a.gather, fq.p, fq.vN, irr, dirv, pm_scratch + (tid >> 5));
+                estimate_irradiance_warp(a.gather, fq.p, fq.vN, irr, dirv, pm_scratch + (tid >> 5), a.cnt->pmprof);
                 if (lane == 0) { Lg.ret = irr; Lg.sw = dirv; pend[gid] = 0; atomicSub(&n_parked_s, 1u); }
             }
             __syncthreads();
@@ -680,6 +856,7 @@ wf_render(SceneView s, WaveArgs a)
                 for (int k = 0; k < WF_NKEYS; k++) { key_base[k] = acc; acc += key_count[k]; }
                 n_live_s = acc;
                 p1_cursor = 0;
+                wf_claim_topup(claim, a);
                 // decisions every thread must agree on, taken while nobody changes their inputs
                 run_mesh_s = round == 0 && n_pending_s > 0 && (mq_tail - mq_head >= a.mesh_batch || acc < WF_BLOCK);
                 done_s = acc == 0 && n_pending_s == 0 && n_parked_s == 0;
