@@ -86,7 +86,9 @@ DEVICE_SYMBOLS = ["bhrt_abi_version", "bhrt_last_error", "bhrt_create", "bhrt_de
                   "bhrt_render", "bhrt_render_device", "bhrt_accum_buffer", "bhrt_aov_buffers", "bhrt_resolve",
                   "bhrt_set_stream", "bhrt_launch_count",
                   "bhrt_photons_emit", "bhrt_photons_buffer", "bhrt_photons_set", "bhrt_photons_get",
-                  "bhrt_photons_build", "bhrt_debug_trace_mesh"]
+                  "bhrt_photons_build", "bhrt_debug_trace_mesh", "bhrt_device_and_stream", "bhrt_frame_size", "bhrt_set_last_error"]
+DIST_SYMBOLS = ["bhrt_dist_shard_rows", "bhrt_dist_shard_samples", "bhrt_dist_shard_photons", "bhrt_dist_unique_id", "bhrt_dist_create",
+                "bhrt_dist_destroy", "bhrt_dist_render", "bhrt_dist_photons"]
 HOST_SYMBOLS = ["bhrt_host_load_scene", "bhrt_host_free_scene", "bhrt_host_last_error", "bhrt_host_scene_desc",
                 "bhrt_host_node_name", "bhrt_host_warnings", "bhrt_host_set_resolution", "bhrt_host_save_png",
                 "bhrt_host_zbuffer_image", "bhrt_host_sample_count_image"]
@@ -146,6 +148,15 @@ def device_lib():
         L.bhrt_photons_set.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int]
         L.bhrt_photons_get.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         L.bhrt_photons_build.argtypes = [C.c_void_p, C.c_int32]
+        L.bhrt_dist_shard_rows.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.bhrt_dist_shard_samples.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.bhrt_dist_shard_photons.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.bhrt_dist_shard_photons.restype = C.c_int32
+        L.bhrt_dist_unique_id.argtypes = [C.c_void_p]
+        L.bhrt_dist_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.bhrt_dist_destroy.argtypes = [C.c_void_p]
+        L.bhrt_dist_render.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int32, C.POINTER(Outputs)]
+        L.bhrt_dist_photons.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
         L.bhrt_debug_trace_mesh.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _dev = L
     return _dev
@@ -373,6 +384,72 @@ class Renderer:
         if getattr(self, "_ctx", None) and self._ctx.value:
             self._L.bhrt_destroy(self._ctx)
             self._ctx = C.c_void_p()
+
+
+def dist_unique_id():
+    """bhrt_dist_unique_id: the 128-byte rendezvous id rank 0 makes (bytes)."""
+    L = device_lib()
+    buf = (C.c_uint8 * 128)()
+    rc = L.bhrt_dist_unique_id(buf)
+    if rc != 0:
+        raise BhrtError("libbhrt error %d: %s" % (rc, L.bhrt_last_error().decode()))
+    return bytes(buf)
+
+
+def dist_shards(kind, n, rank, world):
+    """The C++ host's partitions (bhrt_dist_shard_*): 'rows' -> (begin, end, stride), 'samples' -> (begin, end),
+    'photons' -> quota.  Pure host arithmetic: works without a GPU."""
+    L = device_lib()
+    a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+    if kind == "rows":
+        rc = L.bhrt_dist_shard_rows(n, rank, world, C.byref(a), C.byref(b), C.byref(c))
+        res = (a.value, b.value, c.value)
+    elif kind == "samples":
+        rc = L.bhrt_dist_shard_samples(n, rank, world, C.byref(a), C.byref(b))
+        res = (a.value, b.value)
+    else:
+        res = L.bhrt_dist_shard_photons(n, rank, world)
+        rc = 0 if res >= 0 else -1
+    if rc != 0:
+        raise ValueError(L.bhrt_last_error().decode())
+    return res
+
+
+class Dist:
+    """bhrt_dist (include/bhrt_dist.h): the C++ multi-GPU host -- one per rank, over that rank's Renderer.  The ranks
+    exchange over NCCL inside the library; Python only carries the rendezvous id between the processes."""
+
+    def __init__(self, renderer, rank, world, unique_id):
+        self.r = renderer
+        self._L = renderer._L
+        self._d = C.c_void_p()
+        self.rank, self.world = rank, world
+        idbuf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        renderer._check(self._L.bhrt_dist_create(renderer._ctx, rank, world, idbuf, C.byref(self._d)))
+
+    def render(self, params=None, dst=0, want=("rgb8", "linear", "hit_id", "z"), **kw):
+        p = params or self.r.params(**kw)
+        o, bufs = self.r._alloc_outputs(want if self.rank == dst else ())
+        self.r._check(self._L.bhrt_dist_render(self._d, C.byref(p), dst, C.byref(o)))
+        bufs.update(rays_closest=int(o.rays_closest), rays_shadow=int(o.rays_shadow), kernel_ms=float(o.kernel_ms))
+        return bufs
+
+    def render_into(self, params, dst=0, rgb8=None):
+        """bhrt_dist_render with a caller-owned HOST RGB8 buffer (raw address, e.g. pinned memory) on rank dst."""
+        o = Outputs()
+        o.rgb8 = rgb8 if self.rank == dst else None
+        self.r._check(self._L.bhrt_dist_render(self._d, C.byref(params), dst, C.byref(o)))
+        return dict(rays_closest=int(o.rays_closest), rays_shadow=int(o.rays_shadow), kernel_ms=float(o.kernel_ms))
+
+    def photons(self, total_stored, seed=1):
+        stored, rays = C.c_int32(), C.c_uint64()
+        self.r._check(self._L.bhrt_dist_photons(self._d, int(total_stored), int(seed), C.byref(stored), C.byref(rays)))
+        return stored.value, rays.value
+
+    def close(self):
+        if getattr(self, "_d", None) and self._d.value:
+            self._L.bhrt_dist_destroy(self._d)
+            self._d = C.c_void_p()
 
     def __del__(self):
         try:

@@ -450,9 +450,11 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
 // the frame stacks fit in half of the free device memory.
 static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
 {
+    double ms_all = 0;      // device time of EVERY pass: a frame that had to be rendered again is not reported faster than it was
     for (;;) {
         unsigned long long overflow = 0;
         const int r = launch_render_once(c, p, out, &overflow);
+        if (out) { ms_all += out->kernel_ms; out->kernel_ms = ms_all; }
         if (r != BHRT_OK || overflow == 0 || c->max_frames * 2 > BHRT_MAX_FRAMES_LIMIT) return r;
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return r;
@@ -487,6 +489,24 @@ int bhrt_set_stream(bhrt_ctx *c, void *stream)
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return BHRT_OK;
+}
+
+int bhrt_set_last_error(int code, const char *msg) { return set_err(code, msg ? msg : ""); }
+
+int bhrt_device_and_stream(bhrt_ctx *c, int32_t *device, void **cuda_stream)
+{
+    if (!c) return set_err(BHRT_ERR_ARG, "bhrt_device_and_stream: null ctx");
+    if (device) *device = c->device;
+    if (cuda_stream) *cuda_stream = (void *)c->stream;
+    return BHRT_OK;
+}
+
+int bhrt_frame_size(bhrt_ctx *c, int32_t *width, int32_t *height)
+{
+    if (!c || !c->have_scene) return set_err(BHRT_ERR_STATE, "bhrt_frame_size: no scene uploaded");
+    if (width) *width = c->width;
+    if (height) *height = c->height;
     return BHRT_OK;
 }
 

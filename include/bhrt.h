@@ -207,7 +207,8 @@ typedef struct bhrt_outputs {
     float *z;               /* [H*W]   primary hit distance of sample 0 (1e30 on miss) */
     uint64_t rays_closest;  /* closest-hit rays traced (one per reference recursive() top-level call) */
     uint64_t rays_shadow;   /* any-hit rays traced (one per reference GenLight::Shadow call) */
-    double kernel_ms;       /* device time of the render kernels (CUDA events) */
+    double kernel_ms;       /* device time of the render kernels (CUDA events), summed over every pass when a frame had to be
+                             * rendered again with deeper Shade() stacks; the ray counters are those of the final pass */
 } bhrt_outputs;
 
 typedef struct bhrt_ctx bhrt_ctx;
@@ -226,7 +227,7 @@ int bhrt_upload_scene(bhrt_ctx *ctx, const bhrt_scene_desc *scene);
  * MtlBlinn::Shade recursion is as deep as the scene makes it (the reference has no bound,
  * MtlBlinn.cpp:476-519): a ctx starts with 64 levels per camera sample in flight and renders a
  * frame again with twice as many while any level was refused (up to 4096, device memory
- * permitting); kernel_ms is the time of the last pass. */
+ * permitting); kernel_ms is the time of ALL passes, the ray counters are those of the last one. */
 int bhrt_render(bhrt_ctx *ctx, const bhrt_params *params, bhrt_outputs *out);
 
 /* The same frame, outputs left in device memory (accumulation buffer = sum over the
@@ -251,6 +252,13 @@ int bhrt_resolve(bhrt_ctx *ctx, int32_t total_spp, bhrt_outputs *out);
  * ctx's own stream), so a host that interleaves collectives can order and time everything on
  * one stream. */
 int bhrt_set_stream(bhrt_ctx *ctx, void *cuda_stream);
+
+/* The CUDA device index of a ctx and the stream its work currently runs on (a cudaStream_t), for a host that
+ * enqueues its own work (collectives) behind the render; and the resolution of the uploaded scene. */
+int bhrt_device_and_stream(bhrt_ctx *ctx, int32_t *device, void **cuda_stream);
+int bhrt_frame_size(bhrt_ctx *ctx, int32_t *width, int32_t *height);
+/* Sets the calling thread's bhrt_last_error() text and returns `code` (for the layers built on this ABI). */
+int bhrt_set_last_error(int code, const char *message);
 
 /* Number of kernels this ctx has launched since bhrt_create (bench.py's gpu_launches). */
 int bhrt_launch_count(bhrt_ctx *ctx, uint64_t *launches);

@@ -26,6 +26,34 @@ def test_device_library_exports_every_declared_symbol(built):
         assert hasattr(lib, n), "libbhrt.so does not export " + n
     assert sorted(names) == sorted(b.DEVICE_SYMBOLS), "python binding list out of date"
     assert lib.bhrt_abi_version() == 1
+    # the multi-GPU host lives in the same library (include/bhrt_dist.h)
+    dnames = [n for n in declared_functions("bhrt_dist.h") if n.startswith("bhrt_dist_")]
+    assert len(dnames) >= 8
+    for n in dnames:
+        assert hasattr(lib, n), "libbhrt.so does not export " + n
+    assert sorted(dnames) == sorted(b.DIST_SYMBOLS)
+
+
+def test_dist_partitions_tile_exactly(built):
+    """bhrt_dist_shard_* (the C++ host's partitions) without a GPU: ranges tile, quotas sum, rows interleave."""
+    for spp in (1, 5, 16, 255):
+        for world in (1, 2, 3, 8):
+            r = [b.dist_shards("samples", spp, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == spp
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            assert max(e - s for s, e in r) - min(e - s for s, e in r) <= 1
+            assert sum(b.dist_shards("photons", spp, k, world) for k in range(world)) == spp
+    rows = sorted(j for k in range(3) for j in range(*b.dist_shards("rows", 10, k, 3)))
+    assert rows == list(range(10))
+    with pytest.raises(ValueError):
+        b.dist_shards("rows", 10, 3, 3)
+    # and they are the partitions the Python orchestration of the CPU test tier uses
+    from bhraytracer_b200 import multigpu as mg
+    for world in (1, 2, 3, 8):
+        for k in range(world):
+            assert b.dist_shards("samples", 37, k, world) == mg.shard_samples(37, k, world)
+            assert b.dist_shards("rows", 37, k, world) == mg.shard_rows(37, k, world)
+            assert b.dist_shards("photons", 3001, k, world) == mg.shard_photons(3001, k, world)
 
 
 def test_host_library_exports_every_declared_symbol(built):
