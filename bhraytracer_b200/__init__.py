@@ -86,7 +86,8 @@ DEVICE_SYMBOLS = ["bhrt_abi_version", "bhrt_last_error", "bhrt_create", "bhrt_de
                   "bhrt_render", "bhrt_render_device", "bhrt_accum_buffer", "bhrt_aov_buffers", "bhrt_resolve",
                   "bhrt_set_stream", "bhrt_launch_count",
                   "bhrt_photons_emit", "bhrt_photons_buffer", "bhrt_photons_set", "bhrt_photons_get",
-                  "bhrt_photons_build", "bhrt_debug_trace_mesh", "bhrt_device_and_stream", "bhrt_frame_size", "bhrt_set_last_error"]
+                  "bhrt_photons_build", "bhrt_debug_trace_mesh", "bhrt_device_and_stream", "bhrt_frame_size", "bhrt_set_last_error",
+                  "bhrt_render_async", "bhrt_progress", "bhrt_cancel", "bhrt_wait", "bhrt_sample_counts"]
 DIST_SYMBOLS = ["bhrt_dist_shard_rows", "bhrt_dist_shard_samples", "bhrt_dist_shard_photons", "bhrt_dist_unique_id", "bhrt_dist_create",
                 "bhrt_dist_destroy", "bhrt_dist_render", "bhrt_dist_photons"]
 HOST_SYMBOLS = ["bhrt_host_load_scene", "bhrt_host_free_scene", "bhrt_host_last_error", "bhrt_host_scene_desc",
@@ -148,6 +149,11 @@ def device_lib():
         L.bhrt_photons_set.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int]
         L.bhrt_photons_get.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         L.bhrt_photons_build.argtypes = [C.c_void_p, C.c_int32]
+        L.bhrt_sample_counts.argtypes = [C.c_void_p, C.c_void_p]
+        L.bhrt_render_async.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Outputs)]
+        L.bhrt_progress.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+        L.bhrt_cancel.argtypes = [C.c_void_p]
+        L.bhrt_wait.argtypes = [C.c_void_p]
         L.bhrt_dist_shard_rows.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.bhrt_dist_shard_samples.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.bhrt_dist_shard_photons.argtypes = [C.c_int32, C.c_int32, C.c_int32]
@@ -341,6 +347,36 @@ class Renderer:
         n = C.c_uint64()
         self._check(self._L.bhrt_launch_count(self._ctx, C.byref(n)))
         return n.value
+
+    # ---- the viewer's asynchronous contract (reference viewport.cpp:37-38,395-415,449-453)
+    def render_async(self, params=None, want=("rgb8", "linear", "hit_id", "z"), **kw):
+        """BeginRender() on the library's worker thread; returns at once.  Poll progress(), then wait()."""
+        self._async_p = params or self.params(**kw)
+        self._async_o, self._async_bufs = self._alloc_outputs(want)
+        self._check(self._L.bhrt_render_async(self._ctx, C.byref(self._async_p), C.byref(self._async_o)))
+
+    def progress(self):
+        """(pixels done, pixels total, finished) -- RenderImage::GetNumRenderedPixels / IsRenderDone."""
+        d, t, f = C.c_int64(), C.c_int64(), C.c_int32()
+        self._check(self._L.bhrt_progress(self._ctx, C.byref(d), C.byref(t), C.byref(f)))
+        return d.value, t.value, bool(f.value)
+
+    def cancel(self):
+        """StopRender()."""
+        self._check(self._L.bhrt_cancel(self._ctx))
+
+    def wait(self):
+        """Joins the frame started by render_async; returns its outputs (raises BhrtError -5 after a cancel)."""
+        self._check(self._L.bhrt_wait(self._ctx))
+        o, bufs = self._async_o, self._async_bufs
+        bufs.update(rays_closest=int(o.rays_closest), rays_shadow=int(o.rays_shadow), kernel_ms=float(o.kernel_ms))
+        return bufs
+
+    def sample_counts(self):
+        """bhrt_sample_counts: uint8[H, W] camera samples accumulated per pixel by the last render."""
+        out = np.empty((self.height, self.width), np.uint8)
+        self._check(self._L.bhrt_sample_counts(self._ctx, out.ctypes.data))
+        return out
 
     def debug_trace_mesh(self, mesh, rays):
         """bhrt_debug_trace_mesh: rays float32[n, 8] -> (binary, wide), float32[n, 4] each (result, z, face, front)."""

@@ -11,7 +11,9 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 #include "core.cuh"
 #include "setup.hpp"
@@ -76,6 +78,15 @@ struct bhrt_ctx {
     bool pool_lanes_set = false;
     int trav_min = 3, trav_max = 12, trav_pct = 50;
     DevBuf lanes, frames, samples, wave_counters;
+    // asynchronous frames (bhrt_render_async): worker thread, a second stream for progress / cancel, the cancel flag
+    DevBuf cancel_flag;
+    cudaStream_t aux_stream = nullptr;
+    std::thread worker;
+    std::atomic<int> async_state{0};            // 0 idle, 1 running, 2 finished (not yet waited for)
+    std::atomic<int> cancel_requested{0};
+    int async_status = BHRT_OK;
+    std::string async_error;
+    long long frame_items = 0, frame_pixels = 0; int frame_spp = 1;
 };
 
 // sum/spp (Main.cpp:170), gamma (Main.cpp:220-227), Color24 (Main.cpp:230)
@@ -128,6 +139,15 @@ dbg_trace_wide(SceneView s, int mesh, int n, const float *__restrict__ rays, flo
     }
 }
 
+// RenderImage::GetSampleCount (reference scene.h:534,570): samples accumulated per pixel, clamped to the reference's uint8
+__global__ void sample_count_kernel(const float4 *__restrict__ accum, int n, uint8_t *__restrict__ out)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float w = accum[p].w;
+    out[p] = (uint8_t)(w < 0.f ? 0.f : (w > 255.f ? 255.f : w));
+}
+
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -151,8 +171,11 @@ int bhrt_create(int device, bhrt_ctx **out)
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
+    if (c->cancel_flag.ensure(16)) { delete c; return set_err(BHRT_ERR_CUDA, "cudaMalloc(cancel flag)"); }
+    CU(cudaMemset(c->cancel_flag.p, 0, 16));
     if (c->counters.ensure(8 * sizeof(unsigned long long))) { delete c; return set_err(BHRT_ERR_CUDA, "cudaMalloc(counters)"); }
     // tuning knobs
     if (const char *e = getenv("BHRT_POOL_LANES")) { long v = atol(e); if (v >= 32 && v <= 32768) { c->pool_lanes = (unsigned)v; c->pool_lanes_set = true; } }
@@ -168,8 +191,11 @@ int bhrt_create(int device, bhrt_ctx **out)
 int bhrt_destroy(bhrt_ctx *c)
 {
     if (!c) return BHRT_OK;
+    if (c->worker.joinable()) { bhrt_cancel(c); c->worker.join(); }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    c->cancel_flag.release();
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     DevBuf *bufs[] = { &c->nodes, &c->materials, &c->lights, &c->texmaps, &c->textures, &c->texels, &c->meshes, &c->mesh_data,
                        &c->tex_offsets, &c->accels, &c->accel_data, &c->lanes, &c->frames, &c->samples, &c->wave_counters, &c->accum, &c->hit_id, &c->z, &c->rgb8, &c->linear, &c->counters };
     for (auto b : bufs) b->release();
@@ -391,6 +417,9 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     a.lanes = (Lane *)c->lanes.p; a.frames = (Frame *)c->frames.p; a.samples = (float4 *)c->samples.p;
     a.hit_id = (int *)c->hit_id.p; a.zbuf = (float *)c->z.p;
     a.cnt = (WaveCounters *)c->wave_counters.p;
+    a.cancel = (const unsigned *)c->cancel_flag.p;
+    c->frame_spp = spp; c->frame_pixels = (long long)c->width * a.n_rows;
+    c->frame_items = (long long)a.n_pix_work * (long long)n_spp_share;
 
     // rows / samples outside this launch's share must read as zero for the multi-GPU sum
     const bool partial_rows = a.n_rows != c->height;
@@ -467,6 +496,72 @@ static int launch_render(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
 
 int bhrt_render_device(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out) { return launch_render(c, p, out); }
 
+// ---- asynchronous frames: the reference viewer's BeginRender / IsRenderDone / StopRender contract ----
+int bhrt_render_async(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
+{
+    if (!c || !p) return set_err(BHRT_ERR_ARG, "bhrt_render_async: null argument");
+    if (!c->have_scene) return set_err(BHRT_ERR_STATE, "bhrt_render_async: no scene uploaded");
+    if (c->async_state.load() != 0) return set_err(BHRT_ERR_STATE, "bhrt_render_async: a frame is already in flight (bhrt_wait first)");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemset(c->cancel_flag.p, 0, 16));
+    c->cancel_requested = 0;
+    c->frame_items = 0; c->frame_pixels = (long long)c->width * c->height;
+    c->async_status = BHRT_OK; c->async_error.clear();
+    c->async_state = 1;
+    c->worker = std::thread([c, p, out]() {
+        int r = bhrt_render(c, p, out);
+        if (r != BHRT_OK) c->async_error = g_err;               // (the worker's thread-local message)
+        else if (c->cancel_requested.load()) { r = BHRT_ERR_CANCELLED; c->async_error = "the frame was cancelled (bhrt_cancel)"; }
+        c->async_status = r;
+        c->async_state = 2;
+    });
+    return BHRT_OK;
+}
+
+int bhrt_progress(bhrt_ctx *c, int64_t *pixels_done, int64_t *pixels_total, int32_t *finished)
+{
+    if (!c) return set_err(BHRT_ERR_ARG, "bhrt_progress: null ctx");
+    const int state = c->async_state.load();
+    long long done_items = 0;
+    if (state == 1 && c->wave_counters.p) {
+        // read the claim counter next to the running kernel, on the second stream
+        cudaSetDevice(c->device);
+        unsigned long long v = 0;
+        if (cudaMemcpyAsync(&v, &((WaveCounters *)c->wave_counters.p)->progress, sizeof(v), cudaMemcpyDeviceToHost, c->aux_stream) == cudaSuccess &&
+            cudaStreamSynchronize(c->aux_stream) == cudaSuccess) done_items = (long long)v;
+    }
+    const long long total = c->frame_pixels;
+    long long done = state == 2 ? total : 0;
+    if (state == 1 && c->frame_items > 0) { done = (long long)((double)done_items / (double)c->frame_items * (double)total); if (done > total) done = total; }
+    if (state == 2 && c->cancel_requested.load()) done = -1;        // cancelled: the count is not known any more
+    if (pixels_done) *pixels_done = done;
+    if (pixels_total) *pixels_total = total;
+    if (finished) *finished = state != 1;
+    return BHRT_OK;
+}
+
+int bhrt_cancel(bhrt_ctx *c)
+{
+    if (!c) return set_err(BHRT_ERR_ARG, "bhrt_cancel: null ctx");
+    if (c->async_state.load() != 1) return BHRT_OK;
+    c->cancel_requested = 1;
+    cudaSetDevice(c->device);
+    const unsigned one = 1u;
+    if (cudaMemcpyAsync(c->cancel_flag.p, &one, sizeof(one), cudaMemcpyHostToDevice, c->aux_stream) != cudaSuccess || cudaStreamSynchronize(c->aux_stream) != cudaSuccess)
+        return set_err(BHRT_ERR_CUDA, "bhrt_cancel: could not reach the device");
+    return BHRT_OK;
+}
+
+int bhrt_wait(bhrt_ctx *c)
+{
+    if (!c) return set_err(BHRT_ERR_ARG, "bhrt_wait: null ctx");
+    if (c->async_state.load() == 0) return set_err(BHRT_ERR_STATE, "bhrt_wait: no frame in flight");
+    if (c->worker.joinable()) c->worker.join();
+    c->async_state = 0;
+    if (c->async_status != BHRT_OK) return set_err(c->async_status, c->async_error);
+    return BHRT_OK;
+}
+
 int bhrt_accum_buffer(bhrt_ctx *c, void **ptr, size_t *bytes)
 {
     if (!c || !c->have_scene) return set_err(BHRT_ERR_STATE, "bhrt_accum_buffer: no scene uploaded");
@@ -532,6 +627,20 @@ int bhrt_resolve(bhrt_ctx *c, int32_t total_spp, bhrt_outputs *out)
         if (out->hit_id) CU(cudaMemcpyAsync(out->hit_id, c->hit_id.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
         if (out->z) CU(cudaMemcpyAsync(out->z, c->z.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     }
+    CU(cudaStreamSynchronize(c->stream));
+    return BHRT_OK;
+}
+
+int bhrt_sample_counts(bhrt_ctx *c, uint8_t *host_counts)
+{
+    if (!c || !c->have_scene || !host_counts) return set_err(BHRT_ERR_ARG, "bhrt_sample_counts: bad argument");
+    CU(cudaSetDevice(c->device));
+    const int n = c->width * c->height;
+    // (the RGB8 image buffer is rewritten by every resolve: borrow its first n bytes)
+    sample_count_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>((const float4 *)c->accum.p, n, (uint8_t *)c->rgb8.p);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host_counts, c->rgb8.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return BHRT_OK;
 }

@@ -121,6 +121,7 @@ struct WaveCounters {
     unsigned long long depth_overflow;      // Shade() levels refused because the lanes' frame stacks were full (the host retries deeper)
     // clock64() cycles summed over the CTAs (warp 0): lanes pass, sort, BVH traversal; iterations, traversal phases
     unsigned long long prof[6];
+    unsigned long long progress;            // camera samples claimed by the CTAs so far in this frame (all chunks; bhrt_progress)
     unsigned long long pmprof[16];          // -DBHRT_PM_PROF: per-phase clocks / counts of the caustic gather (see estimate_irradiance_warp)
 };
 
@@ -140,6 +141,7 @@ struct WaveArgs {
     float4 *samples;            // [chunk_spp][n_pix_work]
     int *hit_id; float *zbuf;
     WaveCounters *cnt;
+    const unsigned *cancel;     // set by bhrt_cancel: stop claiming camera samples
     unsigned pool;              // lanes per CTA (<= 65535)
     int mesh_budget;            // traversal trips a thread may still run after the last warp left the lanes pass
     unsigned mesh_batch;        // queued rays that switch the traversal phase on
@@ -247,10 +249,13 @@ __device__ __forceinline__ void wf_claim_topup(WfClaim &c, const WaveArgs &a)
 {
     // (thread 0 only, between passes)
     while (c.claimed - c.taken < (unsigned long long)a.pool + 32ull && c.claimed - c.taken + a.batch <= (unsigned long long)WF_RING * a.batch) {
-        const unsigned long long g = atomicAdd(&a.cnt->next_work, (unsigned long long)a.batch);
+        // (a cancelled frame -- bhrt_cancel, the reference's StopRender -- hands out nothing any more)
+        const bool cancelled = *(const volatile unsigned *)a.cancel != 0u;
+        const unsigned long long g = cancelled ? a.n_work : atomicAdd(&a.cnt->next_work, (unsigned long long)a.batch);
         c.base[(c.claimed / a.batch) % WF_RING] = g;
         c.claimed += a.batch;
         if (g >= a.n_work) break;       // the frame has no work left: everything claimed from here on is past the end
+        atomicAdd(&a.cnt->progress, g + a.batch <= a.n_work ? (unsigned long long)a.batch : a.n_work - g);
     }
 }
 // virtual item v of this CTA -> global item (>= a.n_work: no work)

@@ -34,7 +34,8 @@ typedef enum bhrt_status {
     BHRT_ERR_ARG = -1,      /* bad argument / inconsistent scene description */
     BHRT_ERR_CUDA = -2,     /* CUDA runtime error (no device, out of memory, launch failure) */
     BHRT_ERR_STATE = -3,    /* call order (render before upload, ...) */
-    BHRT_ERR_LIMIT = -4     /* scene exceeds a compiled-in limit (BHRT_MAX_*) */
+    BHRT_ERR_LIMIT = -4,    /* scene exceeds a compiled-in limit (BHRT_MAX_*) */
+    BHRT_ERR_CANCELLED = -5 /* the frame was stopped by bhrt_cancel (StopRender): the outputs hold a partial image */
 } bhrt_status;
 
 /* limits of the constant-memory tables */
@@ -235,6 +236,23 @@ int bhrt_render(bhrt_ctx *ctx, const bhrt_params *params, bhrt_outputs *out);
  * counters / kernel_ms fields are filled. */
 int bhrt_render_device(bhrt_ctx *ctx, const bhrt_params *params, bhrt_outputs *out);
 
+/* ---- the asynchronous seam of the reference's viewer (viewport.cpp:37-38: "Called to start rendering (renderer
+ * must run in a separate thread)"; :395-415 polls RenderImage::IsRenderDone / GetNumRenderedPixels; :449-453 calls
+ * BeginRender / StopRender):
+ *   bhrt_render_async  BeginRender() on a worker thread of the library: returns at once; params / out must stay valid
+ *                      until bhrt_wait.  One frame at a time per ctx; until bhrt_wait returns only bhrt_progress,
+ *                      bhrt_cancel and bhrt_wait may be called on the ctx.
+ *   bhrt_progress      RenderImage::GetNumRenderedPixels / IsRenderDone: pixels whose samples have been handed to the
+ *                      GPU so far (camera samples claimed / spp), the frame's pixel count, and whether it is finished.
+ *   bhrt_cancel        StopRender() (empty in the reference, Main.cpp:243): the kernels stop taking new camera samples;
+ *                      samples in flight finish, so the frame ends within milliseconds.
+ *   bhrt_wait          joins the worker: the frame's status (BHRT_ERR_CANCELLED after a cancel; the outputs then hold
+ *                      what was resolved from the partial accumulation). */
+int bhrt_render_async(bhrt_ctx *ctx, const bhrt_params *params, bhrt_outputs *out);
+int bhrt_progress(bhrt_ctx *ctx, int64_t *pixels_done, int64_t *pixels_total, int32_t *finished);
+int bhrt_cancel(bhrt_ctx *ctx);
+int bhrt_wait(bhrt_ctx *ctx);
+
 /* Device pointer of the accumulation buffer (float[H*W*4]: r,g,b sums + sample count) so a
  * multi-GPU host can all-reduce it (NCCL) between bhrt_render_device and bhrt_resolve. */
 int bhrt_accum_buffer(bhrt_ctx *ctx, void **device_ptr, size_t *bytes);
@@ -247,6 +265,13 @@ int bhrt_aov_buffers(bhrt_ctx *ctx, void **hit_id_device_ptr, void **z_device_pt
 /* Divide by total_spp, gamma, 8-bit; copy requested outputs to HOST buffers (out may be NULL:
  * the resolved image then stays in device memory). */
 int bhrt_resolve(bhrt_ctx *ctx, int32_t total_spp, bhrt_outputs *out);
+
+/* RenderImage::GetSampleCount (reference scene.h:534,570; HEAD itself only ever stores 0 there, Main.cpp:214): the number
+ * of camera samples accumulated in each pixel by the last render (uint8[H*W], clamped at 255) -- after a multi-GPU
+ * reduce the frame's total, after a cancelled or partial (row / sample range) render what was actually taken.  Feed it
+ * to bhrt_host_sample_count_image for the reference's stretched 8-bit view (scene.h:602-626).  Call it before the next
+ * bhrt_resolve / bhrt_render re-uses the image buffers. */
+int bhrt_sample_counts(bhrt_ctx *ctx, uint8_t *host_counts);
 
 /* Run all further work of this ctx on the caller's CUDA stream (a cudaStream_t; NULL = the
  * ctx's own stream), so a host that interleaves collectives can order and time everything on
