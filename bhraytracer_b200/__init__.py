@@ -87,7 +87,7 @@ DEVICE_SYMBOLS = ["bhrt_abi_version", "bhrt_last_error", "bhrt_create", "bhrt_de
                   "bhrt_set_stream", "bhrt_launch_count",
                   "bhrt_photons_emit", "bhrt_photons_buffer", "bhrt_photons_set", "bhrt_photons_get",
                   "bhrt_photons_build", "bhrt_debug_trace_mesh", "bhrt_device_and_stream", "bhrt_frame_size", "bhrt_set_last_error",
-                  "bhrt_render_async", "bhrt_progress", "bhrt_cancel", "bhrt_wait", "bhrt_sample_counts"]
+                  "bhrt_render_async", "bhrt_progress", "bhrt_cancel", "bhrt_wait", "bhrt_sample_counts", "bhrt_photons_emit_global"]
 DIST_SYMBOLS = ["bhrt_dist_shard_rows", "bhrt_dist_shard_samples", "bhrt_dist_shard_photons", "bhrt_dist_unique_id", "bhrt_dist_create",
                 "bhrt_dist_destroy", "bhrt_dist_render", "bhrt_dist_photons"]
 HOST_SYMBOLS = ["bhrt_host_load_scene", "bhrt_host_free_scene", "bhrt_host_last_error", "bhrt_host_scene_desc",
@@ -145,6 +145,7 @@ def device_lib():
         L.bhrt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.bhrt_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.bhrt_photons_emit.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
+        L.bhrt_photons_emit_global.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
         L.bhrt_photons_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
         L.bhrt_photons_set.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int]
         L.bhrt_photons_get.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
@@ -389,9 +390,11 @@ class Renderer:
         return a, w
 
     # ---- caustic photon map -------------------------------------------------------------------
-    def photons_emit(self, target_stored, seed=1):
+    def photons_emit(self, target_stored, seed=1, global_map=False):
+        """BuildCausticPhotonMap's emission loop (or, global_map=True, BuildPhotonMap's); returns (stored, photon rays)."""
         stored, rays = C.c_int32(), C.c_uint64()
-        self._check(self._L.bhrt_photons_emit(self._ctx, int(target_stored), int(seed), C.byref(stored), C.byref(rays)))
+        fn = self._L.bhrt_photons_emit_global if global_map else self._L.bhrt_photons_emit
+        self._check(fn(self._ctx, int(target_stored), int(seed), C.byref(stored), C.byref(rays)))
         return stored.value, rays.value
 
     def photons_buffer(self):

@@ -1871,6 +1871,8 @@ struct PhotonEmitCfg {
                                 // ComparePointLight (Main.cpp:247): ascending intensity.Gray() * int(size)
     int light[BHRT_MAX_LIGHTS]; // indices into SceneView::lights
     float sum;                  // sum of Gray() * int(size)  (Main.cpp:357-361)
+    int global_map;             // 0: caustic map (BuildCausticPhotonMap, Main.cpp:342-386); 1: the global map
+                                // (BuildPhotonMap / TracePhotonRay / MtlBlinn::RandomPhotonBounce, Main.cpp:251-317, MtlBlinn.cpp:140-202)
 };
 enum { PH_TRACE_WAIT = 0, PH_REFR_IN_WAIT = 1 };
 #define BHRT_PHOTON_ABSORB 0.3f     // Photon_AbsorbChance (MtlBlinn.cpp:27)
@@ -1903,6 +1905,51 @@ BHRT_HD void photon_begin(PhotonLane &P, const SceneView &s, const PhotonEmitCfg
     P.stage = PH_TRACE_WAIT;
     P.q.ray = r; P.q.kind = Q_CLOSEST; P.q.hitSide = HIT_FRONT; P.q.t_max = 0;
     rays++;
+}
+
+// The GLOBAL photon map's path (TracePhotonRay, Main.cpp:296-317 + MtlBlinn::RandomPhotonBounce, MtlBlinn.cpp:140-202):
+// stored on every photon surface after the first hit; a refractive surface ends the path, 30 % are absorbed, the
+// rest bounce diffusely or specularly with the colour divided by the lobe's probability.
+BHRT_HD bool photon_advance_global(PhotonLane &P, const SceneView &s, PhotonRecord &rec, bool &store, unsigned long long &rays)
+{
+    Rng &rng = P.rng;
+    store = false;
+    if (!P.hit_ok) return true;                                             // Main.cpp:314-316
+    const Ray ray = P.q.ray;
+    const Hit &h = P.hit;
+    const bhrt_material &M = s.materials[s.nodes[h.node].material];
+    if (!P.first && gray(ld3(M.diffuse.color)) > 0) {                       // IsPhotonSurface (materials.h:49)
+        photon_pack(rec, h.p, normalized(ray.dir), P.c);
+        store = true;
+    }
+    float rnd = rng.rnd01();
+    V3 vN = normalized(h.N);
+    V3 vV = -normalized(ray.dir);
+    if (gray(ld3(M.refraction)) > 0) return true;                           // MtlBlinn.cpp:149-151
+    if (rnd < BHRT_PHOTON_ABSORB) return true;
+    V3 dcol = ld3(M.diffuse.color), scol = ld3(M.specular.color);
+    float kd = fmaxr(fmaxr(dcol.x, dcol.y), dcol.z);
+    float ks = fmaxr(fmaxr(scol.x, scol.y), scol.z);
+    float dTheta = 0;
+    V3 ddir = normalized(sample_semisphere(vN, dTheta, rng));
+    float p_d = m_sin(2 * dTheta);
+    float sTheta = 0;
+    float cvn = dot(vN, vV);
+    V3 vR = 2 * cvn * vN - vV;
+    V3 sdir = sample_along_direction(vR, M.glossiness, sTheta, rng);
+    float p_s = m_pow(m_cos(sTheta), M.glossiness);
+    float P_d = kd * p_d;
+    float P_sum = P_d + ks * p_s;
+    float p_Diff = (P_d / P_sum) * (1 - BHRT_PHOTON_ABSORB) + BHRT_PHOTON_ABSORB;
+    float p_Spec = (1 - p_Diff) * (1 - BHRT_PHOTON_ABSORB) + BHRT_PHOTON_ABSORB;
+    const bool useSpecular = rnd >= p_Diff;
+    P.c = P.c * (useSpecular ? scol / p_Spec : dcol / p_Diff);
+    Ray nr; nr.dir = useSpecular ? sdir : ddir; nr.p = h.p + h.N * BHRT_BIAS;
+    P.first = false;
+    P.stage = PH_TRACE_WAIT;
+    P.q.ray = nr; P.q.kind = Q_CLOSEST; P.q.hitSide = HIT_FRONT;
+    rays++;
+    return false;
 }
 
 // Consumes the answer to P.q.  Returns true when the path ended; `store` tells the caller to

@@ -71,7 +71,7 @@ pm_emit(SceneView s, PhotonEmitCfg cfg, unsigned long long seed, unsigned target
         if (active) {
             P.hit_ok = scene_trace(s, P.q, P.hit);
             PhotonRecord r; bool store;
-            const bool ended = photon_advance(P, s, r, store, rays);
+            const bool ended = cfg.global_map ? photon_advance_global(P, s, r, store, rays) : photon_advance(P, s, r, store, rays);
             if (store) {
                 const unsigned slot = atomicAdd(&cnt->stored, 1u);
                 if (slot < target) records[slot] = r;       // PhotonMap::AddPhoton refuses beyond its size
@@ -172,10 +172,11 @@ struct PhotonState {
 
     // BuildCausticPhotonMap's emission loop.  The emitted records replace the current contents.
     int emit(const SceneView &view, const std::vector<bhrt_light> &sorted_lights, cudaStream_t stream, int sm_count, int target, unsigned long long seed,
-             int *stored, unsigned long long *photon_rays, unsigned long long &launches, std::string &err)
+             int *stored, unsigned long long *photon_rays, unsigned long long &launches, std::string &err, bool global_map = false)
     {
         if (target <= 0) { err = "bhrt_photons_emit: target_stored must be > 0"; return BHRT_ERR_ARG; }
         PhotonEmitCfg cfg = photon_emit_cfg(sorted_lights);
+        cfg.global_map = global_map ? 1 : 0;
         if (cfg.n_lights == 0) { err = "bhrt_photons_emit: the scene has no point light (Main.cpp:354 returns false)"; return BHRT_ERR_STATE; }
         int r;
         count = 0; built = false;

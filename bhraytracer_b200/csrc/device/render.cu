@@ -510,6 +510,7 @@ int bhrt_render_async(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *out)
     c->async_state = 1;
     c->worker = std::thread([c, p, out]() {
         int r = bhrt_render(c, p, out);
+        cudaMemset(c->cancel_flag.p, 0, 16);                    // a cancel ends with its frame (the stream is idle again here)
         if (r != BHRT_OK) c->async_error = g_err;               // (the worker's thread-local message)
         else if (c->cancel_requested.load()) { r = BHRT_ERR_CANCELLED; c->async_error = "the frame was cancelled (bhrt_cancel)"; }
         c->async_status = r;
@@ -557,6 +558,8 @@ int bhrt_wait(bhrt_ctx *c)
     if (!c) return set_err(BHRT_ERR_ARG, "bhrt_wait: null ctx");
     if (c->async_state.load() == 0) return set_err(BHRT_ERR_STATE, "bhrt_wait: no frame in flight");
     if (c->worker.joinable()) c->worker.join();
+    cudaSetDevice(c->device);
+    cudaMemset(c->cancel_flag.p, 0, 16);        // (a cancel that arrived just as the frame ended)
     c->async_state = 0;
     if (c->async_status != BHRT_OK) return set_err(c->async_status, c->async_error);
     return BHRT_OK;
@@ -687,6 +690,15 @@ int bhrt_photons_emit(bhrt_ctx *c, int32_t target_stored, uint64_t seed, int32_t
     CU(cudaSetDevice(c->device));
     std::string err;
     int r = c->photons.emit(c->view, c->sorted_lights, c->stream, c->sm_count, target_stored, seed, stored, (unsigned long long *)photon_rays, c->launches, err);
+    if (r) return set_err(r, err);
+    return BHRT_OK;
+}
+int bhrt_photons_emit_global(bhrt_ctx *c, int32_t target_stored, uint64_t seed, int32_t *stored, uint64_t *photon_rays)
+{
+    if (!c || !c->have_scene) return set_err(BHRT_ERR_STATE, "bhrt_photons_emit_global: no scene uploaded");
+    CU(cudaSetDevice(c->device));
+    std::string err;
+    int r = c->photons.emit(c->view, c->sorted_lights, c->stream, c->sm_count, target_stored, seed, stored, (unsigned long long *)photon_rays, c->launches, err, true);
     if (r) return set_err(r, err);
     return BHRT_OK;
 }

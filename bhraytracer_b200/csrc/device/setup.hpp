@@ -72,7 +72,7 @@ inline void fill_mesh_nodes(SceneView &s, const bhrt_node *host_nodes, int n_nod
 inline PhotonEmitCfg photon_emit_cfg(const std::vector<bhrt_light> &lights)
 {
     PhotonEmitCfg cfg;
-    cfg.n_lights = 0; cfg.sum = 0;
+    cfg.n_lights = 0; cfg.sum = 0; cfg.global_map = 0;
     for (size_t i = 0; i < lights.size() && cfg.n_lights < BHRT_MAX_LIGHTS; i++)
         if (lights[i].kind == BHRT_LIGHT_POINT) cfg.light[cfg.n_lights++] = (int)i;
     auto w = [&](int li) { return gray(ld3(lights[li].intensity)) * (float)(int)lights[li].size; };

@@ -307,6 +307,11 @@ int bhrt_debug_trace_mesh(bhrt_ctx *ctx, int32_t mesh, int32_t n, const float *r
  * the host).  build: scales powers by 1/total_stored (Main.cpp:380) and builds the gather
  * structure over the photons currently set. */
 int bhrt_photons_emit(bhrt_ctx *ctx, int32_t target_stored, uint64_t seed, int32_t *stored, uint64_t *photon_rays);
+/* The GLOBAL photon map the reference also knows how to build (BuildPhotonMap / TracePhotonRay, Main.cpp:251-317, with
+ * MtlBlinn::RandomPhotonBounce, MtlBlinn.cpp:140-202; its only call is commented out at Main.cpp:196 and HEAD never
+ * gathers from it): same records, same get / set / build calls afterwards -- a photon is stored on every diffuse
+ * surface after its first hit, refractive surfaces end the path, 30 % of the bounces are absorbed. */
+int bhrt_photons_emit_global(bhrt_ctx *ctx, int32_t target_stored, uint64_t seed, int32_t *stored, uint64_t *photon_rays);
 int bhrt_photons_buffer(bhrt_ctx *ctx, void **device_ptr, int32_t *count);
 int bhrt_photons_set(bhrt_ctx *ctx, const void *records, int32_t count, int from_device);
 int bhrt_photons_get(bhrt_ctx *ctx, void *host_records, int32_t max_count, int32_t *count);

@@ -14,6 +14,7 @@ Patch list (numbers = SURVEY.md section 8(c)):
   O-3  `return true;` at the end of both photon builders (UB otherwise)
   O-4  per-thread rand() (driver.cpp, link-time; no source edit)
   O-5  AOV + ray-counter hooks
+  O-7  --global-photons: call BuildPhotonMap (Main.cpp:251-295; its call at Main.cpp:196 is commented out at HEAD), dump, exit
   D-1  det mode: no jitter              (Main.cpp:153)
   D-2  det mode: GI term off            (MtlBlinn.cpp:124)
   D-3  det mode: all lights, exact L    (MtlBlinn.cpp:308)
@@ -36,7 +37,7 @@ REF = os.environ.get("BHRT_REFERENCE", "/root/reference") + "/BHRayTracer"
 OUT = os.path.join(HERE, "_ref")
 
 HOOKS = (
-    "extern int g_bhrt_det, g_bhrt_spp, g_bhrt_gi, g_bhrt_photons; extern const char* g_bhrt_photon_path;\n"
+    "extern int g_bhrt_det, g_bhrt_spp, g_bhrt_gi, g_bhrt_photons, g_bhrt_global_pm; extern const char* g_bhrt_photon_path; void bhrt_global_done();\n"
     "class Node; void bhrt_record_primary(int,int,const Node*,float); void bhrt_record_linear(int,int,float,float,float);\n"
     "void bhrt_count_closest(); void bhrt_count_shadow(); void bhrt_photon_begin(); void bhrt_photon_end();\n"
 )
@@ -66,7 +67,7 @@ PATCHES = {
         (158, "recursive(&rootNode, ray, tHitInfo, bHit, HIT_FRONT);",
          lambda s: s + "\t\tif (i == 0) bhrt_record_primary(i_i, i_j, bHit ? tHitInfo.node : nullptr, tHitInfo.z);\n"),
         (197, "BuildCausticPhotonMap(lights, &rootNode);",
-         lambda s: "\tbhrt_photon_begin(); BuildCausticPhotonMap(lights, &rootNode); bhrt_photon_end();\n"),
+         lambda s: "\tbhrt_photon_begin(); if (g_bhrt_global_pm) { BuildPhotonMap(lights, &rootNode); bhrt_global_done(); } BuildCausticPhotonMap(lights, &rootNode); bhrt_photon_end();\n"),
         (218, "outColor = PathTracing(i, j);",
          lambda s: s + "\t\t\tbhrt_record_linear(i, j, outColor.r, outColor.g, outColor.b);\n"),
         (240, "SaveImages();", lambda s: "\t;\n"),

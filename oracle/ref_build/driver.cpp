@@ -39,6 +39,7 @@ int g_bhrt_det = 0;
 int g_bhrt_spp = 32;      // reference Main.cpp:141
 int g_bhrt_gi = 3;        // reference Main.cpp:130
 int g_bhrt_photons = 1000000;  // reference Main.cpp:52-53
+int g_bhrt_global_pm = 0;      // --global-photons: BuildPhotonMap instead of BuildCausticPhotonMap, then exit (patch O-7)
 const char *g_bhrt_photon_path = nullptr;
 
 static std::vector<float> s_linear;
@@ -74,6 +75,8 @@ void bhrt_count(int k) { s_work[omp_get_thread_num() & 511].c[k]++; }
 void bhrt_count_closest() { s_cnt[omp_get_thread_num() & 511].closest++; }
 void bhrt_count_shadow() { s_cnt[omp_get_thread_num() & 511].shadow++; }
 void bhrt_photon_begin() { s_photon_t0 = omp_get_wtime(); }
+static FILE *s_real_out = nullptr;
+void bhrt_global_done() { FILE *o = s_real_out ? s_real_out : stdout; fprintf(o, "{\"global_photon_map\": true, \"photons\": %d, \"photon_build_ms\": %.3f}\n", g_bhrt_photons, (omp_get_wtime() - s_photon_t0) * 1e3); fflush(o); _exit(0); }
 void bhrt_photon_end() { s_photon_ms = (omp_get_wtime() - s_photon_t0) * 1e3; }
 
 // ---- per-thread rand(): glibc's rand() takes a global lock (8 threads run 4x slower than 1,
@@ -129,6 +132,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(argv[a], "--photons") && a + 1 < argc) g_bhrt_photons = atoi(argv[++a]);
 		else if (!strcmp(argv[a], "--png")) writePng = 1;
 		else if (!strcmp(argv[a], "--libc-rand")) s_use_libc_rand = 1;
+		else if (!strcmp(argv[a], "--global-photons")) g_bhrt_global_pm = 1;
 		else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
 	}
 	if (g_bhrt_det) g_bhrt_spp = 1;
@@ -138,6 +142,7 @@ int main(int argc, char **argv)
 
 	// the loader printf()s the whole scene; keep stdout for the JSON line only
 	FILE *realOut = fdopen(dup(fileno(stdout)), "w");
+	s_real_out = realOut;
 	if (!freopen("/dev/null", "w", stdout)) return 3;
 	if (!LoadScene(scene)) { fprintf(stderr, "LoadScene failed: %s\n", scene); return 3; }
 	s_W = camera.imgWidth; s_H = camera.imgHeight;

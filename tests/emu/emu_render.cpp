@@ -6,6 +6,7 @@
 // usage: emu_render <scene.xml> <out_prefix> [--det] [--spp N] [--gi N] [--seed S] [--size W H]
 //                   [--rows B E STRIDE] [--samples B E]
 //                   [--emit N FILE]                 emit N caustic photons (unscaled power) into FILE and exit
+//                   [--emit-global N FILE]          the same for the GLOBAL photon map (BuildPhotonMap, Main.cpp:251-317)
 //                   [--photons FILE TOTAL K RADIUS] render with the caustic gather term over the
 //                                                   24-byte records of FILE, powers scaled by 1/TOTAL
 //                   [--queries IN OUT]              with --photons: evaluate the irradiance estimate at the
@@ -56,7 +57,7 @@ int main(int argc, char **argv)
     if (argc < 3) { fprintf(stderr, "usage: %s scene.xml out_prefix [--det] [--spp N] [--gi N] [--seed S] [--size W H]\n", argv[0]); return 2; }
     int det = 0, spp = 32, gi = 3, W = 0, H = 0;
     int row_b = 0, row_e = 0, row_s = 1, smp_b = 0, smp_e = 0;
-    int emit_n = 0; const char *emit_file = nullptr;
+    int emit_n = 0, emit_global = 0; const char *emit_file = nullptr;
     const char *photon_file = nullptr; int photon_total = 1, photon_k = 1000; float photon_radius = 0.5f;
     const char *query_in = nullptr, *query_out = nullptr;
     const char *pixel_rays = nullptr;
@@ -71,6 +72,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[a], "--rows") && a + 3 < argc) { row_b = atoi(argv[++a]); row_e = atoi(argv[++a]); row_s = atoi(argv[++a]); }
         else if (!strcmp(argv[a], "--samples") && a + 2 < argc) { smp_b = atoi(argv[++a]); smp_e = atoi(argv[++a]); }
         else if (!strcmp(argv[a], "--emit") && a + 2 < argc) { emit_n = atoi(argv[++a]); emit_file = argv[++a]; }
+        else if (!strcmp(argv[a], "--emit-global") && a + 2 < argc) { emit_n = atoi(argv[++a]); emit_file = argv[++a]; emit_global = 1; }
         else if (!strcmp(argv[a], "--photons") && a + 4 < argc) { photon_file = argv[++a]; photon_total = atoi(argv[++a]); photon_k = atoi(argv[++a]); photon_radius = (float)atof(argv[++a]); }
         else if (!strcmp(argv[a], "--pixel-rays") && a + 1 < argc) pixel_rays = argv[++a];
         else if (!strcmp(argv[a], "--max-frames") && a + 1 < argc) max_frames = atoi(argv[++a]);
@@ -135,7 +137,7 @@ int main(int argc, char **argv)
             for (;;) {
                 P.hit_ok = scene_trace(s, P.q, P.hit);
                 PhotonRecord r; bool store;
-                bool ended = photon_advance(P, s, r, store, rays);
+                bool ended = emit_global ? photon_advance_global(P, s, r, store, rays) : photon_advance(P, s, r, store, rays);
                 if (store && (int)recs.size() < emit_n) recs.push_back(r);
                 if (ended) break;
             }

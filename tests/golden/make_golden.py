@@ -165,9 +165,18 @@ def main():
                     os.remove(sp + ".small.xml")
             assert len(rec) == nph
             st = photon_stats(big, len(big))
+            # the GLOBAL map (BuildPhotonMap, Main.cpp:251-295; oracle patch O-7 runs it and exits after its dump): statistics only
+            sp3 = sized_scene(name, 16, 12, tmp)
+            try:
+                prefix3 = os.path.join(tmp, name + "_gpm")
+                subprocess.check_output([REF_PM, sp3, prefix3, "--photons", "300000", "--seed", "5", "--global-photons"], cwd=ROOT)
+                glob = np.fromfile(prefix3 + ".photons.dat", dtype=PHOTON_DT)
+            finally:
+                os.remove(sp3)
+            gst = {"global_" + k: v for k, v in photon_stats(glob, len(glob)).items()}
             outp = os.path.join(ROOT, "tests", "golden", name + "_pm.npz")
             np.savez_compressed(outp, photons=rec.view(np.uint8).reshape(-1, 24), hit_id=a["hit_id"].astype(np.int16), rgb8=a["rgb8"],
-                                width=w, height=h, k=1000, radius=0.5, stats_photons=len(big), **st)
+                                width=w, height=h, k=1000, radius=0.5, stats_photons=len(big), global_stats_photons=len(glob), **st, **gst)
             print("%-28s %dx%d photon map %d photons -> %d bytes" % (name, w, h, nph, os.path.getsize(outp)))
         for name, w, h, spp, ref_spp in STOCH:
             if only and name not in only:

@@ -31,11 +31,21 @@ def check_gather_image(rgb8, hit_id):
     assert d.max() <= 1, "8-bit error %d > 1/255 on %d pixels" % (d.max(), int((d.max(axis=2) > 1).sum()))
 
 
-def check_emission_stats(raw, n_target):
-    """Distribution of OUR photons (unscaled power) vs the reference's 300 k-photon statistics."""
+def check_emission_stats(raw, n_target, prefix=""):
+    """Distribution of OUR photons (unscaled power) vs the reference's 300 k-photon statistics (prefix "global_": of the
+    global map, BuildPhotonMap)."""
     rec = as_records(raw)
     assert len(rec) == n_target
     st = photon_stats(rec, 1.0)
+    G = GOLD
+    if prefix:
+        G = {k[len(prefix):]: GOLD[k] for k in GOLD.files if k.startswith(prefix)}
+        return _compare_stats(st, G, len(rec), caustic=False)
+    return _compare_stats(st, GOLD, len(rec), caustic=True)
+
+
+def _compare_stats(st, GOLD, n_rec, caustic):
+    rec = range(n_rec)
     n_ref = float(GOLD["stats_photons"])
     # binomial standard error of a bin share with both sample sizes, 5 sigma + a small floor
     def tol(p):
@@ -48,7 +58,8 @@ def check_emission_stats(raw, n_target):
     ref_floor = GOLD["floor_hist"].astype(np.float64)
     assert (np.abs(st["floor_hist"] - ref_floor) < tol(ref_floor)).all(), "caustic footprint on the floor differs"
     # the caustic must actually be a concentration: the busiest floor cell holds far more than the uniform share
-    assert st["floor_hist"].max() > 20.0 / (24 * 24)
+    if caustic:
+        assert st["floor_hist"].max() > 20.0 / (24 * 24)
 
 
 def check_record_format(raw):
@@ -221,6 +232,32 @@ def test_gpu_emission_statistics(renderer):
     a = set(np.ascontiguousarray(raw).view(np.dtype((np.void, 24))).reshape(-1).tolist())
     c = set(np.ascontiguousarray(again).view(np.dtype((np.void, 24))).reshape(-1).tolist())
     assert len(a & c) > 0.97 * n        # (the paths in flight when the map filled up race for the last slots)
+
+
+def test_global_photon_map_statistics_on_the_cpu_build(built, tmp_path):
+    """The device code's global-map path (photon_advance_global) through the CPU harness against the reference's statistics."""
+    f = str(tmp_path / "g.dat")
+    subprocess.check_output([EMU_BIN, SCENE, str(tmp_path / "e"), "--size", "16", "12", "--emit-global", "120000", f, "--seed", "3"], cwd=ROOT, stderr=subprocess.DEVNULL)
+    raw = np.fromfile(f, dtype=np.uint8).reshape(-1, 24)
+    check_record_format(raw)
+    check_emission_stats(raw, 120000, prefix="global_")
+
+
+@pytest.mark.gpu
+def test_gpu_global_photon_map_statistics(renderer):
+    """SURVEY 8(f)-2: the GLOBAL photon map (BuildPhotonMap / TracePhotonRay, Main.cpp:251-317; MtlBlinn::RandomPhotonBounce,
+    MtlBlinn.cpp:140-202) against the reference's own 300 k-photon run of that code (oracle patch O-7)."""
+    import bhraytracer_b200 as b
+    scene = b.LoadScene(SCENE, W, H)
+    renderer.upload(scene)
+    n = 200000
+    stored, rays = renderer.photons_emit(n, seed=11, global_map=True)
+    assert stored == n and rays > n
+    raw = renderer.photons_get()
+    check_record_format(raw)
+    check_emission_stats(raw, n, prefix="global_")
+    # and it is a different map from the caustic one: photons everywhere, not only under the glass
+    assert as_records(raw)["pos"][:, 2].max() > 5.0
 
 
 @pytest.mark.gpu
