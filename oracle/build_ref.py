@@ -21,6 +21,8 @@ Patch list (numbers = SURVEY.md section 8(c)):
   D-4  det mode: refraction gloss = 0   (MtlBlinn.cpp:116)
 All D-* patches are runtime-switched by g_bhrt_det, so one binary serves both modes.
 `bhrt_ref_pm` is the same build with -DUSE_PhotonMap (reference Main.cpp:51, MtlBlinn.cpp:25).
+`bhrt_ref_gpu` links the reference's loader and scene classes with ref_build/GpuRender.cpp: the reference-side
+binding of INTEGRATION.md 1 (flattens the reference's loaded globals into include/bhrt.h tables; renders through libbhrt.so).
 `bhrt_ref_cnt` is bhrt_ref with -DBHRT_COUNT_ALL: five more per-thread counters (instances
 tested, BVH boxes tested, triangles tested, triangles accepted, file-texture taps) that define
 the ALGORITHMIC bytes per ray of SURVEY.md 8(d); it is never used for timing.
@@ -151,6 +153,11 @@ def main():
             jobs.append((src, os.path.join(tmp, "V_%s.o" % stem), extra))
             jobs.append((src, os.path.join(tmp, "V_%s_cnt.o" % stem), extra + ["-DBHRT_COUNT_ALL"]))
         jobs.append((main_src, os.path.join(tmp, "V_Main_pm.o"), ["-Dmain=ref_main_unused", "-DUSE_PhotonMap"]))
+        # the reference-side binding of INTEGRATION.md 1 (GpuRender.cpp): the reference's loader + this repository's C ABI
+        ROOT_INC = os.path.join(os.path.dirname(HERE), "include")
+        jobs.append((os.path.join(HERE, "ref_build/GpuRender.cpp"), os.path.join(tmp, "V_GpuRender.o"),
+                     ["-I" + ROOT_INC, "-I" + os.path.join(HERE, "ref_build"), "-std=c++17"]))
+        jobs.append((os.path.join(HERE, "ref_build/driver.cpp"), os.path.join(tmp, "V_driver_nomain.o"), ["-Dmain=bhrt_ref_driver_main_unused"]))
         for tag, extra in (("", []), ("_pm", ["-DUSE_PhotonMap"])):
             jobs.append((mtl_src, os.path.join(tmp, "V_MtlBlinn%s.o" % tag), ["-I" + REF + "/Materials/Blinn"] + extra))
 
@@ -168,10 +175,11 @@ def main():
             "bhrt_ref": plain + [V("Main"), V("MtlBlinn")],
             "bhrt_ref_pm": plain + [V("Main_pm"), V("MtlBlinn_pm")],
             "bhrt_ref_cnt": [V(st + "_cnt") for st in ("GenLight", "Box", "TriObj", "Texture", "driver", "Main")] + [V("MtlBlinn")],
+            "bhrt_ref_gpu": [V("GenLight"), V("Box"), V("TriObj"), V("Texture"), V("driver_nomain"), V("Main"), V("MtlBlinn"), V("GpuRender")],
         }
         for name, extra_objs in variants.items():
             exe = os.path.join(OUT, name)
-            subprocess.check_call(["g++", "-fopenmp", "-o", exe] + common + extra_objs)
+            subprocess.check_call(["g++", "-fopenmp", "-o", exe] + common + extra_objs + ["-ldl"])
             print("built", exe)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

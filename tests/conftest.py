@@ -25,7 +25,7 @@ def assets():
 def built():
     """Make sure the native pieces exist (they are built by __graft_entry__.build())."""
     lib = os.path.join(ROOT, "bhraytracer_b200", "lib")
-    need = [os.path.join(lib, "libbhrt.so"), os.path.join(lib, "libbhrt_host.so"), os.path.join(ROOT, "build", "emu_render")]
+    need = [os.path.join(lib, "libbhrt.so"), os.path.join(lib, "libbhrt_host.so"), os.path.join(ROOT, "build", "emu_render"), os.path.join(ROOT, "build", "desc_dump")]
     if not all(os.path.exists(p) for p in need):
         subprocess.check_call([sys.executable, os.path.join(ROOT, "__graft_entry__.py"), "build"])
     return lib
