@@ -352,9 +352,11 @@ class Renderer:
     # ---- the viewer's asynchronous contract (reference viewport.cpp:37-38,395-415,449-453)
     def render_async(self, params=None, want=("rgb8", "linear", "hit_id", "z"), **kw):
         """BeginRender() on the library's worker thread; returns at once.  Poll progress(), then wait()."""
-        self._async_p = params or self.params(**kw)
-        self._async_o, self._async_bufs = self._alloc_outputs(want)
-        self._check(self._L.bhrt_render_async(self._ctx, C.byref(self._async_p), C.byref(self._async_o)))
+        p = params or self.params(**kw)
+        o, bufs = self._alloc_outputs(want)
+        self._check(self._L.bhrt_render_async(self._ctx, C.byref(p), C.byref(o)))
+        # (kept alive until wait(): the library's worker thread reads params and writes the outputs)
+        self._async_p, self._async_o, self._async_bufs = p, o, bufs
 
     def progress(self):
         """(pixels done, pixels total, finished) -- RenderImage::GetNumRenderedPixels / IsRenderDone."""

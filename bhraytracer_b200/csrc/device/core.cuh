@@ -460,7 +460,11 @@ BHRT_HD void intersect_pair(const PairNode *pn, const Ray &r, float t_max, bool 
 //
 // Result: closest -> number of accepted triangles > 0 (z, front, mh updated);
 //         shadow  -> the reference's bool.
-struct MeshTrav {
+// (the scalars and the deferred-children stack are separate objects on purpose: the traversal phase of the render
+// kernel keeps a COPY of the scalars in registers while it steps -- as members of one struct next to dynamically
+// indexed arrays the compiler has to assume every push may have changed them and re-reads the ray from local memory on
+// every step, which was 37 % of the kernel's local-memory traffic, profiles/r2_cfg2_wf_render_ncu_summary.json)
+struct MeshTravHot {
     Ray ray;
     float len_dir;
     const PairNode *pairs;
@@ -475,12 +479,15 @@ struct MeshTrav {
 #ifndef __CUDACC__
     const WideNode *wide; uint32_t wide_root, wide_root_aux;    // CPU harness only (wide_trav_run)
 #endif
+};
+struct MeshTravStack {
     uint32_t st_word[BHRT_BVH_STACK];
     float st_tmin[BHRT_BVH_STACK];
 #if !BHRT_FAST
     int st_hits[BHRT_BVH_STACK];        // (fast build: only box-hit children are deferred, see mesh_trav_pop)
 #endif
 };
+struct MeshTrav : MeshTravHot { MeshTravStack stk; };
 
 BHRT_HD void mesh_trav_begin(MeshTrav &T, const SceneView &s, const MeshAccel &A, const Ray &ray, bool any_hit, float t_max_shadow,
                              float z, bool front, int hitSide)
@@ -504,7 +511,7 @@ BHRT_HD void mesh_trav_begin(MeshTrav &T, const SceneView &s, const MeshAccel &A
 #define BHRT_TRAV_HOOK(is_leaf, is_shadow)
 #endif
 // after a leaf, or an internal node neither of whose boxes was hit: resume at the deferred child
-BHRT_HD void mesh_trav_pop(MeshTrav &T)
+BHRT_HD void mesh_trav_pop(MeshTravHot &T, MeshTravStack &S)
 {
     while (T.sp > 0) {
         T.sp--;
@@ -513,20 +520,20 @@ BHRT_HD void mesh_trav_pop(MeshTrav &T)
             // only children whose box was hit (tmin < z at that time) are deferred in this build, and z can only
             // have shrunk through a hit in the near child since: the reference's "near child produced a hit and
             // z <= tmin_far" is then the plain distance cull, and no hit count needs to be remembered
-            if (!(T.z > T.st_tmin[T.sp])) continue;
+            if (!(T.z > S.st_tmin[T.sp])) continue;
 #else
-            bool nearHit = (T.hits != T.st_hits[T.sp]);
-            if (nearHit && !(T.z > T.st_tmin[T.sp])) continue;
+            bool nearHit = (T.hits != S.st_hits[T.sp]);
+            if (nearHit && !(T.z > S.st_tmin[T.sp])) continue;
 #endif
         }
-        T.cur = T.st_word[T.sp];
+        T.cur = S.st_word[T.sp];
         return;
     }
     T.result = T.hits > 0;
     T.done = true;
 }
 // T.cur is an internal node: both child boxes, near child first
-BHRT_HD void mesh_trav_internal(MeshTrav &T)
+BHRT_HD void mesh_trav_internal(MeshTravHot &T, MeshTravStack &S)
 {
     BHRT_TRAV_HOOK(false, T.any_hit);
     bool h1, h2; float t1, t2; uint32_t w1, w2;
@@ -543,19 +550,19 @@ BHRT_HD void mesh_trav_internal(MeshTrav &T)
         if (!(h1 && h2)) { T.cur = h1 ? w1 : w2; return; }
 #endif
         if (T.sp < BHRT_BVH_STACK) {
-            T.st_word[T.sp] = second; T.st_tmin[T.sp] = tsecond;
+            S.st_word[T.sp] = second; S.st_tmin[T.sp] = tsecond;
 #if !BHRT_FAST
-            T.st_hits[T.sp] = T.hits;
+            S.st_hits[T.sp] = T.hits;
 #endif
             T.sp++;
         }
         T.cur = first;
         return;
     }
-    mesh_trav_pop(T);
+    mesh_trav_pop(T, S);
 }
 // T.cur is a leaf: its triangles
-BHRT_HD void mesh_trav_leaf(MeshTrav &T)
+BHRT_HD void mesh_trav_leaf(MeshTravHot &T, MeshTravStack &S)
 {
     BHRT_TRAV_HOOK(true, T.any_hit);
     const uint32_t cur = T.cur;
@@ -570,11 +577,11 @@ BHRT_HD void mesh_trav_leaf(MeshTrav &T)
         for (uint32_t i = 0; i < cnt; i++)
             if (intersect_trirec(T.tris + off + i, T.ray, T.len_dir, T.z, T.front, T.hitSide, T.mh)) T.hits++;
     }
-    mesh_trav_pop(T);
+    mesh_trav_pop(T, S);
 }
 BHRT_HD void mesh_trav_step(MeshTrav &T)
 {
-    if (BHRT_BVH_LEAF(T.cur)) mesh_trav_leaf(T); else mesh_trav_internal(T);
+    if (BHRT_BVH_LEAF(T.cur)) mesh_trav_leaf(T, T.stk); else mesh_trav_internal(T, T.stk);
 }
 
 #ifndef __CUDACC__

@@ -190,7 +190,13 @@ struct PhotonState {
         unsigned long long max_paths = 4096ull * (unsigned long long)target;
         if (max_paths < (1ull << 26)) max_paths = 1ull << 26;
         if (const char *e = getenv("BHRT_PHOTON_MAX_PATHS")) { const long long v = atoll(e); if (v > 0) max_paths = (unsigned long long)v; }
-        pm_emit<<<sm_count * per_sm, 128, 0, stream>>>(view, cfg, seed, (unsigned)target, max_paths, records, counters);
+        // The reference's loop is serial: every path but the last one deposits ALL its photons.  Here the paths in
+        // flight when the map fills up are cut short, which under-represents late bounces by (lanes in flight) /
+        // (paths of the whole map): keep that share small -- at most one lane per 64 photons asked for.
+        int blocks = sm_count * per_sm;
+        const int cap = target / (64 * 128) > 1 ? target / (64 * 128) : 1;
+        if (blocks > cap) blocks = cap;
+        pm_emit<<<blocks, 128, 0, stream>>>(view, cfg, seed, (unsigned)target, max_paths, records, counters);
         launches++;
         PmEmitCounters h;
         if (cudaMemcpyAsync(&h, counters, sizeof(h), cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) {

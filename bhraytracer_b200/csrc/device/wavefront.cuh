@@ -65,6 +65,12 @@ namespace BHRT_NS {
 #ifndef WF_BLOCK
 #define WF_BLOCK 1024
 #endif
+// WF_PREFETCH_FRAME: the depth of every lane's frame stack is mirrored in shared memory, so a warp can ask for the top
+// frame's line (prefetch.global.L1) in the same breath as the lane record instead of after it has arrived.
+// MEASURED (round 2, config 2): 1495 Mrays/s with it, 1503 without -- no effect; off.
+#ifndef WF_PREFETCH_FRAME
+#define WF_PREFETCH_FRAME 0
+#endif
 #define WF_NKEYS 49
 #define WF_MESH_BUDGET 4
 // Sort keys.  A lane's key says what its next pass through the estimator will execute, as far as that
@@ -155,7 +161,7 @@ static inline int wf_wave_smem_bytes(unsigned pool, bool gather)
 {
     unsigned counts = (pool / 32 + 1) * WF_NKEYS * 2;       // group counts of the sort; with a photon map also the 4096 cell counters of the gather's query sort
     if (gather && counts < 4096u * 4u) counts = 4096u * 4u;
-    return (int)(pool * 2 /*list*/ + pool * 2 /*mesh queue*/ + pool /*key*/ + pool /*pending*/ + counts + 16);
+    return (int)(pool * 2 /*list*/ + pool * 2 /*mesh queue*/ + pool /*key*/ + pool /*pending*/ + counts + 16 + pool /*frame stack depths*/);
 }
 
 // Stage the small, uniformly-read scene tables in shared memory (node table, materials, lights,
@@ -563,6 +569,7 @@ wf_render(SceneView s, WaveArgs a)
     PmWarpScratch *pm_scratch = (PmWarpScratch *)(smem + a.smem_gather);   // [WF_BLOCK / 32]   (only with a photon map)
     unsigned short *gq = (unsigned short *)(pm_scratch + WF_BLOCK / 32);   // [P] lanes waiting for a caustic gather
     unsigned short *gcount = (unsigned short *)(pend + P);                 // [P/32][WF_NKEYS] per-group key counts / offsets (P is a multiple of 32)
+    unsigned char *lsp = smem + a.smem_gather - P - 16;                     // [P] min(frames in use, 255) of lane id (WF_PREFETCH_FRAME)
     __shared__ unsigned key_count[WF_NKEYS], key_base[WF_NKEYS];
     __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor, gq_count, gq_cursor, run_gather_s, n_parked_s;
     __shared__ WfClaim claim;
@@ -573,7 +580,7 @@ wf_render(SceneView s, WaveArgs a)
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     const bool det = a.cfg.mode == BHRT_MODE_DET;
 
-    for (unsigned i = tid; i < P; i += WF_BLOCK) { list[i] = (unsigned short)i; lkey[i] = WF_KEY_DEAD; pend[i] = 0; }
+    for (unsigned i = tid; i < P; i += WF_BLOCK) { list[i] = (unsigned short)i; lkey[i] = WF_KEY_DEAD; pend[i] = 0; lsp[i] = 0; }
     if (tid < WF_NKEYS) key_count[tid] = 0;
     if (tid == 0) {
         n_live_s = P; n_pending_s = 0; mq_head = 0; mq_tail = 0; p1_cursor = 0; run_mesh_s = 0; done_s = 0; gq_count = 0; gq_cursor = 0; n_parked_s = 0;
@@ -621,6 +628,12 @@ wf_render(SceneView s, WaveArgs a)
             bool want_new = valid && (first || was_idle);
             bool running = valid && !first && !was_idle;
             bool idle = false;
+#if WF_PREFETCH_FRAME
+            if (running) {
+                const unsigned d = lsp[id];
+                if (d > 0u && d < 255u) asm volatile("prefetch.global.L1 [%0];" ::"l"(&frames[(size_t)(d - 1u) * P]));
+            }
+#endif
             if (running) {
                 wf_load_lane(L, &lanes[id]);
                 // the answer of the pending query: winner-only work of a closest hit (a lane that comes
@@ -734,6 +747,7 @@ wf_render(SceneView s, WaveArgs a)
             }
             if (alive) {
                 wf_store_lane(&lanes[id], L);
+                lsp[id] = (unsigned char)(L.sp < 255 ? L.sp : 255);
 #if WF_LOCAL_FRAMES
                 lkey[id] = (unsigned char)wf_key(s, L, F);          // (F is the top level whenever L.sp > 0)
 #else
@@ -986,6 +1000,9 @@ wf_render(SceneView s, WaveArgs a)
                 if (drained && --budget <= 0) break;
             }
 #else
+            // (MEASURED, round 2: a register copy of the traversal's scalars for the length of the phase -- MeshTravHot,
+            // which exists so that it can be tried -- costs more in spills elsewhere than the per-step reloads it
+            // removes: 1437 against 1500 Mrays/s on config 2.  The 64-register budget of a 1024-thread CTA is the wall.)
             for (;;) {
                 const bool need = !have;
                 const unsigned nm = __ballot_sync(0xffffffffu, need);
@@ -1022,9 +1039,9 @@ wf_render(SceneView s, WaveArgs a)
                     const unsigned gm = __ballot_sync(0xffffffffu, go), jm = __ballot_sync(0xffffffffu, in_job);
                     // stop when no lane is at an internal node, or (after a few steps) when most are waiting at a leaf
                     if (!gm || (r >= a.trav_min && 100 * __popc(gm) <= a.trav_pct * __popc(jm))) break;
-                    if (go) mesh_trav_internal(J.T);
+                    if (go) mesh_trav_internal(J.T, J.T.stk);
                 }
-                if (have && !finished && !J.T.done && BHRT_BVH_LEAF(J.T.cur)) mesh_trav_leaf(J.T);
+                if (have && !finished && !J.T.done && BHRT_BVH_LEAF(J.T.cur)) mesh_trav_leaf(J.T, J.T.stk);
                 if (have && !finished && J.T.done) finished = mesh_job_harvest(J);
                 if (finished) {
                     Lane &Lg = lanes[jid];

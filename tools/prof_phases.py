@@ -12,20 +12,45 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import prof_lines as pl
 
 
+def _line_of(path, marker):
+    for i, l in enumerate(open(path), 1):
+        if marker in l:
+            return i
+    raise SystemExit("marker %r not found in %s" % (marker, path))
+
+
+def core_ranges():
+    """Line ranges of core.cuh's sections, found by their own markers (they move with every edit)."""
+    core = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bhraytracer_b200", "csrc", "device", "core.cuh")
+    return {
+        "trav": (_line_of(core, "BHRT_HD bool intersect_box6("), _line_of(core, "// A ray query: the ONE place the estimator meets the geometry")),
+        "graph": (_line_of(core, "BHRT_HD bool scene_trace_graph("), _line_of(core, "BHRT_HD Ray node_local_ray(")),
+        "job": (_line_of(core, "BHRT_HD Ray node_local_ray("), _line_of(core, "// Winner-only part of the closest hit")),
+        "est": (_line_of(core, "struct alignas(128) Frame {"), _line_of(core, "// Caustic photon emission: BuildCausticPhotonMap")),
+    }
+
+
+_R = None
+
+
 def phase(fn, cur):
+    global _R
+    if _R is None:
+        _R = core_ranges()
     if cur is None:
         return "other"
     (f, l), _ = cur
     if fn != "<kernel>":
         return "fn:" + fn.split("::")[-1]
-    if f == "core.cuh" and 285 <= l <= 500:
-        return "P2:traversal (box/tri/step)"
-    if f == "core.cuh" and 620 <= l <= 720:
-        return "P2:job control"
-    if f == "core.cuh" and 500 < l < 620:
-        return "P1:scene graph loop"
-    if f == "core.cuh" and l >= 1250:
-        return "P1:estimator step"
+    if f == "core.cuh":
+        if _R["trav"][0] <= l < _R["trav"][1]:
+            return "P2:traversal (box/tri/step)"
+        if _R["job"][0] <= l < _R["job"][1]:
+            return "P2:job control"
+        if _R["graph"][0] <= l < _R["graph"][1]:
+            return "P1:scene graph loop"
+        if _R["est"][0] <= l < _R["est"][1]:
+            return "P1:estimator step"
     if f == "wavefront.cuh":
         return "wf:%d" % (l // 10 * 10)
     return "inl:%s:%d" % (f, l // 25 * 25)
