@@ -344,7 +344,18 @@ def bench_ours(args):
                 "; ray part only: the 24 B per photon examined by the gather are not in it" if pm else "")
         kernel_ms = kernel_ms_sum / args.steps
         rays_per_launch = total_rays / args.steps / world
-        achieved = bytes_per_ray * rays_per_launch / (kernel_ms * 1e-3) / 1e9
+        frame_bytes = bytes_per_ray * rays_per_launch
+        gather_note = None
+        if pm:
+            # + 24 B per photon the reference's kd-tree search examines, per gather query (counted by bhrt_ref_pm_cnt with the full map)
+            ga = json.load(open(os.path.join(ROOT, "profiles", "algorithmic_bytes.json")))[key].get("gather")
+            if ga:
+                queries = ga["gather_queries_per_camera_sample"] * W * H * SPP / world
+                frame_bytes += queries * ga["photons_examined_per_query"] * ga["bytes_per_photon_examined"]
+                src = src.replace("; ray part only: the 24 B per photon examined by the gather are not in it", "")
+                gather_note = "%.2f gather queries per camera sample x %.0f photons examined x 24 B (reference kd-tree, 10 M photons) added to the ray part" % (
+                    ga["gather_queries_per_camera_sample"], ga["photons_examined_per_query"])
+        achieved = frame_bytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key, {}).get("wf_render_dram_bytes_per_launch")
@@ -353,7 +364,7 @@ def bench_ours(args):
         line["roofline"] = {"bound": "hbm", "kernel": "wf_render (one persistent launch per frame)", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                             "frac": round(achieved / peak, 4), "traffic": traffic, "peak_kind": peak_kind,
                             "algorithmic_bytes_per_ray": round(bytes_per_ray, 1), "bytes_source": src,
-                            "kernel_ms_per_launch": round(kernel_ms, 3), "rays_per_launch": int(rays_per_launch),
+                            "kernel_ms_per_launch": round(kernel_ms, 3), "rays_per_launch": int(rays_per_launch), "gather_bytes": gather_note,
                             "note": "algorithmic bytes are defined on the reference's data structures (SURVEY.md 8d); the scene is L2-resident, the measured DRAM traffic is the kernel's own lane state (profiles/)"}
         line["cpu_baseline"] = cpu_baseline(cfg, SPP) if (world == 1 and os.path.exists(REF_BIN) and not args.no_cpu) else None
         print(json.dumps(line), flush=True)

@@ -363,26 +363,40 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     // photon-mapped frames are dominated by the caustic gathers, whose phase balances its 32 warps the
     // better the more queries it has: four times the lanes, gathered when nearly all of them are parked
     if (a.gather.use && !c->pool_lanes_set) a.pool = 12288;
+    auto al16 = [](int v) { return (v + 15) & ~15; };
+    // the shared-memory layout; a pool whose tables do not fit next to the scene's (large node / material tables) shrinks
+    const int smem_limit = 227 * 1024 - 2048;           // (static shared memory of the kernel included)
+    for (;;) {
+        a.smem_nodes = 0;
+        a.smem_materials = al16(a.smem_nodes + c->view.n_nodes * (int)sizeof(bhrt_node));
+        a.smem_lights = al16(a.smem_materials + c->view.n_materials * (int)sizeof(bhrt_material));
+        a.smem_offsets = al16(a.smem_lights + c->view.n_lights * (int)sizeof(bhrt_light));
+        a.smem_wave = al16(a.smem_offsets + 2 * (BHRT_TEX_SAMPLES - 1) * (int)sizeof(float));
+        a.smem_gather = al16(a.smem_wave + wf_wave_smem_bytes(a.pool, a.gather.use != 0));
+        // (the per-warp gather scratch only when a photon map is in use: without it the CTA stays under 32 KB)
+        a.smem_oct = al16(a.smem_gather + (a.gather.use ? (WF_BLOCK / 32) * (int)sizeof(PmWarpScratch) + (int)a.pool * 4 : 0));
+        if (a.smem_oct <= smem_limit || a.pool <= 1024u) break;
+        a.pool -= 1024u;
+    }
+    if (a.smem_oct > smem_limit) return set_err(BHRT_ERR_LIMIT, "bhrt_render: scene tables do not fit in shared memory");
     // a CTA claims its work in batches of whole super-tiles: one (4096 items) normally, two for photon-mapped frames
     // (measured on BASELINE config 5: 8192 items 7.6 s, 16384 items 8.1 s -- larger batches put whole caustic regions
     // on a few CTAs and the others wait for them)
     a.batch = (unsigned)(WF_ST * WF_ST * 64);
     if (a.gather.use) a.batch *= 2;
+    {
+        // ... but a share with little work (one GPU's 2 spp of a 16-spp frame split over 8) would leave each CTA only a
+        // handful of such batches and the frame would end with most CTAs waiting for the last ones (measured: 29.7 ms
+        // for 1/8 of a 188 ms frame): keep at least ~32 batches per CTA, down to 512 items
+        const unsigned long long per_cta = (unsigned long long)a.n_pix_work * (unsigned long long)(chunk > 0 ? chunk : 1) / (unsigned long long)(c->sm_count > 0 ? c->sm_count : 1) / 32ull;
+        while (a.batch > 512u && (unsigned long long)a.batch > per_cta) a.batch /= 2;
+    }
     while ((unsigned long long)(WF_RING - 1) * a.batch < (unsigned long long)a.pool + 32ull) a.batch *= 2;     // a pass must never run dry (wf_claim_topup)
     if (const char *e = getenv("BHRT_WORK_BATCH")) { const long v = atol(e); if (v >= 1) a.batch = (unsigned)v * (unsigned)(WF_ST * WF_ST * 64); }
     a.mesh_budget = c->mesh_budget;
     a.mesh_batch = c->mesh_batch;
     a.gather_batch = c->gather_batch ? c->gather_batch : a.pool - a.pool / 12;
     a.trav_min = c->trav_min; a.trav_max = c->trav_max; a.trav_pct = c->trav_pct;
-    auto al16 = [](int v) { return (v + 15) & ~15; };
-    a.smem_nodes = 0;
-    a.smem_materials = al16(a.smem_nodes + c->view.n_nodes * (int)sizeof(bhrt_node));
-    a.smem_lights = al16(a.smem_materials + c->view.n_materials * (int)sizeof(bhrt_material));
-    a.smem_offsets = al16(a.smem_lights + c->view.n_lights * (int)sizeof(bhrt_light));
-    a.smem_wave = al16(a.smem_offsets + 2 * (BHRT_TEX_SAMPLES - 1) * (int)sizeof(float));
-    a.smem_gather = al16(a.smem_wave + wf_wave_smem_bytes(a.pool, a.gather.use != 0));
-    // (the per-warp gather scratch only when a photon map is in use: without it the CTA stays under 32 KB)
-    a.smem_oct = al16(a.smem_gather + (a.gather.use ? (WF_BLOCK / 32) * (int)sizeof(PmWarpScratch) + (int)a.pool * 4 : 0));
     // stochastic frames run the fast-math build of the kernel unless the caller asks for the exact one; its
     // traversal phase is one ray per thread over the binary tree, or -- BHRT_FLAG_WIDE_BVH -- 8 lanes per ray over
     // the wide tree (per-octet stacks in shared memory) when every mesh has one and the stacks fit

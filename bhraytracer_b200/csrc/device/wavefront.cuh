@@ -161,7 +161,7 @@ static inline int wf_wave_smem_bytes(unsigned pool, bool gather)
 {
     unsigned counts = (pool / 32 + 1) * WF_NKEYS * 2;       // group counts of the sort; with a photon map also the 4096 cell counters of the gather's query sort
     if (gather && counts < 4096u * 4u) counts = 4096u * 4u;
-    return (int)(pool * 2 /*list*/ + pool * 2 /*mesh queue*/ + pool /*key*/ + pool /*pending*/ + counts + 16 + pool /*frame stack depths*/);
+    return (int)(pool * 2 /*list*/ + pool * 2 /*mesh queue*/ + pool /*key*/ + pool /*pending*/ + counts + 16 + (WF_PREFETCH_FRAME ? pool : 0u) /*frame stack depths*/);
 }
 
 // Stage the small, uniformly-read scene tables in shared memory (node table, materials, lights,
@@ -569,7 +569,9 @@ wf_render(SceneView s, WaveArgs a)
     PmWarpScratch *pm_scratch = (PmWarpScratch *)(smem + a.smem_gather);   // [WF_BLOCK / 32]   (only with a photon map)
     unsigned short *gq = (unsigned short *)(pm_scratch + WF_BLOCK / 32);   // [P] lanes waiting for a caustic gather
     unsigned short *gcount = (unsigned short *)(pend + P);                 // [P/32][WF_NKEYS] per-group key counts / offsets (P is a multiple of 32)
-    unsigned char *lsp = smem + a.smem_gather - P - 16;                     // [P] min(frames in use, 255) of lane id (WF_PREFETCH_FRAME)
+#if WF_PREFETCH_FRAME
+    unsigned char *lsp = smem + a.smem_gather - P - 16;                     // [P] min(frames in use, 255) of lane id
+#endif
     __shared__ unsigned key_count[WF_NKEYS], key_base[WF_NKEYS];
     __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor, gq_count, gq_cursor, run_gather_s, n_parked_s;
     __shared__ WfClaim claim;
@@ -580,7 +582,10 @@ wf_render(SceneView s, WaveArgs a)
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     const bool det = a.cfg.mode == BHRT_MODE_DET;
 
-    for (unsigned i = tid; i < P; i += WF_BLOCK) { list[i] = (unsigned short)i; lkey[i] = WF_KEY_DEAD; pend[i] = 0; lsp[i] = 0; }
+    for (unsigned i = tid; i < P; i += WF_BLOCK) { list[i] = (unsigned short)i; lkey[i] = WF_KEY_DEAD; pend[i] = 0; }
+#if WF_PREFETCH_FRAME
+    for (unsigned i = tid; i < P; i += WF_BLOCK) lsp[i] = 0;
+#endif
     if (tid < WF_NKEYS) key_count[tid] = 0;
     if (tid == 0) {
         n_live_s = P; n_pending_s = 0; mq_head = 0; mq_tail = 0; p1_cursor = 0; run_mesh_s = 0; done_s = 0; gq_count = 0; gq_cursor = 0; n_parked_s = 0;
@@ -747,7 +752,9 @@ wf_render(SceneView s, WaveArgs a)
             }
             if (alive) {
                 wf_store_lane(&lanes[id], L);
+#if WF_PREFETCH_FRAME
                 lsp[id] = (unsigned char)(L.sp < 255 ? L.sp : 255);
+#endif
 #if WF_LOCAL_FRAMES
                 lkey[id] = (unsigned char)wf_key(s, L, F);          // (F is the top level whenever L.sp > 0)
 #else

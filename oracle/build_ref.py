@@ -79,12 +79,16 @@ PATCHES = {
         (385, "fclose(fp);", lambda s: s.rstrip("\n") + " return true;\n"),
         (390, "if (root->GetNumChild() <= 0) return;", lambda s: "\tif (root == &rootNode) bhrt_count_closest();\n" + s),
     ],
+    "DataStructure/cyPhotonMap.h": [
+        (423, "Photon const &p = photons[index];", lambda s: s + "\t\tBHRT_CNT(5);\n"),
+    ],
     "Materials/Blinn/MtlBlinn.cpp": [
-        (1, "", lambda s: "extern int g_bhrt_det;\n" + s),
+        (1, "", lambda s: "extern int g_bhrt_det;\n" + CNT + s),
         (116, "if (glossiness > 50) refraction_glossiness = glossiness;",
          lambda s: s.replace("if (glossiness > 50)", "if (!g_bhrt_det && glossiness > 50)")),
         (124, "outColor += PathTracing_GlobalIllumination(", lambda s: "\tif (!g_bhrt_det) " + s.lstrip()),
         (308, "{", lambda s: DET_DIRECT + s),
+        (334, "causticPhotonMap->EstimateIrradiance<MAX_PhotonCountInArea>(", lambda s: "\t\t\tBHRT_CNT(6);\n" + s),
     ],
     "Lights/GenLight.cpp": [
         (1, "", lambda s: "void bhrt_count_shadow();\n" + CNT + s),
@@ -142,6 +146,11 @@ def main():
         jobs.append((os.path.join(HERE, "ref_build/gl_stubs.cpp"), os.path.join(tmp, "gl_stubs.o"), []))
         main_src = patched_copy("Main.cpp", tmp)
         mtl_src = patched_copy("Materials/Blinn/MtlBlinn.cpp", tmp)
+        # cyPhotonMap.h with the photons-examined counter: a quoted include looks in the including file's directory first,
+        # so the patched copy sits next to each patched source that includes it
+        hdr = patched_copy("DataStructure/cyPhotonMap.h", tmp)
+        shutil.copy(hdr, os.path.join(tmp, "cyPhotonMap.h"))
+        shutil.copy(hdr, os.path.join(tmp, "Materials", "Blinn", "cyPhotonMap.h"))
         # sources whose object differs between the plain and the -DBHRT_COUNT_ALL build
         counted = [(patched_copy("Lights/GenLight.cpp", tmp), "GenLight", ["-I" + REF + "/Lights"]),
                    (patched_copy("Objects/Box/Box.cpp", tmp), "Box", ["-I" + REF + "/Objects/Box"]),
@@ -153,6 +162,8 @@ def main():
             jobs.append((src, os.path.join(tmp, "V_%s.o" % stem), extra))
             jobs.append((src, os.path.join(tmp, "V_%s_cnt.o" % stem), extra + ["-DBHRT_COUNT_ALL"]))
         jobs.append((main_src, os.path.join(tmp, "V_Main_pm.o"), ["-Dmain=ref_main_unused", "-DUSE_PhotonMap"]))
+        jobs.append((main_src, os.path.join(tmp, "V_Main_pm_cnt.o"), ["-Dmain=ref_main_unused", "-DUSE_PhotonMap", "-DBHRT_COUNT_ALL"]))
+        jobs.append((mtl_src, os.path.join(tmp, "V_MtlBlinn_pm_cnt.o"), ["-I" + REF + "/Materials/Blinn", "-DUSE_PhotonMap", "-DBHRT_COUNT_ALL"]))
         # the reference-side binding of INTEGRATION.md 1 (GpuRender.cpp): the reference's loader + this repository's C ABI
         ROOT_INC = os.path.join(os.path.dirname(HERE), "include")
         jobs.append((os.path.join(HERE, "ref_build/GpuRender.cpp"), os.path.join(tmp, "V_GpuRender.o"),
@@ -175,6 +186,7 @@ def main():
             "bhrt_ref": plain + [V("Main"), V("MtlBlinn")],
             "bhrt_ref_pm": plain + [V("Main_pm"), V("MtlBlinn_pm")],
             "bhrt_ref_cnt": [V(st + "_cnt") for st in ("GenLight", "Box", "TriObj", "Texture", "driver", "Main")] + [V("MtlBlinn")],
+            "bhrt_ref_pm_cnt": [V(st + "_cnt") for st in ("GenLight", "Box", "TriObj", "Texture", "driver")] + [V("Main_pm_cnt"), V("MtlBlinn_pm_cnt")],
             "bhrt_ref_gpu": [V("GenLight"), V("Box"), V("TriObj"), V("Texture"), V("driver_nomain"), V("Main"), V("MtlBlinn"), V("GpuRender")],
         }
         for name, extra_objs in variants.items():

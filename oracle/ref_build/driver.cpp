@@ -67,7 +67,8 @@ void bhrt_record_linear(int i, int j, float r, float g, float b)
 }
 #ifdef BHRT_COUNT_ALL
 // work counters of the instrumented build (see build_ref.py): 0 instances tested, 1 BVH boxes
-// tested, 2 triangles tested, 3 triangles accepted (vn+vt fetched), 4 file-texture taps
+// tested, 2 triangles tested, 3 triangles accepted (vn+vt fetched), 4 file-texture taps, 5 photons examined by the gather
+// (LocatePhotons calls, cyPhotonMap.h:421; photon-map build only), 6 gather queries (EstimateIrradiance calls)
 struct alignas(64) Work { long long c[8]; };
 static Work s_work[512];
 void bhrt_count(int k) { s_work[omp_get_thread_num() & 511].c[k]++; }
@@ -176,10 +177,10 @@ int main(int argc, char **argv)
 		scene, s_W, s_H, g_bhrt_spp, g_bhrt_gi, g_bhrt_det, threads, s_use_libc_rand ? "libc" : "per-thread",
 		ms - s_photon_ms, s_photon_ms, closest, shadow, next);
 #ifdef BHRT_COUNT_ALL
-	long long w[5] = { 0, 0, 0, 0, 0 };
-	for (int i = 0; i < 512; i++) for (int k = 0; k < 5; k++) w[k] += s_work[i].c[k];
-	fprintf(realOut, ", \"inst_tested\": %lld, \"boxes_tested\": %lld, \"tris_tested\": %lld, \"tris_accepted\": %lld, \"texture_taps\": %lld",
-		w[0], w[1], w[2], w[3], w[4]);
+	long long w[7] = { 0, 0, 0, 0, 0, 0, 0 };
+	for (int i = 0; i < 512; i++) for (int k = 0; k < 7; k++) w[k] += s_work[i].c[k];
+	fprintf(realOut, ", \"inst_tested\": %lld, \"boxes_tested\": %lld, \"tris_tested\": %lld, \"tris_accepted\": %lld, \"texture_taps\": %lld, \"photons_examined\": %lld, \"gather_queries\": %lld",
+		w[0], w[1], w[2], w[3], w[4], w[5], w[6]);
 #endif
 	fprintf(realOut, "}\n");
 	fclose(realOut);
