@@ -258,9 +258,15 @@ struct PhotonRecord {
 // slip, cyPhotonMap.h:196 -- and the 8-bit colour ratio in the bits of b.w).
 struct alignas(16) GatherRec { F4 a, b; };
 
-#define BHRT_PM_SUB_BITS 4                          // octree levels below a coarse cell (6 -> cell/64 was measured: 3x SLOWER on config 5)
-#define BHRT_PM_LEVELS (BHRT_PM_SUB_BITS + 1)       // grid levels: cell, cell/2, ... cell/16
+// The coarse cell is HALF the gather radius.  Search level 0 looks at the 5x5x5 block of coarse cells (which covers
+// the whole radius: bound = r) -- on a surface that is 6.25 r^2 of photons instead of the 9 r^2 of a 3x3x3 block of
+// radius-sized cells, and rows of it beyond the radius are skipped; 88 % of config 5's queries end at this level.
+// Search level l >= 1 is the 3x3x3 block at grid resolution l - 1 (cell, cell/2, cell/4, cell/8 = r/16) with
+// bound = that cell edge.  (Two more resolutions were measured in round 1: 3x SLOWER on config 5.)
+#define BHRT_PM_SUB_BITS 3                          // octree levels below a coarse cell
+#define BHRT_PM_LEVELS (BHRT_PM_SUB_BITS + 2)       // search levels: 5x5x5 @ cell, then 3x3x3 @ cell, cell/2, cell/4, cell/8
 #define BHRT_PM_FINE_BITS (3 * BHRT_PM_SUB_BITS)    // Morton bits of the finest sub-cell
+#define BHRT_PM_RES(level) ((level) > 0 ? (level) - 1 : 0)      // grid resolution of a search level
 // Read-only view of the gather structure (photon_build.hpp / photon.cuh build it): photons sorted
 // by key = coarse cell << 12 | Morton code of the 1/16 sub-cell.  Every cell of every level is a
 // contiguous key range, so ONE sorted array serves all five resolutions; a query picks the level
@@ -1251,12 +1257,32 @@ BHRT_HD uint32_t pm_lower_bound(const uint32_t *keys, uint32_t lo, uint32_t hi, 
     return lo;
 }
 
-// key ranges of the 27 level-`level` cells around (coarse cell c, sub-cell s)
+// key ranges of the block of search level `level` around (coarse cell c, sub-cell s): level 0 -> the 25 ROWS of the
+// 5x5x5 block of coarse cells (the five x-adjacent cells of a row are consecutive coarse cells, i.e. one contiguous
+// range of records; entries 25, 26 stay empty); level >= 1 -> the 27 cells of the 3x3x3 block at resolution level - 1
 BHRT_HD void pm_ranges(const PhotonGather &pg, int level, const int *c, const int *sub, PmRange &R)
 {
-    const int sh = BHRT_PM_SUB_BITS - level;          // sub-cell bits dropped at this level
-    const int span = 1 << level;                      // level cells per coarse cell edge
-    int g[3] = { (c[0] << level) | (sub[0] >> sh), (c[1] << level) | (sub[1] >> sh), (c[2] << level) | (sub[2] >> sh) };
+    if (level == 0) {
+        int n = 0;
+        for (int dz = -2; dz <= 2; dz++)
+            for (int dy = -2; dy <= 2; dy++, n++) {
+                R.b[n] = 0; R.e[n] = 0;
+                const int y = c[1] + dy, z = c[2] + dz;
+                if (y < 0 || z < 0 || y >= pg.dim[1] || z >= pg.dim[2]) continue;
+                int x0 = c[0] - 2, x1 = c[0] + 2;
+                if (x0 < 0) x0 = 0;
+                if (x1 > pg.dim[0] - 1) x1 = pg.dim[0] - 1;
+                if (x0 > x1) continue;
+                const uint32_t row = (uint32_t)pg.dim[0] * ((uint32_t)y + (uint32_t)pg.dim[1] * (uint32_t)z);
+                R.b[n] = pg.coarse_start[row + (uint32_t)x0]; R.e[n] = pg.coarse_start[row + (uint32_t)x1 + 1u];
+            }
+        R.b[25] = R.e[25] = R.b[26] = R.e[26] = 0;
+        return;
+    }
+    const int res = level - 1;
+    const int sh = BHRT_PM_SUB_BITS - res;            // sub-cell bits dropped at this resolution
+    const int span = 1 << res;                        // cells per coarse cell edge
+    int g[3] = { (c[0] << res) | (sub[0] >> sh), (c[1] << res) | (sub[1] >> sh), (c[2] << res) | (sub[2] >> sh) };
     int n = 0;
     for (int dz = -1; dz <= 1; dz++)
         for (int dy = -1; dy <= 1; dy++)
@@ -1264,11 +1290,11 @@ BHRT_HD void pm_ranges(const PhotonGather &pg, int level, const int *c, const in
                 int x = g[0] + dx, y = g[1] + dy, z = g[2] + dz;
                 R.b[n] = 0; R.e[n] = 0;
                 if (x < 0 || y < 0 || z < 0 || x >= pg.dim[0] * span || y >= pg.dim[1] * span || z >= pg.dim[2] * span) continue;
-                uint32_t cx = (uint32_t)(x >> level), cy = (uint32_t)(y >> level), cz = (uint32_t)(z >> level);
+                uint32_t cx = (uint32_t)(x >> res), cy = (uint32_t)(y >> res), cz = (uint32_t)(z >> res);
                 uint32_t coarse = cx + (uint32_t)pg.dim[0] * (cy + (uint32_t)pg.dim[1] * cz);
                 uint32_t lo = pg.coarse_start[coarse], hi = pg.coarse_start[coarse + 1];
                 if (lo == hi) continue;
-                if (level == 0) { R.b[n] = lo; R.e[n] = hi; continue; }
+                if (res == 0) { R.b[n] = lo; R.e[n] = hi; continue; }
                 uint32_t m = photon_morton((uint32_t)(x & (span - 1)) << sh, (uint32_t)(y & (span - 1)) << sh, (uint32_t)(z & (span - 1)) << sh);
                 uint32_t k0 = (coarse << BHRT_PM_FINE_BITS) | m;
                 uint32_t k1 = k0 + (1u << (3 * sh));
@@ -1296,7 +1322,7 @@ BHRT_FN void estimate_irradiance(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad
     bool inside = true;
     for (int a = 0; a < 3; a++) {
         c[a] = (int)floorf(f[a]);
-        if (c[a] < -1 || c[a] > pg.dim[a]) return;          // farther than one cell from the grid: nothing in range
+        if (c[a] < -2 || c[a] > pg.dim[a] + 1) return;      // farther than two cells (>= the radius) from the grid: nothing in range
         int s_ = (int)((f[a] - c[a]) * (float)(1 << BHRT_PM_SUB_BITS));
         sub[a] = s_ < 0 ? 0 : (s_ > (1 << BHRT_PM_SUB_BITS) - 1 ? (1 << BHRT_PM_SUB_BITS) - 1 : s_);
         if (c[a] < 0 || c[a] >= pg.dim[a]) inside = false;
@@ -1307,7 +1333,7 @@ BHRT_FN void estimate_irradiance(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad
     if (inside) {
         uint32_t coarse = (uint32_t)c[0] + (uint32_t)pg.dim[0] * ((uint32_t)c[1] + (uint32_t)pg.dim[1] * (uint32_t)c[2]);
         float n_c = (float)(pg.coarse_start[coarse + 1] - pg.coarse_start[coarse]) * 3.14159265f;
-        float need = 2.f * pg.k * 4.f;
+        float need = 2.f * pg.k;                            // enough within one coarse cell edge: the 3x3x3 block at that resolution
         while (level < BHRT_PM_LEVELS - 1 && n_c > need) { level++; need *= 4.f; }
     }
     bool coarsened = false;         // a finer level held too few photons: do not try it again
@@ -1315,9 +1341,9 @@ BHRT_FN void estimate_irradiance(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad
     int hist[32];
     for (;;) {
         pm_ranges(pg, level, c, sub, R);
-        const float cell_l = pg.cell / (float)(1 << level);
-        // every photon this close lies in the 3x3x3 block; at level 0 the cell edge exceeds the gather radius
-        // (photon_grid: cell >= 1.001 r), so the radius itself is the bound there
+        const float cell_l = pg.cell / (float)(1 << BHRT_PM_RES(level));
+        // every photon this close lies in the block: level 0 reaches two coarse cells (photon_grid: 2 * cell >= 1.001 r), so
+        // the radius itself is the bound there; a 3x3x3 block is complete up to one cell edge
         float bound2 = level == 0 ? r2 : 0.998f * cell_l * cell_l;
         if (bound2 > r2) bound2 = r2;
         const float scale = 32.f / bound2;

@@ -22,13 +22,13 @@ struct PhotonGrid {
     int dim[3];
 };
 
-// Grid over the bounding box [lo,hi] of the photons.  The coarse cell is slightly larger than the
-// gather radius (so the radius itself is a safe block bound at level 0) and grows if the box would
+// Grid over the bounding box [lo,hi] of the photons.  The coarse cell is slightly larger than HALF the
+// gather radius (so the radius itself is a safe bound for the 5x5x5 block of search level 0) and grows if the box would
 // need more coarse cells than the key has room for (key layout: 32 - BHRT_PM_FINE_BITS bits coarse | BHRT_PM_FINE_BITS bits Morton).
 inline PhotonGrid photon_grid(const float lo[3], const float hi[3], float radius)
 {
     PhotonGrid g;
-    float cell = radius * 1.001f;
+    float cell = radius * 1.001f * 0.5f;
     for (;;) {
         double n = 1;
         for (int a = 0; a < 3; a++) {

@@ -409,7 +409,7 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
         int per_sm = 0;
         if (variant == 0) {
             CU(cudaFuncSetAttribute(wf_render, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-            CU(cudaFuncSetAttribute(wf_render, cudaFuncAttributePreferredSharedMemoryCarveout, (smem_bytes + 2048) * 100 / (228 * 1024) + 1));
+            CU(cudaFuncSetAttribute(wf_render, cudaFuncAttributePreferredSharedMemoryCarveout, WF_MIN_BLOCKS * (smem_bytes + 2048) * 100 / (228 * 1024) + 1));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_render, WF_BLOCK, smem_bytes));
         } else if (int e = (variant == 1 ? bhrt_fast_prepare : bhrt_fastb_prepare)(smem_bytes, &per_sm))
             return set_err(BHRT_ERR_CUDA, std::string("bhrt_render: ") + cudaGetErrorString((cudaError_t)e));

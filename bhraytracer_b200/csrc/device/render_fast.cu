@@ -41,7 +41,7 @@ int BHRT_FAST_ENTRY(prepare)(int smem_bytes, int *blocks_per_sm)
     cudaError_t e = cudaFuncSetAttribute(BHRT_NS::wf_render, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return (int)e;
     // one CTA per SM: leave L1 (where the thread-local lane copies live) all the rest
-    cudaFuncSetAttribute(BHRT_NS::wf_render, cudaFuncAttributePreferredSharedMemoryCarveout, (smem_bytes + 2048) * 100 / (228 * 1024) + 1);
+    cudaFuncSetAttribute(BHRT_NS::wf_render, cudaFuncAttributePreferredSharedMemoryCarveout, WF_MIN_BLOCKS * (smem_bytes + 2048) * 100 / (228 * 1024) + 1);
     return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, BHRT_NS::wf_render, WF_BLOCK, smem_bytes);
 }
 

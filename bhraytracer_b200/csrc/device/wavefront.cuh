@@ -65,6 +65,10 @@ namespace BHRT_NS {
 #ifndef WF_BLOCK
 #define WF_BLOCK 1024
 #endif
+#ifndef WF_MIN_BLOCKS
+#define WF_MIN_BLOCKS 1      // resident CTAs per SM the register budget is sized for (1024 x 1 and 512 x 2 both mean 64 registers;
+                            // 2 x 512 with pools of 1536 / 2048 / 3072 lanes measured 1242 / 1269 / 1293 Mrays/s against 1506)
+#endif
 // WF_PREFETCH_FRAME: the depth of every lane's frame stack is mirrored in shared memory, so a warp can ask for the top
 // frame's line (prefetch.global.L1) in the same breath as the lane record instead of after it has arrived.
 // MEASURED (round 2, config 2): 1495 Mrays/s with it, 1503 without -- no effect; off.
@@ -356,7 +360,7 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
     int c[3], sub[3];
     for (int a = 0; a < 3; a++) {
         c[a] = (int)floorf(f[a]);
-        if (c[a] < -1 || c[a] > pg.dim[a]) return;
+        if (c[a] < -2 || c[a] > pg.dim[a] + 1) return;      // farther than two cells (>= the radius) from the grid
         int s_ = (int)((f[a] - c[a]) * (float)(1 << BHRT_PM_SUB_BITS));
         sub[a] = s_ < 0 ? 0 : (s_ > (1 << BHRT_PM_SUB_BITS) - 1 ? (1 << BHRT_PM_SUB_BITS) - 1 : s_);
     }
@@ -367,18 +371,57 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
     PM_PROF_ADD(0, 1);
     for (;;) {
         PM_PROF_ADD(6, 1);
-        // lane n < 27 owns the key range of cell n of the 3x3x3 block (pm_ranges, one cell per lane)
+        // the record ranges of this search level's block (pm_ranges of core.cuh, one range per lane): level 0 -> lane n < 25
+        // owns ROW n of the 5x5x5 block of coarse cells (five x-adjacent cells = one contiguous range); level >= 1 -> lane
+        // n < 27 owns cell n of the 3x3x3 block at resolution level - 1
         uint32_t my_b = 0, my_e = 0;
-        if (lane < 27u) {
-            const int sh = BHRT_PM_SUB_BITS - level, span = 1 << level;
+        const int res = BHRT_PM_RES(level);
+        const float cell_l = pg.cell / (float)(1 << res);
+        // every photon this close lies in the block: level 0 reaches two coarse cells (>= the radius), so the radius itself is
+        // the bound there; a 3x3x3 block is complete up to one cell edge
+        float bound2 = level == 0 ? r2 : 0.998f * cell_l * cell_l;
+        if (bound2 > r2) bound2 = r2;
+        const float q3[3] = { pos.x, pos.y, pos.z };
+        if (level == 0) {
+            if (lane < 25u) {
+                const int dz = (int)lane / 5 - 2, dy = (int)lane % 5 - 2;
+                const int y = c[1] + dy, z = c[2] + dz;
+                int x0 = c[0] - 2, x1 = c[0] + 2;
+                if (x0 < 0) x0 = 0;
+                if (x1 > pg.dim[0] - 1) x1 = pg.dim[0] - 1;
+                if (!(y < 0 || z < 0 || y >= pg.dim[1] || z >= pg.dim[2] || x0 > x1)) {
+                    // a row farther from the query than the radius holds nothing of interest (the edges of the block)
+                    const int lo3[3] = { x0, y, z }, hi3[3] = { x1 + 1, y + 1, z + 1 };
+                    float md2 = 0;
+                    for (int ax = 0; ax < 3; ax++) {
+                        const float lo = pg.origin[ax] + (float)lo3[ax] * pg.cell, hi = pg.origin[ax] + (float)hi3[ax] * pg.cell;
+                        const float d = q3[ax] < lo ? lo - q3[ax] : (q3[ax] > hi ? q3[ax] - hi : 0.f);
+                        md2 += d * d;
+                    }
+                    if (!(md2 * 0.999f >= bound2)) {
+                        const uint32_t row = (uint32_t)pg.dim[0] * ((uint32_t)y + (uint32_t)pg.dim[1] * (uint32_t)z);
+                        my_b = pg.coarse_start[row + (uint32_t)x0]; my_e = pg.coarse_start[row + (uint32_t)x1 + 1u];
+                    }
+                }
+            }
+        } else if (lane < 27u) {
+            const int sh = BHRT_PM_SUB_BITS - res, span = 1 << res;
             const int dz = (int)lane / 9 - 1, dy = ((int)lane / 3) % 3 - 1, dx = (int)lane % 3 - 1;
-            const int x = ((c[0] << level) | (sub[0] >> sh)) + dx, y = ((c[1] << level) | (sub[1] >> sh)) + dy, z = ((c[2] << level) | (sub[2] >> sh)) + dz;
+            const int x = ((c[0] << res) | (sub[0] >> sh)) + dx, y = ((c[1] << res) | (sub[1] >> sh)) + dy, z = ((c[2] << res) | (sub[2] >> sh)) + dz;
             if (!(x < 0 || y < 0 || z < 0 || x >= pg.dim[0] * span || y >= pg.dim[1] * span || z >= pg.dim[2] * span)) {
-                const uint32_t cx = (uint32_t)(x >> level), cy = (uint32_t)(y >> level), cz = (uint32_t)(z >> level);
+                const uint32_t cx = (uint32_t)(x >> res), cy = (uint32_t)(y >> res), cz = (uint32_t)(z >> res);
                 const uint32_t coarse = cx + (uint32_t)pg.dim[0] * (cy + (uint32_t)pg.dim[1] * cz);
                 const uint32_t lo = pg.coarse_start[coarse], hi = pg.coarse_start[coarse + 1];
-                if (lo != hi) {
-                    if (level == 0) { my_b = lo; my_e = hi; }
+                // a cell farther from the query than the search bound holds nothing of interest (the corners of the block, mostly)
+                const int g3[3] = { x, y, z };
+                float md2 = 0;
+                for (int ax = 0; ax < 3; ax++) {
+                    const float l_ = pg.origin[ax] + (float)g3[ax] * cell_l, h_ = l_ + cell_l;
+                    const float d = q3[ax] < l_ ? l_ - q3[ax] : (q3[ax] > h_ ? q3[ax] - h_ : 0.f);
+                    md2 += d * d;
+                }
+                if (lo != hi && !(md2 * 0.999f >= bound2)) {
+                    if (res == 0) { my_b = lo; my_e = hi; }
                     else {
                         const uint32_t m = photon_morton((uint32_t)(x & (span - 1)) << sh, (uint32_t)(y & (span - 1)) << sh, (uint32_t)(z & (span - 1)) << sh);
                         const uint32_t k0 = (coarse << BHRT_PM_FINE_BITS) | m, k1 = k0 + (1u << (3 * sh));
@@ -388,41 +431,7 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
                 }
             }
         }
-        const float cell_l = pg.cell / (float)(1 << level);
-        // every photon this close lies in the 3x3x3 block; at level 0 the cell edge exceeds the gather radius
-        // (photon_grid: cell >= 1.001 r), so the radius itself is the bound there
-        float bound2 = level == 0 ? r2 : 0.998f * cell_l * cell_l;
-        if (bound2 > r2) bound2 = r2;
-        // a cell farther from the query than the search bound holds nothing of interest (the corners of
-        // the block, mostly): skip it
-        if (lane < 27u && my_e > my_b) {
-            const int sh = BHRT_PM_SUB_BITS - level;
-            const int dz = (int)lane / 9 - 1, dy = ((int)lane / 3) % 3 - 1, dx = (int)lane % 3 - 1;
-            const int g3[3] = { ((c[0] << level) | (sub[0] >> sh)) + dx, ((c[1] << level) | (sub[1] >> sh)) + dy, ((c[2] << level) | (sub[2] >> sh)) + dz };
-            const float q3[3] = { pos.x, pos.y, pos.z };
-            float md2 = 0;
-            for (int ax = 0; ax < 3; ax++) {
-                const float lo = pg.origin[ax] + (float)g3[ax] * cell_l, hi = lo + cell_l;
-                const float d = q3[ax] < lo ? lo - q3[ax] : (q3[ax] > hi ? q3[ax] - hi : 0.f);
-                md2 += d * d;
-            }
-            if (md2 * 0.999f >= bound2) my_e = my_b;
-        }
-        // At level 0 the three cells of a row of the block (dx = -1, 0, 1: lanes 3m, 3m+1, 3m+2) are consecutive coarse
-        // cells, i.e. ONE contiguous range of records: lane 3m takes the whole row (an empty or skipped cell in it only
-        // adds records that fail the distance test), so the scan below walks 9 long runs instead of 27 short ones.
-        const int n_step = level == 0 ? 3 : 1;
-        if (level == 0) {
-            const uint32_t b1 = __shfl_down_sync(0xffffffffu, my_b, 1), e1 = __shfl_down_sync(0xffffffffu, my_e, 1);
-            const uint32_t b2 = __shfl_down_sync(0xffffffffu, my_b, 2), e2 = __shfl_down_sync(0xffffffffu, my_e, 2);
-            if (lane < 27u && lane % 3u == 0u) {
-                uint32_t rb = 0xffffffffu, re = 0u;
-                if (my_e > my_b) { rb = my_b; re = my_e; }
-                if (e1 > b1) { rb = rb < b1 ? rb : b1; re = re > e1 ? re : e1; }
-                if (e2 > b2) { rb = rb < b2 ? rb : b2; re = re > e2 ? re : e2; }
-                if (re > rb) { my_b = rb; my_e = re; } else { my_b = 0u; my_e = 0u; }
-            } else { my_b = 0u; my_e = 0u; }
-        }
+        const int n_step = 1;       // (walking four ranges at a time, eight lanes each, was measured: 12.8 s instead of 6.2 s per frame)
         // far more photons in the block than the k a query needs: the next finer level first
         {
             unsigned visit = my_e - my_b;
@@ -556,7 +565,7 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
 }
 
 // ---- the persistent kernel ------------------------------------------------------------------------
-__global__ void __launch_bounds__(WF_BLOCK, 1)
+__global__ void __launch_bounds__(WF_BLOCK, WF_MIN_BLOCKS)
 wf_render(SceneView s, WaveArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
