@@ -28,6 +28,10 @@ using namespace bhrt;
 extern "C" int bhrt_fast_prepare(int smem_bytes, int *blocks_per_sm);
 extern "C" int bhrt_fast_launch(const void *view, size_t view_bytes, const void *args, size_t args_bytes, unsigned grid, int smem_bytes, cudaStream_t stream);
 // the same with the round-1 traversal phase (one ray per thread, binary tree)
+extern "C" int bhrt_fast_gather_keys(const void *args, size_t args_bytes, unsigned n, int cell_bits, uint32_t *keys, cudaStream_t stream);
+extern "C" int bhrt_fast_gather_queries(const void *args, size_t args_bytes, const unsigned *sorted, unsigned n, unsigned *small, unsigned *heavy, unsigned grid, cudaStream_t stream);
+extern "C" int bhrt_fastb_gather_keys(const void *args, size_t args_bytes, unsigned n, int cell_bits, uint32_t *keys, cudaStream_t stream);
+extern "C" int bhrt_fastb_gather_queries(const void *args, size_t args_bytes, const unsigned *sorted, unsigned n, unsigned *small, unsigned *heavy, unsigned grid, cudaStream_t stream);
 extern "C" int bhrt_fastb_prepare(int smem_bytes, int *blocks_per_sm);
 extern "C" int bhrt_fastb_launch(const void *view, size_t view_bytes, const void *args, size_t args_bytes, unsigned grid, int smem_bytes, cudaStream_t stream);
 
@@ -78,6 +82,9 @@ struct bhrt_ctx {
     bool pool_lanes_set = false;
     int trav_min = 3, trav_max = 12, trav_pct = 50;
     DevBuf lanes, frames, samples, wave_counters;
+    // split gather (wavefront.cuh): the parked queries of a round, their sort keys (double-buffered), per-CTA carry-over state
+    DevBuf gq_list, gq_sorted, gq_keys, gq_keys_sorted, gq_small, cta_state, gq_cub;
+    int gather_mode = 0;                        // env BHRT_GATHER: 1 = inside wf_render, 2 = split, 0 = default (split)
     // asynchronous frames (bhrt_render_async): worker thread, a second stream for progress / cancel, the cancel flag
     DevBuf cancel_flag;
     cudaStream_t aux_stream = nullptr;
@@ -183,6 +190,7 @@ int bhrt_create(int device, bhrt_ctx **out)
     if (const char *e = getenv("BHRT_TRAV")) { int x, y, z; if (sscanf(e, "%d,%d,%d", &x, &y, &z) == 3 && x >= 0 && y >= 1) { c->trav_min = x; c->trav_max = y; c->trav_pct = z; } }
     if (const char *e = getenv("BHRT_GATHER_BATCH")) { long v = atol(e); if (v >= 1) c->gather_batch = (unsigned)v; }
     if (const char *e = getenv("BHRT_MESH_BATCH")) { long v = atol(e); if (v >= 1) c->mesh_batch = (unsigned)v; }
+    if (const char *e = getenv("BHRT_GATHER")) c->gather_mode = !strcmp(e, "inkernel") ? 1 : (!strcmp(e, "split") ? 2 : 0);
     if (const char *e = getenv("BHRT_TRAVERSAL")) c->traversal = !strcmp(e, "wide") ? 1 : (!strcmp(e, "binary") ? 2 : 0);
     *out = c;
     return BHRT_OK;
@@ -197,7 +205,8 @@ int bhrt_destroy(bhrt_ctx *c)
     c->cancel_flag.release();
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     DevBuf *bufs[] = { &c->nodes, &c->materials, &c->lights, &c->texmaps, &c->textures, &c->texels, &c->meshes, &c->mesh_data,
-                       &c->tex_offsets, &c->accels, &c->accel_data, &c->lanes, &c->frames, &c->samples, &c->wave_counters, &c->accum, &c->hit_id, &c->z, &c->rgb8, &c->linear, &c->counters };
+                       &c->tex_offsets, &c->accels, &c->accel_data, &c->lanes, &c->frames, &c->samples, &c->wave_counters, &c->accum, &c->hit_id, &c->z, &c->rgb8, &c->linear, &c->counters,
+                       &c->gq_list, &c->gq_sorted, &c->gq_keys, &c->gq_keys_sorted, &c->gq_small, &c->cta_state, &c->gq_cub };
     for (auto b : bufs) b->release();
     c->photons.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -432,6 +441,22 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     a.hit_id = (int *)c->hit_id.p; a.zbuf = (float *)c->z.p;
     a.cnt = (WaveCounters *)c->wave_counters.p;
     a.cancel = (const unsigned *)c->cancel_flag.p;
+    // split gather: the caustic queries are evaluated between launches of wf_render, device-wide and sorted by photon cell
+    a.ext_gather = a.gather.use && c->gather_mode != 1 ? 1 : 0;
+    a.gather_prof = getenv("BHRT_DEBUG") ? 1 : 0;
+    a.gather_defer = PMQ_DEFER;
+    if (const char *e = getenv("BHRT_GATHER_DEFER")) { const long v = atol(e); if (v >= 1) a.gather_defer = (unsigned)v; }
+    if (a.ext_gather) {
+        if (c->gq_list.ensure(lanes_total * 4) || c->gq_sorted.ensure(lanes_total * 4) || c->gq_keys.ensure(lanes_total * 4) || c->gq_keys_sorted.ensure(lanes_total * 4) ||
+            c->gq_small.ensure(64) || c->cta_state.ensure((size_t)grid * wf_state_bytes(a.pool)))
+            return set_err(BHRT_ERR_CUDA, "cudaMalloc(split gather buffers) failed");
+        size_t need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, (const uint32_t *)c->gq_keys.p, (uint32_t *)c->gq_keys_sorted.p, (const unsigned *)c->gq_list.p, (unsigned *)c->gq_sorted.p,
+                                        (int)lanes_total, 0, 32, c->stream);
+        if (c->gq_cub.ensure(need)) return set_err(BHRT_ERR_CUDA, "cudaMalloc(split gather sort) failed");
+        a.gq_list = (unsigned *)c->gq_list.p; a.gq_total = (unsigned *)c->gq_small.p; a.cta_state = (unsigned char *)c->cta_state.p;
+        CU(cudaMemsetAsync(c->gq_small.p, 0, 64, c->stream));
+    }
     c->frame_spp = spp; c->frame_pixels = (long long)c->width * a.n_rows;
     c->frame_items = (long long)a.n_pix_work * (long long)n_spp_share;
 
@@ -450,12 +475,55 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
         a.chunk_spp = (sample_end - s0 < chunk) ? (sample_end - s0) : chunk;
         a.n_work = (unsigned long long)a.n_pix_work * (unsigned long long)a.chunk_spp;
         CU(cudaMemsetAsync(&((WaveCounters *)c->wave_counters.p)->next_work, 0, sizeof(unsigned long long), c->stream));
-        if (variant) {
-            if (int e = (variant == 1 ? bhrt_fast_launch : bhrt_fastb_launch)(&c->view, sizeof(c->view), &a, sizeof(a), grid, smem_bytes, c->stream))
-                return set_err(BHRT_ERR_CUDA, std::string("wf_render (fast-math build): ") + cudaGetErrorString((cudaError_t)e));
-        } else wf_render<<<grid, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a);
+        a.resume = 0;
+        for (;;) {
+            if (variant) {
+                if (int e = (variant == 1 ? bhrt_fast_launch : bhrt_fastb_launch)(&c->view, sizeof(c->view), &a, sizeof(a), grid, smem_bytes, c->stream))
+                    return set_err(BHRT_ERR_CUDA, std::string("wf_render (fast-math build): ") + cudaGetErrorString((cudaError_t)e));
+            } else wf_render<<<grid, WF_BLOCK, smem_bytes, c->stream>>>(c->view, a);
+            c->launches++;
+            if (!a.ext_gather) break;
+            // the round's parked queries: sort by photon cell, evaluate, carry on (until a round parks nothing: the chunk is done)
+            unsigned nq = 0;
+            CU(cudaMemcpyAsync(&nq, a.gq_total, 4, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            if (nq == 0) break;
+            if ((size_t)nq > lanes_total) return set_err(BHRT_ERR_STATE, "split gather: more queries than lanes");
+            unsigned *const small = (unsigned *)c->gq_small.p;         // [0] query count, [1] cursor of pm_gather_queries
+            uint32_t key_max = 1;
+            for (int ax = 0; ax < 3; ax++) key_max *= (uint32_t)(a.gather.dim[ax] + 4);
+            int bits = 1;
+            while (bits < 32 && (1ull << bits) < (unsigned long long)key_max) bits++;
+            const unsigned ggrid = (unsigned)(c->sm_count * 2);
+            if (variant) {
+                if (int e = (variant == 1 ? bhrt_fast_gather_keys : bhrt_fastb_gather_keys)(&a, sizeof(a), nq, bits, (uint32_t *)c->gq_keys.p, c->stream))
+                    return set_err(BHRT_ERR_CUDA, std::string("pm_query_keys: ") + cudaGetErrorString((cudaError_t)e));
+            } else pm_query_keys<<<(nq + 255u) / 256u, 256, 0, c->stream>>>(a, nq, bits, (uint32_t *)c->gq_keys.p);
+            size_t tmp_bytes = c->gq_cub.bytes;
+            CU(cub::DeviceRadixSort::SortPairs(c->gq_cub.p, tmp_bytes, (const uint32_t *)c->gq_keys.p, (uint32_t *)c->gq_keys_sorted.p, (const unsigned *)c->gq_list.p,
+                                               (unsigned *)c->gq_sorted.p, (int)nq, 0, bits + 3 <= 32 ? bits + 3 : bits, c->stream));
+            CU(cudaMemsetAsync(small, 0, 16, c->stream));
+            // (the sorted keys are not needed any more: their buffer takes the queries the warp routine defers to the CTA-wide one)
+            unsigned *const heavy = (unsigned *)c->gq_keys_sorted.p;
+            if (variant) {
+                if (int e = (variant == 1 ? bhrt_fast_gather_queries : bhrt_fastb_gather_queries)(&a, sizeof(a), (const unsigned *)c->gq_sorted.p, nq, small, heavy, ggrid, c->stream))
+                    return set_err(BHRT_ERR_CUDA, std::string("pm_gather_queries: ") + cudaGetErrorString((cudaError_t)e));
+            } else {
+                pm_gather_queries<<<ggrid, PMQ_BLOCK, 0, c->stream>>>(a, (const unsigned *)c->gq_sorted.p, nq, small + 1, heavy, small + 2);
+                pm_gather_heavy<<<ggrid, PMQ_BLOCK, 0, c->stream>>>(a, heavy, small + 2, small + 3);
+            }
+            c->launches += 5;
+            a.resume = 1;
+            if (a.gather_prof) {
+                unsigned long long pp[4]; unsigned sm4[4];
+                CU(cudaMemcpyAsync(pp, &((WaveCounters *)c->wave_counters.p)->pmprof[12], sizeof(pp), cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaMemcpyAsync(sm4, small, sizeof(sm4), cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                fprintf(stderr, "[bhrt] gather round: %u queries, %u of them CTA-wide; so far: slowest warp query %.2f Mcycles, %llu above 1 Mcycle, mean %.1f kcycles\n", nq, sm4[2], pp[0] / 1e6, pp[1], pp[3] ? pp[2] / (double)pp[3] / 1e3 : 0.0);
+            }
+        }
         wf_reduce<<<(a.n_pix_work + 255) / 256, 256, 0, c->stream>>>(c->view, a, (float4 *)c->accum.p, s0 == sample_begin ? 1 : 0);
-        c->launches += 2;
+        c->launches += 1;
     }
     unsigned long long rays[4] = { 0, 0, 0, 0 };      // rays_closest, rays_shadow, next_work, depth_overflow
     CU(cudaMemcpyAsync(rays, &((WaveCounters *)c->wave_counters.p)->rays_closest, sizeof(rays), cudaMemcpyDeviceToHost, c->stream));

@@ -57,4 +57,26 @@ int BHRT_FAST_ENTRY(launch)(const void *view, size_t view_bytes, const void *arg
     return (int)cudaGetLastError();
 }
 
+// split gather (wavefront.cuh): sort keys of the parked queries; the queries in sorted order
+__attribute__((visibility("hidden")))
+int BHRT_FAST_ENTRY(gather_keys)(const void *args, size_t args_bytes, unsigned n, int cell_bits, uint32_t *keys, cudaStream_t stream)
+{
+    if (args_bytes != sizeof(BHRT_NS::WaveArgs)) return (int)cudaErrorInvalidValue;
+    BHRT_NS::WaveArgs a;
+    memcpy(&a, args, sizeof(a));
+    BHRT_NS::pm_query_keys<<<(n + 255u) / 256u, 256, 0, stream>>>(a, n, cell_bits, keys);
+    return (int)cudaGetLastError();
+}
+__attribute__((visibility("hidden")))
+int BHRT_FAST_ENTRY(gather_queries)(const void *args, size_t args_bytes, const unsigned *sorted, unsigned n, unsigned *small, unsigned *heavy, unsigned grid, cudaStream_t stream)
+{
+    if (args_bytes != sizeof(BHRT_NS::WaveArgs)) return (int)cudaErrorInvalidValue;
+    BHRT_NS::WaveArgs a;
+    memcpy(&a, args, sizeof(a));
+    // small[1] = cursor of the sorted queries, small[2] = number of deferred queries, small[3] = their cursor
+    BHRT_NS::pm_gather_queries<<<grid, PMQ_BLOCK, 0, stream>>>(a, sorted, n, small + 1, heavy, small + 2);
+    BHRT_NS::pm_gather_heavy<<<grid, PMQ_BLOCK, 0, stream>>>(a, heavy, small + 2, small + 3);
+    return (int)cudaGetLastError();
+}
+
 }  // extern "C"

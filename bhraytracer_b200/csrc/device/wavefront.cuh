@@ -158,7 +158,19 @@ struct WaveArgs {
     unsigned gather_batch;      // parked caustic queries that switch the gather phase on
     int trav_min, trav_max, trav_pct;   // internal-node steps per trip: at least / at most / until this % of the job lanes is still at an internal node
     int smem_nodes, smem_materials, smem_lights, smem_offsets, smem_wave, smem_gather, smem_oct;   // byte offsets into dynamic shared memory
+    // ---- split gather: the caustic queries are NOT evaluated inside this kernel.  A CTA runs until every one of
+    // its lanes is parked at a query (or dead), appends its queries to gq_list, saves what it needs to carry on and EXITS;
+    // the host sorts the queries of ALL CTAs by photon cell, pm_gather_queries evaluates them (neighbouring warps stream
+    // the same photon rows, which the in-kernel phase could only arrange for the primary hits of a CTA's image patch),
+    // and the kernel is launched again with `resume` set.
+    int ext_gather, resume, gather_prof;
+    unsigned gather_defer;      // records per pass above which a query goes to the CTA-wide routine (estimate_irradiance_cta)
+    unsigned *gq_list;          // [gridDim.x * pool] global lane index (CTA * pool + lane) of every parked query of this round
+    unsigned *gq_total;         // number of entries
+    unsigned char *cta_state;   // [gridDim.x][wf_state_bytes(pool)] per-CTA state carried from one launch to the next
 };
+struct WfClaim;
+__host__ __device__ static inline size_t wf_state_bytes(unsigned pool) { return (((size_t)pool + 15u) & ~(size_t)15u) + 256u; }     // lane keys + the work ring
 
 // dynamic shared memory needed by the CTA-local wavefront for `pool` lanes
 static inline int wf_wave_smem_bytes(unsigned pool, bool gather)
@@ -255,6 +267,7 @@ struct WfClaim {
     unsigned long long taken;           // virtual items handed to warps so far (monotonic)
     unsigned long long claimed;         // virtual items claimed from the global counter so far (multiple of a.batch)
 };
+static_assert(sizeof(WfClaim) <= 256, "wf_state_bytes reserves 256 bytes for the work ring");
 __device__ __forceinline__ void wf_claim_topup(WfClaim &c, const WaveArgs &a)
 {
     // (thread 0 only, between passes)
@@ -347,20 +360,89 @@ __device__ __forceinline__ V3 wf_sum3(V3 v) { return V3(wf_sum(v.x), wf_sum(v.y)
 #define PM_PROF_ADD(i, v)
 #define PM_PROF_MARK(i)
 #endif
-__device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction, PmWarpScratch *wsm, unsigned long long *prof)
+// The record ranges of one search level's block (pm_ranges of core.cuh, one range per lane): level 0 -> lane n < 25 owns ROW n
+// of the 5x5x5 block of coarse cells (five x-adjacent cells = one contiguous range); level >= 1 -> lane n < 27 owns cell n of the
+// 3x3x3 block at resolution level - 1.  bound2 = the squared distance up to which the block is complete.
+__device__ __forceinline__ void pm_level_ranges(const PhotonGather &pg, int level, const int (&c)[3], const int (&sub)[3], V3 pos, float r2, unsigned lane,
+                                                uint32_t &my_b_out, uint32_t &my_e_out, float &bound2_out)
+{
+    uint32_t my_b = 0, my_e = 0;
+    const int res = BHRT_PM_RES(level);
+    const float cell_l = pg.cell / (float)(1 << res);
+    // every photon this close lies in the block: level 0 reaches two coarse cells (>= the radius), so the radius itself is
+    // the bound there; a 3x3x3 block is complete up to one cell edge
+    float bound2 = level == 0 ? r2 : 0.998f * cell_l * cell_l;
+    if (bound2 > r2) bound2 = r2;
+    const float q3[3] = { pos.x, pos.y, pos.z };
+    if (level == 0) {
+        if (lane < 25u) {
+            const int dz = (int)lane / 5 - 2, dy = (int)lane % 5 - 2;
+            const int y = c[1] + dy, z = c[2] + dz;
+            int x0 = c[0] - 2, x1 = c[0] + 2;
+            if (x0 < 0) x0 = 0;
+            if (x1 > pg.dim[0] - 1) x1 = pg.dim[0] - 1;
+            if (!(y < 0 || z < 0 || y >= pg.dim[1] || z >= pg.dim[2] || x0 > x1)) {
+                // a row farther from the query than the radius holds nothing of interest (the edges of the block)
+                const int lo3[3] = { x0, y, z }, hi3[3] = { x1 + 1, y + 1, z + 1 };
+                float md2 = 0;
+                for (int ax = 0; ax < 3; ax++) {
+                    const float lo = pg.origin[ax] + (float)lo3[ax] * pg.cell, hi = pg.origin[ax] + (float)hi3[ax] * pg.cell;
+                    const float d = q3[ax] < lo ? lo - q3[ax] : (q3[ax] > hi ? q3[ax] - hi : 0.f);
+                    md2 += d * d;
+                }
+                if (!(md2 * 0.999f >= bound2)) {
+                    const uint32_t row = (uint32_t)pg.dim[0] * ((uint32_t)y + (uint32_t)pg.dim[1] * (uint32_t)z);
+                    my_b = pg.coarse_start[row + (uint32_t)x0]; my_e = pg.coarse_start[row + (uint32_t)x1 + 1u];
+                }
+            }
+        }
+    } else if (lane < 27u) {
+        const int sh = BHRT_PM_SUB_BITS - res, span = 1 << res;
+        const int dz = (int)lane / 9 - 1, dy = ((int)lane / 3) % 3 - 1, dx = (int)lane % 3 - 1;
+        const int x = ((c[0] << res) | (sub[0] >> sh)) + dx, y = ((c[1] << res) | (sub[1] >> sh)) + dy, z = ((c[2] << res) | (sub[2] >> sh)) + dz;
+        if (!(x < 0 || y < 0 || z < 0 || x >= pg.dim[0] * span || y >= pg.dim[1] * span || z >= pg.dim[2] * span)) {
+            const uint32_t cx = (uint32_t)(x >> res), cy = (uint32_t)(y >> res), cz = (uint32_t)(z >> res);
+            const uint32_t coarse = cx + (uint32_t)pg.dim[0] * (cy + (uint32_t)pg.dim[1] * cz);
+            const uint32_t lo = pg.coarse_start[coarse], hi = pg.coarse_start[coarse + 1];
+            // a cell farther from the query than the search bound holds nothing of interest (the corners of the block, mostly)
+            const int g3[3] = { x, y, z };
+            float md2 = 0;
+            for (int ax = 0; ax < 3; ax++) {
+                const float l_ = pg.origin[ax] + (float)g3[ax] * cell_l, h_ = l_ + cell_l;
+                const float d = q3[ax] < l_ ? l_ - q3[ax] : (q3[ax] > h_ ? q3[ax] - h_ : 0.f);
+                md2 += d * d;
+            }
+            if (lo != hi && !(md2 * 0.999f >= bound2)) {
+                if (res == 0) { my_b = lo; my_e = hi; }
+                else {
+                    const uint32_t m = photon_morton((uint32_t)(x & (span - 1)) << sh, (uint32_t)(y & (span - 1)) << sh, (uint32_t)(z & (span - 1)) << sh);
+                    const uint32_t k0 = (coarse << BHRT_PM_FINE_BITS) | m, k1 = k0 + (1u << (3 * sh));
+                    my_b = pm_lower_bound(pg.keys, lo, hi, k0);
+                    my_e = pm_lower_bound(pg.keys, my_b, hi, k1);
+                }
+            }
+        }
+    }
+    my_b_out = my_b; my_e_out = my_e; bound2_out = bound2;
+}
+
+// defer_visit > 0: a query that would have to scan more than that many records per pass is NOT evaluated (returns true): the
+// caller hands it to estimate_irradiance_cta, where a whole CTA shares the scan -- one warp alone needs tens of milliseconds
+// for a query in a caustic's focus, and everybody else ends up waiting for it.
+__device__ __noinline__ bool estimate_irradiance_warp(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction, PmWarpScratch *wsm, unsigned long long *prof, unsigned defer_visit = 0u)
 {
 #ifdef BHRT_PM_PROF
     long long pm_t = clock64();
 #endif
     const unsigned lane = threadIdx.x & 31u;
     irrad = V3(0, 0, 0); direction = V3(0, 0, 0);
-    if (pg.n_photons <= 0) return;
+    if (pg.n_photons <= 0) return false;
     const float r2 = pg.radius * pg.radius;
     float f[3] = { (pos.x - pg.origin[0]) / pg.cell, (pos.y - pg.origin[1]) / pg.cell, (pos.z - pg.origin[2]) / pg.cell };
     int c[3], sub[3];
     for (int a = 0; a < 3; a++) {
         c[a] = (int)floorf(f[a]);
-        if (c[a] < -2 || c[a] > pg.dim[a] + 1) return;      // farther than two cells (>= the radius) from the grid
+        if (c[a] < -2 || c[a] > pg.dim[a] + 1) return false;      // farther than two cells (>= the radius) from the grid
         int s_ = (int)((f[a] - c[a]) * (float)(1 << BHRT_PM_SUB_BITS));
         sub[a] = s_ < 0 ? 0 : (s_ > (1 << BHRT_PM_SUB_BITS) - 1 ? (1 << BHRT_PM_SUB_BITS) - 1 : s_);
     }
@@ -371,72 +453,15 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
     PM_PROF_ADD(0, 1);
     for (;;) {
         PM_PROF_ADD(6, 1);
-        // the record ranges of this search level's block (pm_ranges of core.cuh, one range per lane): level 0 -> lane n < 25
-        // owns ROW n of the 5x5x5 block of coarse cells (five x-adjacent cells = one contiguous range); level >= 1 -> lane
-        // n < 27 owns cell n of the 3x3x3 block at resolution level - 1
-        uint32_t my_b = 0, my_e = 0;
-        const int res = BHRT_PM_RES(level);
-        const float cell_l = pg.cell / (float)(1 << res);
-        // every photon this close lies in the block: level 0 reaches two coarse cells (>= the radius), so the radius itself is
-        // the bound there; a 3x3x3 block is complete up to one cell edge
-        float bound2 = level == 0 ? r2 : 0.998f * cell_l * cell_l;
-        if (bound2 > r2) bound2 = r2;
-        const float q3[3] = { pos.x, pos.y, pos.z };
-        if (level == 0) {
-            if (lane < 25u) {
-                const int dz = (int)lane / 5 - 2, dy = (int)lane % 5 - 2;
-                const int y = c[1] + dy, z = c[2] + dz;
-                int x0 = c[0] - 2, x1 = c[0] + 2;
-                if (x0 < 0) x0 = 0;
-                if (x1 > pg.dim[0] - 1) x1 = pg.dim[0] - 1;
-                if (!(y < 0 || z < 0 || y >= pg.dim[1] || z >= pg.dim[2] || x0 > x1)) {
-                    // a row farther from the query than the radius holds nothing of interest (the edges of the block)
-                    const int lo3[3] = { x0, y, z }, hi3[3] = { x1 + 1, y + 1, z + 1 };
-                    float md2 = 0;
-                    for (int ax = 0; ax < 3; ax++) {
-                        const float lo = pg.origin[ax] + (float)lo3[ax] * pg.cell, hi = pg.origin[ax] + (float)hi3[ax] * pg.cell;
-                        const float d = q3[ax] < lo ? lo - q3[ax] : (q3[ax] > hi ? q3[ax] - hi : 0.f);
-                        md2 += d * d;
-                    }
-                    if (!(md2 * 0.999f >= bound2)) {
-                        const uint32_t row = (uint32_t)pg.dim[0] * ((uint32_t)y + (uint32_t)pg.dim[1] * (uint32_t)z);
-                        my_b = pg.coarse_start[row + (uint32_t)x0]; my_e = pg.coarse_start[row + (uint32_t)x1 + 1u];
-                    }
-                }
-            }
-        } else if (lane < 27u) {
-            const int sh = BHRT_PM_SUB_BITS - res, span = 1 << res;
-            const int dz = (int)lane / 9 - 1, dy = ((int)lane / 3) % 3 - 1, dx = (int)lane % 3 - 1;
-            const int x = ((c[0] << res) | (sub[0] >> sh)) + dx, y = ((c[1] << res) | (sub[1] >> sh)) + dy, z = ((c[2] << res) | (sub[2] >> sh)) + dz;
-            if (!(x < 0 || y < 0 || z < 0 || x >= pg.dim[0] * span || y >= pg.dim[1] * span || z >= pg.dim[2] * span)) {
-                const uint32_t cx = (uint32_t)(x >> res), cy = (uint32_t)(y >> res), cz = (uint32_t)(z >> res);
-                const uint32_t coarse = cx + (uint32_t)pg.dim[0] * (cy + (uint32_t)pg.dim[1] * cz);
-                const uint32_t lo = pg.coarse_start[coarse], hi = pg.coarse_start[coarse + 1];
-                // a cell farther from the query than the search bound holds nothing of interest (the corners of the block, mostly)
-                const int g3[3] = { x, y, z };
-                float md2 = 0;
-                for (int ax = 0; ax < 3; ax++) {
-                    const float l_ = pg.origin[ax] + (float)g3[ax] * cell_l, h_ = l_ + cell_l;
-                    const float d = q3[ax] < l_ ? l_ - q3[ax] : (q3[ax] > h_ ? q3[ax] - h_ : 0.f);
-                    md2 += d * d;
-                }
-                if (lo != hi && !(md2 * 0.999f >= bound2)) {
-                    if (res == 0) { my_b = lo; my_e = hi; }
-                    else {
-                        const uint32_t m = photon_morton((uint32_t)(x & (span - 1)) << sh, (uint32_t)(y & (span - 1)) << sh, (uint32_t)(z & (span - 1)) << sh);
-                        const uint32_t k0 = (coarse << BHRT_PM_FINE_BITS) | m, k1 = k0 + (1u << (3 * sh));
-                        my_b = pm_lower_bound(pg.keys, lo, hi, k0);
-                        my_e = pm_lower_bound(pg.keys, my_b, hi, k1);
-                    }
-                }
-            }
-        }
+        uint32_t my_b, my_e; float bound2;
+        pm_level_ranges(pg, level, c, sub, pos, r2, lane, my_b, my_e, bound2);
         const int n_step = 1;       // (walking four ranges at a time, eight lanes each, was measured: 12.8 s instead of 6.2 s per frame)
         // far more photons in the block than the k a query needs: the next finer level first
         {
             unsigned visit = my_e - my_b;
             for (int o = 16; o > 0; o >>= 1) visit += __shfl_xor_sync(0xffffffffu, visit, o);
             if (!coarsened && level < BHRT_PM_LEVELS - 1 && visit > 12u * (unsigned)pg.k) { PM_PROF_MARK(1); level++; continue; }
+            if (defer_visit && visit > defer_visit) return true;
             PM_PROF_ADD(5, visit);
         }
         PM_PROF_MARK(1);
@@ -462,11 +487,11 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
         if (total <= pg.k) {
             PM_PROF_ADD(7, 1);
             if (level > 0) { level--; coarsened = true; continue; }
-            if (total == 0) return;
+            if (total == 0) return false;
             sumP = wf_sum3(sumP); sumD = wf_sum3(sumD);
             irrad = sumP * (1.0f / (3.14159265358979323846f * r2));
             direction = normalized(sumD);
-            return;
+            return false;
         }
         if (!coarsened && level < BHRT_PM_LEVELS - 1 && total > 8 * pg.k) { PM_PROF_ADD(10, 1); level++; continue; }
         PM_PROF_ADD(11, total);
@@ -560,6 +585,174 @@ __device__ __noinline__ void estimate_irradiance_warp(const PhotonGather &pg, V3
         direction = normalized(sumD);
         PM_PROF_MARK(4);
         PM_PROF_ADD(8, 1);
+        return false;
+    }
+}
+
+// ---- the same estimate for a WHOLE CTA: every warp scans its own slice of each record range, the histogram and the
+// candidate list are shared, and the per-lane sums meet in a cross-warp reduction after every pass.  For the queries the
+// warp routine defers (a caustic's focus: hundreds of thousands of photons within the finest block).  Every decision is
+// taken from CTA-uniform values, so all warps follow the same path and the barriers line up; all threads return the same.
+// scr[0] holds the shared tables, scr[warp] the warp's compaction ring; red = [warps][16] floats.
+__device__ __forceinline__ void pm_cta_reduce(float *v, int n_sum, int n_max, float (*red)[16], unsigned w, unsigned W, unsigned lane)
+{
+    // v[0 .. n_sum) are summed, v[n_sum .. n_sum + n_max) maximised: over the lanes, then over the warps (in warp order)
+    for (int i = 0; i < n_sum; i++) v[i] = wf_sum(v[i]);
+    for (int i = n_sum; i < n_sum + n_max; i++) v[i] = wf_max(v[i]);
+    __syncthreads();
+    if (lane == 0) for (int i = 0; i < n_sum + n_max; i++) red[w][i] = v[i];
+    __syncthreads();
+    for (int i = 0; i < n_sum + n_max; i++) {
+        float acc = red[0][i];
+        for (unsigned k = 1; k < W; k++) acc = i < n_sum ? acc + red[k][i] : fmaxf(acc, red[k][i]);
+        v[i] = acc;
+    }
+}
+__device__ __noinline__ void estimate_irradiance_cta(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction, PmWarpScratch *scr, float (*red)[16])
+{
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+    PmWarpScratch *const sh = scr, *const ring = scr + w;
+    irrad = V3(0, 0, 0); direction = V3(0, 0, 0);
+    if (pg.n_photons <= 0) return;
+    const float r2 = pg.radius * pg.radius;
+    float f[3] = { (pos.x - pg.origin[0]) / pg.cell, (pos.y - pg.origin[1]) / pg.cell, (pos.z - pg.origin[2]) / pg.cell };
+    int c[3], sub[3];
+    for (int a = 0; a < 3; a++) {
+        c[a] = (int)floorf(f[a]);
+        if (c[a] < -2 || c[a] > pg.dim[a] + 1) return;
+        int s_ = (int)((f[a] - c[a]) * (float)(1 << BHRT_PM_SUB_BITS));
+        sub[a] = s_ < 0 ? 0 : (s_ > (1 << BHRT_PM_SUB_BITS) - 1 ? (1 << BHRT_PM_SUB_BITS) - 1 : s_);
+    }
+    int level = 0;
+    bool coarsened = false;
+    for (;;) {
+        uint32_t my_b, my_e; float bound2;
+        pm_level_ranges(pg, level, c, sub, pos, r2, lane, my_b, my_e, bound2);
+        {
+            unsigned visit = my_e - my_b;
+            for (int o = 16; o > 0; o >>= 1) visit += __shfl_xor_sync(0xffffffffu, visit, o);
+            if (!coarsened && level < BHRT_PM_LEVELS - 1 && visit > 12u * (unsigned)pg.k) { level++; continue; }
+        }
+        // this warp's slice of every range
+        {
+            const uint32_t len = my_e - my_b;
+            const uint32_t lo = (uint32_t)(((unsigned long long)len * w) / W), hi = (uint32_t)(((unsigned long long)len * (w + 1u)) / W);
+            my_e = my_b + hi; my_b = my_b + lo;
+        }
+        const float scale = 32.f / bound2;
+        __syncthreads();
+        for (int j = (int)threadIdx.x; j < 256; j += (int)blockDim.x) sh->hist[j] = 0;
+        __syncthreads();
+        float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };         // total, sumP, sumD
+        {
+            int total = 0;
+            V3 sumP(0, 0, 0), sumD(0, 0, 0);
+            pm_scan(pg, my_b, my_e, 1, pos, bound2, ring, lane, [&](uint32_t i, float d2, bool act) {
+                if (!act) return;
+                const F4 B = ld4(&pg.recs[i].b);
+                if (dot(V3(B.x, B.y, B.z), N) >= 0) return;
+                uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
+                atomicAdd(&sh->hist[u >> 16], 1);
+                total++;
+                if (level == 0) { const float pw = ld4(&pg.recs[i].a).w; sumP = sumP + pm_power(&pg.recs[i], pw); sumD = sumD + V3(B.x, B.y, B.z) * pw; }
+            });
+            acc[0] = (float)total; acc[1] = sumP.x; acc[2] = sumP.y; acc[3] = sumP.z; acc[4] = sumD.x; acc[5] = sumD.y; acc[6] = sumD.z;
+        }
+        pm_cta_reduce(acc, 7, 0, red, w, W, lane);
+        const int total = (int)(acc[0] + 0.5f);             // (counts below 2^24: exact in float)
+        if (total <= pg.k) {
+            if (level > 0) { level--; coarsened = true; continue; }
+            if (total == 0) return;
+            irrad = V3(acc[1], acc[2], acc[3]) * (1.0f / (3.14159265358979323846f * r2));
+            direction = normalized(V3(acc[4], acc[5], acc[6]));
+            return;
+        }
+        if (!coarsened && level < BHRT_PM_LEVELS - 1 && total > 8 * pg.k) { level++; continue; }
+        // ---- radix-256 select of the k-th smallest squared distance: every warp reads the shared histogram
+        uint32_t prefix = 0;
+        int shift = 16, need = pg.k;
+        for (;;) {
+            int hb8[8], mine = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { hb8[j] = sh->hist[lane * 8 + j]; mine += hb8[j]; }
+            int incl = mine;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+            const unsigned m = __ballot_sync(0xffffffffu, incl >= need);
+            const int owner = m ? __ffs(m) - 1 : 31;
+            int b = 0, cum = 0, hb = 0;
+            if ((int)lane == owner) {
+                cum = incl - mine;
+                int j = 0;
+                for (; j < 7; j++) { if (cum + hb8[j] >= need) break; cum += hb8[j]; }
+                b = (int)lane * 8 + j; hb = hb8[j];
+            }
+            b = __shfl_sync(0xffffffffu, b, owner); cum = __shfl_sync(0xffffffffu, cum, owner); hb = __shfl_sync(0xffffffffu, hb, owner);
+            need -= cum;
+            prefix = (prefix << 8) | (uint32_t)b;
+            if (hb <= BHRT_PM_CAND || shift == 0) break;
+            shift -= 8;
+            __syncthreads();
+            for (int j = (int)threadIdx.x; j < 256; j += (int)blockDim.x) sh->hist[j] = 0;
+            __syncthreads();
+            pm_scan(pg, my_b, my_e, 1, pos, bound2, ring, lane, [&](uint32_t i, float d2, bool act) {
+                if (!act) return;
+                uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
+                if ((u >> (shift + 8)) != prefix) return;
+                const F4 B = ld4(&pg.recs[i].b);
+                if (dot(V3(B.x, B.y, B.z), N) >= 0) return;
+                atomicAdd(&sh->hist[(u >> shift) & 255u], 1);
+            });
+            __syncthreads();
+        }
+        // ---- last pass: everything below the crossing bin is in; the crossing bin's photons are candidates
+        __syncthreads();
+        if (threadIdx.x == 0) sh->ncand = 0;
+        __syncthreads();
+        V3 sumP(0, 0, 0), sumD(0, 0, 0), subP(0, 0, 0), subD(0, 0, 0);
+        float kth2 = 0, sub_max = 0;
+        pm_scan(pg, my_b, my_e, 1, pos, bound2, ring, lane, [&](uint32_t i, float d2, bool act) {
+            if (!act) return;
+            uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
+            const uint32_t top = u >> shift;
+            if (top > prefix) return;
+            const F4 B = ld4(&pg.recs[i].b);
+            if (dot(V3(B.x, B.y, B.z), N) >= 0) return;
+            const float pw = ld4(&pg.recs[i].a).w;
+            if (top < prefix) {
+                sumP = sumP + pm_power(&pg.recs[i], pw); sumD = sumD + V3(B.x, B.y, B.z) * pw;
+                kth2 = fmaxf(kth2, d2);
+            } else {
+                subP = subP + pm_power(&pg.recs[i], pw); subD = subD + V3(B.x, B.y, B.z) * pw;
+                sub_max = fmaxf(sub_max, d2);
+                const int slot = atomicAdd(&sh->ncand, 1);
+                if (slot < BHRT_PM_CAND) { sh->cd2[slot] = d2; sh->cidx[slot] = i; }
+            }
+        });
+        __syncthreads();
+        const int ncand = sh->ncand;
+        if (ncand > BHRT_PM_CAND) {
+            sumP = sumP + subP; sumD = sumD + subD;
+            kth2 = fmaxf(kth2, sub_max);
+        } else if (w == 0) {
+            // exact: candidate j is in iff fewer than `need` candidates are nearer (ties by slot); one warp ranks them
+            for (int j = (int)lane; j < ncand; j += 32) {
+                const float dj = sh->cd2[j];
+                int rank = 0;
+                for (int i = 0; i < ncand; i++) { const float di = sh->cd2[i]; rank += (di < dj || (di == dj && i < j)) ? 1 : 0; }
+                if (rank < need) {
+                    const uint32_t ix = sh->cidx[j];
+                    F4 A = ld4(&pg.recs[ix].a); F4 B = ld4(&pg.recs[ix].b);
+                    sumP = sumP + pm_power(&pg.recs[ix], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w;
+                    kth2 = fmaxf(kth2, dj);
+                }
+            }
+        }
+        float fin[7] = { sumP.x, sumP.y, sumP.z, sumD.x, sumD.y, sumD.z, kth2 };
+        pm_cta_reduce(fin, 6, 1, red, w, W, lane);
+        const float area = 3.14159265358979323846f * fin[6];
+        const V3 sp(fin[0], fin[1], fin[2]);
+        irrad = area > 0 ? sp * (1.0f / area) : sp;
+        direction = normalized(V3(fin[3], fin[4], fin[5]));
         return;
     }
 }
@@ -582,7 +775,7 @@ wf_render(SceneView s, WaveArgs a)
     unsigned char *lsp = smem + a.smem_gather - P - 16;                     // [P] min(frames in use, 255) of lane id
 #endif
     __shared__ unsigned key_count[WF_NKEYS], key_base[WF_NKEYS];
-    __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor, gq_count, gq_cursor, run_gather_s, n_parked_s;
+    __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor, gq_count, gq_cursor, run_gather_s, n_parked_s, exit_s, gq_base_s;
     __shared__ WfClaim claim;
     __shared__ unsigned scan_part[32];
 
@@ -591,14 +784,20 @@ wf_render(SceneView s, WaveArgs a)
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     const bool det = a.cfg.mode == BHRT_MODE_DET;
 
-    for (unsigned i = tid; i < P; i += WF_BLOCK) { list[i] = (unsigned short)i; lkey[i] = WF_KEY_DEAD; pend[i] = 0; }
+    // (split gather, resumed launch: the lanes' keys and the work ring come from the previous launch; every lane that was
+    // parked has its answer now.  The first pass finds an empty live list, and the sort that follows rebuilds it.)
+    unsigned char *const state = a.ext_gather ? a.cta_state + (size_t)blockIdx.x * wf_state_bytes(P) : (unsigned char *)0;
+    const bool resumed = a.ext_gather && a.resume;
+    for (unsigned i = tid; i < P; i += WF_BLOCK) { list[i] = (unsigned short)i; lkey[i] = resumed ? state[i] : (unsigned char)WF_KEY_DEAD; pend[i] = 0; }
 #if WF_PREFETCH_FRAME
     for (unsigned i = tid; i < P; i += WF_BLOCK) lsp[i] = 0;
 #endif
     if (tid < WF_NKEYS) key_count[tid] = 0;
     if (tid == 0) {
-        n_live_s = P; n_pending_s = 0; mq_head = 0; mq_tail = 0; p1_cursor = 0; run_mesh_s = 0; done_s = 0; gq_count = 0; gq_cursor = 0; n_parked_s = 0;
-        claim.taken = 0; claim.claimed = 0;
+        n_live_s = resumed ? 0u : P; n_pending_s = 0; mq_head = 0; mq_tail = 0; p1_cursor = 0; run_mesh_s = 0; done_s = 0; gq_count = 0; gq_cursor = 0; n_parked_s = 0;
+        exit_s = 0;
+        if (resumed) claim = *(const WfClaim *)(state + wf_state_bytes(P) - 256u);
+        else { claim.taken = 0; claim.claimed = 0; }
         wf_claim_topup(claim, a);
     }
     __syncthreads();
@@ -616,7 +815,7 @@ wf_render(SceneView s, WaveArgs a)
 #endif
     bool have = false;
     unsigned jid = 0;
-    bool first = true;
+    bool first = !resumed;
 
     long long t_p1 = 0, t_sort = 0, t_mesh = 0, n_iter = 0;
     for (;;) {
@@ -794,12 +993,12 @@ wf_render(SceneView s, WaveArgs a)
         // ================= caustic gathers of the parked lanes: one query per warp at a time =================
         // (evaluated here rather than inside the pass: the queries of a pass sit in a few chunks, and the
         // warps that own those chunks would keep all the others waiting at the barrier)
-        if (a.gather.use) {
+        if (a.gather.use && !a.ext_gather) {
             // (batched like the BVH traversal: a phase with few queries cannot keep 32 warps evenly busy)
             if (tid == 0) run_gather_s = gq_count > 0 && (gq_count >= a.gather_batch || n_live <= P / 4);
             __syncthreads();
         }
-        if (a.gather.use && run_gather_s) {
+        if (a.gather.use && !a.ext_gather && run_gather_s) {
             const unsigned ng = gq_count;
             // ---- order the parked queries by photon cell (counting sort on a 12-bit key: the low 4 bits of each coarse
             // cell coordinate; putting the queries of the most populated cells first was measured too: no gain).  The gather is bound by the L2 -> SM bandwidth of the records it streams (77 KB per
@@ -895,6 +1094,9 @@ wf_render(SceneView s, WaveArgs a)
                 // decisions every thread must agree on, taken while nobody changes their inputs
                 run_mesh_s = round == 0 && n_pending_s > 0 && (mq_tail - mq_head >= a.mesh_batch || acc < WF_BLOCK);
                 done_s = acc == 0 && n_pending_s == 0 && n_parked_s == 0;
+                // split gather: nothing left to do but the parked queries -> hand them over and leave
+                exit_s = a.ext_gather && acc == 0 && n_pending_s == 0 && n_parked_s > 0;
+                if (exit_s) gq_base_s = atomicAdd(a.gq_total, gq_count);
             }
             __syncthreads();
             for (unsigned g = tid >> 5; g < n_groups; g += WF_BLOCK / 32) {
@@ -1078,7 +1280,14 @@ wf_render(SceneView s, WaveArgs a)
             if (tid == 0 && mq_head > mq_tail) mq_head = mq_tail;       // over-claimed pops of an empty queue
             { const long long c = clock64(); t_mesh += c - c_mark; c_mark = c; }
         }
-        if (done_s) break;
+        if (done_s || exit_s) break;
+    }
+    if (a.ext_gather) {
+        // what the next launch needs: the lanes' keys (dead lanes stay dead, parked ones come back with the key they were
+        // parked with) and the work ring; the parked queries go to the device-wide list
+        for (unsigned i = tid; i < P; i += WF_BLOCK) state[i] = lkey[i];
+        if (tid == 0) *(WfClaim *)(state + wf_state_bytes(P) - 256u) = claim;
+        if (exit_s) for (unsigned i = tid; i < gq_count; i += WF_BLOCK) a.gq_list[gq_base_s + i] = blockIdx.x * P + (unsigned)gq[i];
     }
     unsigned long long c0 = rc.closest, c1 = rc.shadow;
     for (int o = 16; o > 0; o >>= 1) {
@@ -1090,6 +1299,120 @@ wf_render(SceneView s, WaveArgs a)
     if (tid == 0) {
         atomicAdd(&a.cnt->prof[0], (unsigned long long)t_p1); atomicAdd(&a.cnt->prof[1], (unsigned long long)t_sort);
         atomicAdd(&a.cnt->prof[2], (unsigned long long)t_mesh); atomicAdd(&a.cnt->prof[3], (unsigned long long)n_iter);
+    }
+}
+
+// ---- split gather: the parked queries of ALL CTAs, sorted by photon cell --------------------------
+// pm_query_keys: sort key of every parked query = its coarse photon cell (x fastest: a level-0 search reads ROWS of
+// five x-adjacent cells, so queries that are neighbours in the sorted order stream nearly the same records).
+__device__ __forceinline__ const Frame &wf_query_frame(const WaveArgs &a, unsigned entry)
+{
+    const unsigned cta = entry / a.pool, id = entry % a.pool;
+    return a.frames[(size_t)cta * a.pool * (size_t)a.cfg.max_frames + (size_t)(a.lanes[entry].sp - 1) * a.pool + id];
+}
+__global__ void pm_query_keys(WaveArgs a, unsigned n, int cell_bits, uint32_t *__restrict__ keys)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V3 qp = wf_query_frame(a, a.gq_list[i]).p;
+    const float q3[3] = { qp.x, qp.y, qp.z };
+    const PhotonGather &pg = a.gather;
+    uint32_t key = 0, mul = 1;
+    int c[3];
+    for (int ax = 0; ax < 3; ax++) {
+        // (cells up to two beyond the grid still reach photons; everything farther away shares the border key and ends at once)
+        float f = floorf((q3[ax] - pg.origin[ax]) / pg.cell);
+        const float hi = (float)(pg.dim[ax] + 1);
+        f = f < -2.f ? -2.f : (f > hi ? hi : f);
+        c[ax] = (int)f;
+        key += mul * (uint32_t)(c[ax] + 2);
+        mul *= (uint32_t)(pg.dim[ax] + 4);
+    }
+    // Cost class of the query = log2 of the photons in its level-0 block (what a query costs follows it: a sparse block is
+    // summed once, a dense one is scanned several times at a finer level).  The EXPENSIVE classes come first in the sorted
+    // order: the queries of a caustic's focus cost a hundred times the average, and handed out last a few CTAs would still
+    // be working on them long after the rest of the device has run out of work (measured: SMs busy 27 % of the kernel's time).
+    if (cell_bits + 3 <= 32) {
+        uint32_t visit = 0;
+        int x0 = c[0] - 2, x1 = c[0] + 2;
+        if (x0 < 0) x0 = 0;
+        if (x1 > pg.dim[0] - 1) x1 = pg.dim[0] - 1;
+        if (x0 <= x1)
+            for (int dz = -2; dz <= 2; dz++)
+                for (int dy = -2; dy <= 2; dy++) {
+                    const int y = c[1] + dy, z = c[2] + dz;
+                    if (y < 0 || z < 0 || y >= pg.dim[1] || z >= pg.dim[2]) continue;
+                    const uint32_t row = (uint32_t)pg.dim[0] * ((uint32_t)y + (uint32_t)pg.dim[1] * (uint32_t)z);
+                    visit += pg.coarse_start[row + (uint32_t)x1 + 1u] - pg.coarse_start[row + (uint32_t)x0];
+                }
+        int cls = 23 - __clz(visit | 1u);       // < 512 photons: 0 ... >= 32768: 7
+        cls = cls < 0 ? 0 : (cls > 7 ? 7 : cls);
+        key |= (uint32_t)(7 - cls) << cell_bits;
+    }
+    keys[i] = key;
+}
+// pm_gather_queries: one query per warp at a time, taken IN SORTED ORDER -- a CTA claims PMQ_CLAIM consecutive queries (two per warp: small claims keep the device balanced) and
+// its warps walk them together, so the warps of an SM stream the same photon rows at about the same time: the first one
+// brings a line in, the others find it in L1 (hit rate of the in-kernel phase, where three quarters of a CTA's queries
+// are GI hits scattered over the scene: 25 %).  The per-query routine is the one the in-kernel phase runs: same result.
+#define PMQ_BLOCK 512
+#define PMQ_CLAIM 32
+#define PMQ_DEFER 16384      // default of WaveArgs::gather_defer
+__global__ void __launch_bounds__(PMQ_BLOCK, 2)
+pm_gather_queries(WaveArgs a, const unsigned *__restrict__ sorted, unsigned n, unsigned *cursor, unsigned *__restrict__ heavy, unsigned *n_heavy)
+{
+    __shared__ PmWarpScratch scratch[PMQ_BLOCK / 32];
+    __shared__ unsigned base_s, next_s;
+    const unsigned lane = threadIdx.x & 31u;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) { base_s = atomicAdd(cursor, (unsigned)PMQ_CLAIM); next_s = 0; }
+        __syncthreads();
+        const unsigned base = base_s;
+        if (base >= n) break;
+        const unsigned cnt = n - base < (unsigned)PMQ_CLAIM ? n - base : (unsigned)PMQ_CLAIM;
+        for (;;) {
+            unsigned i = 0;
+            if (lane == 0) i = atomicAdd(&next_s, 1u);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (i >= cnt) break;
+            const unsigned entry = sorted[base + i];
+            const Frame &fq = wf_query_frame(a, entry);
+            V3 irr, dirv;
+            const long long t0 = clock64();
+            const bool deferred = estimate_irradiance_warp(a.gather, fq.p, fq.vN, irr, dirv, scratch + (threadIdx.x >> 5), a.cnt->pmprof, a.gather_defer);
+            if (deferred) { if (lane == 0) heavy[atomicAdd(n_heavy, 1u)] = entry; }
+            else if (lane == 0) {
+                Lane &Lg = a.lanes[entry]; Lg.ret = irr; Lg.sw = dirv;
+                if (a.gather_prof) {        // BHRT_DEBUG: the cost distribution of the queries (the slowest one bounds the kernel)
+                    const unsigned long long dt = (unsigned long long)(clock64() - t0);
+                    atomicMax(&a.cnt->pmprof[12], dt); atomicAdd(&a.cnt->pmprof[14], dt); atomicAdd(&a.cnt->pmprof[15], 1ull);
+                    if (dt > 1000000ull) atomicAdd(&a.cnt->pmprof[13], 1ull);
+                }
+            }
+        }
+    }
+}
+
+// the deferred queries: one per CTA at a time
+__global__ void __launch_bounds__(PMQ_BLOCK, 2)
+pm_gather_heavy(WaveArgs a, const unsigned *__restrict__ heavy, const unsigned *__restrict__ n_heavy, unsigned *cursor)
+{
+    __shared__ PmWarpScratch scratch[PMQ_BLOCK / 32];
+    __shared__ float red[PMQ_BLOCK / 32][16];
+    __shared__ unsigned next_s;
+    const unsigned n = *n_heavy;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) next_s = atomicAdd(cursor, 1u);
+        __syncthreads();
+        const unsigned i = next_s;
+        if (i >= n) break;
+        const unsigned entry = heavy[i];
+        const Frame &fq = wf_query_frame(a, entry);
+        V3 irr, dirv;
+        estimate_irradiance_cta(a.gather, fq.p, fq.vN, irr, dirv, scratch, red);
+        if (threadIdx.x == 0) { Lane &Lg = a.lanes[entry]; Lg.ret = irr; Lg.sw = dirv; }
     }
 }
 
