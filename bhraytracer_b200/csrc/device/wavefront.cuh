@@ -349,6 +349,11 @@ __device__ __forceinline__ void pm_scan(const PhotonGather &pg, uint32_t my_b, u
     __syncwarp();
 }
 
+// After pass A the k-th nearest photon is known to lie in distance bin `top` of 256 (the top 8 bits of the 24-bit key
+// u = d2 / bound2 * 2^24): the later passes only need the photons up to that bin, so their distance test -- all that
+// most records ever see -- can use (top + 1) / 256 of the bound (with a margin for the rounding of u; the body still
+// decides on the exact key).  In a caustic's focus that turns three of the four passes into plain scans.
+__device__ __forceinline__ float pm_tight_bound(float bound2, uint32_t top) { return fminf(bound2, bound2 * (((float)top + 1.01f) * (1.0f / 256.0f))); }
 __device__ __forceinline__ float wf_sum(float v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
 __device__ __forceinline__ float wf_max(float v) { for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
 __device__ __forceinline__ V3 wf_sum3(V3 v) { return V3(wf_sum(v.x), wf_sum(v.y), wf_sum(v.z)); }
@@ -382,17 +387,26 @@ __device__ __forceinline__ void pm_level_ranges(const PhotonGather &pg, int leve
             if (x0 < 0) x0 = 0;
             if (x1 > pg.dim[0] - 1) x1 = pg.dim[0] - 1;
             if (!(y < 0 || z < 0 || y >= pg.dim[1] || z >= pg.dim[2] || x0 > x1)) {
-                // a row farther from the query than the radius holds nothing of interest (the edges of the block)
-                const int lo3[3] = { x0, y, z }, hi3[3] = { x1 + 1, y + 1, z + 1 };
-                float md2 = 0;
-                for (int ax = 0; ax < 3; ax++) {
-                    const float lo = pg.origin[ax] + (float)lo3[ax] * pg.cell, hi = pg.origin[ax] + (float)hi3[ax] * pg.cell;
-                    const float d = q3[ax] < lo ? lo - q3[ax] : (q3[ax] > hi ? q3[ax] - hi : 0.f);
-                    md2 += d * d;
+                // a row farther from the query than the radius holds nothing of interest (the edges of the block), and of a
+                // row that passes by at distance d only the cells within sqrt(r^2 - d^2) along x do (a third fewer records)
+                float dyz2 = 0;
+                {
+                    const int lo2[2] = { y, z };
+                    for (int ax = 1; ax < 3; ax++) {
+                        const float lo = pg.origin[ax] + (float)lo2[ax - 1] * pg.cell, hi = lo + pg.cell;
+                        const float d = q3[ax] < lo ? lo - q3[ax] : (q3[ax] > hi ? q3[ax] - hi : 0.f);
+                        dyz2 += d * d;
+                    }
                 }
-                if (!(md2 * 0.999f >= bound2)) {
-                    const uint32_t row = (uint32_t)pg.dim[0] * ((uint32_t)y + (uint32_t)pg.dim[1] * (uint32_t)z);
-                    my_b = pg.coarse_start[row + (uint32_t)x0]; my_e = pg.coarse_start[row + (uint32_t)x1 + 1u];
+                if (!(dyz2 * 0.999f >= bound2)) {
+                    const float xr = sqrtf(fmaxf(bound2 - dyz2 * 0.999f, 0.f)) * 1.001f + 1.0e-6f * pg.cell;
+                    const int xa = (int)floorf((q3[0] - xr - pg.origin[0]) / pg.cell), xb = (int)floorf((q3[0] + xr - pg.origin[0]) / pg.cell);
+                    if (xa > x0) x0 = xa;
+                    if (xb < x1) x1 = xb;
+                    if (x0 <= x1) {
+                        const uint32_t row = (uint32_t)pg.dim[0] * ((uint32_t)y + (uint32_t)pg.dim[1] * (uint32_t)z);
+                        my_b = pg.coarse_start[row + (uint32_t)x0]; my_e = pg.coarse_start[row + (uint32_t)x1 + 1u];
+                    }
                 }
             }
         }
@@ -429,7 +443,9 @@ __device__ __forceinline__ void pm_level_ranges(const PhotonGather &pg, int leve
 // defer_visit > 0: a query that would have to scan more than that many records per pass is NOT evaluated (returns true): the
 // caller hands it to estimate_irradiance_cta, where a whole CTA shares the scan -- one warp alone needs tens of milliseconds
 // for a query in a caustic's focus, and everybody else ends up waiting for it.
-__device__ __noinline__ bool estimate_irradiance_warp(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction, PmWarpScratch *wsm, unsigned long long *prof, unsigned defer_visit = 0u)
+// (inlined into the dedicated gather kernel, where the structure's fields are kernel parameters -- uniform registers, no
+// reloads of the record pointer from a local copy; wf_render calls it out of line, below)
+__device__ __forceinline__ bool estimate_irradiance_warp_inl(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction, PmWarpScratch *wsm, unsigned long long *prof, unsigned defer_visit)
 {
 #ifdef BHRT_PM_PROF
     long long pm_t = clock64();
@@ -523,7 +539,7 @@ __device__ __noinline__ bool estimate_irradiance_warp(const PhotonGather &pg, V3
             __syncwarp();
             for (int j = (int)lane; j < 256; j += 32) wsm->hist[j] = 0;
             __syncwarp();
-            pm_scan(pg, my_b, my_e, n_step, pos, bound2, wsm, lane, [&](uint32_t i, float d2, bool act) {
+            pm_scan(pg, my_b, my_e, n_step, pos, pm_tight_bound(bound2, prefix >> (16 - shift - 8)), wsm, lane, [&](uint32_t i, float d2, bool act) {
                 if (!act) return;
                 uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
                 if ((u >> (shift + 8)) != prefix) return;
@@ -540,7 +556,7 @@ __device__ __noinline__ bool estimate_irradiance_warp(const PhotonGather &pg, V3
         sumP = V3(0, 0, 0); sumD = V3(0, 0, 0);
         V3 subP(0, 0, 0), subD(0, 0, 0);
         float kth2 = 0, sub_max = 0;
-        pm_scan(pg, my_b, my_e, n_step, pos, bound2, wsm, lane, [&](uint32_t i, float d2, bool act) {
+        pm_scan(pg, my_b, my_e, n_step, pos, pm_tight_bound(bound2, prefix >> (16 - shift)), wsm, lane, [&](uint32_t i, float d2, bool act) {
             if (!act) return;
             uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
             const uint32_t top = u >> shift;
@@ -589,6 +605,11 @@ __device__ __noinline__ bool estimate_irradiance_warp(const PhotonGather &pg, V3
     }
 }
 
+__device__ __noinline__ bool estimate_irradiance_warp(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction, PmWarpScratch *wsm, unsigned long long *prof, unsigned defer_visit = 0u)
+{
+    return estimate_irradiance_warp_inl(pg, pos, N, irrad, direction, wsm, prof, defer_visit);
+}
+
 // ---- the same estimate for a WHOLE CTA: every warp scans its own slice of each record range, the histogram and the
 // candidate list are shared, and the per-lane sums meet in a cross-warp reduction after every pass.  For the queries the
 // warp routine defers (a caustic's focus: hundreds of thousands of photons within the finest block).  Every decision is
@@ -608,7 +629,7 @@ __device__ __forceinline__ void pm_cta_reduce(float *v, int n_sum, int n_max, fl
         v[i] = acc;
     }
 }
-__device__ __noinline__ void estimate_irradiance_cta(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction, PmWarpScratch *scr, float (*red)[16])
+__device__ __forceinline__ void estimate_irradiance_cta(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction, PmWarpScratch *scr, float (*red)[16])
 {
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5, W = blockDim.x >> 5;
     PmWarpScratch *const sh = scr, *const ring = scr + w;
@@ -694,7 +715,7 @@ __device__ __noinline__ void estimate_irradiance_cta(const PhotonGather &pg, V3 
             __syncthreads();
             for (int j = (int)threadIdx.x; j < 256; j += (int)blockDim.x) sh->hist[j] = 0;
             __syncthreads();
-            pm_scan(pg, my_b, my_e, 1, pos, bound2, ring, lane, [&](uint32_t i, float d2, bool act) {
+            pm_scan(pg, my_b, my_e, 1, pos, pm_tight_bound(bound2, prefix >> (16 - shift - 8)), ring, lane, [&](uint32_t i, float d2, bool act) {
                 if (!act) return;
                 uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
                 if ((u >> (shift + 8)) != prefix) return;
@@ -710,7 +731,7 @@ __device__ __noinline__ void estimate_irradiance_cta(const PhotonGather &pg, V3 
         __syncthreads();
         V3 sumP(0, 0, 0), sumD(0, 0, 0), subP(0, 0, 0), subD(0, 0, 0);
         float kth2 = 0, sub_max = 0;
-        pm_scan(pg, my_b, my_e, 1, pos, bound2, ring, lane, [&](uint32_t i, float d2, bool act) {
+        pm_scan(pg, my_b, my_e, 1, pos, pm_tight_bound(bound2, prefix >> (16 - shift)), ring, lane, [&](uint32_t i, float d2, bool act) {
             if (!act) return;
             uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
             const uint32_t top = u >> shift;
@@ -1380,7 +1401,7 @@ pm_gather_queries(WaveArgs a, const unsigned *__restrict__ sorted, unsigned n, u
             const Frame &fq = wf_query_frame(a, entry);
             V3 irr, dirv;
             const long long t0 = clock64();
-            const bool deferred = estimate_irradiance_warp(a.gather, fq.p, fq.vN, irr, dirv, scratch + (threadIdx.x >> 5), a.cnt->pmprof, a.gather_defer);
+            const bool deferred = estimate_irradiance_warp_inl(a.gather, fq.p, fq.vN, irr, dirv, scratch + (threadIdx.x >> 5), a.cnt->pmprof, a.gather_defer);
             if (deferred) { if (lane == 0) heavy[atomicAdd(n_heavy, 1u)] = entry; }
             else if (lane == 0) {
                 Lane &Lg = a.lanes[entry]; Lg.ret = irr; Lg.sw = dirv;
