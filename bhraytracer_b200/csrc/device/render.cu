@@ -444,6 +444,8 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     // split gather: the caustic queries are evaluated between launches of wf_render, device-wide and sorted by photon cell
     a.ext_gather = a.gather.use && c->gather_mode != 1 ? 1 : 0;
     a.gather_prof = getenv("BHRT_DEBUG") ? 1 : 0;
+    a.exit_live = 0;            // (measured on config 5: leaving with up to 1/32 ... 1/4 of the lanes still live is no faster than waiting for all)
+    if (const char *e = getenv("BHRT_EXIT_LIVE")) { const long v = atol(e); a.exit_live = v > 0 ? a.pool / (unsigned)v : 0u; }
     a.gather_defer = PMQ_DEFER;
     if (const char *e = getenv("BHRT_GATHER_DEFER")) { const long v = atol(e); if (v >= 1) a.gather_defer = (unsigned)v; }
     if (a.ext_gather) {

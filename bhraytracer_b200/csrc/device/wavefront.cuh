@@ -164,6 +164,7 @@ struct WaveArgs {
     // the same photon rows, which the in-kernel phase could only arrange for the primary hits of a CTA's image patch),
     // and the kernel is launched again with `resume` set.
     int ext_gather, resume, gather_prof;
+    unsigned exit_live;         // split gather: a CTA leaves when no more than this many of its lanes are still live
     unsigned gather_defer;      // records per pass above which a query goes to the CTA-wide routine (estimate_irradiance_cta)
     unsigned *gq_list;          // [gridDim.x * pool] global lane index (CTA * pool + lane) of every parked query of this round
     unsigned *gq_total;         // number of entries
@@ -581,17 +582,23 @@ __device__ __forceinline__ bool estimate_irradiance_warp_inl(const PhotonGather 
             sumP = sumP + subP; sumD = sumD + subD;
             kth2 = fmaxf(kth2, sub_max);
         } else {
-            // exact: candidate j is in iff fewer than `need` candidates are nearer (ties by slot)
+            // exact: a candidate is in iff fewer than `need` candidates are nearer (ties: the lower record index).  The slots
+            // were handed out in the order the atomics arrived; ranks are unique, and lane r adds the candidate of RANK r, so
+            // neither the chosen set nor the order of the float sums depends on that order
+            int *const order = wsm->hist;       // (the histogram is not needed any more)
             for (int j = (int)lane; j < ncand; j += 32) {
-                const float dj = wsm->cd2[j];
+                const float dj = wsm->cd2[j]; const uint32_t xj = wsm->cidx[j];
                 int rank = 0;
-                for (int i = 0; i < ncand; i++) { const float di = wsm->cd2[i]; rank += (di < dj || (di == dj && i < j)) ? 1 : 0; }
-                if (rank < need) {
-                    const uint32_t ix = wsm->cidx[j];
-                    F4 A = ld4(&pg.recs[ix].a); F4 B = ld4(&pg.recs[ix].b);
-                    sumP = sumP + pm_power(&pg.recs[ix], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w;
-                    kth2 = fmaxf(kth2, dj);
-                }
+                for (int i = 0; i < ncand; i++) { const float di = wsm->cd2[i]; rank += (di < dj || (di == dj && wsm->cidx[i] < xj)) ? 1 : 0; }
+                order[rank] = j;
+            }
+            __syncwarp();
+            for (int r = (int)lane; r < ncand && r < need; r += 32) {
+                const int j = order[r];
+                const uint32_t ix = wsm->cidx[j];
+                F4 A = ld4(&pg.recs[ix].a); F4 B = ld4(&pg.recs[ix].b);
+                sumP = sumP + pm_power(&pg.recs[ix], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w;
+                kth2 = fmaxf(kth2, wsm->cd2[j]);
             }
         }
         sumP = wf_sum3(sumP); sumD = wf_sum3(sumD); kth2 = wf_max(kth2);
@@ -755,17 +762,22 @@ __device__ __forceinline__ void estimate_irradiance_cta(const PhotonGather &pg, 
             sumP = sumP + subP; sumD = sumD + subD;
             kth2 = fmaxf(kth2, sub_max);
         } else if (w == 0) {
-            // exact: candidate j is in iff fewer than `need` candidates are nearer (ties by slot); one warp ranks them
+            // exact, by one warp: a candidate is in iff fewer than `need` candidates are nearer (ties: the lower record index);
+            // lane r adds the candidate of rank r (see estimate_irradiance_warp: independent of the order of the atomics)
+            int *const order = sh->hist;
             for (int j = (int)lane; j < ncand; j += 32) {
-                const float dj = sh->cd2[j];
+                const float dj = sh->cd2[j]; const uint32_t xj = sh->cidx[j];
                 int rank = 0;
-                for (int i = 0; i < ncand; i++) { const float di = sh->cd2[i]; rank += (di < dj || (di == dj && i < j)) ? 1 : 0; }
-                if (rank < need) {
-                    const uint32_t ix = sh->cidx[j];
-                    F4 A = ld4(&pg.recs[ix].a); F4 B = ld4(&pg.recs[ix].b);
-                    sumP = sumP + pm_power(&pg.recs[ix], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w;
-                    kth2 = fmaxf(kth2, dj);
-                }
+                for (int i = 0; i < ncand; i++) { const float di = sh->cd2[i]; rank += (di < dj || (di == dj && sh->cidx[i] < xj)) ? 1 : 0; }
+                order[rank] = j;
+            }
+            __syncwarp();
+            for (int r = (int)lane; r < ncand && r < need; r += 32) {
+                const int j = order[r];
+                const uint32_t ix = sh->cidx[j];
+                F4 A = ld4(&pg.recs[ix].a); F4 B = ld4(&pg.recs[ix].b);
+                sumP = sumP + pm_power(&pg.recs[ix], A.w); sumD = sumD + V3(B.x, B.y, B.z) * A.w;
+                kth2 = fmaxf(kth2, sh->cd2[j]);
             }
         }
         float fin[7] = { sumP.x, sumP.y, sumP.z, sumD.x, sumD.y, sumD.z, kth2 };
@@ -1116,7 +1128,9 @@ wf_render(SceneView s, WaveArgs a)
                 run_mesh_s = round == 0 && n_pending_s > 0 && (mq_tail - mq_head >= a.mesh_batch || acc < WF_BLOCK);
                 done_s = acc == 0 && n_pending_s == 0 && n_parked_s == 0;
                 // split gather: nothing left to do but the parked queries -> hand them over and leave
-                exit_s = a.ext_gather && acc == 0 && n_pending_s == 0 && n_parked_s > 0;
+                // (not waiting for the last few live lanes -- a pass over a handful of lanes costs a sort and four barriers like any
+                // other: they keep their keys and carry on after the gather, with everybody else)
+                exit_s = a.ext_gather && acc <= a.exit_live && n_pending_s == 0 && n_parked_s > 0;
                 if (exit_s) gq_base_s = atomicAdd(a.gq_total, gq_count);
             }
             __syncthreads();
