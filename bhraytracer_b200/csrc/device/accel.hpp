@@ -150,7 +150,7 @@ inline bool build_wide(const bhrt_mesh &m, const bhrt_bvh_node *bvh, MeshAccel &
     return true;
 }
 
-inline bool build_accel(const bhrt_scene_desc &D, AccelBlob &out, std::string *err)
+inline bool build_accel(const bhrt_scene_desc &D, AccelBlob &out, std::string *err, bool with_wide = true)
 {
     out.meshes.clear();
     out.data.clear();
@@ -232,7 +232,7 @@ inline bool build_accel(const bhrt_scene_desc &D, AccelBlob &out, std::string *e
             memcpy(&t.c.w, &tag, 4);
         }
         // ---- the wide tree: the same cyBVH collapsed to <= 8 children per node (fast build of the kernels)
-        if (!build_wide(m, bvh, A, out.data, err)) return false;
+        if (with_wide && !build_wide(m, bvh, A, out.data, err)) return false;
         out.meshes.push_back(A);
     }
     accel_align(out.data);

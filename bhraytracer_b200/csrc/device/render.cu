@@ -70,6 +70,9 @@ struct bhrt_ctx {
     int rendered_spp = 0;
     int n_materials = 0;
     DevBuf accels, accel_data;
+    // the 8-wide regrouping of the BVHs is built on first use (it is two thirds of the host time of an upload and only the
+    // BHRT_FLAG_WIDE_BVH traversal reads it): what ensure_wide() needs to build it later
+    std::vector<bhrt_mesh> host_meshes; size_t host_mesh_bytes = 0; bool wide_built = false;
     // per kernel variant (0 exact, 1 fast + wide traversal, 2 fast + binary traversal): prepared for this much shared memory
     int kernel_smem[3] = { -1, -1, -1 }, render_blocks[3] = { 1, 1, 1 };
     int traversal = 0;                          // env BHRT_TRAVERSAL: 1 = wide, 2 = binary, 0 = what the flags say
@@ -282,7 +285,9 @@ int bhrt_upload_scene(bhrt_ctx *c, const bhrt_scene_desc *d)
     if ((r = upload(c, c->tex_offsets, offs.data(), sizeof(float) * offs.size()))) return r;
     AccelBlob accel;
     std::string aerr;
-    if (!build_accel(*d, accel, &aerr)) return set_err(BHRT_ERR_ARG, "bhrt_upload_scene: " + aerr);
+    const bool wide_now = c->traversal == 1;             // env BHRT_TRAVERSAL=wide: every frame will want it
+    if (!build_accel(*d, accel, &aerr, wide_now)) return set_err(BHRT_ERR_ARG, "bhrt_upload_scene: " + aerr);
+    c->host_meshes.assign(d->meshes, d->meshes + d->n_meshes); c->host_mesh_bytes = d->mesh_bytes; c->wide_built = wide_now;
     if ((r = upload(c, c->accels, accel.meshes.data(), sizeof(MeshAccel) * accel.meshes.size()))) return r;
     if ((r = upload(c, c->accel_data, accel.data.data(), accel.data.size()))) return r;
     CU(cudaStreamSynchronize(c->stream));      // the staging vectors above die with this scope
@@ -304,7 +309,7 @@ int bhrt_upload_scene(bhrt_ctx *c, const bhrt_scene_desc *d)
     s.accel_data = (const uint8_t *)c->accel_data.p;
     c->n_materials = d->n_materials;
     fill_mesh_nodes(s, d->nodes, d->n_nodes);
-    s.use_wide = 1;
+    s.use_wide = wide_now ? 1 : 0;
     for (const MeshAccel &A : accel.meshes) if (!A.wide_stack) s.use_wide = 0;
     s.background = d->background; s.environment = d->environment;
     s.all_light_intensity = allI;
@@ -316,6 +321,34 @@ int bhrt_upload_scene(bhrt_ctx *c, const bhrt_scene_desc *d)
         return set_err(BHRT_ERR_CUDA, "cudaMalloc(frame buffers) failed");
     c->have_scene = true;
     c->rendered_spp = 0;
+    return BHRT_OK;
+}
+
+// The wide BVHs, on first use: the mesh blob comes back from the device, the tables are built again with the wide
+// trees appended and replace the ones uploaded with the scene.
+static int ensure_wide(bhrt_ctx *c)
+{
+    if (c->wide_built || !c->have_scene) return BHRT_OK;
+    c->wide_built = true;
+    if (c->host_meshes.empty()) return BHRT_OK;
+    CU(cudaSetDevice(c->device));
+    std::vector<uint8_t> blob(c->host_mesh_bytes);
+    CU(cudaMemcpyAsync(blob.data(), c->mesh_data.p, blob.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    bhrt_scene_desc d;
+    memset(&d, 0, sizeof(d));
+    d.n_meshes = (int32_t)c->host_meshes.size(); d.meshes = c->host_meshes.data(); d.mesh_data = blob.data(); d.mesh_bytes = blob.size();
+    AccelBlob accel;
+    std::string aerr;
+    if (!build_accel(d, accel, &aerr, true)) return set_err(BHRT_ERR_ARG, "wide BVH: " + aerr);
+    int r;
+    if ((r = upload(c, c->accels, accel.meshes.data(), sizeof(MeshAccel) * accel.meshes.size()))) return r;
+    if ((r = upload(c, c->accel_data, accel.data.data(), accel.data.size()))) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    c->view.accels = (const MeshAccel *)c->accels.p;
+    c->view.accel_data = (const uint8_t *)c->accel_data.p;
+    c->view.use_wide = 1;
+    for (const MeshAccel &A : accel.meshes) if (!A.wide_stack) c->view.use_wide = 0;
     return BHRT_OK;
 }
 
@@ -411,6 +444,7 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     // the wide tree (per-octet stacks in shared memory) when every mesh has one and the stacks fit
     const bool fast = p->mode == BHRT_MODE_PATH && !(p->flags & BHRT_FLAG_EXACT_MATH);
     const bool want_wide = c->traversal ? c->traversal == 1 : (p->flags & BHRT_FLAG_WIDE_BVH) != 0;
+    if (fast && want_wide) if (int wr = ensure_wide(c)) return wr;
     const int smem_wide = al16(a.smem_oct + (WF_BLOCK / 8) * (int)sizeof(OctShared));
     const int variant = !fast ? 0 : ((want_wide && c->view.use_wide && smem_wide <= 200 * 1024) ? 1 : 2);
     const int smem_bytes = variant == 1 ? smem_wide : a.smem_oct;
@@ -446,6 +480,8 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     a.gather_prof = getenv("BHRT_DEBUG") ? 1 : 0;
     a.exit_live = 0;            // (measured on config 5: leaving with up to 1/32 ... 1/4 of the lanes still live is no faster than waiting for all)
     if (const char *e = getenv("BHRT_EXIT_LIVE")) { const long v = atol(e); a.exit_live = v > 0 ? a.pool / (unsigned)v : 0u; }
+    a.key_mask = 0x3fu;
+    if (const char *e = getenv("BHRT_KEY_MASK")) a.key_mask = (unsigned)strtoul(e, nullptr, 0) & 0x3fu;
     a.gather_defer = PMQ_DEFER;
     if (const char *e = getenv("BHRT_GATHER_DEFER")) { const long v = atol(e); if (v >= 1) a.gather_defer = (unsigned)v; }
     if (a.ext_gather) {
@@ -744,6 +780,7 @@ int bhrt_debug_trace_mesh(bhrt_ctx *c, int32_t mesh, int32_t n, const float *ray
 {
     if (!c || !c->have_scene || !rays || n <= 0) return set_err(BHRT_ERR_ARG, "bhrt_debug_trace_mesh: bad argument");
     if (mesh < 0 || (size_t)mesh * sizeof(MeshAccel) >= c->accels.bytes) return set_err(BHRT_ERR_ARG, "bhrt_debug_trace_mesh: bad mesh index");
+    if (int wr = ensure_wide(c)) return wr;
     if (!c->view.use_wide) return set_err(BHRT_ERR_STATE, "bhrt_debug_trace_mesh: the scene has a mesh without a wide tree");
     CU(cudaSetDevice(c->device));
     DevBuf dr, d0, d1;

@@ -164,6 +164,7 @@ struct WaveArgs {
     // the same photon rows, which the in-kernel phase could only arrange for the primary hits of a CTA's image patch),
     // and the kernel is launched again with `resume` set.
     int ext_gather, resume, gather_prof;
+    unsigned key_mask;          // bits of the sort key in use (0x3f all; 0x38 = the stage only -- fewer, fuller chunks, less coherent branches)
     unsigned exit_live;         // split gather: a CTA leaves when no more than this many of its lanes are still live
     unsigned gather_defer;      // records per pass above which a query goes to the CTA-wide routine (estimate_irradiance_cta)
     unsigned *gq_list;          // [gridDim.x * pool] global lane index (CTA * pool + lane) of every parked query of this round
@@ -999,7 +1000,7 @@ wf_render(SceneView s, WaveArgs a)
 #if WF_LOCAL_FRAMES
                 lkey[id] = (unsigned char)wf_key(s, L, F);          // (F is the top level whenever L.sp > 0)
 #else
-                lkey[id] = (unsigned char)wf_key(s, L, frames[(size_t)(L.sp > 0 ? L.sp - 1 : 0) * P]);
+                lkey[id] = (unsigned char)(wf_key(s, L, frames[(size_t)(L.sp > 0 ? L.sp - 1 : 0) * P]) & a.key_mask);
 #endif
             } else if (valid) lkey[id] = idle ? (unsigned char)WF_KEY_IDLE : (unsigned char)WF_KEY_DEAD;
             // park the lanes that wait for a caustic gather
@@ -1243,7 +1244,7 @@ wf_render(SceneView s, WaveArgs a)
                             const int hn = OS->hnode;
                             Lg.hit.z = OS->hz; Lg.hit.node = hn; Lg.hit.front = OS->hfront != 0;
                             Lg.hit.uvw = V3(OS->ha0, OS->ha1, OS->ha2); Lg.hit.duvw0.x = u2f(OS->hface);
-                            lkey[jid] = (unsigned char)wf_key_patch(s, lkey[jid], hn);
+                            lkey[jid] = (unsigned char)(wf_key_patch(s, lkey[jid], hn) & a.key_mask);
                         }
                         pend[jid] = 0;
                         atomicSub(&n_pending_s, 1u);
@@ -1302,7 +1303,7 @@ wf_render(SceneView s, WaveArgs a)
                     else if (J.q.kind == Q_CLOSEST) {
                         Lg.hit.z = J.h.z; Lg.hit.node = J.h.node; Lg.hit.front = J.h.front;
                         Lg.hit.uvw = J.h.uvw; Lg.hit.duvw0.x = J.h.duvw0.x;
-                        lkey[jid] = (unsigned char)wf_key_patch(s, lkey[jid], J.h.node);
+                        lkey[jid] = (unsigned char)(wf_key_patch(s, lkey[jid], J.h.node) & a.key_mask);
                     }
                     pend[jid] = 0;
                     atomicSub(&n_pending_s, 1u);
