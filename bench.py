@@ -356,12 +356,15 @@ def bench_ours(args):
                 gather_note = "%.2f gather queries per camera sample x %.0f photons examined x 24 B (reference kd-tree, 10 M photons) added to the ray part" % (
                     ga["gather_queries_per_camera_sample"], ga["photons_examined_per_query"])
         achieved = frame_bytes / (kernel_ms * 1e-3) / 1e9
+        RK = "wf_render (one persistent launch per frame)" if not pm else (
+            "photon-mapped frame = pm_emit + build + rounds of [wf_render until every lane is parked at a gather, pm_query_keys, radix sort, "
+            "pm_gather_queries, pm_gather_heavy] (split gather; pm_gather_queries is the dominant kernel, profiles/r2_cfg5_pm_gather_queries_ncu_summary.json)")
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key, {}).get("wf_render_dram_bytes_per_launch")
         except (OSError, ValueError, AttributeError):
             pass
-        line["roofline"] = {"bound": "hbm", "kernel": "wf_render (one persistent launch per frame)", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+        line["roofline"] = {"bound": "hbm", "kernel": RK, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                             "frac": round(achieved / peak, 4), "traffic": traffic, "peak_kind": peak_kind,
                             "algorithmic_bytes_per_ray": round(bytes_per_ray, 1), "bytes_source": src,
                             "kernel_ms_per_launch": round(kernel_ms, 3), "rays_per_launch": int(rays_per_launch), "gather_bytes": gather_note,

@@ -220,7 +220,7 @@ int bhrt_destroy(bhrt_ctx *c)
 
 static int upload(bhrt_ctx *c, DevBuf &b, const void *src, size_t bytes)
 {
-    if (b.ensure(bytes)) return set_err(BHRT_ERR_CUDA, "cudaMalloc failed");
+    if (b.ensure(bytes + 16)) return set_err(BHRT_ERR_CUDA, "cudaMalloc failed");    // (+16: the kernels' bulk copies move whole 16-byte units)
     if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
     return BHRT_OK;
 }

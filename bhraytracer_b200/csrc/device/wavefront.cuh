@@ -182,20 +182,42 @@ static inline int wf_wave_smem_bytes(unsigned pool, bool gather)
     return (int)(pool * 2 /*list*/ + pool * 2 /*mesh queue*/ + pool /*key*/ + pool /*pending*/ + counts + 16 + (WF_PREFETCH_FRAME ? pool : 0u) /*frame stack depths*/);
 }
 
-// Stage the small, uniformly-read scene tables in shared memory (node table, materials, lights,
-// texture-filter taps) and redirect the view to them.
-__device__ __forceinline__ void stage_tables(SceneView &s, const WaveArgs &a, unsigned char *smem)
+// Stage the small, uniformly-read scene tables in shared memory (node table, materials, lights, texture-filter
+// taps) and redirect the view to them.  The four tables arrive as TMA bulk copies (cp.async.bulk, global -> shared,
+// completion counted in bytes on an mbarrier): one thread issues four instructions and the copy engine does the rest
+// while the CTA initialises its lists -- with the split gather a photon-mapped frame launches this kernel a couple of
+// hundred times, so the prologue is no longer paid once per frame.  Sizes are rounded up to the 16 bytes a bulk copy
+// moves (the device buffers and the shared-memory regions are padded accordingly: render.cu upload(), al16()).
+__device__ __forceinline__ uint32_t wf_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void wf_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint32_t bar)
 {
-    const uint32_t *src; uint32_t *dst; int n;
-    src = (const uint32_t *)s.nodes; dst = (uint32_t *)(smem + a.smem_nodes); n = s.n_nodes * (int)(sizeof(bhrt_node) / 4);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-    src = (const uint32_t *)s.materials; dst = (uint32_t *)(smem + a.smem_materials); n = s.n_materials * (int)(sizeof(bhrt_material) / 4);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-    src = (const uint32_t *)s.lights; dst = (uint32_t *)(smem + a.smem_lights); n = s.n_lights * (int)(sizeof(bhrt_light) / 4);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-    src = (const uint32_t *)s.tex_offsets; dst = (uint32_t *)(smem + a.smem_offsets); n = 2 * (BHRT_TEX_SAMPLES - 1);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(wf_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void stage_tables_begin(const SceneView &s, const WaveArgs &a, unsigned char *smem, unsigned long long *bar_storage)
+{
+    const uint32_t bar = wf_smem_u32(bar_storage);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t nb[4] = { ((uint32_t)s.n_nodes * (uint32_t)sizeof(bhrt_node) + 15u) & ~15u, ((uint32_t)s.n_materials * (uint32_t)sizeof(bhrt_material) + 15u) & ~15u,
+                                 ((uint32_t)s.n_lights * (uint32_t)sizeof(bhrt_light) + 15u) & ~15u, (2u * (BHRT_TEX_SAMPLES - 1) * 4u + 15u) & ~15u };
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(nb[0] + nb[1] + nb[2] + nb[3]) : "memory");
+        if (nb[0]) wf_bulk_g2s(smem + a.smem_nodes, s.nodes, nb[0], bar);
+        if (nb[1]) wf_bulk_g2s(smem + a.smem_materials, s.materials, nb[1], bar);
+        if (nb[2]) wf_bulk_g2s(smem + a.smem_lights, s.lights, nb[2], bar);
+        if (nb[3]) wf_bulk_g2s(smem + a.smem_offsets, s.tex_offsets, nb[3], bar);
+    }
+}
+// every thread: wait for the bytes (phase 0 of the barrier), then read the tables from shared memory
+__device__ __forceinline__ void stage_tables_end(SceneView &s, const WaveArgs &a, unsigned char *smem, unsigned long long *bar_storage)
+{
+    const uint32_t bar = wf_smem_u32(bar_storage);
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(0) : "memory");
+    } while (!ok);
     s.nodes = (const bhrt_node *)(smem + a.smem_nodes);
     s.materials = (const bhrt_material *)(smem + a.smem_materials);
     s.lights = (const bhrt_light *)(smem + a.smem_lights);
@@ -796,7 +818,8 @@ __global__ void __launch_bounds__(WF_BLOCK, WF_MIN_BLOCKS)
 wf_render(SceneView s, WaveArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    stage_tables(s, a, smem);
+    __shared__ __align__(8) unsigned long long tma_bar;
+    stage_tables_begin(s, a, smem, &tma_bar);       // (the copies run while the lists below are initialised)
     const unsigned P = a.pool;
     unsigned short *list = (unsigned short *)(smem + a.smem_wave);         // [P] live lanes sorted by key
     unsigned short *mq = list + P;                                         // [P] mesh queue (ring)
@@ -834,7 +857,8 @@ wf_render(SceneView s, WaveArgs a)
         else { claim.taken = 0; claim.claimed = 0; }
         wf_claim_topup(claim, a);
     }
-    __syncthreads();
+    __syncthreads();        // (also publishes the barrier's initialisation to the threads that wait on it)
+    stage_tables_end(s, a, smem, &tma_bar);
 
     RayCounters rc; rc.closest = 0; rc.shadow = 0;
 #if BHRT_WIDE_P2
