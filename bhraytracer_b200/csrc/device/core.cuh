@@ -40,6 +40,11 @@
 #endif
 namespace BHRT_NS {
 
+#ifdef __CUDA_ARCH__
+#define BHRT_ON_DEVICE 1
+#else
+#define BHRT_ON_DEVICE 0
+#endif
 #define BHRT_BIGFLOAT 1.0e30f          // reference Scenes/scene.h:38
 #define BHRT_BIAS 0.0001f              // reference MtlBlinn.cpp:10, TriObj.cpp:9
 #define BHRT_SHADOW_BIAS 0.00001f      // reference GenLight.cpp:5
@@ -1558,14 +1563,14 @@ BHRT_HD void frame_begin(Frame &f, const SceneView &s, V3 ray_p, const Hit &h, i
     f.out = V3(0, 0, 0);
 }
 
-BHRT_HD void issue_closest(Lane &L, const Ray &r, int hitSide, RayCounters &rc)
+template <class RC> BHRT_HD void issue_closest(Lane &L, const Ray &r, int hitSide, RC &rc)
 {
     L.q.ray = r; L.q.kind = Q_CLOSEST; L.q.hitSide = hitSide; L.q.t_max = 0;
     rc.closest++;
 }
 
 // Start one camera sample (the body of the loop in PathTracing(), Main.cpp:150-169)
-BHRT_HD void sample_begin(Lane &L, const Ray &primary, RayCounters &rc)
+template <class RC> BHRT_HD void sample_begin(Lane &L, const Ray &primary, RC &rc)
 {
     L.sp = 0;
     issue_closest(L, primary, HIT_FRONT, rc);
@@ -1612,10 +1617,13 @@ BHRT_EST_FN void direct_finish(const SceneView &s, bool have_gather, V3 irr, V3 
 // calls again.
 enum { STEP_CONT = 0, STEP_RAY = 1, STEP_DONE = 2, STEP_GATHER = 3 };
 // `f` = the top frame (fr[sp-1]; unused while sp == 0), `child` = the slot above it (fr[sp]).
-BHRT_HD int sample_step(Lane &BHRT_RESTRICT L, Frame &BHRT_RESTRICT f, Frame &BHRT_RESTRICT child, const SceneView &s, const ShadeCfg &cfg, const PhotonGather &pg, float bgu, float bgv,
-                        RayCounters &rc, V3 &color)
+// (RC = RayCounters, or the render kernel's shared-memory counters: five registers fewer in a kernel that has none to spare)
+template <class RC> BHRT_HD int sample_step(Lane &BHRT_RESTRICT L, Frame &BHRT_RESTRICT f, Frame &BHRT_RESTRICT child, const SceneView &s, const ShadeCfg &cfg, const PhotonGather &pg, float bgu, float bgv,
+                        RC &rc, V3 &color)
 {
-    const bool det = (cfg.mode == BHRT_MODE_DET);
+    // (the fast-math kernels only ever render the stochastic mode -- render.cu picks the exact build for deterministic
+    // frames -- so the deterministic branches are compiled out of them)
+    const bool det = BHRT_FAST && BHRT_ON_DEVICE ? false : (cfg.mode == BHRT_MODE_DET);
     Rng &rng = L.rng;
     if (L.sp == 0) {
         L.hit_id = L.hit_ok ? L.hit.node : -1;

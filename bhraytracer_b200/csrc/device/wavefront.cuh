@@ -832,6 +832,7 @@ wf_render(SceneView s, WaveArgs a)
     unsigned char *lsp = smem + a.smem_gather - P - 16;                     // [P] min(frames in use, 255) of lane id
 #endif
     __shared__ unsigned key_count[WF_NKEYS], key_base[WF_NKEYS];
+    __shared__ unsigned ray_count_s[3];      // rays_closest, rays_shadow, depth_overflow of this CTA and launch
     __shared__ unsigned n_live_s, n_pending_s, mq_head, mq_tail, run_mesh_s, done_s, p1_cursor, gq_count, gq_cursor, run_gather_s, n_parked_s, exit_s, gq_base_s;
     __shared__ WfClaim claim;
     __shared__ unsigned scan_part[32];
@@ -839,7 +840,7 @@ wf_render(SceneView s, WaveArgs a)
     Lane *const lanes = a.lanes + (size_t)blockIdx.x * P;
     Frame *const frames_all = a.frames + (size_t)blockIdx.x * P * (size_t)a.cfg.max_frames;
     const unsigned tid = threadIdx.x, lane = tid & 31u;
-    const bool det = a.cfg.mode == BHRT_MODE_DET;
+    const bool det = BHRT_FAST ? false : a.cfg.mode == BHRT_MODE_DET;
 
     // (split gather, resumed launch: the lanes' keys and the work ring come from the previous launch; every lane that was
     // parked has its answer now.  The first pass finds an empty live list, and the sort that follows rebuilds it.)
@@ -850,6 +851,7 @@ wf_render(SceneView s, WaveArgs a)
     for (unsigned i = tid; i < P; i += WF_BLOCK) lsp[i] = 0;
 #endif
     if (tid < WF_NKEYS) key_count[tid] = 0;
+    if (tid < 3) ray_count_s[tid] = 0;
     if (tid == 0) {
         n_live_s = resumed ? 0u : P; n_pending_s = 0; mq_head = 0; mq_tail = 0; p1_cursor = 0; run_mesh_s = 0; done_s = 0; gq_count = 0; gq_cursor = 0; n_parked_s = 0;
         exit_s = 0;
@@ -860,7 +862,9 @@ wf_render(SceneView s, WaveArgs a)
     __syncthreads();        // (also publishes the barrier's initialisation to the threads that wait on it)
     stage_tables_end(s, a, smem, &tma_bar);
 
-    RayCounters rc; rc.closest = 0; rc.shadow = 0;
+    // ray counters of the CTA in shared memory (one ATOMS per ray against five registers per thread)
+    struct SharedCount { unsigned *p; __device__ __forceinline__ void operator++(int) { atomicAdd(p, 1u); } };
+    struct { SharedCount closest, shadow, overflow; } rc = { { &ray_count_s[0] }, { &ray_count_s[1] }, { &ray_count_s[2] } };
 #if BHRT_WIDE_P2
     // this OCTET's BVH traversal, kept across iterations (identical in its 8 lanes)
     OctTrav OT; OT.done = true; OT.cur = 0; OT.sp = 0;
@@ -1349,13 +1353,12 @@ wf_render(SceneView s, WaveArgs a)
         if (tid == 0) *(WfClaim *)(state + wf_state_bytes(P) - 256u) = claim;
         if (exit_s) for (unsigned i = tid; i < gq_count; i += WF_BLOCK) a.gq_list[gq_base_s + i] = blockIdx.x * P + (unsigned)gq[i];
     }
-    unsigned long long c0 = rc.closest, c1 = rc.shadow;
-    for (int o = 16; o > 0; o >>= 1) {
-        c0 += __shfl_down_sync(0xffffffffu, c0, o);
-        c1 += __shfl_down_sync(0xffffffffu, c1, o);
+    __syncthreads();
+    if (tid == 0) {
+        if (ray_count_s[0]) atomicAdd(&a.cnt->rays_closest, (unsigned long long)ray_count_s[0]);
+        if (ray_count_s[1]) atomicAdd(&a.cnt->rays_shadow, (unsigned long long)ray_count_s[1]);
+        if (ray_count_s[2]) atomicAdd(&a.cnt->depth_overflow, (unsigned long long)ray_count_s[2]);
     }
-    if (lane == 0 && (c0 | c1)) { atomicAdd(&a.cnt->rays_closest, c0); atomicAdd(&a.cnt->rays_shadow, c1); }
-    if (rc.overflow) atomicAdd(&a.cnt->depth_overflow, (unsigned long long)rc.overflow);
     if (tid == 0) {
         atomicAdd(&a.cnt->prof[0], (unsigned long long)t_p1); atomicAdd(&a.cnt->prof[1], (unsigned long long)t_sort);
         atomicAdd(&a.cnt->prof[2], (unsigned long long)t_mesh); atomicAdd(&a.cnt->prof[3], (unsigned long long)n_iter);
