@@ -879,10 +879,11 @@ wf_render(SceneView s, WaveArgs a)
     unsigned jid = 0;
     bool first = !resumed;
 
-    long long t_p1 = 0, t_sort = 0, t_mesh = 0, n_iter = 0;
+    // phase clocks (BHRT_DEBUG's breakdown): kept by thread 0 in shared memory, not in eight registers of every thread
+    __shared__ long long prof_s[5];         // lanes pass, sort, traversal, iterations, last mark
+    if (tid == 0) { prof_s[0] = prof_s[1] = prof_s[2] = prof_s[3] = 0; }
     for (;;) {
-        const long long c_begin = clock64();
-        n_iter++;
+        if (tid == 0) { prof_s[4] = clock64(); prof_s[3]++; }
         // ================= P1: one pass over the live lanes =================
         // Warps take 32-lane chunks of the sorted list in order (shared cursor): the CTA walks the
         // stages together and no warp waits at the barrier for a slower one's fixed share.
@@ -1119,8 +1120,7 @@ wf_render(SceneView s, WaveArgs a)
             __syncthreads();
             if (tid == 0) { gq_count = 0; gq_cursor = 0; }
         }
-        long long c_mark = clock64();
-        t_p1 += c_mark - c_begin;
+        if (tid == 0) { const long long c = clock64(); prof_s[0] += c - prof_s[4]; prof_s[4] = c; }
 
         // Sort first: the lanes that did not go to a mesh are ready for the next pass.  The traversal
         // phase runs only when it has enough rays to keep every thread busy (or the live list has run
@@ -1170,7 +1170,7 @@ wf_render(SceneView s, WaveArgs a)
                 if (k != WF_KEY_DEAD) list[key_base[k] + gcount[g * WF_NKEYS + k] + __popc(peers & ((1u << lane) - 1u))] = (unsigned short)i;
             }
             __syncthreads();
-            { const long long c = clock64(); t_sort += c - c_mark; c_mark = c; }
+            if (tid == 0) { const long long c = clock64(); prof_s[1] += c - prof_s[4]; prof_s[4] = c; }
             if (!run_mesh_s) break;
 
             // ================= P2: BVH traversal of the queued rays =================
@@ -1342,7 +1342,7 @@ wf_render(SceneView s, WaveArgs a)
 #endif
             __syncthreads();
             if (tid == 0 && mq_head > mq_tail) mq_head = mq_tail;       // over-claimed pops of an empty queue
-            { const long long c = clock64(); t_mesh += c - c_mark; c_mark = c; }
+            if (tid == 0) { const long long c = clock64(); prof_s[2] += c - prof_s[4]; prof_s[4] = c; }
         }
         if (done_s || exit_s) break;
     }
@@ -1360,8 +1360,8 @@ wf_render(SceneView s, WaveArgs a)
         if (ray_count_s[2]) atomicAdd(&a.cnt->depth_overflow, (unsigned long long)ray_count_s[2]);
     }
     if (tid == 0) {
-        atomicAdd(&a.cnt->prof[0], (unsigned long long)t_p1); atomicAdd(&a.cnt->prof[1], (unsigned long long)t_sort);
-        atomicAdd(&a.cnt->prof[2], (unsigned long long)t_mesh); atomicAdd(&a.cnt->prof[3], (unsigned long long)n_iter);
+        atomicAdd(&a.cnt->prof[0], (unsigned long long)prof_s[0]); atomicAdd(&a.cnt->prof[1], (unsigned long long)prof_s[1]);
+        atomicAdd(&a.cnt->prof[2], (unsigned long long)prof_s[2]); atomicAdd(&a.cnt->prof[3], (unsigned long long)prof_s[3]);
     }
 }
 
