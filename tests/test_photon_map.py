@@ -319,3 +319,57 @@ def test_gpu_photon_mapped_frame_loses_no_sample(renderer):
     acc = torch.as_tensor(_A(), device="cuda").cpu().numpy().reshape(37, 53, 4)
     assert (acc[:, :, 3] == 3).all()
     assert np.isfinite(acc).all()
+
+
+# ---- the schedules of the gather: inside wf_render, split (the default), split with every query that scans
+# more than a handful of records handed to the CTA-wide routine -- same photons, same queries, same frame
+def _render_with_env(env, mode, **kw):
+    import bhraytracer_b200 as b
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        r = b.Renderer(0)               # (the knobs are read by bhrt_create)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    try:
+        scene = b.LoadScene(SCENE, W, H)
+        r.upload(scene)
+        r.photons_set(GOLD["photons"])
+        r.photons_build(1)
+        return r.render(mode=mode, use_photon_map=True, photon_k=K, photon_radius=RADIUS, **kw)
+    finally:
+        r.close()
+
+
+@pytest.mark.gpu
+def test_gpu_gather_schedules_agree_in_the_deterministic_mode(built):
+    """Exact build: the in-kernel and the split schedule run the same routine on the same queries -- identical frames, both
+    equal to the reference's; the CTA-wide routine adds its sums in another order -- within the 1/255 bar of the fixture."""
+    import bhraytracer_b200 as b
+    inker = _render_with_env({"BHRT_GATHER": "inkernel"}, b.MODE_DET)
+    split = _render_with_env({"BHRT_GATHER": "split"}, b.MODE_DET)
+    cta = _render_with_env({"BHRT_GATHER": "split", "BHRT_GATHER_DEFER": "64"}, b.MODE_DET)
+    for o in (inker, split, cta):
+        check_gather_image(o["rgb8"], o["hit_id"])
+    assert (inker["rgb8"] == split["rgb8"]).all() and (inker["linear"] == split["linear"]).all()
+    assert (inker["rays_closest"], inker["rays_shadow"]) == (split["rays_closest"], split["rays_shadow"]) == (cta["rays_closest"], cta["rays_shadow"])
+    assert np.abs(cta["linear"] - split["linear"]).max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_gpu_gather_schedules_agree_in_the_stochastic_mode(built):
+    """Fast-math build, 8 spp: same samples (the RNG is keyed by pixel and sample), same photons; the schedules may differ
+    in the last bits of a query's float sums (the inlined and the out-of-line copy of the routine are compiled apart),
+    which moves single samples, not the image."""
+    import bhraytracer_b200 as b
+    frames = [_render_with_env(env, b.MODE_PATH, spp=8, seed=3) for env in
+              ({"BHRT_GATHER": "inkernel"}, {"BHRT_GATHER": "split"}, {"BHRT_GATHER": "split", "BHRT_GATHER_DEFER": "64"})]
+    ref = frames[0]
+    for o in frames[1:]:
+        assert abs(o["rays_closest"] + o["rays_shadow"] - ref["rays_closest"] - ref["rays_shadow"]) <= 1e-4 * (ref["rays_closest"] + ref["rays_shadow"])
+        assert np.abs(o["linear"] - ref["linear"]).mean() < 2e-4
+        assert (np.abs(o["rgb8"].astype(int) - ref["rgb8"].astype(int)) > 1).mean() < 1e-3
