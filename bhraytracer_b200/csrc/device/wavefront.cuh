@@ -331,35 +331,58 @@ struct PmWarpScratch {
 // only the distance test, the survivors' indices go into a 64-entry ring in shared memory, and whenever the ring holds
 // 32 of them `body(index, d2, true)` runs for a FULL warp (and once more, partially filled, at the end).
 // my_b / my_e: lane n < 27 holds the record range of cell n.  Warp-convergent.
-template <typename Body>
+// STREAM = false (what every caller uses): four records per lane and trip, the loads issued back to back.
+// STREAM = true: one group of 32 records per iteration with the next group's load in flight -- fewer instructions (the four
+// predicated loads, their addresses and fill values are half of a trip's), same groups, same order, same result; tried for
+// the dedicated kernels, whose limit is instruction issue.  MEASURED on BASELINE config 5: 3.22 s per frame against 2.88 s
+// -- even at a 90 % L1 hit rate the four loads in flight are worth more than the instructions they cost.  Kept, unused.
+template <bool STREAM, typename Body>
 __device__ __forceinline__ void pm_scan(const PhotonGather &pg, uint32_t my_b, uint32_t my_e, int n_step, V3 pos, float bound2, PmWarpScratch *wsm, unsigned lane, Body body)
 {
     unsigned head = 0, fill = 0;        // ring state (warp-uniform)
+    // one group: distance test, survivors into the ring, a full ring runs the body
+    auto group = [&](uint32_t i, bool in_range, const F4 &A) {
+        const float d2 = length2(V3(A.x - pos.x, A.y - pos.y, A.z - pos.z));
+        const bool ok = in_range && d2 < bound2;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) { const unsigned slot = (head + fill + __popc(m & ((1u << lane) - 1u))) & 63u; wsm->qidx[slot] = i; wsm->qd2[slot] = d2; }
+        fill += __popc(m);
+        if (fill >= 32u) {
+            __syncwarp();
+            const unsigned slot = (head + lane) & 63u;
+            body(wsm->qidx[slot], wsm->qd2[slot], true);
+            __syncwarp();
+            head += 32u; fill -= 32u;
+        }
+    };
     for (int n = 0; n < 27; n += n_step) {
         const uint32_t b = __shfl_sync(0xffffffffu, my_b, n), e = __shfl_sync(0xffffffffu, my_e, n);
-        // four records per lane and trip: the loads are issued back to back (the pass is bound by their latency)
-        for (uint32_t base = b; base < e; base += 128u) {
-            F4 A[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t i = base + 32u * k + lane;
-                if (i < e) A[k] = ld4(&pg.recs[i].a); else { A[k].x = A[k].y = A[k].z = 3.0e18f; A[k].w = 0.f; }
+        if (STREAM) {
+            if (b >= e) continue;
+            uint32_t base = b;
+            F4 A; A.x = A.y = A.z = A.w = 0.f;
+            if (base + lane < e) A = ld4(&pg.recs[base + lane].a);
+            for (;;) {
+                const uint32_t next = base + 32u;
+                const bool more = next < e;         // (warp-uniform)
+                F4 An; An.x = An.y = An.z = An.w = 0.f;
+                if (more && next + lane < e) An = ld4(&pg.recs[next + lane].a);
+                group(base + lane, base + lane < e, A);
+                if (!more) break;
+                A = An; base = next;
             }
+        } else {
+            for (uint32_t base = b; base < e; base += 128u) {
+                F4 A[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (base + 32u * k >= e) break;         // (warp-uniform)
-                const uint32_t i = base + 32u * k + lane;
-                const float d2 = length2(V3(A[k].x - pos.x, A[k].y - pos.y, A[k].z - pos.z));
-                const bool ok = d2 < bound2;            // (records past the end sit at 3e18: never inside)
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) { const unsigned slot = (head + fill + __popc(m & ((1u << lane) - 1u))) & 63u; wsm->qidx[slot] = i; wsm->qd2[slot] = d2; }
-                fill += __popc(m);
-                if (fill >= 32u) {
-                    __syncwarp();
-                    const unsigned slot = (head + lane) & 63u;
-                    body(wsm->qidx[slot], wsm->qd2[slot], true);
-                    __syncwarp();
-                    head += 32u; fill -= 32u;
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t i = base + 32u * k + lane;
+                    if (i < e) A[k] = ld4(&pg.recs[i].a); else { A[k].x = A[k].y = A[k].z = 3.0e18f; A[k].w = 0.f; }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (base + 32u * k >= e) break;         // (warp-uniform)
+                    group(base + 32u * k + lane, true, A[k]);       // (records past the end sit at 3e18: never inside)
                 }
             }
         }
@@ -469,6 +492,7 @@ __device__ __forceinline__ void pm_level_ranges(const PhotonGather &pg, int leve
 // for a query in a caustic's focus, and everybody else ends up waiting for it.
 // (inlined into the dedicated gather kernel, where the structure's fields are kernel parameters -- uniform registers, no
 // reloads of the record pointer from a local copy; wf_render calls it out of line, below)
+template <bool STREAM>
 __device__ __forceinline__ bool estimate_irradiance_warp_inl(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction, PmWarpScratch *wsm, unsigned long long *prof, unsigned defer_visit)
 {
 #ifdef BHRT_PM_PROF
@@ -512,7 +536,7 @@ __device__ __forceinline__ bool estimate_irradiance_warp_inl(const PhotonGather 
         __syncwarp();
         int total = 0;
         V3 sumP(0, 0, 0), sumD(0, 0, 0);
-        pm_scan(pg, my_b, my_e, n_step, pos, bound2, wsm, lane, [&](uint32_t i, float d2, bool act) {
+        pm_scan<STREAM>(pg, my_b, my_e, n_step, pos, bound2, wsm, lane, [&](uint32_t i, float d2, bool act) {
             if (!act) return;
             const F4 B = ld4(&pg.recs[i].b);
             if (dot(V3(B.x, B.y, B.z), N) >= 0) return;
@@ -563,7 +587,7 @@ __device__ __forceinline__ bool estimate_irradiance_warp_inl(const PhotonGather 
             __syncwarp();
             for (int j = (int)lane; j < 256; j += 32) wsm->hist[j] = 0;
             __syncwarp();
-            pm_scan(pg, my_b, my_e, n_step, pos, pm_tight_bound(bound2, prefix >> (16 - shift - 8)), wsm, lane, [&](uint32_t i, float d2, bool act) {
+            pm_scan<STREAM>(pg, my_b, my_e, n_step, pos, pm_tight_bound(bound2, prefix >> (16 - shift - 8)), wsm, lane, [&](uint32_t i, float d2, bool act) {
                 if (!act) return;
                 uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
                 if ((u >> (shift + 8)) != prefix) return;
@@ -580,7 +604,7 @@ __device__ __forceinline__ bool estimate_irradiance_warp_inl(const PhotonGather 
         sumP = V3(0, 0, 0); sumD = V3(0, 0, 0);
         V3 subP(0, 0, 0), subD(0, 0, 0);
         float kth2 = 0, sub_max = 0;
-        pm_scan(pg, my_b, my_e, n_step, pos, pm_tight_bound(bound2, prefix >> (16 - shift)), wsm, lane, [&](uint32_t i, float d2, bool act) {
+        pm_scan<STREAM>(pg, my_b, my_e, n_step, pos, pm_tight_bound(bound2, prefix >> (16 - shift)), wsm, lane, [&](uint32_t i, float d2, bool act) {
             if (!act) return;
             uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
             const uint32_t top = u >> shift;
@@ -637,7 +661,7 @@ __device__ __forceinline__ bool estimate_irradiance_warp_inl(const PhotonGather 
 
 __device__ __noinline__ bool estimate_irradiance_warp(const PhotonGather &pg, V3 pos, V3 N, V3 &irrad, V3 &direction, PmWarpScratch *wsm, unsigned long long *prof, unsigned defer_visit = 0u)
 {
-    return estimate_irradiance_warp_inl(pg, pos, N, irrad, direction, wsm, prof, defer_visit);
+    return estimate_irradiance_warp_inl<false>(pg, pos, N, irrad, direction, wsm, prof, defer_visit);
 }
 
 // ---- the same estimate for a WHOLE CTA: every warp scans its own slice of each record range, the histogram and the
@@ -698,7 +722,7 @@ __device__ __forceinline__ void estimate_irradiance_cta(const PhotonGather &pg, 
         {
             int total = 0;
             V3 sumP(0, 0, 0), sumD(0, 0, 0);
-            pm_scan(pg, my_b, my_e, 1, pos, bound2, ring, lane, [&](uint32_t i, float d2, bool act) {
+            pm_scan<false>(pg, my_b, my_e, 1, pos, bound2, ring, lane, [&](uint32_t i, float d2, bool act) {
                 if (!act) return;
                 const F4 B = ld4(&pg.recs[i].b);
                 if (dot(V3(B.x, B.y, B.z), N) >= 0) return;
@@ -745,7 +769,7 @@ __device__ __forceinline__ void estimate_irradiance_cta(const PhotonGather &pg, 
             __syncthreads();
             for (int j = (int)threadIdx.x; j < 256; j += (int)blockDim.x) sh->hist[j] = 0;
             __syncthreads();
-            pm_scan(pg, my_b, my_e, 1, pos, pm_tight_bound(bound2, prefix >> (16 - shift - 8)), ring, lane, [&](uint32_t i, float d2, bool act) {
+            pm_scan<false>(pg, my_b, my_e, 1, pos, pm_tight_bound(bound2, prefix >> (16 - shift - 8)), ring, lane, [&](uint32_t i, float d2, bool act) {
                 if (!act) return;
                 uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
                 if ((u >> (shift + 8)) != prefix) return;
@@ -761,7 +785,7 @@ __device__ __forceinline__ void estimate_irradiance_cta(const PhotonGather &pg, 
         __syncthreads();
         V3 sumP(0, 0, 0), sumD(0, 0, 0), subP(0, 0, 0), subD(0, 0, 0);
         float kth2 = 0, sub_max = 0;
-        pm_scan(pg, my_b, my_e, 1, pos, pm_tight_bound(bound2, prefix >> (16 - shift)), ring, lane, [&](uint32_t i, float d2, bool act) {
+        pm_scan<false>(pg, my_b, my_e, 1, pos, pm_tight_bound(bound2, prefix >> (16 - shift)), ring, lane, [&](uint32_t i, float d2, bool act) {
             if (!act) return;
             uint32_t u = (uint32_t)((d2 * scale) * 524288.f); if (u > 0xffffffu) u = 0xffffffu;
             const uint32_t top = u >> shift;
@@ -1443,7 +1467,7 @@ pm_gather_queries(WaveArgs a, const unsigned *__restrict__ sorted, unsigned n, u
             const Frame &fq = wf_query_frame(a, entry);
             V3 irr, dirv;
             const long long t0 = clock64();
-            const bool deferred = estimate_irradiance_warp_inl(a.gather, fq.p, fq.vN, irr, dirv, scratch + (threadIdx.x >> 5), a.cnt->pmprof, a.gather_defer);
+            const bool deferred = estimate_irradiance_warp_inl<false>(a.gather, fq.p, fq.vN, irr, dirv, scratch + (threadIdx.x >> 5), a.cnt->pmprof, a.gather_defer);
             if (deferred) { if (lane == 0) heavy[atomicAdd(n_heavy, 1u)] = entry; }
             else if (lane == 0) {
                 Lane &Lg = a.lanes[entry]; Lg.ret = irr; Lg.sw = dirv;
