@@ -228,7 +228,9 @@ int bhrt_upload_scene(bhrt_ctx *ctx, const bhrt_scene_desc *scene);
  * MtlBlinn::Shade recursion is as deep as the scene makes it (the reference has no bound,
  * MtlBlinn.cpp:476-519): a ctx starts with 64 levels per camera sample in flight and renders a
  * frame again with twice as many while any level was refused (up to 4096, device memory
- * permitting); kernel_ms is the time of ALL passes, the ray counters are those of the last one. */
+ * permitting); kernel_ms is the time of ALL passes, the ray counters are those of the last one.
+ * With use_photon_map the frame is many launches on the ctx's stream (the render kernel alternates with the kernels of the
+ * caustic gather) and the call reads a 4-byte counter back between them; kernel_ms spans all of it. */
 int bhrt_render(bhrt_ctx *ctx, const bhrt_params *params, bhrt_outputs *out);
 
 /* The same frame, outputs left in device memory (accumulation buffer = sum over the
