@@ -63,6 +63,7 @@ class SceneDesc(C.Structure):
 
 FLAG_EXACT_MATH = 1      # BHRT_FLAG_EXACT_MATH
 FLAG_WIDE_BVH = 2        # BHRT_FLAG_WIDE_BVH
+FLAG_FACE_MATERIALS = 4  # BHRT_FLAG_FACE_MATERIALS
 
 
 class Params(C.Structure):
@@ -267,7 +268,7 @@ class Renderer:
 
     @staticmethod
     def params(mode=MODE_PATH, spp=32, gi_depth=3, tir_budget=16, seed=1, sample_range=None, rows=None,
-               row_stride=1, use_photon_map=False, photon_k=1000, photon_radius=0.5, exact_math=False, wide_bvh=False):
+               row_stride=1, use_photon_map=False, photon_k=1000, photon_radius=0.5, exact_math=False, wide_bvh=False, face_materials=False):
         p = Params()
         p.mode, p.spp, p.gi_depth, p.tir_budget, p.seed = mode, spp, gi_depth, tir_budget, seed
         if sample_range:
@@ -276,7 +277,7 @@ class Renderer:
             p.row_begin, p.row_end = rows
         p.row_stride = row_stride
         p.use_photon_map, p.photon_k, p.photon_radius = int(use_photon_map), photon_k, photon_radius
-        p.flags = (FLAG_EXACT_MATH if exact_math else 0) | (FLAG_WIDE_BVH if wide_bvh else 0)
+        p.flags = (FLAG_EXACT_MATH if exact_math else 0) | (FLAG_WIDE_BVH if wide_bvh else 0) | (FLAG_FACE_MATERIALS if face_materials else 0)
         return p
 
     def _alloc_outputs(self, want):

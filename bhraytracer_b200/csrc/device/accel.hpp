@@ -163,6 +163,7 @@ inline bool build_accel(const bhrt_scene_desc &D, AccelBlob &out, std::string *e
         MeshAccel A;
         memset(&A, 0, sizeof(A));
         A.vn_off = m.vn_off; A.vt_off = m.vt_off; A.fn_off = m.fn_off; A.ft_off = m.ft_off;
+        A.n_groups = m.n_groups; A.groups_off = (m.elems_off + 4 * (int64_t)m.nf + 15) & ~(int64_t)15;
 
         // ---- pair nodes: DFS pre-order numbering of the internal nodes (root first)
         std::vector<int> pair_of(m.n_bvh_nodes + 2, -1);

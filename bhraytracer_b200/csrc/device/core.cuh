@@ -149,9 +149,10 @@ struct alignas(16) Hit {    // reference scene.h:62-75 (HitInfo)
     bool front;
     V3 uvw, duvw0;
     V3 p, N, duvw1;
+    int sub;                // sub-material of the hit face (HitInfo::mtlID, scene.h:71): 0 unless BHRT_FLAG_FACE_MATERIALS (scene_trace_finish)
     BHRT_HD void init()
     {
-        z = BHRT_BIGFLOAT; node = -1; front = true;
+        z = BHRT_BIGFLOAT; node = -1; front = true; sub = 0;
         uvw = V3(0.5f, 0.5f, 0.5f); duvw0 = V3(0, 0, 0); duvw1 = V3(0, 0, 0);
         p = V3(0, 0, 0); N = V3(0, 0, 0);
     }
@@ -219,6 +220,8 @@ struct MeshAccel {
     int64_t wide_off;                       // WideNode array (accel_data)
     uint32_t wide_root, wide_root_aux;      // word / aux of the root (a leaf group when the mesh has <= 8 triangles)
     uint32_t wide_stack, wide_nodes;        // worst-case deferred entries of a traversal (0: no wide tree), node count
+    int64_t groups_off;                     // int32 group_end[n_groups] in SceneView::mesh_data (bhrt.h: bhrt_mesh::n_groups)
+    int32_t n_groups, pad_;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -244,6 +247,7 @@ struct SceneView {
     float all_light_intensity;          // Main.cpp:119-122
     V3 cam_pos, top_left, dd_x, dd_y;   // Main.cpp:179-192, computed on the host
     int width, height;
+    int face_materials;                 // BHRT_FLAG_FACE_MATERIALS of the frame being rendered
 };
 
 struct RayCounters { unsigned long long closest, shadow; unsigned overflow = 0; };   // overflow: Shade() levels refused for lack of frames
@@ -891,6 +895,7 @@ BHRT_HD bool scene_trace_meshes(const SceneView &s, const Query &q, Hit &h, uint
 // 1322 instead of 390 bytes, and the compiler's spill placement is worse than the plain local-memory copy.)
 BHRT_FN bool scene_trace_finish(const SceneView &s, const Query &q, Hit &h)
 {
+    h.sub = 0;
     if (h.node < 0) return false;
     const bhrt_node &nd = s.nodes[h.node];
     const Ray wr = node_local_ray(s, h.node, q.ray);
@@ -939,6 +944,16 @@ BHRT_FN bool scene_trace_finish(const SceneView &s, const Query &q, Hit &h)
         const float a0 = h.uvw.x, a1 = h.uvw.y, a2 = h.uvw.z;
         const uint32_t face = f2u(h.duvw0.x);
         mesh_attributes(s, s.accels[nd.mesh], face, a0, a1, a2, lN, h.uvw);
+        if (s.face_materials && (hm.flags & BHRT_MTL_MULTI)) {
+            // hInfo.mtlID = the usemtl group of the face (what the reference's MultiMtl::Shade expects and
+            // TriObj::IntersectTriangle never sets, materials.h:71 / TriObj.cpp:68-189; cyTriMesh::GetMaterialIndex,
+            // cyTriMesh.h:221-227: the first group whose cumulative face count exceeds the face index, none -> 0)
+            const MeshAccel &MA = s.accels[nd.mesh];
+            const int32_t *group_end = (const int32_t *)(s.mesh_data + MA.groups_off);
+            int g = 0;
+            while (g < MA.n_groups && (int)face >= group_end[g]) g++;
+            if (g < MA.n_groups && g < BHRT_MTL_SUBCOUNT(hm.flags)) h.sub = g;
+        }
         h.duvw0 = V3(0, 0, 0); h.duvw1 = V3(0, 0, 0);
     }
     // Node::FromNodeCoords of the hit node (Main.cpp:401) and then of its parent
@@ -1558,7 +1573,7 @@ BHRT_HD void frame_begin(Frame &f, const SceneView &s, V3 ray_p, const Hit &h, i
     f.p = h.p; f.uvw = h.uvw; f.duvw0 = h.duvw0; f.duvw1 = h.duvw1;
     f.vN = normalized(h.N);
     f.vV = normalized(ray_p - h.p);
-    f.mtl = s.nodes[h.node].material;
+    f.mtl = s.nodes[h.node].material + h.sub;
     f.bounce = bounce; f.gi = gi;
     f.out = V3(0, 0, 0);
 }

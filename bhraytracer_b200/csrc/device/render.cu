@@ -248,6 +248,8 @@ int bhrt_upload_scene(bhrt_ctx *c, const bhrt_scene_desc *d)
         const bhrt_mesh &m = d->meshes[i];
         if (m.nf <= 0 || m.n_bvh_nodes <= 0) return set_err(BHRT_ERR_ARG, "bhrt_upload_scene: empty mesh");
         if ((size_t)m.bvh_off + (size_t)(m.n_bvh_nodes + 1) * sizeof(bhrt_bvh_node) > d->mesh_bytes) return set_err(BHRT_ERR_ARG, "bhrt_upload_scene: mesh blob too small");
+        if (m.n_groups < 0 || (m.n_groups > 0 && (size_t)((m.elems_off + 4 * (int64_t)m.nf + 15) & ~(int64_t)15) + 4 * (size_t)m.n_groups > d->mesh_bytes))
+            return set_err(BHRT_ERR_ARG, "bhrt_upload_scene: mesh blob too small for its usemtl group table");
     }
     CU(cudaSetDevice(c->device));
     std::vector<bhrt_light> lights(d->lights, d->lights + d->n_lights);
@@ -366,6 +368,7 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     a.cfg.gi_depth = p->gi_depth;
     a.cfg.tir_budget = p->tir_budget > 0 ? p->tir_budget : 16;
     a.cfg.max_frames = c->max_frames;
+    c->view.face_materials = (p->flags & BHRT_FLAG_FACE_MATERIALS) ? 1 : 0;
     a.seed = p->seed;
     int spp = p->mode == BHRT_MODE_DET ? 1 : p->spp;
     if (spp <= 0) return set_err(BHRT_ERR_ARG, "bhrt_render: spp must be > 0");

@@ -88,8 +88,10 @@ struct Flattener {
             // MultiMtl::Shade uses mtls[hInfo.mtlID] and mtlID is never set (materials.h:71,
             // TriObj.cpp:68-189), so sub-material 0 shades every face.
             const MultiMtl *mm = static_cast<const MultiMtl *>(m);
-            if (mm->mtls.empty()) { ok = false; return -1; }
-            idx = AddBlinn(*mm->mtls[0], BHRT_MTL_MULTI);
+            if (mm->mtls.empty() || mm->mtls.size() > 255) { ok = false; return -1; }
+            idx = AddBlinn(*mm->mtls[0], BHRT_MTL_MULTI | ((uint32_t)mm->mtls.size() << 8));
+            // the other sub-materials follow contiguously (BHRT_FLAG_FACE_MATERIALS; bhrt.h)
+            for (size_t i = 1; i < mm->mtls.size(); i++) AddBlinn(*mm->mtls[i], 0);
         }
         mtlIndex[m] = idx;
         return idx;
@@ -124,6 +126,9 @@ struct Flattener {
         }
         d.bvh_off = AppendBlob(nodes.data(), nodes.size());
         d.elems_off = AppendBlob(t->bvhElements.data(), t->bvhElements.size());
+        // usemtl groups: cumulative face counts (cyTriMesh mcfc), right behind the elems array (bhrt.h: bhrt_mesh::n_groups)
+        d.n_groups = (int)t->mcfc.size();
+        if (d.n_groups > 0) AppendBlob(t->mcfc.data(), t->mcfc.size());
         int idx = (int)out.meshes.size();
         out.meshes.push_back(d);
         meshIndex[t] = idx;

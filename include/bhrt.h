@@ -89,7 +89,11 @@ typedef struct bhrt_texture {
     float color1[3], color2[3];
 } bhrt_texture;
 
-enum { BHRT_MTL_MULTI = 1 };   /* flattened from a MultiMtl: sub-material 0 (mtlID is never set, TriObj.cpp:68-189) */
+/* bhrt_material.flags.  BHRT_MTL_MULTI: flattened from a MultiMtl (xmlload.cpp:219-250) -- this entry is its sub-material 0,
+ * which shades every face in the reference (hInfo.mtlID is never set, TriObj.cpp:68-189); bits 8..15 hold the number of
+ * sub-materials, the others follow at the next indices of the material table (read only with BHRT_FLAG_FACE_MATERIALS). */
+enum { BHRT_MTL_MULTI = 1 };
+#define BHRT_MTL_SUBCOUNT(flags) ((int)(((uint32_t)(flags) >> 8) & 0xffu))
 
 /* reference Materials/materials.h:20-61 (MtlBlinn).  emission / reflection /
  * reflectionGlossiness are parsed by the reference loader but never read by its renderer
@@ -134,7 +138,9 @@ typedef struct bhrt_bvh_node {
 typedef struct bhrt_mesh {
     int32_t nv, nf, nvn, nvt;
     int32_t n_bvh_nodes;
-    int32_t pad;
+    int32_t n_groups;   /* usemtl groups of the OBJ (cyTriMesh mcfc, cyTriMesh.h:467-490; faces are stored group by group); when
+                         * > 0, int32 group_end[n_groups] -- face f belongs to the first group g with f < group_end[g] -- follows
+                         * the elems array, at elems_off + 4 * nf rounded up to 16 bytes */
     int64_t v_off, vn_off, vt_off;
     int64_t f_off, fn_off, ft_off;
     int64_t bvh_off, elems_off;
@@ -198,6 +204,11 @@ typedef struct bhrt_params {
  * the wide stack, and when the scene tables plus the stacks do not fit in shared memory.
  * Environment override for all renders of a ctx: BHRT_TRAVERSAL=wide|binary. */
 #define BHRT_FLAG_WIDE_BVH 2u
+/* Quirk switch: shade every face of an OBJ with the sub-material of ITS usemtl group -- what MultiMtl::Shade
+ * (materials.h:71) would do if TriObj::IntersectTriangle set hInfo.mtlID, which the reference at HEAD never does
+ * (TriObj.cpp:68-189), so that sub-material 0 shades the whole mesh.  Off by default: parity is against the reference as
+ * it is; the switched-on behaviour is pinned against the reference with that one assignment added (oracle patch Q-1). */
+#define BHRT_FLAG_FACE_MATERIALS 4u
 
 /* Any pointer may be NULL to skip that output.  Layouts follow the reference's
  * colorArray / RenderImage (Main.cpp:202,229-230): row-major, j*W+i, row 0 at the top. */

@@ -15,6 +15,9 @@ Patch list (numbers = SURVEY.md section 8(c)):
   O-4  per-thread rand() (driver.cpp, link-time; no source edit)
   O-5  AOV + ray-counter hooks
   O-7  --global-photons: call BuildPhotonMap (Main.cpp:251-295; its call at Main.cpp:196 is commented out at HEAD), dump, exit
+  Q-1  --face-materials: TriObj::IntersectTriangle sets hInfo.mtlID = the usemtl group of the face, which HEAD never does
+       (TriObj.cpp:68-189; MultiMtl::Shade dispatches on it, materials.h:71) -- the reference behaviour behind the product's
+       optional BHRT_FLAG_FACE_MATERIALS; off unless asked for, so every other fixture is the unmodified behaviour
   D-1  det mode: no jitter              (Main.cpp:153)
   D-2  det mode: GI term off            (MtlBlinn.cpp:124)
   D-3  det mode: all lights, exact L    (MtlBlinn.cpp:308)
@@ -100,9 +103,10 @@ PATCHES = {
         (4, "{", lambda s: "{ BHRT_CNT(1);\n"),
     ],
     "Objects/TriObj/TriObj.cpp": [
-        (1, "", lambda s: CNT + s),
+        (1, "", lambda s: "extern int g_bhrt_face_mtl;\n" + CNT + s),
         (69, "{", lambda s: "{ BHRT_CNT(2);\n"),
-        (169, "Vec3f hitPointNormal = GetNormal(faceID, bc);", lambda s: "\tBHRT_CNT(3);\n" + s),
+        (169, "Vec3f hitPointNormal = GetNormal(faceID, bc);",
+         lambda s: "\tBHRT_CNT(3);\n\tif (g_bhrt_face_mtl) { int m_ = GetMaterialIndex((int)faceID); hInfo.mtlID = m_ > 0 ? m_ : 0; }\n" + s),
     ],
     "Textures/Texture.cpp": [
         (1, "", lambda s: CNT + s),

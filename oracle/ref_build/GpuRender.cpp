@@ -113,8 +113,9 @@ int addMaterial(Flat &F, const Material *m)
     else {
         // MultiMtl::Shade uses mtls[hInfo.mtlID] and mtlID is never set (materials.h:71, TriObj.cpp:68-189)
         const MultiMtl *mm = static_cast<const MultiMtl *>(m);
-        if (mm->mtls.empty()) return -1;
-        idx = addBlinn(F, *static_cast<const MtlBlinn *>(mm->mtls[0]), BHRT_MTL_MULTI);
+        if (mm->mtls.empty() || mm->mtls.size() > 255) return -1;
+        idx = addBlinn(F, *static_cast<const MtlBlinn *>(mm->mtls[0]), BHRT_MTL_MULTI | ((uint32_t)mm->mtls.size() << 8));
+        for (size_t i = 1; i < mm->mtls.size(); i++) addBlinn(F, *static_cast<const MtlBlinn *>(mm->mtls[i]), 0);     // (BHRT_FLAG_FACE_MATERIALS)
     }
     F.mtlIndex[m] = idx;
     return idx;
@@ -150,6 +151,8 @@ int addMesh(Flat &F, const TriObj *t)
     d.n_bvh_nodes = (int)maxNode;
     d.bvh_off = appendBlob(F, nodes.data(), nodes.size());
     d.elems_off = appendBlob(F, bvh.elements, t->nf);
+    d.n_groups = (int)t->nm;                                    // usemtl groups: cyTriMesh's cumulative face counts behind the elems
+    if (t->nm > 0) appendBlob(F, t->mcfc, t->nm);
     int idx = (int)F.meshes.size();
     F.meshes.push_back(d); F.meshIndex[t] = idx;
     return idx;

@@ -44,6 +44,9 @@ static inline bool desc_dump(const bhrt_scene_desc &D, const char *path)
         // (node 0 of the cyBVH array is never initialised by the reference: skip it)
         dd_put(f, "bvh", D.mesh_data + m.bvh_off + sizeof(bhrt_bvh_node), sizeof(bhrt_bvh_node) * (size_t)m.n_bvh_nodes);
         dd_put(f, "elems", D.mesh_data + m.elems_off, (size_t)m.nf * 4);
+        // usemtl groups: cumulative face counts behind the elems array (bhrt.h: bhrt_mesh::n_groups)
+        dd_put(f, "groups", &m.n_groups, sizeof(m.n_groups));
+        if (m.n_groups > 0) dd_put(f, "group_end", D.mesh_data + ((m.elems_off + 4 * (int64_t)m.nf + 15) & ~(int64_t)15), (size_t)m.n_groups * 4);
     }
     dd_put(f, "bg", &D.background, sizeof(D.background));
     dd_put(f, "env", &D.environment, sizeof(D.environment));

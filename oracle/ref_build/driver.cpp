@@ -36,6 +36,7 @@ void BeginRender();
 
 // knobs the patched reference reads (see build_ref.sh)
 int g_bhrt_det = 0;
+int g_bhrt_face_mtl = 0;      // patch Q-1 (oracle/build_ref.py): per-face sub-materials
 int g_bhrt_spp = 32;      // reference Main.cpp:141
 int g_bhrt_gi = 3;        // reference Main.cpp:130
 int g_bhrt_photons = 1000000;  // reference Main.cpp:52-53
@@ -134,6 +135,7 @@ int main(int argc, char **argv)
 		else if (!strcmp(argv[a], "--png")) writePng = 1;
 		else if (!strcmp(argv[a], "--libc-rand")) s_use_libc_rand = 1;
 		else if (!strcmp(argv[a], "--global-photons")) g_bhrt_global_pm = 1;
+		else if (!strcmp(argv[a], "--face-materials")) g_bhrt_face_mtl = 1;
 		else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
 	}
 	if (g_bhrt_det) g_bhrt_spp = 1;

@@ -61,7 +61,7 @@ int main(int argc, char **argv)
     const char *photon_file = nullptr; int photon_total = 1, photon_k = 1000; float photon_radius = 0.5f;
     const char *query_in = nullptr, *query_out = nullptr;
     const char *pixel_rays = nullptr;
-    int max_frames = 0, wide = 0;
+    int max_frames = 0, wide = 0, face_materials = 0;
     unsigned long long seed = 1;
     for (int a = 3; a < argc; a++) {
         if (!strcmp(argv[a], "--det")) det = 1;
@@ -77,6 +77,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[a], "--pixel-rays") && a + 1 < argc) pixel_rays = argv[++a];
         else if (!strcmp(argv[a], "--max-frames") && a + 1 < argc) max_frames = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--wide")) wide = 1;
+        else if (!strcmp(argv[a], "--face-materials")) face_materials = 1;
         else if (!strcmp(argv[a], "--queries") && a + 2 < argc) { query_in = argv[++a]; query_out = argv[++a]; }
         else { fprintf(stderr, "unknown arg %s\n", argv[a]); return 2; }
     }
@@ -108,6 +109,7 @@ int main(int argc, char **argv)
     AccelBlob accel;
     if (!build_accel(D, accel, &err)) { fprintf(stderr, "accel: %s\n", err.c_str()); return 3; }
     s.accels = accel.meshes.data(); s.accel_data = accel.data.data();
+    s.face_materials = face_materials;          // BHRT_FLAG_FACE_MATERIALS (bhrt.h)
     if (wide) {
         // traverse the 8-wide collapse of the BVH (the structure the kernels' fast build uses) instead of the binary tree
         s.use_wide = 1;

@@ -31,6 +31,13 @@ DET = [
     ("det_textured", 400, 300),
     ("det_mesh", 400, 300),
     ("det_objmtl", 320, 240),
+    ("det_facemtl", 320, 240),
+]
+# (scene, width, height, fixture tag, extra arguments of the reference driver) more D-mode fixtures.  det_facemtl with
+# --face-materials = the reference with oracle patch Q-1 (hInfo.mtlID set to the face's usemtl group): what
+# BHRT_FLAG_FACE_MATERIALS must reproduce; the plain det_facemtl fixture above is the reference as it is.
+DET_EXTRA = [
+    ("det_facemtl", 320, 240, "facemtl", ["--face-materials"]),
 ]
 # (scene, width, height, test spp, reference spp) rendered in H-mode
 STOCH = [
@@ -145,6 +152,18 @@ def main():
             np.savez_compressed(out, hit_id=a["hit_id"].astype(np.int16), rgb8=a["rgb8"], z_bits=a["z"].view(np.uint32),
                                 rays_closest=info["rays_closest"], rays_shadow=info["rays_shadow"], width=w, height=h)
             print("%-28s %dx%d rays %d+%d -> %d bytes" % (name, w, h, info["rays_closest"], info["rays_shadow"], os.path.getsize(out)))
+        for name, w, h, tag, extra in DET_EXTRA:
+            if only and name + "_" + tag not in only:
+                continue
+            sp = sized_scene(name, w, h, tmp)
+            try:
+                info, a = run_ref(sp, os.path.join(tmp, name + tag), "--det", *extra)
+            finally:
+                os.remove(sp)
+            out = os.path.join(ROOT, "tests", "golden", "%s_%s_det.npz" % (name, tag))
+            np.savez_compressed(out, hit_id=a["hit_id"].astype(np.int16), rgb8=a["rgb8"], z_bits=a["z"].view(np.uint32),
+                                rays_closest=info["rays_closest"], rays_shadow=info["rays_shadow"], width=w, height=h)
+            print("%-28s %dx%d %s rays %d+%d -> %d bytes" % (name, w, h, " ".join(extra), info["rays_closest"], info["rays_shadow"], os.path.getsize(out)))
         for name, w, h, nph in PHOTON:
             if only and name not in only:
                 continue

@@ -20,7 +20,7 @@ def emu(scene, prefix, *args):
     return json.loads(out.decode().splitlines()[-1]), read_aov(prefix + ".aov")
 
 
-@pytest.mark.parametrize("name", ["cfg1_spheres_plane", "det_refract", "det_textured", "det_mesh", "det_objmtl"])
+@pytest.mark.parametrize("name", ["cfg1_spheres_plane", "det_refract", "det_textured", "det_mesh", "det_objmtl", "det_facemtl"])
 def test_det_mode_matches_reference_golden(built, tmp_path, name):
     g = np.load(os.path.join(GOLD, name + "_det.npz"))
     w, h = int(g["width"]), int(g["height"])
@@ -29,6 +29,22 @@ def test_det_mode_matches_reference_golden(built, tmp_path, name):
     assert (a["z"].view(np.uint32) == g["z_bits"]).all()
     d = np.abs(a["rgb8"].astype(np.int32) - g["rgb8"].astype(np.int32))
     assert d.max() <= 1
+    assert info["rays_closest"] == int(g["rays_closest"]) and info["rays_shadow"] == int(g["rays_shadow"])
+
+
+def test_face_materials_flag_matches_the_patched_reference(built, tmp_path):
+    """BHRT_FLAG_FACE_MATERIALS (bhrt.h; SURVEY.md H4 quirk switch): every face shaded with the sub-material of its usemtl
+    group.  The fixture is the reference with ONE assignment added -- hInfo.mtlID = GetMaterialIndex(faceID) in
+    TriObj::IntersectTriangle (oracle/build_ref.py patch Q-1), which is what its own MultiMtl::Shade expects
+    (materials.h:71).  Without the flag the frame is the unpatched reference's (det_facemtl in the test above), and the
+    two fixtures differ in thousands of pixels."""
+    g = np.load(os.path.join(GOLD, "det_facemtl_facemtl_det.npz"))
+    plain = np.load(os.path.join(GOLD, "det_facemtl_det.npz"))
+    assert int((g["rgb8"] != plain["rgb8"]).any(axis=2).sum()) > 1000
+    w, h = int(g["width"]), int(g["height"])
+    info, a = emu(os.path.join("scenes", "det_facemtl.xml"), str(tmp_path / "fm"), "--det", "--size", w, h, "--face-materials")
+    assert (a["hit_id"] == g["hit_id"]).all() and (a["z"].view(np.uint32) == g["z_bits"]).all()
+    assert np.abs(a["rgb8"].astype(np.int32) - g["rgb8"].astype(np.int32)).max() <= 1
     assert info["rays_closest"] == int(g["rays_closest"]) and info["rays_shadow"] == int(g["rays_shadow"])
 
 

@@ -70,3 +70,36 @@ def test_cancel_stops_a_long_frame_early(renderer):
         renderer.render_async(mode=b.MODE_PATH, spp=1)
         renderer.render_async(mode=b.MODE_PATH, spp=1)        # second one while the first is in flight: refused
     renderer.wait()
+
+
+def test_cancel_stops_a_photon_mapped_frame_between_its_gather_rounds(renderer):
+    """A photon-mapped frame is hundreds of launches (render kernel / caustic gather in turns): progress moves
+    across them, a cancel ends the frame after the samples in flight have had their remaining gathers, and the ctx renders
+    the same frame completely afterwards."""
+    scene = b.LoadScene("scenes/cfg5_caustics.xml", 960, 540)
+    renderer.upload(scene)
+    stored, _ = renderer.photons_emit(1_000_000, seed=1)
+    renderer.photons_build(stored)
+    t0 = time.perf_counter()
+    full = renderer.render(mode=b.MODE_PATH, spp=64, seed=4, use_photon_map=True, want=("rgb8",))
+    t_full = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    renderer.render_async(mode=b.MODE_PATH, spp=64, seed=4, use_photon_map=True, want=("rgb8",))
+    seen = []
+    while True:
+        done, total, finished = renderer.progress()
+        seen.append(done)
+        if finished or done > total // 8:
+            break
+        time.sleep(0.001)
+    assert not finished, "the frame finished before it could be cancelled"
+    assert seen == sorted(seen)
+    renderer.cancel()
+    with pytest.raises(b.BhrtError) as e:
+        renderer.wait()
+    t_cancelled = time.perf_counter() - t0
+    assert "cancel" in str(e.value)
+    assert t_cancelled < 0.6 * t_full, "cancelled frame took %.3f s of %.3f s" % (t_cancelled, t_full)
+    again = renderer.render(mode=b.MODE_PATH, spp=64, seed=4, use_photon_map=True, want=("rgb8",))
+    assert (again["rays_closest"], again["rays_shadow"]) == (full["rays_closest"], full["rays_shadow"])
+    assert (again["rgb8"] == full["rgb8"]).all()

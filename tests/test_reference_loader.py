@@ -21,7 +21,7 @@ from conftest import ROOT
 REF_GPU = os.path.join(ROOT, "oracle", "_ref", "bhrt_ref_gpu")
 DUMP = os.path.join(ROOT, "build", "desc_dump")
 GOLD = os.path.join(ROOT, "tests", "golden")
-SCENES = ["cfg1_spheres_plane", "det_refract", "det_textured", "det_mesh", "det_objmtl", "det_caustics",
+SCENES = ["cfg1_spheres_plane", "det_refract", "det_textured", "det_mesh", "det_objmtl", "det_facemtl", "det_caustics",
           "cfg2_mesh_refract", "cfg3_textured_arealight", "cfg4_gi", "cfg5_caustics"]
 
 pytestmark = pytest.mark.skipif(not os.path.exists(REF_GPU), reason="oracle/_ref/bhrt_ref_gpu not built (needs /root/reference once)")
