@@ -479,18 +479,21 @@ BHRT_HD void intersect_pair(const PairNode *pn, const Ray &r, float t_max, bool 
 // kernel keeps a COPY of the scalars in registers while it steps -- as members of one struct next to dynamically
 // indexed arrays the compiler has to assume every push may have changed them and re-reads the ray from local memory on
 // every step, which was 37 % of the kernel's local-memory traffic, profiles/r2_cfg2_wf_render_ncu_summary.json)
-struct MeshTravHot {
+struct MeshTravHot {        // what EVERY BVH step reads and writes: 44 bytes = 11 words (odd: one per thread in shared memory is conflict-free)
     Ray ray;
-    float len_dir;
-    const PairNode *pairs;
-    const TriRec *tris;
+    float z;                // running closest hit distance (in/out)
     uint32_t cur;
-    int sp, hits;
-    float z; bool front; MeshHit mh;        // running closest hit (in/out)
+    uint16_t sp, hits;      // deferred children on the stack; triangles accepted so far
+    uint32_t pairs_off;     // the mesh's PairNode array: byte offset into SceneView::accel_data
+    bool any_hit, done, result, front;
+};
+static_assert(sizeof(MeshTravHot) == 44, "MeshTravHot: 11 words");
+struct MeshTravCold {       // leaves and accepted hits only
+    float len_dir;
+    uint32_t tris_off;      // the mesh's TriRec array (accel_data)
+    MeshHit mh;             // the winning triangle (in/out)
     float t_max_shadow;
     int hitSide;
-    bool any_hit;
-    bool done, result;
 #ifndef __CUDACC__
     const WideNode *wide; uint32_t wide_root, wide_root_aux;    // CPU harness only (wide_trav_run)
 #endif
@@ -502,22 +505,26 @@ struct MeshTravStack {
     int st_hits[BHRT_BVH_STACK];        // (fast build: only box-hit children are deferred, see mesh_trav_pop)
 #endif
 };
-struct MeshTrav : MeshTravHot { MeshTravStack stk; };
+// the three parts of one traversal.  They are separate objects on purpose: the render kernel keeps the hot part of every
+// thread in SHARED memory (wavefront.cuh) -- in local memory, next to the dynamically indexed stack and competing with a
+// thousand threads' lane copies for L1, its dozen reloads per step missed L1 half of the time and DRAM half of that
+// (profiles/r2_cfg2_wf_render_ncu_summary.json: a BVH step took ~5 000 cycles).
+struct MeshTrav { MeshTravHot hot; MeshTravCold cold; MeshTravStack stk; };
 
-BHRT_HD void mesh_trav_begin(MeshTrav &T, const SceneView &s, const MeshAccel &A, const Ray &ray, bool any_hit, float t_max_shadow,
+BHRT_HD void mesh_trav_begin(MeshTravHot &T, MeshTravCold &C, const SceneView &s, const MeshAccel &A, const Ray &ray, bool any_hit, float t_max_shadow,
                              float z, bool front, int hitSide)
 {
-    T.ray = ray; T.any_hit = any_hit; T.t_max_shadow = t_max_shadow; T.z = z; T.front = front; T.hitSide = hitSide;
-    T.mh.face = 0; T.mh.a0 = T.mh.a1 = T.mh.a2 = 0;
+    T.ray = ray; T.any_hit = any_hit; C.t_max_shadow = t_max_shadow; T.z = z; T.front = front; C.hitSide = hitSide;
+    C.mh.face = 0; C.mh.a0 = C.mh.a1 = C.mh.a2 = 0;
     T.sp = 0; T.hits = 0; T.result = false;
     float tmin = -1;
     if (!intersect_box(A.root_box, ray, any_hit ? BHRT_BIGFLOAT : z, tmin)) { T.done = true; return; }
-    T.pairs = (const PairNode *)(s.accel_data + A.pairs_off);
-    T.tris = (const TriRec *)(s.accel_data + A.tris_off);
+    T.pairs_off = (uint32_t)A.pairs_off;
+    C.tris_off = (uint32_t)A.tris_off;
 #ifndef __CUDACC__
-    T.wide = (const WideNode *)(s.accel_data + A.wide_off); T.wide_root = A.wide_root; T.wide_root_aux = A.wide_root_aux;
+    C.wide = (const WideNode *)(s.accel_data + A.wide_off); C.wide_root = A.wide_root; C.wide_root_aux = A.wide_root_aux;
 #endif
-    T.len_dir = length(ray.dir);
+    C.len_dir = length(ray.dir);
     T.cur = A.root_word;
     T.done = false;
 }
@@ -537,7 +544,7 @@ BHRT_HD void mesh_trav_pop(MeshTravHot &T, MeshTravStack &S)
             // z <= tmin_far" is then the plain distance cull, and no hit count needs to be remembered
             if (!(T.z > S.st_tmin[T.sp])) continue;
 #else
-            bool nearHit = (T.hits != S.st_hits[T.sp]);
+            bool nearHit = ((int)T.hits != S.st_hits[T.sp]);
             if (nearHit && !(T.z > S.st_tmin[T.sp])) continue;
 #endif
         }
@@ -547,12 +554,12 @@ BHRT_HD void mesh_trav_pop(MeshTravHot &T, MeshTravStack &S)
     T.result = T.hits > 0;
     T.done = true;
 }
-// T.cur is an internal node: both child boxes, near child first
-BHRT_HD void mesh_trav_internal(MeshTravHot &T, MeshTravStack &S)
+// T.cur is an internal node: both child boxes, near child first.  accel = SceneView::accel_data
+BHRT_HD void mesh_trav_internal(MeshTravHot &T, MeshTravStack &S, const uint8_t *accel)
 {
     BHRT_TRAV_HOOK(false, T.any_hit);
     bool h1, h2; float t1, t2; uint32_t w1, w2;
-    intersect_pair(T.pairs + T.cur, T.ray, T.any_hit ? BHRT_BIGFLOAT : T.z, h1, t1, h2, t2, w1, w2);
+    intersect_pair((const PairNode *)(accel + T.pairs_off) + T.cur, T.ray, T.any_hit ? BHRT_BIGFLOAT : T.z, h1, t1, h2, t2, w1, w2);
     if (h1 || h2) {
         uint32_t first, second; float tsecond;
         if (T.any_hit || t1 < t2) { first = w1; second = w2; tsecond = t2; }
@@ -567,7 +574,7 @@ BHRT_HD void mesh_trav_internal(MeshTravHot &T, MeshTravStack &S)
         if (T.sp < BHRT_BVH_STACK) {
             S.st_word[T.sp] = second; S.st_tmin[T.sp] = tsecond;
 #if !BHRT_FAST
-            S.st_hits[T.sp] = T.hits;
+            S.st_hits[T.sp] = (int)T.hits;
 #endif
             T.sp++;
         }
@@ -577,26 +584,27 @@ BHRT_HD void mesh_trav_internal(MeshTravHot &T, MeshTravStack &S)
     mesh_trav_pop(T, S);
 }
 // T.cur is a leaf: its triangles
-BHRT_HD void mesh_trav_leaf(MeshTravHot &T, MeshTravStack &S)
+BHRT_HD void mesh_trav_leaf(MeshTravHot &T, MeshTravCold &C, MeshTravStack &S, const uint8_t *accel)
 {
     BHRT_TRAV_HOOK(true, T.any_hit);
     const uint32_t cur = T.cur;
     const uint32_t cnt = BHRT_BVH_COUNT(cur), off = BHRT_BVH_OFFSET(cur);
+    const TriRec *tris = (const TriRec *)(accel + C.tris_off) + off;
     if (T.any_hit) {
         float lz = BHRT_BIGFLOAT; bool lf; MeshHit lm;
         bool any = false;
         for (uint32_t i = 0; i < cnt; i++)
-            if (intersect_trirec(T.tris + off + i, T.ray, T.len_dir, lz, lf, HIT_FRONT, lm)) any = true;
-        if (any) { T.result = lz > BHRT_BIAS && lz < T.t_max_shadow; T.done = true; return; }
+            if (intersect_trirec(tris + i, T.ray, C.len_dir, lz, lf, HIT_FRONT, lm)) any = true;
+        if (any) { T.result = lz > BHRT_BIAS && lz < C.t_max_shadow; T.done = true; return; }
     } else {
         for (uint32_t i = 0; i < cnt; i++)
-            if (intersect_trirec(T.tris + off + i, T.ray, T.len_dir, T.z, T.front, T.hitSide, T.mh)) T.hits++;
+            if (intersect_trirec(tris + i, T.ray, C.len_dir, T.z, T.front, C.hitSide, C.mh)) T.hits++;
     }
     mesh_trav_pop(T, S);
 }
-BHRT_HD void mesh_trav_step(MeshTrav &T)
+BHRT_HD void mesh_trav_step(MeshTrav &M, const uint8_t *accel)
 {
-    if (BHRT_BVH_LEAF(T.cur)) mesh_trav_leaf(T, T.stk); else mesh_trav_internal(T, T.stk);
+    if (BHRT_BVH_LEAF(M.hot.cur)) mesh_trav_leaf(M.hot, M.cold, M.stk, accel); else mesh_trav_internal(M.hot, M.stk, accel);
 }
 
 #ifndef __CUDACC__
@@ -611,18 +619,19 @@ BHRT_HD void mesh_trav_step(MeshTrav &T)
 //            reference's order; the first of the reference's leaves that holds a front-face hit decides
 //            (TraceBVHShadow, TriObj.cpp:272-291).  Like the fast build of the binary traversal, a child whose
 //            box the ray misses is not visited.
-inline void wide_trav_run(MeshTrav &T)
+inline void wide_trav_run(MeshTravHot &T, MeshTravCold &C, const uint8_t *accel)
 {
+    const TriRec *T_tris = (const TriRec *)(accel + C.tris_off);
     uint32_t st_w[BHRT_WIDE_STACK]; float st_t[BHRT_WIDE_STACK]; uint32_t st_a[BHRT_WIDE_STACK];
     int sp = 0;
-    uint32_t cur = T.wide_root, aux = T.wide_root_aux;
+    uint32_t cur = C.wide_root, aux = C.wide_root_aux;
     for (;;) {
         if (BHRT_BVH_LEAF(cur)) {
             const uint32_t cnt = BHRT_BVH_COUNT(cur), off = BHRT_BVH_OFFSET(cur);
             bool hit[8]; float t[8]; bool fr[8]; MeshHit mh[8];
             for (uint32_t j = 0; j < cnt; j++) {
                 t[j] = T.any_hit ? BHRT_BIGFLOAT : T.z;
-                hit[j] = intersect_trirec(T.tris + off + j, T.ray, T.len_dir, t[j], fr[j], T.any_hit ? (int)HIT_FRONT : T.hitSide, mh[j]);
+                hit[j] = intersect_trirec(T_tris + off + j, T.ray, C.len_dir, t[j], fr[j], T.any_hit ? (int)HIT_FRONT : C.hitSide, mh[j]);
             }
             if (T.any_hit) {
                 int f = -1;
@@ -632,15 +641,15 @@ inline void wide_trav_run(MeshTrav &T)
                     uint32_t e = (uint32_t)f + 1; while (e < cnt && !((aux >> e) & 1u)) e++;
                     float lz = BHRT_BIGFLOAT;
                     for (uint32_t j = (uint32_t)b; j < e; j++) if (hit[j] && t[j] < lz) lz = t[j];
-                    T.result = lz > BHRT_BIAS && lz < T.t_max_shadow; T.done = true; return;
+                    T.result = lz > BHRT_BIAS && lz < C.t_max_shadow; T.done = true; return;
                 }
             } else {
                 int w = -1;
                 for (uint32_t j = 0; j < cnt; j++) if (hit[j] && (w < 0 || t[j] <= t[w])) w = (int)j;
-                if (w >= 0) { T.z = t[w]; T.front = fr[w]; T.mh = mh[w]; T.hits++; }
+                if (w >= 0) { T.z = t[w]; T.front = fr[w]; C.mh = mh[w]; T.hits++; }
             }
         } else {
-            const WideNode &nd = T.wide[cur];
+            const WideNode &nd = C.wide[cur];
             int order[8], n = 0; float tm[8];
             for (int j = 0; j < 8; j++) {
                 if (nd.c[j].word == BHRT_WIDE_EMPTY) continue;
@@ -810,7 +819,8 @@ struct MeshJob {
     int extra;              // next node index to scan for mesh nodes beyond the mask
     int k;                  // mesh node being traversed
     bool in_trav, strict, blocked;
-    MeshTrav T;
+    MeshTravCold C;         // (the hot part of the traversal is the caller's: shared memory in the render kernel)
+    MeshTravStack stk;
 };
 
 BHRT_HD void mesh_job_begin(MeshJob &J, const SceneView &s, const Query &q, float z, int node, bool front, uint32_t mask)
@@ -827,7 +837,7 @@ BHRT_HD void mesh_job_begin(MeshJob &J, const SceneView &s, const Query &q, floa
 
 // Pick the next mesh node the ray has to visit and start its traversal (root box included).
 // false = no mesh node left: the job is finished.
-BHRT_HD bool mesh_job_next(MeshJob &J, const SceneView &s)
+BHRT_HD bool mesh_job_next(MeshJob &J, MeshTravHot &T, const SceneView &s)
 {
     const bool shadow = (J.q.kind == Q_SHADOW);
     int k;
@@ -844,45 +854,47 @@ BHRT_HD bool mesh_job_next(MeshJob &J, const SceneView &s)
     J.k = k;
     const bhrt_node &nd = s.nodes[k];
     Ray r = node_local_ray(s, k, J.q.ray);
-    if (shadow) mesh_trav_begin(J.T, s, s.accels[nd.mesh], r, true, J.q.t_max, BHRT_BIGFLOAT, true, J.q.hitSide);
+    if (shadow) mesh_trav_begin(T, J.C, s, s.accels[nd.mesh], r, true, J.q.t_max, BHRT_BIGFLOAT, true, J.q.hitSide);
     else {
         // an equal-t candidate of an EARLIER node loses against the current winner
         J.strict = J.h.node > k;
-        mesh_trav_begin(J.T, s, s.accels[nd.mesh], r, false, 0.f, J.strict ? prev_float(J.h.z) : J.h.z, J.h.front, J.q.hitSide);
+        mesh_trav_begin(T, J.C, s, s.accels[nd.mesh], r, false, 0.f, J.strict ? prev_float(J.h.z) : J.h.z, J.h.front, J.q.hitSide);
     }
     J.in_trav = true;
     return true;
 }
 // Collect a finished traversal (J.T.done).  true = the job is finished (shadow ray blocked).
-BHRT_HD bool mesh_job_harvest(MeshJob &J)
+BHRT_HD bool mesh_job_harvest(MeshJob &J, const MeshTravHot &T)
 {
     J.in_trav = false;
-    if (J.T.result) {
+    if (T.result) {
         if (J.q.kind == Q_SHADOW) { J.blocked = true; return true; }
-        J.h.z = J.T.z; J.h.front = J.T.front; J.h.node = J.k;
-        J.h.uvw = V3(J.T.mh.a0, J.T.mh.a1, J.T.mh.a2); J.h.duvw0.x = u2f(J.T.mh.face);
+        J.h.z = T.z; J.h.front = T.front; J.h.node = J.k;
+        J.h.uvw = V3(J.C.mh.a0, J.C.mh.a1, J.C.mh.a2); J.h.duvw0.x = u2f(J.C.mh.face);
     }
     return false;
 }
 // one action per call; returns true when the job is finished
-BHRT_HD bool mesh_job_step(MeshJob &J, const SceneView &s)
+BHRT_HD bool mesh_job_step(MeshJob &J, MeshTravHot &T, const SceneView &s)
 {
     if (!J.in_trav) {
-        if (!mesh_job_next(J, s)) return true;
+        if (!mesh_job_next(J, T, s)) return true;
 #ifndef __CUDACC__
-        if (s.use_wide && !J.T.done) wide_trav_run(J.T);
+        if (s.use_wide && !T.done) wide_trav_run(T, J.C, s.accel_data);
 #endif
     }
-    else mesh_trav_step(J.T);
-    if (J.T.done) return mesh_job_harvest(J);
+    else if (BHRT_BVH_LEAF(T.cur)) mesh_trav_leaf(T, J.C, J.stk, s.accel_data);
+    else mesh_trav_internal(T, J.stk, s.accel_data);
+    if (T.done) return mesh_job_harvest(J, T);
     return false;
 }
 
 BHRT_HD bool scene_trace_meshes(const SceneView &s, const Query &q, Hit &h, uint32_t mesh_mask)
 {
     MeshJob J;
+    MeshTravHot T;
     mesh_job_begin(J, s, q, h.z, h.node, h.front, mesh_mask);
-    while (!mesh_job_step(J, s)) {}
+    while (!mesh_job_step(J, T, s)) {}
     if (J.blocked) return true;
     h = J.h;
     return false;

@@ -122,10 +122,10 @@ __global__ void dbg_trace_binary(SceneView s, int mesh, int n, const float *__re
     Ray r; r.p = V3(q[0], q[1], q[2]); r.dir = V3(q[3], q[4], q[5]);
     const bool shadow = q[7] == 2.f;
     MeshTrav T;
-    mesh_trav_begin(T, s, s.accels[mesh], r, shadow, q[6], shadow ? BHRT_BIGFLOAT : q[6], true, shadow ? (int)HIT_FRONT : (int)HIT_FRONT_AND_BACK);
-    while (!T.done) mesh_trav_step(T);
+    mesh_trav_begin(T.hot, T.cold, s, s.accels[mesh], r, shadow, q[6], shadow ? BHRT_BIGFLOAT : q[6], true, shadow ? (int)HIT_FRONT : (int)HIT_FRONT_AND_BACK);
+    while (!T.hot.done) mesh_trav_step(T, s.accel_data);
     float *o = out + 4 * (size_t)i;
-    o[0] = T.result ? 1.f : 0.f; o[1] = T.z; o[2] = (float)T.mh.face; o[3] = T.front ? 1.f : 0.f;
+    o[0] = T.hot.result ? 1.f : 0.f; o[1] = T.hot.z; o[2] = (float)T.cold.mh.face; o[3] = T.hot.front ? 1.f : 0.f;
 }
 __global__ void __launch_bounds__(256)
 dbg_trace_wide(SceneView s, int mesh, int n, const float *__restrict__ rays, float *__restrict__ out)
@@ -411,19 +411,23 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     auto al16 = [](int v) { return (v + 15) & ~15; };
     // the shared-memory layout; a pool whose tables do not fit next to the scene's (large node / material tables) shrinks
     const int smem_limit = 227 * 1024 - 2048;           // (static shared memory of the kernel included)
+    // (split gather: the render kernel only parks the queries -- no per-warp scratch, one list instead of two)
+    a.ext_gather = a.gather.use && c->gather_mode != 1 ? 1 : 0;
+    // the hot part of every thread's BVH traversal (binary traversal; nothing for a scene without meshes)
+    const int hot_bytes = c->view.n_mesh_nodes > 0 ? WF_BLOCK * (int)sizeof(MeshTravHot) : 0;
     for (;;) {
         a.smem_nodes = 0;
         a.smem_materials = al16(a.smem_nodes + c->view.n_nodes * (int)sizeof(bhrt_node));
         a.smem_lights = al16(a.smem_materials + c->view.n_materials * (int)sizeof(bhrt_material));
         a.smem_offsets = al16(a.smem_lights + c->view.n_lights * (int)sizeof(bhrt_light));
         a.smem_wave = al16(a.smem_offsets + 2 * (BHRT_TEX_SAMPLES - 1) * (int)sizeof(float));
-        a.smem_gather = al16(a.smem_wave + wf_wave_smem_bytes(a.pool, a.gather.use != 0));
-        // (the per-warp gather scratch only when a photon map is in use: without it the CTA stays under 32 KB)
-        a.smem_oct = al16(a.smem_gather + (a.gather.use ? (WF_BLOCK / 32) * (int)sizeof(PmWarpScratch) + (int)a.pool * 4 : 0));
-        if (a.smem_oct <= smem_limit || a.pool <= 1024u) break;
+        a.smem_gather = al16(a.smem_wave + wf_wave_smem_bytes(a.pool, a.gather.use != 0 && !a.ext_gather));
+        // (the per-warp gather scratch only when a photon map is gathered in this kernel: without it the CTA stays small)
+        a.smem_oct = al16(a.smem_gather + (!a.gather.use ? 0 : (a.ext_gather ? (int)a.pool * 2 : (WF_BLOCK / 32) * (int)sizeof(PmWarpScratch) + (int)a.pool * 4)));
+        if (a.smem_oct + hot_bytes <= smem_limit || a.pool <= 1024u) break;
         a.pool -= 1024u;
     }
-    if (a.smem_oct > smem_limit) return set_err(BHRT_ERR_LIMIT, "bhrt_render: scene tables do not fit in shared memory");
+    if (a.smem_oct + hot_bytes > smem_limit) return set_err(BHRT_ERR_LIMIT, "bhrt_render: scene tables do not fit in shared memory");
     // a CTA claims its work in batches of whole super-tiles: one (4096 items) normally, two for photon-mapped frames
     // (measured on BASELINE config 5: 8192 items 7.6 s, 16384 items 8.1 s -- larger batches put whole caustic regions
     // on a few CTAs and the others wait for them)
@@ -449,8 +453,12 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     const bool want_wide = c->traversal ? c->traversal == 1 : (p->flags & BHRT_FLAG_WIDE_BVH) != 0;
     if (fast && want_wide) if (int wr = ensure_wide(c)) return wr;
     const int smem_wide = al16(a.smem_oct + (WF_BLOCK / 8) * (int)sizeof(OctShared));
+    a.smem_hot = a.smem_oct;                            // (binary traversal: the hot part of every thread's BVH traversal)
+    const int smem_binary = al16(a.smem_oct + hot_bytes);
     const int variant = !fast ? 0 : ((want_wide && c->view.use_wide && smem_wide <= 200 * 1024) ? 1 : 2);
-    const int smem_bytes = variant == 1 ? smem_wide : a.smem_oct;
+    // (BHRT_EXTRA_SMEM: unused dynamic shared memory on top, i.e. that much less L1 -- the experiment behind DESIGN.md 4.1's
+    // "what would a shared-memory home for the traversal state cost the rest of the kernel")
+    const int smem_bytes = (variant == 1 ? smem_wide : smem_binary) + (getenv("BHRT_EXTRA_SMEM") ? atoi(getenv("BHRT_EXTRA_SMEM")) : 0);
     if (c->kernel_smem[variant] != smem_bytes) {
         int per_sm = 0;
         if (variant == 0) {
@@ -479,7 +487,6 @@ static int launch_render_once(bhrt_ctx *c, const bhrt_params *p, bhrt_outputs *o
     a.cnt = (WaveCounters *)c->wave_counters.p;
     a.cancel = (const unsigned *)c->cancel_flag.p;
     // split gather: the caustic queries are evaluated between launches of wf_render, device-wide and sorted by photon cell
-    a.ext_gather = a.gather.use && c->gather_mode != 1 ? 1 : 0;
     a.gather_prof = getenv("BHRT_DEBUG") ? 1 : 0;
     a.exit_live = 0;            // (measured on config 5: leaving with up to 1/32 ... 1/4 of the lanes still live is no faster than waiting for all)
     if (const char *e = getenv("BHRT_EXIT_LIVE")) { const long v = atol(e); a.exit_live = v > 0 ? a.pool / (unsigned)v : 0u; }

@@ -157,7 +157,7 @@ struct WaveArgs {
     unsigned mesh_batch;        // queued rays that switch the traversal phase on
     unsigned gather_batch;      // parked caustic queries that switch the gather phase on
     int trav_min, trav_max, trav_pct;   // internal-node steps per trip: at least / at most / until this % of the job lanes is still at an internal node
-    int smem_nodes, smem_materials, smem_lights, smem_offsets, smem_wave, smem_gather, smem_oct;   // byte offsets into dynamic shared memory
+    int smem_nodes, smem_materials, smem_lights, smem_offsets, smem_wave, smem_gather, smem_oct, smem_hot;   // byte offsets into dynamic shared memory
     // ---- split gather: the caustic queries are NOT evaluated inside this kernel.  A CTA runs until every one of
     // its lanes is parked at a query (or dead), appends its queries to gq_list, saves what it needs to carry on and EXITS;
     // the host sorts the queries of ALL CTAs by photon cell, pm_gather_queries evaluates them (neighbouring warps stream
@@ -850,7 +850,8 @@ wf_render(SceneView s, WaveArgs a)
     unsigned char *lkey = (unsigned char *)(mq + P);                       // [P] key of lane id
     unsigned char *pend = lkey + P;                                        // [P] lane id is queued / being traversed
     PmWarpScratch *pm_scratch = (PmWarpScratch *)(smem + a.smem_gather);   // [WF_BLOCK / 32]   (only with a photon map)
-    unsigned short *gq = (unsigned short *)(pm_scratch + WF_BLOCK / 32);   // [P] lanes waiting for a caustic gather
+    // [P] lanes waiting for a caustic gather (split gather: the only thing this kernel keeps of the gather)
+    unsigned short *gq = a.ext_gather ? (unsigned short *)(smem + a.smem_gather) : (unsigned short *)(pm_scratch + WF_BLOCK / 32);
     unsigned short *gcount = (unsigned short *)(pend + P);                 // [P/32][WF_NKEYS] per-group key counts / offsets (P is a multiple of 32)
 #if WF_PREFETCH_FRAME
     unsigned char *lsp = smem + a.smem_gather - P - 16;                     // [P] min(frames in use, 255) of lane id
@@ -897,7 +898,11 @@ wf_render(SceneView s, WaveArgs a)
     uint32_t jmask = 0; int jextra = 0, jk = -1, jkind = Q_NONE;
     bool in_trav = false, jblocked = false, jfirst = false;
 #else
-    MeshJob J;                      // this thread's BVH traversal, kept across iterations
+    MeshJob J;                      // this thread's BVH traversal, kept across iterations: the job, the cold part, the stack ...
+    // ... and the part every BVH step touches, in SHARED memory (44 bytes per thread, stride 11 words: conflict-free).  In
+    // local memory its reloads -- a dozen per step -- missed L1 half of the time (a thousand threads' lane copies and
+    // stacks go through the same 200 KB) and a BVH step took ~5 000 cycles; shared memory costs 44 KB of L1 instead.
+    MeshTravHot &H = ((MeshTravHot *)(smem + a.smem_hot))[tid];
 #endif
     bool have = false;
     unsigned jid = 0;
@@ -1336,19 +1341,19 @@ wf_render(SceneView s, WaveArgs a)
                 if (!__any_sync(0xffffffffu, have)) break;
                 // job control: next mesh node of the ray (or none left: finished)
                 bool finished = false;
-                if (have && !J.in_trav) finished = !mesh_job_next(J, s);
+                if (have && !J.in_trav) finished = !mesh_job_next(J, H, s);
                 // internal nodes: lanes that reach a leaf wait here for the others (a few trips),
                 // then all leaves are processed together -- the triangle tests run converged
                 for (int r = 0; r < a.trav_max; r++) {
-                    const bool in_job = have && !finished && !J.T.done;
-                    const bool go = in_job && !BHRT_BVH_LEAF(J.T.cur);
+                    const bool in_job = have && !finished && !H.done;
+                    const bool go = in_job && !BHRT_BVH_LEAF(H.cur);
                     const unsigned gm = __ballot_sync(0xffffffffu, go), jm = __ballot_sync(0xffffffffu, in_job);
                     // stop when no lane is at an internal node, or (after a few steps) when most are waiting at a leaf
                     if (!gm || (r >= a.trav_min && 100 * __popc(gm) <= a.trav_pct * __popc(jm))) break;
-                    if (go) mesh_trav_internal(J.T, J.T.stk);
+                    if (go) mesh_trav_internal(H, J.stk, s.accel_data);
                 }
-                if (have && !finished && !J.T.done && BHRT_BVH_LEAF(J.T.cur)) mesh_trav_leaf(J.T, J.T.stk);
-                if (have && !finished && J.T.done) finished = mesh_job_harvest(J);
+                if (have && !finished && !H.done && BHRT_BVH_LEAF(H.cur)) mesh_trav_leaf(H, J.C, J.stk, s.accel_data);
+                if (have && !finished && H.done) finished = mesh_job_harvest(J, H);
                 if (finished) {
                     Lane &Lg = lanes[jid];
                     if (J.blocked) Lg.hit_ok = true;
