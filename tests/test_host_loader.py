@@ -137,3 +137,30 @@ def test_render_image_side_buffers(built):
     assert (simg == (255 * (cnt.astype(np.int32) - cnt.min())) // (int(cnt.max()) - int(cnt.min()))).all()
     flat, m = b.sample_count_image(np.full((4, 4), 7, np.uint8))
     assert m == 7 and (flat == 0).all()
+
+
+def test_usemtl_groups_and_sub_materials_are_flattened(built):
+    """An OBJ's usemtl groups (cyTriMesh.h:467-490: faces regrouped by material, cumulative counts in mcfc) reach the ABI as
+    bhrt_mesh::n_groups + int32 group_end[] behind the elems array, and ALL sub-materials of the auto-MultiMtl
+    (xmlload.cpp:219-250) follow the first one in the material table (bhrt.h: BHRT_MTL_MULTI / BHRT_MTL_SUBCOUNT) -- what
+    BHRT_FLAG_FACE_MATERIALS reads; the default frame only ever uses sub-material 0, like the reference."""
+    s = b.LoadScene("scenes/det_facemtl.xml")
+    d = s.desc.contents
+    assert d.n_meshes == 1
+    raw = bytes((C.c_uint8 * 88).from_address(d.meshes))
+    nv, nf, nvn, nvt, nb, n_groups = np.frombuffer(raw[:24], np.int32)
+    offs = np.frombuffer(raw[24:], np.int64)
+    assert (nf, n_groups) == (12, 2)                # six quads fanned into triangles, two usemtl groups
+    blob = np.ctypeslib.as_array((C.c_uint8 * d.mesh_bytes).from_address(d.mesh_data))
+    at = (int(offs[7]) + 4 * int(nf) + 15) & ~15
+    group_end = np.frombuffer(blob[at:at + 4 * n_groups].tobytes(), np.int32)
+    assert list(group_end) == [6, 12]
+    # the cube's node -> the MultiMtl's first entry, flagged with its sub-material count; matB right behind it
+    cube = [d.nodes[i] for i in range(d.n_nodes) if d.nodes[i].kind == 3][0]
+    mraw = bytes((C.c_uint8 * (72 * d.n_materials)).from_address(d.materials))      # bhrt_material: 72 bytes, flags at offset 64
+    def mtl(i):
+        r = mraw[72 * i:72 * (i + 1)]
+        return np.frombuffer(r[:12], np.float32), int(np.frombuffer(r[64:68], np.int32)[0])
+    (kd0, flags0), (kd1, flags1) = mtl(cube.material), mtl(cube.material + 1)
+    assert flags0 & 1 and (flags0 >> 8) & 0xff == 2 and flags1 == 0
+    assert np.allclose(kd0, [0.8, 0.3, 0.2]) and np.allclose(kd1, [0.2, 0.3, 0.8])
