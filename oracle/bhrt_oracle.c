@@ -83,9 +83,13 @@ static ray_t to_node_coords(const bhrt_xform *t, ray_t r)
     return o;
 }
 
-typedef struct { float z; v3 p, N, uvw, duvw[2]; int node; int front; } hit_t;     /* scene.h:62-75 (mtlID: meshes only) */
+typedef struct { float z; v3 p, N, uvw, duvw[2]; int node; int front; int mtlID; } hit_t;     /* scene.h:62-75 */
+/* oracle patch Q-1 of build_ref.py / BHRT_FLAG_FACE_MATERIALS of the product: TriObj::IntersectTriangle sets hInfo.mtlID to the
+ * usemtl group of the face (HEAD never does, TriObj.cpp:68-189); 0 = the reference as it is */
+static int g_face_materials = 0;
+void bhrt_oracle_set_face_materials(int on) { g_face_materials = on; }
 /* HitInfo::Init (scene.h:74) */
-static void hit_init(hit_t *h) { h->z = BIGFLOAT; h->node = -1; h->front = 1; h->p = V(0, 0, 0); h->N = V(0, 0, 0); h->uvw = V(0.5f, 0.5f, 0.5f); h->duvw[0] = V(0, 0, 0); h->duvw[1] = V(0, 0, 0); }
+static void hit_init(hit_t *h) { h->z = BIGFLOAT; h->node = -1; h->front = 1; h->mtlID = 0; h->p = V(0, 0, 0); h->N = V(0, 0, 0); h->uvw = V(0.5f, 0.5f, 0.5f); h->duvw[0] = V(0, 0, 0); h->duvw[1] = V(0, 0, 0); }
 
 /* Sphere::IntersectRay (Objects/Sphere/Sphere.cpp:8-75), unit sphere at the origin */
 static int sphere_intersect(ray_t ray, hit_t *h, int hitSide)
@@ -166,6 +170,7 @@ typedef struct {
     const uint32_t *f, *fn, *ft;
     const bhrt_bvh_node *bvh;
     const uint32_t *elems;
+    const int32_t *group_end; int n_groups;   /* cyTriMesh mcfc (cyTriMesh.h:113,467-490): bhrt_mesh::n_groups */
 } mesh_t;
 static mesh_t mesh_view(const bhrt_scene_desc *d, int i)
 {
@@ -173,7 +178,8 @@ static mesh_t mesh_view(const bhrt_scene_desc *d, int i)
     const uint8_t *b = d->mesh_data;
     mesh_t r = { (const float *)(b + m->v_off), (const float *)(b + m->vn_off), (const float *)(b + m->vt_off),
                  (const uint32_t *)(b + m->f_off), (const uint32_t *)(b + m->fn_off), (const uint32_t *)(b + m->ft_off),
-                 (const bhrt_bvh_node *)(b + m->bvh_off), (const uint32_t *)(b + m->elems_off) };
+                 (const bhrt_bvh_node *)(b + m->bvh_off), (const uint32_t *)(b + m->elems_off),
+                 (const int32_t *)(b + ((m->elems_off + 4 * (int64_t)m->nf + 15) & ~(int64_t)15)), m->n_groups };
     return r;
 }
 /* Box::IntersectRay (Objects/Box/Box.cpp:3-46); Corner(0) = pmin, Corner(7) = pmax (scene.h:100-107) */
@@ -233,6 +239,11 @@ static int triangle_intersect(const mesh_t *m, ray_t ray, hit_t *h, int hitSide,
     h->front = front;
     h->uvw = interpolate(m->vt, m->ft, face, bc);
     h->duvw[0] = V(0, 0, 0); h->duvw[1] = V(0, 0, 0);
+    if (g_face_materials) {                                /* TriMesh::GetMaterialIndex (cyTriMesh.h:221-227); none -> 0 */
+        int g = 0;
+        while (g < m->n_groups && (int)face >= m->group_end[g]) g++;
+        h->mtlID = g < m->n_groups ? g : 0;
+    }
     return 1;
 }
 #define BVH_LEAF(d) ((d) >> 31)                            /* cyBVH.h:187-203 */
@@ -691,7 +702,10 @@ static v3 shade(scene_t *s, ray_t ray, const hit_t *h, int bounceCount)
 }
 static v3 shade_body(scene_t *s, ray_t ray, const hit_t *h, int bounceCount)
 {
+    /* Node::GetMaterial()->Shade: a MultiMtl dispatches on hInfo.mtlID (materials.h:71; its sub-materials are contiguous in the
+     * flattened table, bhrt.h), which stays 0 in the reference as it is */
     const bhrt_material *M = &s->d->materials[s->d->nodes[h->node].material];
+    if ((M->flags & BHRT_MTL_MULTI) && h->mtlID > 0 && h->mtlID < BHRT_MTL_SUBCOUNT(M->flags)) M += h->mtlID;
     v3 vN = norm(h->N);
     v3 vV = norm(sub(ray.p, h->p));
     float cosPhi1 = dot(vN, vV);

@@ -28,7 +28,7 @@ def in_scope(scene):
     return bool(lib().bhrt_oracle_in_scope(C.cast(scene.desc, C.c_void_p)))
 
 
-def render_det(scene, tir_budget=16):
+def render_det(scene, tir_budget=16, face_materials=False):
     """scene: bhraytracer_b200.Scene (the host loader's flattened description).  Also returns the
     per-pixel (closest, shadow) ray counts as pixel_rays[h, w, 2]."""
     w, h = scene.width, scene.height
@@ -38,10 +38,12 @@ def render_det(scene, tir_budget=16):
     pix = np.zeros(n * 2, np.uint32)
     rays = (C.c_uint64 * 2)()
     L = lib()
+    L.bhrt_oracle_set_face_materials(1 if face_materials else 0)       # (oracle patch Q-1 / BHRT_FLAG_FACE_MATERIALS)
     L.bhrt_oracle_render_det3.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
     L.bhrt_oracle_render_det3.restype = C.c_int
     rc = L.bhrt_oracle_render_det3(C.cast(scene.desc, C.c_void_p), tir_budget, hit.ctypes.data, z.ctypes.data, lin.ctypes.data, rgb.ctypes.data,
                                    C.cast(rays, C.c_void_p), pix.ctypes.data)
+    L.bhrt_oracle_set_face_materials(0)
     if rc != 0:
         raise ValueError("scene outside the restatement's scope (rc %d)" % rc)
     return dict(hit_id=hit.reshape(h, w), z=z.reshape(h, w), linear=lin.reshape(h, w, 3), rgb8=rgb.reshape(h, w, 3),

@@ -43,7 +43,20 @@ def same(a, o):
     assert np.abs(a["rgb8"].astype(np.int32) - o["rgb8"].astype(np.int32)).max() <= 1
 
 
-@pytest.mark.parametrize("name", ["cfg1_spheres_plane", "det_refract", "det_textured", "det_mesh", "det_objmtl"])
+def test_restatement_with_face_materials_is_pinned_by_the_patched_reference(built):
+    """hInfo.mtlID = the usemtl group of the face (oracle patch Q-1 of build_ref.py): the restatement with that switch on
+    reproduces the patched reference's fixture in every bit, and its default stays the unpatched reference's."""
+    g = np.load(os.path.join(GOLD, "det_facemtl_facemtl_det.npz"))
+    plain = np.load(os.path.join(GOLD, "det_facemtl_det.npz"))
+    scene = b.LoadScene("scenes/det_facemtl.xml", int(g["width"]), int(g["height"]))
+    for gold, flag in ((g, True), (plain, False)):
+        o = oracle_c.render_det(scene, face_materials=flag)
+        assert (o["hit_id"] == gold["hit_id"]).all() and (o["z"].view(np.uint32) == gold["z_bits"]).all()
+        assert (o["rgb8"] == gold["rgb8"]).all()
+        assert (o["rays_closest"], o["rays_shadow"]) == (int(gold["rays_closest"]), int(gold["rays_shadow"]))
+
+
+@pytest.mark.parametrize("name", ["cfg1_spheres_plane", "det_refract", "det_textured", "det_mesh", "det_objmtl", "det_facemtl"])
 def test_restatement_is_pinned_by_the_reference_golden(built, name):
     g = np.load(os.path.join(GOLD, name + "_det.npz"))
     scene = b.LoadScene("scenes/%s.xml" % name, int(g["width"]), int(g["height"]))
