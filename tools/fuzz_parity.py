@@ -11,7 +11,10 @@ direct / ambient lights -- and renders each in deterministic mode with
 
 then compares primary hit ids, z bits, 8-bit pixels and the ray counters.
 
-usage: fuzz_parity.py [--seeds A:B] [--size WxH] [--keep DIR] [--no-ref] [--photon-map N]
+usage: fuzz_parity.py [--seeds A:B] [--size WxH] [--keep DIR] [--no-ref] [--photon-map N] [--face-materials]
+
+--face-materials: every scene gets OBJs whose usemtl groups become a MultiMtl (no material= attribute) and all three
+renderers run with per-face sub-materials on (the reference with oracle patch Q-1, ours with BHRT_FLAG_FACE_MATERIALS).
 
 --photon-map N: the caustic gather instead -- the reference emits N photons and renders the gather-lit
 frame, the restatement and our device code render the same frame from its photon dump.
@@ -34,6 +37,7 @@ EMU_BIN = os.path.join(ROOT, "build", "emu_render")
 MESHES = ["scenes/assets/torus_small.obj", "scenes/assets/blob_small.obj", "scenes/assets/cube_mtl.obj"]
 BITMAPS = ["scenes/assets/bricks.png", "scenes/assets/clouds.png"]
 MAX_LEVELS = 4096       # BHRT_MAX_FRAMES_LIMIT (csrc/device/core.cuh)
+FACE_MATERIALS = False  # --face-materials
 
 
 def f(x):
@@ -100,8 +104,16 @@ def obj(rng, depth, mats, counter, meshes, dialect):
     name = "n%d" % counter[0]
     if kind is None:
         s = ind + '<object name="%s">\n' % name
+    elif kind == "obj" and FACE_MATERIALS and not counter[1] and rng.random() < 0.7:
+        # usemtl groups -> MultiMtl (xmlload.cpp:219-250).  Only ONE such node per scene: the loader creates the MultiMtl and
+        # its node binding for the first instance of the file only, a second one is left without a material and the
+        # reference dereferences null when it is hit (Main.cpp:161; our loader refuses such a scene)
+        counter[1] = 1
+        s = ind + '<object type="obj" name="scenes/assets/cube_mtl.obj">\n'
     elif kind == "obj":
-        s = ind + '<object type="obj" name="%s" material="%s">\n' % (rng.choice(MESHES), rng.choice(mats))
+        # (with --face-materials the cube only appears WITHOUT a material attribute: a file already loaded for a node that has
+        # one is found in the object list and never gets its MultiMtl, xmlload.cpp:208-217)
+        s = ind + '<object type="obj" name="%s" material="%s">\n' % (rng.choice(MESHES[:2] if FACE_MATERIALS else MESHES), rng.choice(mats))
     else:
         s = ind + '<object type="%s" name="%s" material="%s">\n' % (kind, name, rng.choice(mats))
     s += transform(rng, ind + "  ", scale=(3, 12) if kind == "plane" else (0.5, 4.0), dialect=dialect)
@@ -138,7 +150,7 @@ def scene_xml(seed, w, h, meshes=True, dialect=None):
     else:
         s += '    <environment value="%s"/>\n' % f(rng.uniform(0, 1))
     # a ground plane most of the time, then random objects
-    counter = [0]
+    counter = [0, 0]       # objects so far; a material-less OBJ was placed (--face-materials)
     if rng.random() < 0.8:
         s += '    <object type="plane" name="ground" material="%s">\n      <scale value="30"/>\n    </object>\n' % mats[0]
     for _ in range(rng.randint(2, 6)):
@@ -183,7 +195,7 @@ def compare(a, b, what):
 
 def run_binary(binary, path, out_prefix):
     from aovio import read_aov
-    out = subprocess.check_output([binary, path, out_prefix, "--det"] + (["--threads", "2"] if binary == REF_BIN else []),
+    out = subprocess.check_output([binary, path, out_prefix, "--det"] + (["--threads", "2"] if binary == REF_BIN else []) + (["--face-materials"] if FACE_MATERIALS else []),
                                   cwd=ROOT, stderr=subprocess.DEVNULL)
     info = json.loads(out.decode().splitlines()[-1])
     r = read_aov(out_prefix + ".aov")
@@ -201,7 +213,7 @@ def check_seed(seed, w, h, workdir, use_ref=True, meshes=True):
     os.chdir(ROOT)                      # asset paths in the scenes are relative to the repository root
     try:
         scene = b.LoadScene(path)
-        o = oracle_c.render_det(scene)
+        o = oracle_c.render_det(scene, face_materials=FACE_MATERIALS)
     finally:
         os.chdir(cwd)
     e = run_binary(EMU_BIN, path, os.path.join(workdir, "emu_%d" % seed))
@@ -280,7 +292,10 @@ def main():
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--no-meshes", action="store_true")
     ap.add_argument("--photon-map", type=int, default=0, metavar="N", help="gather-lit frames from N photons emitted by the reference")
+    ap.add_argument("--face-materials", action="store_true", help="per-face sub-materials on in all three renderers (patch Q-1 / BHRT_FLAG_FACE_MATERIALS)")
     a = ap.parse_args()
+    global FACE_MATERIALS
+    FACE_MATERIALS = a.face_materials
     lo, hi = (int(x) for x in a.seeds.split(":"))
     w, h = (int(x) for x in a.size.split("x"))
     workdir = a.keep or tempfile.mkdtemp(prefix="bhrt_fuzz_")
